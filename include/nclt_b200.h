@@ -1,0 +1,111 @@
+/*
+ * nclt_b200.h - C ABI of the B200 (sm_100a) landmark matcher / teach-map builder.
+ *
+ * This is the drop-in boundary for the ONE hot path named in BASELINE.json (SURVEY.md
+ * section 8).  The reference has no plugin/FFI layer for this path: the seam is three OpenCV
+ * call sites and one Python class.  Every entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/simulation/isaac).
+ *
+ * Conventions: every function returns 0 on success or a negative NCLT_ERR_* code; the text
+ * of the last failure on a context is nclt_last_error(ctx).  Nothing throws, no allocation
+ * ownership crosses the boundary except the opaque handles.  One context = one GPU + one CUDA
+ * stream + one caller at a time (the reference nodes are single-threaded executors,
+ * scripts/common/visual_landmark_matcher.py:513, teach_run_depth_mapper.py:256).
+ * Functions without a suffix take HOST pointers and copy in/out on the context's stream;
+ * *_dev variants take DEVICE pointers, enqueue on the stream and return without waiting.
+ * There is no CPU fallback: nclt_ctx_create fails if no CUDA device is usable.
+ */
+#ifndef NCLT_B200_H
+#define NCLT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCLT_OK 0
+#define NCLT_ERR_CUDA (-1)
+#define NCLT_ERR_ARG (-2)
+#define NCLT_ERR_NOMEM (-3)
+#define NCLT_ERR_STATE (-4)
+
+typedef struct nclt_ctx nclt_ctx;
+typedef struct nclt_lib nclt_lib;
+typedef struct nclt_occ nclt_occ;
+
+/* ---- context ---------------------------------------------------------------------- */
+/* stream: a cudaStream_t created by the caller (e.g. torch's current stream), or NULL to let
+ * the context own a non-blocking stream. */
+int nclt_ctx_create(int device, void* stream, nclt_ctx** out);
+int nclt_ctx_destroy(nclt_ctx* ctx);
+int nclt_ctx_sync(nclt_ctx* ctx);
+const char* nclt_last_error(nclt_ctx* ctx);
+/* kernels launched through this context so far (bench.py's gpu_launches) */
+unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
+/* library ABI version, bumped on any signature change */
+int nclt_abi_version(void);
+/* measured POPC32 op/s of a register-only kernel: roofline denominator for the matcher */
+double nclt_popc_peak(nclt_ctx* ctx, int iters, float* ms_out);
+
+/* ---- teach library ---------------------------------------------------------------- */
+/* Device copy of landmarks.pkl's per-keyframe 'descriptors' u8[n,32] and 'keypoints_3d_cam'
+ * f32[n,3] (scripts/common/visual_landmark_recorder.py:290-297; loaded at
+ * visual_landmark_matcher.py:179-187).  kf_offsets[n_kf+1] are row offsets into desc/pts3d. */
+int nclt_lib_create(nclt_ctx* ctx, int n_kf, const int32_t* kf_offsets, const uint8_t* desc,
+                    const float* pts3d, nclt_lib** out);
+/* append one keyframe (visual_landmark_matcher.py:492-496 _maybe_accumulate) */
+int nclt_lib_append(nclt_ctx* ctx, nclt_lib* lib, const uint8_t* desc, const float* pts3d, int n);
+int nclt_lib_destroy(nclt_ctx* ctx, nclt_lib* lib);
+int nclt_lib_size(const nclt_lib* lib, int* n_kf, int* n_desc, int* max_kf_rows);
+
+/* ---- descriptor matching ---------------------------------------------------------- */
+/* Common arguments: q u8[B,Nq,32] live-frame descriptors (row stride Nq per frame), q_n i32[B]
+ * valid rows per frame (NULL = Nq), cand i32[B,C] keyframe ids per frame, -1 = empty slot
+ * (NULL = keyframes 0..C-1 for every frame). */
+
+/* replaces cv2.BFMatcher(NORM_HAMMING).knnMatch(desc_curr, desc_t, k=2)
+ * (routes/03_south/teach/scripts/checkpoint_a_selftest.py:46,68) for every (frame, candidate).
+ * out_idx i32[B,C,Nq,2] trainIdx (-1 = missing), out_dist u16[B,C,Nq,2] (65535 = missing);
+ * ascending distance, ties -> lowest trainIdx. */
+int nclt_match_knn2(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                    int Nq, const int32_t* cand, int C, int32_t* out_idx, uint16_t* out_dist);
+int nclt_match_knn2_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                        int Nq, const int32_t* cand, int C, int32_t* out_idx, uint16_t* out_dist);
+
+/* knnMatch(k=2) + Lowe ratio `m.distance < LOWE_RATIO * n.distance` (checkpoint_a_selftest.py:71)
+ * evaluated exactly as den*d1 < num*d2 (0.80 -> num=4, den=5).  out_pairs i32[B,C,Nq,2] =
+ * (queryIdx, trainIdx) in increasing queryIdx, out_n i32[B,C].  A keyframe with < 2 rows yields 0. */
+int nclt_match_ratio(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                     int Nq, const int32_t* cand, int C, int num, int den, int32_t* out_pairs,
+                     int32_t* out_n);
+int nclt_match_ratio_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                         int Nq, const int32_t* cand, int C, int num, int den, int32_t* out_pairs,
+                         int32_t* out_n);
+
+/* replaces cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match(desc_t, desc_curr)
+ * (scripts/common/visual_landmark_matcher.py:211,327).  out_pairs i32[B,C,Nmax,2] =
+ * (queryIdx = teach row, trainIdx = frame row) in increasing queryIdx, out_dist u16[B,C,Nmax],
+ * out_n i32[B,C]; Nmax >= the largest candidate keyframe. */
+int nclt_match_cross(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                     int Nq, const int32_t* cand, int C, int Nmax, int32_t* out_pairs, uint16_t* out_dist,
+                     int32_t* out_n);
+int nclt_match_cross_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                         int Nq, const int32_t* cand, int C, int Nmax, int32_t* out_pairs,
+                         uint16_t* out_dist, int32_t* out_n);
+
+/* BASELINE config 5 (no reference analogue; closest: experiments/63_global_reloc/scripts/
+ * visual_landmark_matcher.py:314-345): flat global top-2 of every query row over ALL library
+ * rows of this rank.  out_keys u32[B,Nq,2]: key = dist<<23 | (idx_offset + library row),
+ * 0xFFFFFFFF = missing; keys from several ranks merge with nclt_merge_top2_dev. */
+int nclt_match_flat2_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
+                         int Nq, uint32_t idx_offset, uint32_t* out_keys);
+/* parts u32[nparts,B*Nq,2] -> out_keys u32[B*Nq,2], out_idx i32[B*Nq,2], out_dist u16[B*Nq,2]
+ * (any output may be NULL); tie -> lowest global index. */
+int nclt_merge_top2_dev(nclt_ctx* ctx, const uint32_t* parts, int nparts, int rows, uint32_t* out_keys,
+                        int32_t* out_idx, uint16_t* out_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCLT_B200_H */

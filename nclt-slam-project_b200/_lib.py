@@ -1,0 +1,127 @@
+"""ctypes binding of libnclt_b200.so (the C ABI in include/nclt_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a
+Context without a usable B200, raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnclt_b200.so')
+
+
+class NcltError(RuntimeError):
+    """Raised for any non-zero return code of the C ABI (plays the role cv2.error plays at
+    visual_landmark_matcher.py:328)."""
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+        '(nvcc, sm_100a). There is no CPU fallback.')
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _u32, _dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_double
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_sig('nclt_abi_version', _i)
+_sig('nclt_ctx_create', _i, _i, _vp, C.POINTER(_vp))
+_sig('nclt_ctx_destroy', _i, _vp)
+_sig('nclt_ctx_sync', _i, _vp)
+_sig('nclt_last_error', C.c_char_p, _vp)
+_sig('nclt_ctx_launches', C.c_ulonglong, _vp)
+_sig('nclt_popc_peak', _dbl, _vp, _i, C.POINTER(C.c_float))
+_sig('nclt_lib_create', _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp))
+_sig('nclt_lib_append', _i, _vp, _vp, _vp, _vp, _i)
+_sig('nclt_lib_destroy', _i, _vp, _vp)
+_sig('nclt_lib_size', _i, _vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i))
+for _n in ('nclt_match_knn2', 'nclt_match_knn2_dev'):
+    _sig(_n, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp)
+for _n in ('nclt_match_ratio', 'nclt_match_ratio_dev'):
+    _sig(_n, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp)
+for _n in ('nclt_match_cross', 'nclt_match_cross_dev'):
+    _sig(_n, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp)
+_sig('nclt_match_flat2_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _u32, _vp)
+_sig('nclt_merge_top2_dev', _i, _vp, _vp, _i, _i, _vp, _vp, _vp)
+
+
+def ptr(x):
+    """Raw address of a numpy array / torch tensor / None / int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, 'data_ptr'):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+def as_c(x, dtype):
+    """C-contiguous numpy view/copy of the wanted dtype (None passes through)."""
+    if x is None:
+        return None
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class Context:
+    """One GPU + one CUDA stream + scratch (include/nclt_b200.h: nclt_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        h = _vp()
+        rc = lib.nclt_ctx_create(int(device), stream, C.byref(h))
+        if rc != 0 or not h.value:
+            raise NcltError(f'nclt_ctx_create(device={device}) failed with {rc}: no usable sm_100 GPU; '
+                            'this package has no CPU fallback')
+        self.h = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            raise NcltError(f'[{rc}] {lib.nclt_last_error(self.h).decode()}')
+
+    def sync(self):
+        self.check(lib.nclt_ctx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(lib.nclt_ctx_launches(self.h))
+
+    def popc_peak(self, iters=4096):
+        ms = C.c_float()
+        v = lib.nclt_popc_peak(self.h, iters, C.byref(ms))
+        if v <= 0:
+            raise NcltError('popc peak probe failed')
+        return v, ms.value
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h.value:
+            lib.nclt_ctx_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    c = _default_ctx.get(device)
+    if c is None:
+        c = _default_ctx[device] = Context(device)
+    return c

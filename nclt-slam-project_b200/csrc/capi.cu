@@ -1,0 +1,466 @@
+// extern "C" entry points declared in include/nclt_b200.h: context, teach library, matching.
+#include "../../include/nclt_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+
+// ---------------------------------------------------------------------------------------
+// scratch: one grow-only device buffer per context, carved as a stack inside one API call
+// ---------------------------------------------------------------------------------------
+struct Carver {
+    nclt_ctx* c;
+    size_t off;
+    explicit Carver(nclt_ctx* ctx) : c(ctx), off(ctx->scratch_off) {}
+    template <typename T>
+    T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T* p = reinterpret_cast<T*>(static_cast<char*>(c->scratch) + off);
+        off += bytes;
+        c->scratch_off = off;
+        return p;
+    }
+};
+static inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
+    size_t need = c->scratch_off + bytes + 4096;
+    if (need <= c->scratch_bytes) return NCLT_OK;
+    if (c->scratch_off != 0) return nclt_fail(c, NCLT_ERR_STATE, "scratch grow while in use");
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&c->scratch, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = need;
+        e = cudaMalloc(&c->scratch, want);
+        if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc scratch", e);
+    }
+    c->scratch_bytes = want;
+    return NCLT_OK;
+}
+
+struct ScratchScope {   // resets the stack when the outermost API call returns
+    nclt_ctx* c;
+    size_t saved;
+    explicit ScratchScope(nclt_ctx* ctx) : c(ctx), saved(ctx->scratch_off) {}
+    ~ScratchScope() { c->scratch_off = saved; }
+};
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int nclt_abi_version(void) { return 1; }
+
+extern "C" int nclt_ctx_create(int device, void* stream, nclt_ctx** out) {
+    if (!out) return NCLT_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return NCLT_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return NCLT_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NCLT_ERR_CUDA;
+    if (prop.major < 10) return NCLT_ERR_CUDA;   // sm_100a-only binary
+    nclt_ctx* c = new nclt_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return NCLT_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
+    if (!c) return NCLT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_ctx_sync(nclt_ctx* c) {
+    if (!c) return NCLT_ERR_ARG;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+extern "C" const char* nclt_last_error(nclt_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" unsigned long long nclt_ctx_launches(nclt_ctx* c) { return c ? c->launches : 0ull; }
+
+extern "C" double nclt_popc_peak(nclt_ctx* c, int iters, float* ms_out) {
+    if (!c) return -1.0;
+    cudaSetDevice(c->device);
+    return run_popc_peak(c, iters, ms_out);
+}
+
+// ---------------------------------------------------------------------------------------
+// teach library
+// ---------------------------------------------------------------------------------------
+static int lib_grow(nclt_ctx* c, nclt_lib* L, int need_desc, int need_kf) {
+    if (need_desc > L->cap_desc) {
+        int cap = std::max(need_desc, L->cap_desc + L->cap_desc / 2);
+        uint4* nd = nullptr;
+        float* np = nullptr;
+        CU_TRY(c, cudaMalloc(&nd, (size_t)cap * 32));
+        CU_TRY(c, cudaMalloc(&np, (size_t)cap * 12));
+        if (L->n_desc) {
+            CU_TRY(c, cudaMemcpyAsync(nd, L->d_desc, (size_t)L->n_desc * 32, cudaMemcpyDeviceToDevice, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(np, L->d_pts3d, (size_t)L->n_desc * 12, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (L->d_desc) cudaFree(L->d_desc);
+        if (L->d_pts3d) cudaFree(L->d_pts3d);
+        L->d_desc = nd;
+        L->d_pts3d = np;
+        L->cap_desc = cap;
+    }
+    if (need_kf > L->cap_kf) {
+        int cap = std::max(need_kf, L->cap_kf + L->cap_kf / 2 + 16);
+        int *ns = nullptr, *nc = nullptr;
+        CU_TRY(c, cudaMalloc(&ns, (size_t)cap * 4));
+        CU_TRY(c, cudaMalloc(&nc, (size_t)cap * 4));
+        if (L->n_kf) {
+            CU_TRY(c, cudaMemcpyAsync(ns, L->d_start, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(nc, L->d_count, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (L->d_start) cudaFree(L->d_start);
+        if (L->d_count) cudaFree(L->d_count);
+        L->d_start = ns;
+        L->d_count = nc;
+        L->cap_kf = cap;
+    }
+    return NCLT_OK;
+}
+
+extern "C" int nclt_lib_create(nclt_ctx* c, int n_kf, const int32_t* kf_offsets, const uint8_t* desc,
+                               const float* pts3d, nclt_lib** out) {
+    if (!c || !out || n_kf < 0 || (n_kf > 0 && !kf_offsets)) return nclt_fail(c, NCLT_ERR_ARG, "lib_create args");
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    const int N = n_kf ? kf_offsets[n_kf] : 0;
+    if (N < 0 || N > (int)NCLT_KEY_IDX_MASK) return nclt_fail(c, NCLT_ERR_ARG, "library too large for 23-bit index");
+    if (N > 0 && !desc) return nclt_fail(c, NCLT_ERR_ARG, "lib_create: desc is null");
+    nclt_lib* L = new nclt_lib();
+    L->device = c->device;
+    int rc = lib_grow(c, L, std::max(N, 1), std::max(n_kf, 1));
+    if (rc) { delete L; return rc; }
+    L->h_start.resize(n_kf);
+    L->h_count.resize(n_kf);
+    for (int k = 0; k < n_kf; ++k) {
+        int cnt = kf_offsets[k + 1] - kf_offsets[k];
+        if (cnt < 0) { nclt_lib_destroy(c, L); return nclt_fail(c, NCLT_ERR_ARG, "kf_offsets not monotone"); }
+        L->h_start[k] = kf_offsets[k];
+        L->h_count[k] = cnt;
+        L->max_count = std::max(L->max_count, cnt);
+    }
+    if (N) {
+        CU_TRY(c, cudaMemcpyAsync(L->d_desc, desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
+        if (pts3d) CU_TRY(c, cudaMemcpyAsync(L->d_pts3d, pts3d, (size_t)N * 12, cudaMemcpyHostToDevice, c->stream));
+        else CU_TRY(c, cudaMemsetAsync(L->d_pts3d, 0, (size_t)N * 12, c->stream));
+    }
+    if (n_kf) {
+        CU_TRY(c, cudaMemcpyAsync(L->d_start, L->h_start.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(L->d_count, L->h_count.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    L->n_kf = n_kf;
+    L->n_desc = N;
+    *out = L;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_lib_append(nclt_ctx* c, nclt_lib* L, const uint8_t* desc, const float* pts3d, int n) {
+    if (!c || !L || n < 0 || (n > 0 && !desc)) return nclt_fail(c, NCLT_ERR_ARG, "lib_append args");
+    cudaSetDevice(c->device);
+    if ((long long)L->n_desc + n > (long long)NCLT_KEY_IDX_MASK) return nclt_fail(c, NCLT_ERR_ARG, "library too large");
+    int rc = lib_grow(c, L, L->n_desc + n, L->n_kf + 1);
+    if (rc) return rc;
+    int start = L->n_desc;
+    if (n) {
+        CU_TRY(c, cudaMemcpyAsync(L->d_desc + (size_t)start * 2, desc, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+        if (pts3d)
+            CU_TRY(c, cudaMemcpyAsync(L->d_pts3d + (size_t)start * 3, pts3d, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        else
+            CU_TRY(c, cudaMemsetAsync(L->d_pts3d + (size_t)start * 3, 0, (size_t)n * 12, c->stream));
+    }
+    L->h_start.push_back(start);
+    L->h_count.push_back(n);
+    CU_TRY(c, cudaMemcpyAsync(L->d_start + L->n_kf, &L->h_start[L->n_kf], 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(L->d_count + L->n_kf, &L->h_count[L->n_kf], 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    L->n_kf += 1;
+    L->n_desc += n;
+    L->max_count = std::max(L->max_count, n);
+    return NCLT_OK;
+}
+
+extern "C" int nclt_lib_destroy(nclt_ctx* c, nclt_lib* L) {
+    if (!L) return NCLT_OK;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    if (L->d_desc) cudaFree(L->d_desc);
+    if (L->d_pts3d) cudaFree(L->d_pts3d);
+    if (L->d_start) cudaFree(L->d_start);
+    if (L->d_count) cudaFree(L->d_count);
+    delete L;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_lib_size(const nclt_lib* L, int* n_kf, int* n_desc, int* max_kf_rows) {
+    if (!L) return NCLT_ERR_ARG;
+    if (n_kf) *n_kf = L->n_kf;
+    if (n_desc) *n_desc = L->n_desc;
+    if (max_kf_rows) *max_kf_rows = L->max_count;
+    return NCLT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// matching
+// ---------------------------------------------------------------------------------------
+static SegView lib_view(const nclt_lib* L) { return SegView{L->d_desc, L->d_start, L->d_count, 0}; }
+static SegView frame_view(const uint8_t* q, const int32_t* q_n, int Nq) {
+    return SegView{reinterpret_cast<const uint4*>(q), nullptr, q_n, Nq};
+}
+
+static int check_match_args(nclt_ctx* c, const nclt_lib* L, const void* q, int B, int Nq, int C) {
+    if (!c || !L) return nclt_fail(c, NCLT_ERR_ARG, "null handle");
+    if (L->device != c->device) return nclt_fail(c, NCLT_ERR_ARG, "library lives on another device");
+    if (B < 0 || Nq <= 0 || C <= 0) return nclt_fail(c, NCLT_ERR_ARG, "bad B/Nq/C");
+    if (B > 0 && !q) return nclt_fail(c, NCLT_ERR_ARG, "q is null");
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return nclt_fail(c, NCLT_ERR_ARG, "q must be 16-byte aligned");
+    if (Nq > (int)NCLT_KEY_IDX_MASK) return nclt_fail(c, NCLT_ERR_ARG, "Nq too large");
+    cudaSetDevice(c->device);
+    return NCLT_OK;
+}
+// when cand == NULL the candidates are keyframes 0..C-1: they must exist
+static int check_cand_null(nclt_ctx* c, const nclt_lib* L, const int32_t* cand, int C) {
+    if (!cand && C > L->n_kf) return nclt_fail(c, NCLT_ERR_ARG, "C exceeds keyframe count with cand == NULL");
+    return NCLT_OK;
+}
+
+extern "C" int nclt_match_knn2_dev(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B,
+                                   int Nq, const int32_t* cand, int C, int32_t* out_idx, uint16_t* out_dist) {
+    int rc = check_match_args(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if ((rc = check_cand_null(c, L, cand, C))) return rc;
+    if (B == 0) return NCLT_OK;
+    MatchLaunch m{};
+    m.A = frame_view(q, q_n, Nq);
+    m.B = lib_view(L);
+    m.cand = cand; m.n_outer = B; m.C = C; m.swap = 0; m.a_rows_max = Nq; m.nsplit = 1; m.b_seg_fixed = -1;
+    m.out_idx = reinterpret_cast<int2*>(out_idx);
+    m.out_dist = reinterpret_cast<ushort2*>(out_dist);
+    return launch_hamming_top2(c, m, 0u);
+}
+
+extern "C" int nclt_match_ratio_dev(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B,
+                                    int Nq, const int32_t* cand, int C, int num, int den, int32_t* out_pairs,
+                                    int32_t* out_n) {
+    int rc = check_match_args(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if ((rc = check_cand_null(c, L, cand, C))) return rc;
+    if (num <= 0 || den <= 0 || !out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio args");
+    if (B == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    size_t items = (size_t)B * C;
+    if ((rc = nclt_scratch_reserve(c, pad256(items * Nq * sizeof(uint2))))) return rc;
+    Carver cv(c);
+    uint2* keys = cv.take<uint2>(items * Nq);
+    MatchLaunch m{};
+    m.A = frame_view(q, q_n, Nq);
+    m.B = lib_view(L);
+    m.cand = cand; m.n_outer = B; m.C = C; m.swap = 0; m.a_rows_max = Nq; m.nsplit = 1; m.b_seg_fixed = -1;
+    m.out_keys = keys;
+    if ((rc = launch_hamming_top2(c, m, 0u))) return rc;
+    return launch_ratio_compact(c, keys, q_n, Nq, cand, B, C, Nq, num, den, reinterpret_cast<int2*>(out_pairs),
+                                out_n);
+}
+
+extern "C" int nclt_match_cross_dev(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B,
+                                    int Nq, const int32_t* cand, int C, int Nmax, int32_t* out_pairs,
+                                    uint16_t* out_dist, int32_t* out_n) {
+    int rc = check_match_args(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if ((rc = check_cand_null(c, L, cand, C))) return rc;
+    if (!out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "cross outputs null");
+    if (Nmax < L->max_count) return nclt_fail(c, NCLT_ERR_ARG, "Nmax smaller than the largest keyframe");
+    if (B == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    size_t items = (size_t)B * C;
+    if ((rc = nclt_scratch_reserve(c, pad256(items * Nmax * sizeof(uint2)) + pad256(items * Nq * sizeof(uint2)))))
+        return rc;
+    Carver cv(c);
+    uint2* fwd = cv.take<uint2>(items * Nmax);
+    uint2* bwd = cv.take<uint2>(items * Nq);
+    MatchLaunch m{};
+    // forward: teach rows (query side of match(desc_t, desc_curr)) against the frame
+    m.A = lib_view(L);
+    m.B = frame_view(q, q_n, Nq);
+    m.cand = cand; m.n_outer = B; m.C = C; m.swap = 1; m.a_rows_max = Nmax; m.nsplit = 1; m.b_seg_fixed = -1;
+    m.out_keys = fwd;
+    if ((rc = launch_hamming_top2(c, m, 0u))) return rc;
+    // backward: frame rows against the teach keyframe
+    m.A = frame_view(q, q_n, Nq);
+    m.B = lib_view(L);
+    m.swap = 0; m.a_rows_max = Nq; m.out_keys = bwd;
+    if ((rc = launch_hamming_top2(c, m, 0u))) return rc;
+    return launch_cross_combine(c, fwd, bwd, lib_view(L), cand, B, C, Nmax, Nq,
+                                reinterpret_cast<int2*>(out_pairs), out_dist, out_n, Nmax);
+}
+
+extern "C" int nclt_match_flat2_dev(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B,
+                                    int Nq, uint32_t idx_offset, uint32_t* out_keys) {
+    int rc = check_match_args(c, L, q, B, Nq, 1);
+    if (rc) return rc;
+    if (!out_keys) return nclt_fail(c, NCLT_ERR_ARG, "out_keys null");
+    if ((unsigned long long)idx_offset + (unsigned)L->n_desc > NCLT_KEY_IDX_MASK)
+        return nclt_fail(c, NCLT_ERR_ARG, "global index exceeds 23 bits");
+    if (B == 0) return NCLT_OK;
+    // the whole library is one segment; split its rows so that the grid fills the GPU
+    int want = (c->sm_count * 8 + B - 1) / B;
+    int max_split = std::max(1, (L->n_desc + 2047) / 2048);
+    int nsplit = std::max(1, std::min(want, max_split));
+    ScratchScope scope(c);
+    size_t part = (size_t)B * Nq;
+    if ((rc = nclt_scratch_reserve(c, pad256(part * nsplit * sizeof(uint2)) + 512))) return rc;
+    Carver cv(c);
+    uint2* parts = cv.take<uint2>(part * nsplit);
+    int* seg = cv.take<int>(2);
+    int h[2] = {0, L->n_desc};
+    CU_TRY(c, cudaMemcpyAsync(seg, h, 8, cudaMemcpyHostToDevice, c->stream));
+    MatchLaunch m{};
+    m.A = frame_view(q, q_n, Nq);
+    m.B = SegView{L->d_desc, seg, seg + 1, 0};
+    m.cand = nullptr; m.n_outer = B; m.C = 1; m.swap = 0; m.a_rows_max = Nq; m.nsplit = nsplit; m.b_seg_fixed = 0;
+    m.out_keys = parts;
+    if ((rc = launch_hamming_top2(c, m, idx_offset))) return rc;
+    // parts layout: [(item*nsplit + split), row]
+    return launch_merge_top2(c, parts, B, nsplit, Nq, (long long)Nq, (long long)nsplit * Nq,
+                             reinterpret_cast<uint2*>(out_keys), nullptr, nullptr);
+}
+
+extern "C" int nclt_merge_top2_dev(nclt_ctx* c, const uint32_t* parts, int nparts, int rows, uint32_t* out_keys,
+                                   int32_t* out_idx, uint16_t* out_dist) {
+    if (!c || !parts || nparts <= 0 || rows < 0) return nclt_fail(c, NCLT_ERR_ARG, "merge args");
+    cudaSetDevice(c->device);
+    return launch_merge_top2(c, reinterpret_cast<const uint2*>(parts), 1, nparts, rows, (long long)rows, 0LL,
+                             reinterpret_cast<uint2*>(out_keys), reinterpret_cast<int2*>(out_idx),
+                             reinterpret_cast<ushort2*>(out_dist));
+}
+
+// ---- host-pointer variants: stage through device scratch -------------------------------
+struct HostStage {
+    const uint8_t* d_q = nullptr;
+    const int32_t* d_qn = nullptr;
+    const int32_t* d_cand = nullptr;
+};
+static int stage_inputs(nclt_ctx* c, Carver& cv, const uint8_t* q, const int32_t* q_n, int B, int Nq,
+                        const int32_t* cand, int C, HostStage& s) {
+    uint8_t* dq = cv.take<uint8_t>((size_t)B * Nq * 32);
+    CU_TRY(c, cudaMemcpyAsync(dq, q, (size_t)B * Nq * 32, cudaMemcpyHostToDevice, c->stream));
+    s.d_q = dq;
+    if (q_n) {
+        int32_t* d = cv.take<int32_t>(B);
+        CU_TRY(c, cudaMemcpyAsync(d, q_n, (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
+        s.d_qn = d;
+    }
+    if (cand) {
+        int32_t* d = cv.take<int32_t>((size_t)B * C);
+        CU_TRY(c, cudaMemcpyAsync(d, cand, (size_t)B * C * 4, cudaMemcpyHostToDevice, c->stream));
+        s.d_cand = d;
+    }
+    return NCLT_OK;
+}
+static size_t stage_bytes(int B, int Nq, int C) {
+    return pad256((size_t)B * Nq * 32) + pad256((size_t)B * 4) + pad256((size_t)B * C * 4);
+}
+static int check_host(nclt_ctx* c, const nclt_lib* L, const void* q, int B, int Nq, int C) {
+    if (!c || !L) return nclt_fail(c, NCLT_ERR_ARG, "null handle");
+    if (B < 0 || Nq <= 0 || C <= 0 || (B > 0 && !q)) return nclt_fail(c, NCLT_ERR_ARG, "bad B/Nq/C/q");
+    cudaSetDevice(c->device);
+    return NCLT_OK;
+}
+
+extern "C" int nclt_match_knn2(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
+                               const int32_t* cand, int C, int32_t* out_idx, uint16_t* out_dist) {
+    int rc = check_host(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if (B == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    size_t rows = (size_t)B * C * Nq;
+    if ((rc = nclt_scratch_reserve(c, stage_bytes(B, Nq, C) + pad256(rows * 8) + pad256(rows * 4)))) return rc;
+    Carver cv(c);
+    HostStage s;
+    if ((rc = stage_inputs(c, cv, q, q_n, B, Nq, cand, C, s))) return rc;
+    int32_t* d_idx = cv.take<int32_t>(rows * 2);
+    uint16_t* d_dist = cv.take<uint16_t>(rows * 2);
+    if ((rc = nclt_match_knn2_dev(c, L, s.d_q, s.d_qn, B, Nq, s.d_cand, C, d_idx, d_dist))) return rc;
+    if (out_idx) CU_TRY(c, cudaMemcpyAsync(out_idx, d_idx, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dist) CU_TRY(c, cudaMemcpyAsync(out_dist, d_dist, rows * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+extern "C" int nclt_match_ratio(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
+                                const int32_t* cand, int C, int num, int den, int32_t* out_pairs, int32_t* out_n) {
+    int rc = check_host(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if (!out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio outputs null");
+    if (B == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    size_t items = (size_t)B * C, rows = items * Nq;
+    if ((rc = nclt_scratch_reserve(c, stage_bytes(B, Nq, C) + pad256(rows * 8) + pad256(items * 4) +
+                                          pad256(rows * sizeof(uint2)))))
+        return rc;
+    Carver cv(c);
+    HostStage s;
+    if ((rc = stage_inputs(c, cv, q, q_n, B, Nq, cand, C, s))) return rc;
+    int32_t* d_pairs = cv.take<int32_t>(rows * 2);
+    int32_t* d_n = cv.take<int32_t>(items);
+    if ((rc = nclt_match_ratio_dev(c, L, s.d_q, s.d_qn, B, Nq, s.d_cand, C, num, den, d_pairs, d_n))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(out_pairs, d_pairs, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(out_n, d_n, items * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+extern "C" int nclt_match_cross(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
+                                const int32_t* cand, int C, int Nmax, int32_t* out_pairs, uint16_t* out_dist,
+                                int32_t* out_n) {
+    int rc = check_host(c, L, q, B, Nq, C);
+    if (rc) return rc;
+    if (!out_pairs || !out_n || Nmax <= 0) return nclt_fail(c, NCLT_ERR_ARG, "cross outputs null");
+    if (B == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    size_t items = (size_t)B * C, rows = items * Nmax;
+    if ((rc = nclt_scratch_reserve(c, stage_bytes(B, Nq, C) + pad256(rows * 8) + pad256(rows * 2) +
+                                          pad256(items * 4) + pad256(rows * sizeof(uint2)) +
+                                          pad256(items * Nq * sizeof(uint2)))))
+        return rc;
+    Carver cv(c);
+    HostStage s;
+    if ((rc = stage_inputs(c, cv, q, q_n, B, Nq, cand, C, s))) return rc;
+    int32_t* d_pairs = cv.take<int32_t>(rows * 2);
+    uint16_t* d_dist = cv.take<uint16_t>(rows);
+    int32_t* d_n = cv.take<int32_t>(items);
+    if ((rc = nclt_match_cross_dev(c, L, s.d_q, s.d_qn, B, Nq, s.d_cand, C, Nmax, d_pairs, d_dist, d_n))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(out_pairs, d_pairs, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out_dist) CU_TRY(c, cudaMemcpyAsync(out_dist, d_dist, rows * 2, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(out_n, d_n, items * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}

@@ -1,0 +1,98 @@
+// Shared declarations for the sm_100a kernels behind the C ABI (include/nclt_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/nclt_b200.h"
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+
+// top-2 key: dist (9 bits, 0..256) << 23 | row index (23 bits). min() on the key is the
+// reference's tie rule (lowest train index wins on equal distance).
+#define NCLT_KEY_SHIFT 23
+#define NCLT_KEY_IDX_MASK 0x7FFFFFu
+#define NCLT_KEY_INVALID 0xFFFFFFFFu
+
+struct nclt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    // grow-only device scratch
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    size_t scratch_off = 0;      // stack pointer inside one API call
+    // pinned host staging for small result reads
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // counts of kernel launches issued through this context (bench.py gpu_launches)
+    unsigned long long launches = 0;
+};
+
+struct nclt_lib {
+    int device = 0;
+    int n_kf = 0;
+    int n_desc = 0;          // total rows in use
+    int cap_desc = 0;        // allocated rows
+    int cap_kf = 0;
+    uint4* d_desc = nullptr;     // [cap_desc][2] uint4 = 32 B per descriptor
+    float* d_pts3d = nullptr;    // [cap_desc][3]
+    int* d_start = nullptr;      // [cap_kf] first row of keyframe
+    int* d_count = nullptr;      // [cap_kf] rows in keyframe
+    std::vector<int> h_start, h_count;
+    int max_count = 0;
+};
+
+// A ragged set of 32-byte descriptors on the device.
+struct SegView {
+    const uint4* base;   // 2 uint4 per row
+    const int* start;    // per-segment first row, or nullptr -> seg * stride
+    const int* count;    // per-segment rows, or nullptr -> stride
+    int stride;
+};
+
+static inline int nclt_fail(nclt_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                         \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return nclt_fail((ctx), NCLT_ERR_CUDA, #call, _e); \
+    } while (0)
+
+int nclt_scratch_reserve(nclt_ctx* c, size_t bytes);
+int nclt_pinned_reserve(nclt_ctx* c, size_t bytes);
+
+// ---- hamming.cu ----
+struct MatchLaunch {
+    SegView A, B;            // rows of A are matched against rows of B
+    const int* cand;         // [n_outer, C] B-segment (or A-segment when swap) ids, -1 = skip; nullptr -> c
+    int n_outer;             // frames
+    int C;                   // candidates per frame
+    int swap;                // 0: A-seg = frame, B-seg = cand ; 1: A-seg = cand, B-seg = frame
+    int a_rows_max;          // output row stride per item
+    int nsplit;              // split B rows over this many CTAs (flat mode); 1 otherwise
+    int b_seg_fixed;         // >=0: every item uses this B segment (flat mode)
+    uint2* out_keys;         // [n_items*nsplit, a_rows_max] (best, second) keys, or nullptr
+    int2* out_idx;           // [n_items, a_rows_max] or nullptr   (only when nsplit==1)
+    ushort2* out_dist;       // [n_items, a_rows_max] or nullptr
+};
+int launch_hamming_top2(nclt_ctx* c, const MatchLaunch& m, uint32_t idx_offset);
+int launch_merge_top2(nclt_ctx* c, const uint2* parts, int n_items, int nparts, int rows, long long part_stride,
+                      long long item_stride, uint2* out_keys, int2* out_idx, ushort2* out_dist);
+int launch_cross_combine(nclt_ctx* c, const uint2* fwd_keys, const uint2* bwd_keys, const SegView& Lib,
+                         const int* cand, int n_outer, int C, int fwd_rows_max, int bwd_rows_max, int2* out_pairs,
+                         unsigned short* out_dist, int* out_n, int out_stride);
+int launch_ratio_compact(nclt_ctx* c, const uint2* keys, const int* a_count, int a_stride_cnt, const int* cand,
+                         int n_outer, int C, int a_rows_max, int num, int den, int2* out_pairs, int* out_n);
+double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
