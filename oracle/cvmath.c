@@ -1,0 +1,688 @@
+/*
+ * TEST INFRASTRUCTURE (CPU oracle) - not product code.
+ *
+ * Plain-C restatement of the OpenCV numerics that cv2.solvePnPRansac runs underneath the
+ * reference's call sites (visual_landmark_matcher.py:342-346, checkpoint_a_selftest.py:78-82).
+ * OpenCV is a third-party dependency (opencv-python>=4.8.0, datasets/nclt/requirements.txt:3;
+ * "OpenCV 4.13", datasets/nclt/README.md:353) and is NOT vendored under /root/reference, so
+ * this file restates its published algorithms:
+ *   - one-sided Jacobi SVD used by cv::SVD for small matrices (modules/core/src/lapack.cpp)
+ *   - SVD back-substitution (cv::solve / cv::invert with DECOMP_SVD)
+ *   - Rodrigues in both directions (modules/calib3d)
+ *   - EPnP (Lepetit, Moreno-Noguer, Fua 2009) as implemented in modules/calib3d/src/epnp.cpp
+ *   - the RANSAC driver of modules/calib3d/src/ptsetreg.cpp + solvepnp.cpp
+ * Every function is pinned against cv2 4.13.0 itself by tests/test_oracle_pnp.py (cv2.SVDecomp,
+ * cv2.solve, cv2.invert, cv2.Rodrigues, cv2.solvePnP(EPNP), cv2.solvePnPRansac).
+ *
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction: operation order is part of the
+ * contract - EPnP on 5 points is numerically chaotic).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAXN 12
+
+/* lapack.cpp carries its own hypot (not libm's) */
+static double cv_hypot(double a, double b) {
+    a = fabs(a);
+    b = fabs(b);
+    if (a > b) {
+        b /= a;
+        return a * sqrt(1 + b * b);
+    }
+    if (b > 0) {
+        a /= b;
+        return b * sqrt(1 + a * a);
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * One-sided Jacobi SVD on At (n rows of length m): on exit the rows of At are the left
+ * singular vectors scaled to unit length, W the singular values (descending), Vt the right
+ * singular vectors as rows.
+ * ------------------------------------------------------------------------------------- */
+static void jacobi_svd(double* At, int astep, double* W_out, double* Vt, int vstep, int m, int n, int n1) {
+    const double eps = DBL_EPSILON * 10;
+    const double minval = DBL_MIN;
+    double W[MAXN];
+    int i, j, k, iter, max_iter = m > 30 ? m : 30;
+    double c, s, sd;
+
+    for (i = 0; i < n; i++) {
+        for (k = 0, sd = 0; k < m; k++) {
+            double t = At[i * astep + k];
+            sd += t * t;
+        }
+        W[i] = sd;
+        if (Vt) {
+            for (k = 0; k < n; k++) Vt[i * vstep + k] = 0;
+            Vt[i * vstep + i] = 1;
+        }
+    }
+
+    for (iter = 0; iter < max_iter; iter++) {
+        int changed = 0;
+        for (i = 0; i < n - 1; i++)
+            for (j = i + 1; j < n; j++) {
+                double *Ai = At + i * astep, *Aj = At + j * astep;
+                double a = W[i], p = 0, b = W[j];
+                for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = cv_hypot(p, beta);
+                if (beta < 0) {
+                    double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (k = 0; k < m; k++) {
+                    double t0 = c * Ai[k] + s * Aj[k];
+                    double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0;
+                    Aj[k] = t1;
+                    a += t0 * t0;
+                    b += t1 * t1;
+                }
+                W[i] = a;
+                W[j] = b;
+                changed = 1;
+                if (Vt) {
+                    double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+                    for (k = 0; k < n; k++) {
+                        double t0 = c * Vi[k] + s * Vj[k];
+                        double t1 = -s * Vi[k] + c * Vj[k];
+                        Vi[k] = t0;
+                        Vj[k] = t1;
+                    }
+                }
+            }
+        if (!changed) break;
+    }
+
+    for (i = 0; i < n; i++) {
+        for (k = 0, sd = 0; k < m; k++) {
+            double t = At[i * astep + k];
+            sd += t * t;
+        }
+        W[i] = sqrt(sd);
+    }
+
+    for (i = 0; i < n - 1; i++) {
+        j = i;
+        for (k = i + 1; k < n; k++)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            if (Vt) {
+                for (k = 0; k < m; k++) { t = At[i * astep + k]; At[i * astep + k] = At[j * astep + k]; At[j * astep + k] = t; }
+                for (k = 0; k < n; k++) { t = Vt[i * vstep + k]; Vt[i * vstep + k] = Vt[j * vstep + k]; Vt[j * vstep + k] = t; }
+            }
+        }
+    }
+    for (i = 0; i < n; i++) W_out[i] = W[i];
+    if (!Vt) return;
+
+    /* OpenCV's RNG(0x12345678), used only when a singular value is (numerically) zero */
+    uint64_t rng = 0x12345678;
+    for (i = 0; i < n1; i++) {
+        sd = i < n ? W[i] : 0;
+        for (int ii = 0; ii < 100 && sd <= minval; ii++) {
+            /* replace the degenerate left vector by a random one, orthogonalised against the
+             * previous ones (two passes), then normalised */
+            const double val0 = 1. / m;
+            for (k = 0; k < m; k++) {
+                rng = (uint64_t)(unsigned)rng * 4164903690U + (unsigned)(rng >> 32);
+                unsigned r = (unsigned)rng;
+                double val = (r & 256) != 0 ? val0 : -val0;
+                At[i * astep + k] = val;
+            }
+            for (iter = 0; iter < 2; iter++) {
+                for (j = 0; j < i; j++) {
+                    sd = 0;
+                    for (k = 0; k < m; k++) sd += At[i * astep + k] * At[j * astep + k];
+                    double asum = 0;
+                    for (k = 0; k < m; k++) {
+                        double t = At[i * astep + k] - sd * At[j * astep + k];
+                        At[i * astep + k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (k = 0; k < m; k++) At[i * astep + k] *= asum;
+                }
+            }
+            sd = 0;
+            for (k = 0; k < m; k++) {
+                double t = At[i * astep + k];
+                sd += t * t;
+            }
+            sd = sqrt(sd);
+        }
+        s = sd > minval ? 1 / sd : 0.;
+        for (k = 0; k < m; k++) At[i * astep + k] *= s;
+    }
+}
+
+/* cv::SVD::compute(A[m x n], m >= n): w[n], u[m x n] (row-major), vt[n x n]. */
+void orc_svd(const double* A, int m, int n, double* w, double* u, double* vt) {
+    double At[MAXN * MAXN], Vt[MAXN * MAXN];
+    int i, j;
+    for (i = 0; i < m; i++)
+        for (j = 0; j < n; j++) At[j * m + i] = A[i * n + j];
+    jacobi_svd(At, m, w, Vt, n, m, n, n);
+    if (u)
+        for (i = 0; i < m; i++)
+            for (j = 0; j < n; j++) u[i * n + j] = At[j * m + i];
+    if (vt) memcpy(vt, Vt, sizeof(double) * n * n);
+}
+
+/* cv::solve(A[m x n], b[m], DECOMP_SVD) -> x[n] */
+void orc_solve_svd(const double* A, int m, int n, const double* b, double* x) {
+    double At[MAXN * MAXN], Vt[MAXN * MAXN], w[MAXN];
+    int i, j;
+    for (i = 0; i < m; i++)
+        for (j = 0; j < n; j++) At[j * m + i] = A[i * n + j];
+    jacobi_svd(At, m, w, Vt, n, m, n, n);
+    /* SVBkSb with uT = true (rows of At are u), vT = true, nb = 1 */
+    double threshold = 0;
+    for (i = 0; i < n; i++) x[i] = 0;
+    for (i = 0; i < n; i++) threshold += w[i];
+    threshold *= DBL_EPSILON * 2;
+    for (i = 0; i < n; i++) {
+        double wi = w[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        double s = 0;
+        for (j = 0; j < m; j++) s += At[i * m + j] * b[j];
+        s *= wi;
+        for (j = 0; j < n; j++) x[j] = x[j] + s * Vt[i * n + j];
+    }
+}
+
+/* cv::invert(A[3x3], DECOMP_SVD) */
+void orc_invert3_svd(const double* A, double* Ainv) {
+    double w[3], u[9], vt[9];
+    int i, j, k;
+    orc_svd(A, 3, 3, w, u, vt);
+    double threshold = (w[0] + w[1] + w[2]) * (DBL_EPSILON * 2);
+    for (i = 0; i < 9; i++) Ainv[i] = 0;
+    for (i = 0; i < 3; i++) {
+        double wi = w[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        double buffer[3];
+        for (j = 0; j < 3; j++) buffer[j] = u[j * 3 + i] * wi;
+        for (k = 0; k < 3; k++) {
+            double s = vt[i * 3 + k];
+            for (j = 0; j < 3; j++) Ainv[k * 3 + j] = Ainv[k * 3 + j] + s * buffer[j];
+        }
+    }
+}
+
+/* cv::Rodrigues, matrix -> vector */
+void orc_rodrigues_m2v(const double* Rin, double* rvec) {
+    double w[3], U[9], Vt[9], R[9];
+    int i, j, k;
+    orc_svd(Rin, 3, 3, w, U, Vt);
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) {
+            double s = 0;
+            for (k = 0; k < 3; k++) s += U[i * 3 + k] * Vt[k * 3 + j];
+            R[i * 3 + j] = s;
+        }
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5) {
+        double t;
+        if (c > 0)
+            rx = ry = rz = 0;
+        else {
+            t = (R[0] + 1) * 0.5;
+            rx = sqrt(t > 0. ? t : 0.);
+            t = (R[4] + 1) * 0.5;
+            ry = sqrt(t > 0. ? t : 0.) * (R[1] < 0 ? -1. : 1.);
+            t = (R[8] + 1) * 0.5;
+            rz = sqrt(t > 0. ? t : 0.) * (R[2] < 0 ? -1. : 1.);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        double vth = 1 / (2 * s);
+        vth *= theta;
+        rx *= vth; ry *= vth; rz *= vth;
+    }
+    rvec[0] = rx; rvec[1] = ry; rvec[2] = rz;
+}
+
+/* cv::Rodrigues, vector -> matrix */
+void orc_rodrigues_v2m(const double* r, double* R) {
+    double rx = r[0], ry = r[1], rz = r[2];
+    double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if (theta < DBL_EPSILON) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = theta ? 1. / theta : 0.;
+    rx *= itheta; ry *= itheta; rz *= itheta;
+    double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+    double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+    static const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; k++) R[k] = c * eye[k] + c1 * rrt[k] + s * r_x[k];
+}
+
+/* ---------------------------------------------------------------------------------------
+ * EPnP on n points, identity intrinsics (solvePnP normalises the image points first).
+ * pws: n*3 world points, us: n*2 normalised image points. Outputs R[9], t[3].
+ * ------------------------------------------------------------------------------------- */
+#define EPNP_MAXPTS 16
+
+typedef struct {
+    int n;
+    double pws[EPNP_MAXPTS * 3], us[EPNP_MAXPTS * 2], alphas[EPNP_MAXPTS * 4], pcs[EPNP_MAXPTS * 3];
+    double cws[4][3], ccs[4][3];
+    double fu, fv, uc, vc;
+} epnp_t;
+
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double dist2(const double* p1, const double* p2) {
+    return (p1[0] - p2[0]) * (p1[0] - p2[0]) + (p1[1] - p2[1]) * (p1[1] - p2[1]) + (p1[2] - p2[2]) * (p1[2] - p2[2]);
+}
+
+static void choose_control_points(epnp_t* e) {
+    int n = e->n, i, j, k;
+    e->cws[0][0] = e->cws[0][1] = e->cws[0][2] = 0;
+    for (i = 0; i < n; i++)
+        for (j = 0; j < 3; j++) e->cws[0][j] += e->pws[3 * i + j];
+    for (j = 0; j < 3; j++) e->cws[0][j] /= n;
+
+    double pw0[EPNP_MAXPTS * 3], pw0tpw0[9], dc[3], uct[9];
+    for (i = 0; i < n; i++)
+        for (j = 0; j < 3; j++) pw0[3 * i + j] = e->pws[3 * i + j] - e->cws[0][j];
+    /* mulTransposed(PW0, aTa=true): upper triangle, sums over rows in order, mirrored */
+    for (i = 0; i < 3; i++)
+        for (j = i; j < 3; j++) {
+            double s = 0;
+            for (k = 0; k < n; k++) s += pw0[3 * k + i] * pw0[3 * k + j];
+            pw0tpw0[i * 3 + j] = s;
+            pw0tpw0[j * 3 + i] = s;
+        }
+    /* cvSVD(&PW0tPW0, &DC, &UCt, 0, CV_SVD_MODIFY_A | CV_SVD_U_T): rows of UCt = left vectors */
+    double u[9];
+    orc_svd(pw0tpw0, 3, 3, dc, u, NULL);
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) uct[i * 3 + j] = u[j * 3 + i];
+    for (i = 1; i < 4; i++) {
+        double kk = sqrt(dc[i - 1] / n);
+        for (j = 0; j < 3; j++) e->cws[i][j] = e->cws[0][j] + kk * uct[3 * (i - 1) + j];
+    }
+}
+
+static void compute_barycentric_coordinates(epnp_t* e) {
+    double cc[9], ci[9];
+    int i, j;
+    for (i = 0; i < 3; i++)
+        for (j = 1; j < 4; j++) cc[3 * i + j - 1] = e->cws[j][i] - e->cws[0][i];
+    orc_invert3_svd(cc, ci);
+    for (i = 0; i < e->n; i++) {
+        const double* pi = e->pws + 3 * i;
+        double* a = e->alphas + 4 * i;
+        for (j = 0; j < 3; j++)
+            a[1 + j] = ci[3 * j] * (pi[0] - e->cws[0][0]) + ci[3 * j + 1] * (pi[1] - e->cws[0][1]) +
+                       ci[3 * j + 2] * (pi[2] - e->cws[0][2]);
+        a[0] = 1.0f - a[1] - a[2] - a[3];
+    }
+}
+
+static void compute_L_6x10(const double* ut, double* l_6x10) {
+    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+    double dv[4][6][3];
+    int i, j;
+    for (i = 0; i < 4; i++) {
+        int a = 0, b = 1;
+        for (j = 0; j < 6; j++) {
+            dv[i][j][0] = v[i][3 * a] - v[i][3 * b];
+            dv[i][j][1] = v[i][3 * a + 1] - v[i][3 * b + 1];
+            dv[i][j][2] = v[i][3 * a + 2] - v[i][3 * b + 2];
+            b++;
+            if (b > 3) { a++; b = a + 1; }
+        }
+    }
+    for (i = 0; i < 6; i++) {
+        double* row = l_6x10 + 10 * i;
+        row[0] = dot3(dv[0][i], dv[0][i]);
+        row[1] = 2.0f * dot3(dv[0][i], dv[1][i]);
+        row[2] = dot3(dv[1][i], dv[1][i]);
+        row[3] = 2.0f * dot3(dv[0][i], dv[2][i]);
+        row[4] = 2.0f * dot3(dv[1][i], dv[2][i]);
+        row[5] = dot3(dv[2][i], dv[2][i]);
+        row[6] = 2.0f * dot3(dv[0][i], dv[3][i]);
+        row[7] = 2.0f * dot3(dv[1][i], dv[3][i]);
+        row[8] = 2.0f * dot3(dv[2][i], dv[3][i]);
+        row[9] = dot3(dv[3][i], dv[3][i]);
+    }
+}
+
+static void find_betas_approx_1(const double* L, const double* rho, double* betas) {
+    double l[24], b4[4];
+    for (int i = 0; i < 6; i++) {
+        l[i * 4 + 0] = L[i * 10 + 0]; l[i * 4 + 1] = L[i * 10 + 1];
+        l[i * 4 + 2] = L[i * 10 + 3]; l[i * 4 + 3] = L[i * 10 + 6];
+    }
+    orc_solve_svd(l, 6, 4, rho, b4);
+    if (b4[0] < 0) {
+        betas[0] = sqrt(-b4[0]);
+        betas[1] = -b4[1] / betas[0];
+        betas[2] = -b4[2] / betas[0];
+        betas[3] = -b4[3] / betas[0];
+    } else {
+        betas[0] = sqrt(b4[0]);
+        betas[1] = b4[1] / betas[0];
+        betas[2] = b4[2] / betas[0];
+        betas[3] = b4[3] / betas[0];
+    }
+}
+
+static void find_betas_approx_2(const double* L, const double* rho, double* betas) {
+    double l[18], b3[3];
+    for (int i = 0; i < 6; i++) {
+        l[i * 3 + 0] = L[i * 10 + 0]; l[i * 3 + 1] = L[i * 10 + 1]; l[i * 3 + 2] = L[i * 10 + 2];
+    }
+    orc_solve_svd(l, 6, 3, rho, b3);
+    if (b3[0] < 0) {
+        betas[0] = sqrt(-b3[0]);
+        betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
+    } else {
+        betas[0] = sqrt(b3[0]);
+        betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0;
+    }
+    if (b3[1] < 0) betas[0] = -betas[0];
+    betas[2] = 0.0;
+    betas[3] = 0.0;
+}
+
+static void find_betas_approx_3(const double* L, const double* rho, double* betas) {
+    double l[30], b5[5];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 5; j++) l[i * 5 + j] = L[i * 10 + j];
+    orc_solve_svd(l, 6, 5, rho, b5);
+    if (b5[0] < 0) {
+        betas[0] = sqrt(-b5[0]);
+        betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;
+    } else {
+        betas[0] = sqrt(b5[0]);
+        betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0;
+    }
+    if (b5[1] < 0) betas[0] = -betas[0];
+    betas[2] = b5[3] / betas[0];
+    betas[3] = 0.0;
+}
+
+static void qr_solve(double* pA, int nr, int nc, double* pb, double* pX) {
+    double A1[8], A2[8];
+    double* ppAkk = pA;
+    for (int k = 0; k < nc; k++) {
+        double *ppAik1 = ppAkk, eta = fabs(*ppAik1);
+        for (int i = k + 1; i < nr; i++) {
+            double elt = fabs(*ppAik1);
+            if (eta < elt) eta = elt;
+            ppAik1 += nc;
+        }
+        if (eta == 0) {
+            A1[k] = A2[k] = 0.0;
+            return;
+        } else {
+            double *ppAik2 = ppAkk, sum2 = 0.0, inv_eta = 1. / eta;
+            for (int i = k; i < nr; i++) {
+                *ppAik2 *= inv_eta;
+                sum2 += *ppAik2 * *ppAik2;
+                ppAik2 += nc;
+            }
+            double sigma = sqrt(sum2);
+            if (*ppAkk < 0) sigma = -sigma;
+            *ppAkk += sigma;
+            A1[k] = sigma * *ppAkk;
+            A2[k] = -eta * sigma;
+            for (int j = k + 1; j < nc; j++) {
+                double *ppAik = ppAkk, sum = 0;
+                for (int i = k; i < nr; i++) {
+                    sum += *ppAik * ppAik[j - k];
+                    ppAik += nc;
+                }
+                double tau = sum / A1[k];
+                ppAik = ppAkk;
+                for (int i = k; i < nr; i++) {
+                    ppAik[j - k] -= tau * *ppAik;
+                    ppAik += nc;
+                }
+            }
+        }
+        ppAkk += nc + 1;
+    }
+    double* ppAjj = pA;
+    for (int j = 0; j < nc; j++) {
+        double *ppAij = ppAjj, tau = 0;
+        for (int i = j; i < nr; i++) {
+            tau += *ppAij * pb[i];
+            ppAij += nc;
+        }
+        tau /= A1[j];
+        ppAij = ppAjj;
+        for (int i = j; i < nr; i++) {
+            pb[i] -= tau * *ppAij;
+            ppAij += nc;
+        }
+        ppAjj += nc + 1;
+    }
+    pX[nc - 1] = pb[nc - 1] / A2[nc - 1];
+    for (int i = nc - 2; i >= 0; i--) {
+        double *ppAij = pA + i * nc + (i + 1), sum = 0;
+        for (int j = i + 1; j < nc; j++) {
+            sum += *ppAij * pX[j];
+            ppAij++;
+        }
+        pX[i] = (pb[i] - sum) / A2[i];
+    }
+}
+
+static void gauss_newton(const double* L, const double* rho, double betas[4]) {
+    double a[24], b[6], x[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 5; k++) {
+        for (int i = 0; i < 6; i++) {
+            const double* rowL = L + i * 10;
+            double* rowA = a + i * 4;
+            rowA[0] = 2 * rowL[0] * betas[0] + rowL[1] * betas[1] + rowL[3] * betas[2] + rowL[6] * betas[3];
+            rowA[1] = rowL[1] * betas[0] + 2 * rowL[2] * betas[1] + rowL[4] * betas[2] + rowL[7] * betas[3];
+            rowA[2] = rowL[3] * betas[0] + rowL[4] * betas[1] + 2 * rowL[5] * betas[2] + rowL[8] * betas[3];
+            rowA[3] = rowL[6] * betas[0] + rowL[7] * betas[1] + rowL[8] * betas[2] + 2 * rowL[9] * betas[3];
+            b[i] = rho[i] - (rowL[0] * betas[0] * betas[0] + rowL[1] * betas[0] * betas[1] +
+                             rowL[2] * betas[1] * betas[1] + rowL[3] * betas[0] * betas[2] +
+                             rowL[4] * betas[1] * betas[2] + rowL[5] * betas[2] * betas[2] +
+                             rowL[6] * betas[0] * betas[3] + rowL[7] * betas[1] * betas[3] +
+                             rowL[8] * betas[2] * betas[3] + rowL[9] * betas[3] * betas[3]);
+        }
+        qr_solve(a, 6, 4, b, x);
+        for (int i = 0; i < 4; i++) betas[i] += x[i];
+    }
+}
+
+static void estimate_R_and_t(epnp_t* e, double R[3][3], double t[3]) {
+    int n = e->n, i, j;
+    double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
+    for (i = 0; i < n; i++)
+        for (j = 0; j < 3; j++) {
+            pc0[j] += e->pcs[3 * i + j];
+            pw0[j] += e->pws[3 * i + j];
+        }
+    for (j = 0; j < 3; j++) {
+        pc0[j] /= n;
+        pw0[j] /= n;
+    }
+    double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, abt_d[3], abt_u[9], abt_vt[9], abt_v[9];
+    for (i = 0; i < n; i++) {
+        const double* pc = e->pcs + 3 * i;
+        const double* pw = e->pws + 3 * i;
+        for (j = 0; j < 3; j++) {
+            abt[3 * j] += (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
+            abt[3 * j + 1] += (pc[j] - pc0[j]) * (pw[1] - pw0[1]);
+            abt[3 * j + 2] += (pc[j] - pc0[j]) * (pw[2] - pw0[2]);
+        }
+    }
+    /* cvSVD(&ABt, &ABt_D, &ABt_U, &ABt_V, CV_SVD_MODIFY_A): U and V (not transposed) */
+    orc_svd(abt, 3, 3, abt_d, abt_u, abt_vt);
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) abt_v[i * 3 + j] = abt_vt[j * 3 + i];
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) R[i][j] = dot3(abt_u + 3 * i, abt_v + 3 * j);
+    const double det = R[0][0] * R[1][1] * R[2][2] + R[0][1] * R[1][2] * R[2][0] + R[0][2] * R[1][0] * R[2][1] -
+                       R[0][2] * R[1][1] * R[2][0] - R[0][1] * R[1][0] * R[2][2] - R[0][0] * R[1][2] * R[2][1];
+    if (det < 0) {
+        R[2][0] = -R[2][0];
+        R[2][1] = -R[2][1];
+        R[2][2] = -R[2][2];
+    }
+    t[0] = pc0[0] - dot3(R[0], pw0);
+    t[1] = pc0[1] - dot3(R[1], pw0);
+    t[2] = pc0[2] - dot3(R[2], pw0);
+}
+
+static double compute_R_and_t(epnp_t* e, const double* ut, const double* betas, double R[3][3], double t[3]) {
+    int i, j, k, n = e->n;
+    for (i = 0; i < 4; i++) e->ccs[i][0] = e->ccs[i][1] = e->ccs[i][2] = 0.0f;
+    for (i = 0; i < 4; i++) {
+        const double* v = ut + 12 * (11 - i);
+        for (j = 0; j < 4; j++)
+            for (k = 0; k < 3; k++) e->ccs[j][k] += betas[i] * v[3 * j + k];
+    }
+    for (i = 0; i < n; i++) {
+        const double* a = e->alphas + 4 * i;
+        double* pc = e->pcs + 3 * i;
+        for (j = 0; j < 3; j++)
+            pc[j] = a[0] * e->ccs[0][j] + a[1] * e->ccs[1][j] + a[2] * e->ccs[2][j] + a[3] * e->ccs[3][j];
+    }
+    if (e->pcs[2] < 0.0) {
+        for (i = 0; i < 4; i++)
+            for (j = 0; j < 3; j++) e->ccs[i][j] = -e->ccs[i][j];
+        for (i = 0; i < n; i++) {
+            e->pcs[3 * i] = -e->pcs[3 * i];
+            e->pcs[3 * i + 1] = -e->pcs[3 * i + 1];
+            e->pcs[3 * i + 2] = -e->pcs[3 * i + 2];
+        }
+    }
+    estimate_R_and_t(e, R, t);
+    /* reprojection error with uc = vc = 0, fu = fv = 1 */
+    double sum2 = 0.0;
+    for (i = 0; i < n; i++) {
+        const double* pw = e->pws + 3 * i;
+        double Xc = dot3(R[0], pw) + t[0];
+        double Yc = dot3(R[1], pw) + t[1];
+        double inv_Zc = 1.0 / (dot3(R[2], pw) + t[2]);
+        double ue = e->uc + e->fu * Xc * inv_Zc;
+        double ve = e->vc + e->fv * Yc * inv_Zc;
+        double u = e->us[2 * i], v = e->us[2 * i + 1];
+        sum2 += sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
+    }
+    return sum2 / n;
+}
+
+/* Full EPnP. pws n*3 (world), us n*2 (normalised image coords). Returns chosen branch N. */
+int orc_epnp(const double* pws, const double* us, int n, const double* intr, double* R_out, double* t_out) {
+    epnp_t e;
+    e.fu = intr[0]; e.fv = intr[1]; e.uc = intr[2]; e.vc = intr[3];
+    int i, j, k;
+    if (n > EPNP_MAXPTS) return -1;
+    e.n = n;
+    memcpy(e.pws, pws, sizeof(double) * 3 * n);
+    memcpy(e.us, us, sizeof(double) * 2 * n);
+    choose_control_points(&e);
+    compute_barycentric_coordinates(&e);
+
+    double M[2 * EPNP_MAXPTS * 12];
+    for (i = 0; i < n; i++) {
+        const double* as = e.alphas + 4 * i;
+        double u = e.us[2 * i], v = e.us[2 * i + 1];
+        double* M1 = M + (2 * i) * 12;
+        double* M2 = M1 + 12;
+        for (j = 0; j < 4; j++) {
+            M1[3 * j] = as[j] * e.fu;
+            M1[3 * j + 1] = 0.0;
+            M1[3 * j + 2] = as[j] * (e.uc - u);
+            M2[3 * j] = 0.0;
+            M2[3 * j + 1] = as[j] * e.fv;
+            M2[3 * j + 2] = as[j] * (e.vc - v);
+        }
+    }
+    double mtm[144], d[12], ut[144], u[144];
+    for (i = 0; i < 12; i++)
+        for (j = i; j < 12; j++) {
+            double s = 0;
+            for (k = 0; k < 2 * n; k++) s += M[k * 12 + i] * M[k * 12 + j];
+            mtm[i * 12 + j] = s;
+            mtm[j * 12 + i] = s;
+        }
+    orc_svd(mtm, 12, 12, d, u, NULL);
+    for (i = 0; i < 12; i++)
+        for (j = 0; j < 12; j++) ut[i * 12 + j] = u[j * 12 + i];
+
+    double l_6x10[60], rho[6];
+    compute_L_6x10(ut, l_6x10);
+    rho[0] = dist2(e.cws[0], e.cws[1]);
+    rho[1] = dist2(e.cws[0], e.cws[2]);
+    rho[2] = dist2(e.cws[0], e.cws[3]);
+    rho[3] = dist2(e.cws[1], e.cws[2]);
+    rho[4] = dist2(e.cws[1], e.cws[3]);
+    rho[5] = dist2(e.cws[2], e.cws[3]);
+
+    double Betas[4][4], rep_errors[4], Rs[4][3][3], ts[4][3];
+    memset(Betas, 0, sizeof(Betas));
+    find_betas_approx_1(l_6x10, rho, Betas[1]);
+    gauss_newton(l_6x10, rho, Betas[1]);
+    rep_errors[1] = compute_R_and_t(&e, ut, Betas[1], Rs[1], ts[1]);
+    find_betas_approx_2(l_6x10, rho, Betas[2]);
+    gauss_newton(l_6x10, rho, Betas[2]);
+    rep_errors[2] = compute_R_and_t(&e, ut, Betas[2], Rs[2], ts[2]);
+    find_betas_approx_3(l_6x10, rho, Betas[3]);
+    gauss_newton(l_6x10, rho, Betas[3]);
+    rep_errors[3] = compute_R_and_t(&e, ut, Betas[3], Rs[3], ts[3]);
+
+    int N = 1;
+    if (rep_errors[2] < rep_errors[1]) N = 2;
+    if (rep_errors[3] < rep_errors[N]) N = 3;
+    for (i = 0; i < 3; i++) {
+        t_out[i] = ts[N][i];
+        for (j = 0; j < 3; j++) R_out[i * 3 + j] = Rs[N][i][j];
+    }
+    return N;
+}
+
+/* cv2.solvePnP(obj f32, img f32, K(fx,fy,cx,cy), dist=0, flags=EPNP) on n points
+ * (the RANSAC kernel of solvePnPRansac): undistortPoints writes NORMALISED coordinates as
+ * float32; the epnp constructor maps them back to pixels in double (x*fu + uc); EPnP runs with
+ * the real intrinsics; Rodrigues converts R. Bit-exact vs cv2 4.13 (tests/test_oracle_pnp.py). */
+int orc_solvepnp_epnp(const float* obj, const float* img, int n, double fx, double fy, double cx, double cy,
+                      double* rvec, double* tvec) {
+    double pws[EPNP_MAXPTS * 3], us[EPNP_MAXPTS * 2], R[9];
+    if (n > EPNP_MAXPTS) return -1;
+    double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        pws[3 * i] = obj[3 * i]; pws[3 * i + 1] = obj[3 * i + 1]; pws[3 * i + 2] = obj[3 * i + 2];
+        double x = ((double)img[2 * i] - cx) * ifx;
+        double y = ((double)img[2 * i + 1] - cy) * ify;
+        us[2 * i] = (double)(float)x * fx + cx;
+        us[2 * i + 1] = (double)(float)y * fy + cy;
+    }
+    double intr[4] = {fx, fy, cx, cy};
+    int N = orc_epnp(pws, us, n, intr, R, tvec);
+    orc_rodrigues_m2v(R, rvec);
+    return N;
+}
