@@ -105,6 +105,44 @@ int nclt_match_flat2_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, c
 int nclt_merge_top2_dev(nclt_ctx* ctx, const uint32_t* parts, int nparts, int rows, uint32_t* out_keys,
                         int32_t* out_idx, uint16_t* out_dist);
 
+/* ---- PnP-RANSAC -------------------------------------------------------------------- */
+/* K = [[fx,0,cx],[0,fy,cy],[0,0,1]] (visual_landmark_matcher.py:49-51), distortion is zero
+ * (matcher:52).  iterations/reproj_error/confidence = iterationsCount, reprojectionError,
+ * confidence of cv2.solvePnPRansac; refine != 0 runs the SOLVEPNP_ITERATIVE refinement. */
+typedef struct nclt_pnp_params {
+    double fx, fy, cx, cy;
+    int iterations;       /* RANSAC_ITERATIONS = 200 (matcher:69) */
+    float reproj_error;   /* RANSAC_REPROJ_PX = 3.0 (matcher:68) */
+    double confidence;    /* cv2 default 0.99 */
+    int refine;           /* 1 = flags=SOLVEPNP_ITERATIVE */
+} nclt_pnp_params;
+
+/* replaces cv2.solvePnPRansac(obj_pts, img_pts, K, DIST, iterationsCount=200,
+ * reprojectionError=3.0, flags=cv2.SOLVEPNP_ITERATIVE) (visual_landmark_matcher.py:342-346,
+ * checkpoint_a_selftest.py:78-82) and the cv2.projectPoints mean-error computation of
+ * matcher:353-355, for P independent problems.
+ * obj f32[P,Nmax,3], img f32[P,Nmax,2], n i32[P] valid correspondences per problem (n < 5 -> ok=0;
+ * the reference gates at >= 10, matcher:330).
+ * out_ok u8[P], out_rvec f64[P,3], out_tvec f64[P,3], out_n_inliers i32[P] (= len(inliers)),
+ * out_mask u8[P,Nmax] inlier mask (NULL ok), out_mean_err f32[P] (NULL ok).
+ * Debug outputs (NULL ok): out_sets i32[P,iters,5] minimal sets, out_models f64[P,iters,6]
+ * (rvec,tvec) per hypothesis, out_counts i32[P,iters], out_best_iter i32[P], out_niters i32[P]. */
+int nclt_pnp_ransac(nclt_ctx* ctx, const float* obj, const float* img, const int32_t* n, int P, int Nmax,
+                    const nclt_pnp_params* prm, uint8_t* out_ok, double* out_rvec, double* out_tvec,
+                    int32_t* out_n_inliers, uint8_t* out_mask, float* out_mean_err, int32_t* out_sets,
+                    double* out_models, int32_t* out_counts, int32_t* out_best_iter, int32_t* out_niters);
+/* device-pointer variant; debug outputs are not available here */
+int nclt_pnp_ransac_dev(nclt_ctx* ctx, const float* obj, const float* img, const int32_t* n, int P, int Nmax,
+                        const nclt_pnp_params* prm, uint8_t* out_ok, double* out_rvec, double* out_tvec,
+                        int32_t* out_n_inliers, uint8_t* out_mask, float* out_mean_err);
+/* K4 alone: inlier counts of caller-supplied hypotheses models f64[P,iters,6] (staged parity,
+ * SURVEY.md section 7 (ii)); out_counts i32[P,iters]. Host pointers. */
+int nclt_pnp_score(nclt_ctx* ctx, const float* obj, const float* img, const int32_t* n, int P, int Nmax,
+                   const nclt_pnp_params* prm, const double* models, int32_t* out_counts);
+/* replaces cv2.projectPoints(obj, rvec, tvec, K, DIST) (matcher:353): out f32[n,2]. Host pointers. */
+int nclt_project_points(nclt_ctx* ctx, const float* obj, int n, const double* rvec, const double* tvec,
+                        double fx, double fy, double cx, double cy, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,23 @@ _sig('nclt_match_flat2_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _u32, _vp)
 _sig('nclt_merge_top2_dev', _i, _vp, _vp, _i, _i, _vp, _vp, _vp)
 
 
+class PnpParams(C.Structure):
+    """nclt_pnp_params; defaults = the constants at visual_landmark_matcher.py:49-52,67-70."""
+    _fields_ = [('fx', _dbl), ('fy', _dbl), ('cx', _dbl), ('cy', _dbl), ('iterations', _i),
+                ('reproj_error', C.c_float), ('confidence', _dbl), ('refine', _i)]
+
+    def __init__(self, fx=320.0, fy=320.0, cx=320.0, cy=240.0, iterations=200, reproj_error=3.0,
+                 confidence=0.99, refine=1):
+        super().__init__(fx, fy, cx, cy, iterations, reproj_error, confidence, refine)
+
+
+_pp = C.POINTER(PnpParams)
+_sig('nclt_pnp_ransac', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 11))
+_sig('nclt_pnp_ransac_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 6))
+_sig('nclt_pnp_score', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, _vp, _vp)
+_sig('nclt_project_points', _i, _vp, _vp, _i, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp)
+
+
 def ptr(x):
     """Raw address of a numpy array / torch tensor / None / int."""
     if x is None:

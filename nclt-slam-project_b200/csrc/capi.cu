@@ -1,28 +1,10 @@
 // extern "C" entry points declared in include/nclt_b200.h: context, teach library, matching.
 #include "../../include/nclt_b200.h"
 #include "common.cuh"
+#include "scratch.cuh"
 
 #include <algorithm>
 #include <cstring>
-
-
-// ---------------------------------------------------------------------------------------
-// scratch: one grow-only device buffer per context, carved as a stack inside one API call
-// ---------------------------------------------------------------------------------------
-struct Carver {
-    nclt_ctx* c;
-    size_t off;
-    explicit Carver(nclt_ctx* ctx) : c(ctx), off(ctx->scratch_off) {}
-    template <typename T>
-    T* take(size_t n) {
-        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
-        T* p = reinterpret_cast<T*>(static_cast<char*>(c->scratch) + off);
-        off += bytes;
-        c->scratch_off = off;
-        return p;
-    }
-};
-static inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
 int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
     size_t need = c->scratch_off + bytes + 4096;
@@ -43,13 +25,6 @@ int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
     c->scratch_bytes = want;
     return NCLT_OK;
 }
-
-struct ScratchScope {   // resets the stack when the outermost API call returns
-    nclt_ctx* c;
-    size_t saved;
-    explicit ScratchScope(nclt_ctx* ctx) : c(ctx), saved(ctx->scratch_off) {}
-    ~ScratchScope() { c->scratch_off = saved; }
-};
 
 // ---------------------------------------------------------------------------------------
 // context

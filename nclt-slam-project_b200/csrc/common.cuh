@@ -96,3 +96,16 @@ int launch_cross_combine(nclt_ctx* c, const uint2* fwd_keys, const uint2* bwd_ke
 int launch_ratio_compact(nclt_ctx* c, const uint2* keys, const int* a_count, int a_stride_cnt, const int* cand,
                          int n_outer, int C, int a_rows_max, int num, int den, int2* out_pairs, int* out_n);
 double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
+
+// ---- pnp.cu ----
+struct PnpBuffers {
+    int* sets;         // [P][iters][5]
+    double* models;    // [P][iters][6]
+    int* counts;       // [P][iters]
+};
+int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, int Nmax,
+               const nclt_pnp_params* prm, const PnpBuffers& buf, const double* models_override,
+               unsigned char* ok, double* rvec, double* tvec, int* n_inl, unsigned char* mask, float* mean_err,
+               int* best_iter, int* niters, bool score_only);
+int launch_project_points(nclt_ctx* c, const float* obj, int n, const double* rvec, const double* tvec, double fx,
+                          double fy, double cx, double cy, float* out);

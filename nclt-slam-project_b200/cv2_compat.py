@@ -102,3 +102,63 @@ class BFMatcher:
             lib.close()
         m = int(n[0, 0])
         return [DMatch(int(pairs[0, 0, i, 0]), int(pairs[0, 0, i, 1]), float(dist[0, 0, i])) for i in range(m)]
+
+
+def _intrinsics(cameraMatrix, distCoeffs):
+    K = np.asarray(cameraMatrix, dtype=np.float64)
+    if K.shape != (3, 3):
+        raise error('cameraMatrix must be 3x3')
+    if distCoeffs is not None and np.any(np.asarray(distCoeffs) != 0):
+        raise error('only zero distortion is implemented (DIST = zeros, visual_landmark_matcher.py:52)')
+    return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+
+def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, iterationsCount=100,
+                   reprojectionError=8.0, confidence=0.99, flags=SOLVEPNP_ITERATIVE, ctx=None):
+    """cv2.solvePnPRansac as called at visual_landmark_matcher.py:342-346.
+
+    Returns (ok, rvec f64[3,1], tvec f64[3,1], inliers i32[m,1] | None).  Fewer than 4 points
+    raises `error` like cv2; exactly 4 points is cv2's P3P branch, which the reference can never
+    reach (MIN_MATCHES = 10, matcher:330) and is not implemented."""
+    from .pnp import pnp_ransac_batch
+    from ._lib import PnpParams
+    if flags != SOLVEPNP_ITERATIVE:
+        raise error('only flags=SOLVEPNP_ITERATIVE is implemented (the reference uses nothing else)')
+    obj = np.ascontiguousarray(objectPoints, dtype=np.float32).reshape(-1, 3)
+    img = np.ascontiguousarray(imagePoints, dtype=np.float32).reshape(-1, 2)
+    if len(obj) != len(img) or len(obj) < 4:
+        raise error('solvePnPRansac needs >= 4 matching object/image points')
+    if len(obj) == 4:
+        raise error('4-point (P3P) problems are outside the reference call sites and not implemented')
+    fx, fy, cx, cy = _intrinsics(cameraMatrix, distCoeffs)
+    prm = PnpParams(fx, fy, cx, cy, int(iterationsCount), float(reprojectionError), float(confidence), 1)
+    o = pnp_ransac_batch(obj[None], img[None], None, prm, ctx=ctx)
+    ok = bool(o['ok'][0])
+    rvec = o['rvec'][0].reshape(3, 1).copy()
+    tvec = o['tvec'][0].reshape(3, 1).copy()
+    if not ok:
+        return False, rvec, tvec, None
+    inl = np.nonzero(o['mask'][0, :len(obj)])[0].astype(np.int32).reshape(-1, 1)
+    return True, rvec, tvec, inl
+
+
+def projectPoints(objectPoints, rvec, tvec, cameraMatrix, distCoeffs, ctx=None):
+    """cv2.projectPoints (matcher:353): returns (f32[n,1,2], None)."""
+    from .pnp import project_points
+    fx, fy, cx, cy = _intrinsics(cameraMatrix, distCoeffs)
+    out = project_points(objectPoints, rvec, tvec, fx, fy, cx, cy, ctx=ctx)
+    return out.reshape(-1, 1, 2), None
+
+
+def Rodrigues(rvec):
+    """cv2.Rodrigues(rvec) -> (R f64[3,3], None): 3x3 host arithmetic (matcher:361 keeps the
+    pose composition in NumPy; SURVEY 8a row a8 'keep on host, not a kernel')."""
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = float(np.sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]))
+    if th < np.finfo(np.float64).eps:
+        return np.eye(3), None
+    c, s = np.cos(th), np.sin(th)
+    k = r / th
+    rrt = np.outer(k, k)
+    kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return c * np.eye(3) + (1 - c) * rrt + s * kx, None
