@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py - query frames/s through the repeat-time hot path (match + PnP-RANSAC).
+
+Workload (BASELINE.json configs[1]): synthetic 03_south-sized library of
+400 keyframes x 1000 ORB descriptors; query frames of 1000 descriptors with 500 planted
+correspondences into one keyframe; every frame is matched against ALL 400 keyframes
+(knnMatch k=2 + Lowe 0.80), survivors with >= 10 matches go through PnP-RANSAC (200 hypotheses,
+3 px, LM refine) and the inlier / reprojection gates.  A step = one batch of B frames.
+
+  value  : frames/s with the batch already resident in HBM (device-pointer C ABI)
+  e2e    : frames/s through the host-pointer C ABI: pinned host buffers in, per-frame results out,
+           H2D and D2H inside the timed region
+  roofline: the Hamming top-2 kernel against the POPC-pipe peak measured on this GPU in this run
+  cpu_baseline: the reference-structured loop making the reference's own cv2 calls, timed on this
+           box's host cores on a bounded sample of the same workload
+
+`--impl reference` times only that CPU loop (rank 0), on the same config and metric.
+Under torchrun (N > 1) every rank owns one GPU, the library is replicated and frames are sharded
+(weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_KF, N_DESC, N_QUERY, N_PLANTED = 400, 1000, 1000, 500
+LIB_SEED = 20261018
+METRIC = 'query frames/s (match+PnP-RANSAC)'
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_inputs(n_frames, seed0, lib=None):
+    import nclt_slam_project_b200  # noqa: F401
+    from nclt_slam_project_b200 import synth
+    if lib is None:
+        lib = synth.make_library(LIB_SEED, n_kf=N_KF, n_desc=N_DESC)
+    desc, pts2d, kstar, _ = synth.make_frame_batch(lib, range(seed0, seed0 + n_frames), n_desc=N_QUERY,
+                                                   n_planted=N_PLANTED)
+    return lib, desc, pts2d, kstar
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_reference_frames(lib, desc, pts2d, n_frames):
+    """The reference-structured loop (checkpoint_a_selftest.py:62-103 over all keyframes) making the
+    reference's own cv2 calls. Returns (seconds, frames, accepted)."""
+    from oracle import localize as ol
+    cand = list(range(len(lib['landmarks'])))
+    acc = 0
+    t0 = time.perf_counter()
+    for b in range(n_frames):
+        r = ol.localize_frame(lib['landmarks'], desc[b], pts2d[b], cand, 0, backend='cv2')
+        acc += r['best_slot'] >= 0
+    return time.perf_counter() - t0, n_frames, acc
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import cv2
+    cores = cv2.getNumThreads()
+    per_step = args.ref_frames_per_step
+    lib, desc, pts2d, _ = make_inputs(per_step * min(args.steps + args.warmup, 4), 0)
+    nb = desc.shape[0] // per_step
+    for w in range(args.warmup):
+        i = (w % nb) * per_step
+        cpu_reference_frames(lib, desc[i:i + per_step], pts2d[i:i + per_step], per_step)
+    t = 0.0
+    for s in range(args.steps):
+        i = ((s + args.warmup) % nb) * per_step
+        dt, _, _ = cpu_reference_frames(lib, desc[i:i + per_step], pts2d[i:i + per_step], per_step)
+        t += dt
+    fps = per_step * args.steps / t
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 match, f64 PnP',
+        'data': 'synthetic',
+        'config': {'workload': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
+                               'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
+                   'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{per_step} frames per step x {args.steps} steps; reference-structured loop '
+                                   '(selftest:62-103) calling cv2.BFMatcher.knnMatch / solvePnPRansac / '
+                                   'projectPoints, cv2 threads = all cores'},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
+    ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
+    ap.add_argument('--ref-frames-per-step', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    import nclt_slam_project_b200  # noqa: F401
+    from nclt_slam_project_b200.pipeline import DeviceLocalizer, localize_batch
+    from nclt_slam_project_b200._lib import LocalizeParams
+
+    B = args.batch
+    n_batches = 2                       # distinct input batches, rotated; L2 is flushed between steps
+    t_gen = time.perf_counter()
+    lib, desc, pts2d, kstar = make_inputs(B * n_batches, 1000003 * rank)
+    log(f'[rank {rank}] generated {B * n_batches} frames in {time.perf_counter() - t_gen:.1f}s')
+    lms = lib['landmarks']
+    eng = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
+                          device=local_rank, params=LocalizeParams(mode=0))
+    d_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
+    d_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------
+    for w in range(max(args.warmup, 3)):
+        out = eng.run(d_desc[w % n_batches], d_pts[w % n_batches])
+    torch.cuda.synchronize()
+    got = out['best_cand'].cpu().numpy()
+    i_last = (max(args.warmup, 3) - 1) % n_batches
+    acc_rate = float((got == kstar[i_last * B:(i_last + 1) * B]).mean())
+    log(f'[rank {rank}] warm-up ok: {acc_rate * 100:.1f}% of frames localised to their planted keyframe; '
+        f'{out["n_problems"]} PnP problems in the last batch')
+
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    eng.ctx.profile(True)
+    eng.ctx.profile_read()
+    barrier()
+    launches0 = eng.ctx.launches
+    sampler.start()
+    n_prob = 0
+    for s in range(args.steps):
+        flush.zero_()                                   # evict L2 between timed steps (outside the events)
+        ev[s][0].record()
+        out = eng.run(d_desc[s % n_batches], d_pts[s % n_batches])
+        ev[s][1].record()
+        n_prob += out['n_problems']
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.ctx.launches - launches0
+    k_ms, k_n = eng.ctx.profile_read()
+    eng.ctx.profile(False)
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = B * args.steps * world / (total_ms_max * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI ------------------------------------------
+    h_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
+    h_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
+    prm = LocalizeParams(mode=0)
+    for w in range(2):
+        localize_batch(eng.library, h_desc[w % n_batches].numpy(), h_pts[w % n_batches].numpy(), params=prm)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        r = localize_batch(eng.library, h_desc[s % n_batches].numpy(), h_pts[s % n_batches].numpy(), params=prm)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * args.steps * world / float(t.item())
+    h2d = B * N_QUERY * (32 + 8)
+    d2h = B * (4 + 4 + 4 + 24 + 24)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    popc_peak, _ = eng.ctx.popc_peak(8192)
+    cmp_per_launch = float(B) * N_KF * N_QUERY * N_DESC
+    popc_per_launch = cmp_per_launch * 8.0               # 8 POPC32 per 256-bit comparison
+    k_avg_s = (k_ms / max(k_n, 1)) * 1e-3
+    achieved = popc_per_launch / k_avg_s if k_avg_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic_hamming.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'int-pipe (POPC)', 'achieved': achieved / 1e12, 'peak': popc_peak / 1e12,
+                'unit': 'Tpopc32/s', 'frac': achieved / popc_peak, 'traffic': traffic,
+                'kernel': 'k_hamming_top2<4>', 'kernel_ms_per_launch': k_avg_s * 1e3, 'kernel_launches': k_n,
+                'kernel_share_of_step': k_ms / total_ms if total_ms > 0 else None,
+                'hamming_cmp_per_s': cmp_per_launch / k_avg_s if k_avg_s > 0 else 0.0,
+                'peak_source': 'register-only POPC probe (nclt_popc_peak) on this GPU in this run; '
+                               'MEASURED_PEAKS.json carries no integer-pipe figure'}
+
+    # ---- CPU baseline (rank 0, bounded sample) ----------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        import cv2
+        n_cpu = min(args.cpu_frames, B)
+        dt, nf, acc = cpu_reference_frames(lib, desc[:n_cpu], pts2d[:n_cpu], n_cpu)
+        cpu = {'value': nf / dt, 'unit': 'frames/s', 'cores': cv2.getNumThreads(), 'kind': 'port',
+               'sample': f'{nf} frames of the same workload ({dt:.1f} s): reference-structured loop '
+                         '(checkpoint_a_selftest.py:62-103 over all 400 keyframes) calling cv2 4.x '
+                         'BFMatcher.knnMatch / solvePnPRansac / projectPoints with all host threads'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 match, f64 PnP', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
+                               'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
+                   'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY,
+                   'frames_per_step_per_gpu': B, 'sharding': f'frames x {world} GPUs, library replicated, no collective',
+                   'cache': 'L2 flushed (256 MB write) between timed steps; per-step CUDA events',
+                   'pnp_problems_per_step': n_prob / args.steps, 'localised_to_planted_keyframe': acc_rate},
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

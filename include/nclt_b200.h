@@ -43,6 +43,11 @@ int nclt_ctx_sync(nclt_ctx* ctx);
 const char* nclt_last_error(nclt_ctx* ctx);
 /* kernels launched through this context so far (bench.py's gpu_launches) */
 unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
+/* enable/disable CUDA-event timing of the dominant kernel (the Hamming top-2 launches) on this
+ * context; nclt_ctx_profile_read synchronises, returns the summed device time and launch count
+ * since the last read, and resets. Used by bench.py for the live roofline figure. */
+int nclt_ctx_profile(nclt_ctx* ctx, int enable);
+int nclt_ctx_profile_read(nclt_ctx* ctx, double* ms_total, int* n_launches);
 /* library ABI version, bumped on any signature change */
 int nclt_abi_version(void);
 /* measured POPC32 op/s of a register-only kernel: roofline denominator for the matcher */
@@ -142,6 +147,43 @@ int nclt_pnp_score(nclt_ctx* ctx, const float* obj, const float* img, const int3
 /* replaces cv2.projectPoints(obj, rvec, tvec, K, DIST) (matcher:353): out f32[n,2]. Host pointers. */
 int nclt_project_points(nclt_ctx* ctx, const float* obj, int n, const double* rvec, const double* tvec,
                         double fx, double fy, double cx, double cy, float* out);
+
+/* ---- the whole repeat-time path for a batch of frames ------------------------------------ */
+typedef struct nclt_localize_params {
+    int mode;              /* 0: knnMatch(k=2)+Lowe ratio (checkpoint_a_selftest.py:68-71);
+                              1: crossCheck match(desc_t, desc_curr) (visual_landmark_matcher.py:327) */
+    int ratio_num, ratio_den; /* LOWE_RATIO = 0.80 -> 4, 5 (matcher:66) */
+    int min_matches;       /* MIN_MATCHES = 10 (matcher:65; gate at matcher:330, selftest:72) */
+    int min_inliers;       /* MIN_INLIERS = 10 (matcher:70; gate at matcher:349) */
+    float reproj_max_px;   /* REPROJ_MAX_PX = 2.0 (matcher:67; gate at matcher:356) */
+    nclt_pnp_params pnp;
+} nclt_localize_params;
+
+/* replaces the per-candidate loop body of visual_landmark_matcher.py:318-380 and
+ * checkpoint_a_selftest.py:62-103 for B frames x C candidates: match, MIN_MATCHES gate, gather
+ * obj/img points, solvePnPRansac, MIN_INLIERS and mean-reprojection gates, and the "most inliers,
+ * earliest candidate on ties" selection (matcher:379-380).
+ * q u8[B,Nq,32], q_pts2d f32[B,Nq,2] keypoint pixel coordinates, q_n/cand as for nclt_match_*.
+ * Per frame: out_best_cand i32[B] winning candidate SLOT (-1 = none accepted), out_n_inliers i32[B],
+ * out_reproj f32[B], out_rvec/out_tvec f64[B,3] (teach camera in the current camera frame, as
+ * solvePnPRansac returns it).  out_n_problems: HOST int, PnP problems solved (NULL ok).
+ * Optional per (frame, candidate) outputs (NULL ok): out_item_nmatch i32[B,C] matches after the
+ * ratio / crossCheck filter, out_item_ok u8[B,C], out_item_ninl i32[B,C], out_item_err f32[B,C],
+ * out_item_rvec/out_item_tvec f64[B,C,3] (valid where nmatch >= min_matches). */
+int nclt_localize_batch(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const float* q_pts2d,
+                        const int32_t* q_n, int B, int Nq, const int32_t* cand, int C,
+                        const nclt_localize_params* prm, int32_t* out_best_cand, int32_t* out_n_inliers,
+                        float* out_reproj, double* out_rvec, double* out_tvec, int32_t* out_n_problems,
+                        int32_t* out_item_nmatch, uint8_t* out_item_ok, int32_t* out_item_ninl,
+                        float* out_item_err, double* out_item_rvec, double* out_item_tvec);
+/* device pointers for every array argument; out_n_problems stays a HOST int (the problem count is
+ * the one value read back inside the call). Returns with the remaining work enqueued. */
+int nclt_localize_batch_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const float* q_pts2d,
+                            const int32_t* q_n, int B, int Nq, const int32_t* cand, int C,
+                            const nclt_localize_params* prm, int32_t* out_best_cand, int32_t* out_n_inliers,
+                            float* out_reproj, double* out_rvec, double* out_tvec, int32_t* out_n_problems,
+                            int32_t* out_item_nmatch, uint8_t* out_item_ok, int32_t* out_item_ninl,
+                            float* out_item_err, double* out_item_rvec, double* out_item_tvec);
 
 #ifdef __cplusplus
 }

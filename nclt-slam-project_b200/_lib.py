@@ -40,6 +40,8 @@ _sig('nclt_ctx_destroy', _i, _vp)
 _sig('nclt_ctx_sync', _i, _vp)
 _sig('nclt_last_error', C.c_char_p, _vp)
 _sig('nclt_ctx_launches', C.c_ulonglong, _vp)
+_sig('nclt_ctx_profile', _i, _vp, _i)
+_sig('nclt_ctx_profile_read', _i, _vp, C.POINTER(_dbl), C.POINTER(_i))
 _sig('nclt_popc_peak', _dbl, _vp, _i, C.POINTER(C.c_float))
 _sig('nclt_lib_create', _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp))
 _sig('nclt_lib_append', _i, _vp, _vp, _vp, _vp, _i)
@@ -70,6 +72,21 @@ _sig('nclt_pnp_ransac', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 11))
 _sig('nclt_pnp_ransac_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 6))
 _sig('nclt_pnp_score', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, _vp, _vp)
 _sig('nclt_project_points', _i, _vp, _vp, _i, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp)
+
+
+class LocalizeParams(C.Structure):
+    """nclt_localize_params; defaults = visual_landmark_matcher.py:65-70."""
+    _fields_ = [('mode', _i), ('ratio_num', _i), ('ratio_den', _i), ('min_matches', _i), ('min_inliers', _i),
+                ('reproj_max_px', C.c_float), ('pnp', PnpParams)]
+
+    def __init__(self, mode=0, ratio_num=4, ratio_den=5, min_matches=10, min_inliers=10, reproj_max_px=2.0,
+                 pnp=None):
+        super().__init__(mode, ratio_num, ratio_den, min_matches, min_inliers, reproj_max_px, pnp or PnpParams())
+
+
+_lp = C.POINTER(LocalizeParams)
+for _n in ('nclt_localize_batch', 'nclt_localize_batch_dev'):
+    _sig(_n, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _lp, *([_vp] * 12))
 
 
 def ptr(x):
@@ -114,6 +131,15 @@ class Context:
     @property
     def launches(self):
         return int(lib.nclt_ctx_launches(self.h))
+
+    def profile(self, enable=True):
+        self.check(lib.nclt_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> (summed device ms of the Hamming top-2 launches since the last read, launches)."""
+        ms, n = _dbl(), _i()
+        self.check(lib.nclt_ctx_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def popc_peak(self, iters=4096):
         ms = C.c_float()

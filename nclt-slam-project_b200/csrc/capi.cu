@@ -26,6 +26,17 @@ int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
     return NCLT_OK;
 }
 
+int nclt_pinned_reserve(nclt_ctx* c, size_t bytes) {
+    if (bytes <= c->pinned_bytes) return NCLT_OK;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->pinned_bytes = 0;
+    CU_TRY(c, cudaMallocHost(&c->pinned, bytes));
+    c->pinned_bytes = bytes;
+    return NCLT_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
@@ -62,6 +73,7 @@ extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return NCLT_OK;
@@ -75,6 +87,29 @@ extern "C" int nclt_ctx_sync(nclt_ctx* c) {
 
 extern "C" const char* nclt_last_error(nclt_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" unsigned long long nclt_ctx_launches(nclt_ctx* c) { return c ? c->launches : 0ull; }
+
+extern "C" int nclt_ctx_profile(nclt_ctx* c, int enable) {
+    if (!c) return NCLT_ERR_ARG;
+    c->prof = enable != 0;
+    c->prof_used = 0;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_ctx_profile_read(nclt_ctx* c, double* ms_total, int* n_launches) {
+    if (!c) return NCLT_ERR_ARG;
+    cudaSetDevice(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    double ms = 0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]) == cudaSuccess) { ms += t; n++; }
+    }
+    if (ms_total) *ms_total = ms;
+    if (n_launches) *n_launches = n;
+    c->prof_used = 0;
+    return NCLT_OK;
+}
 
 extern "C" double nclt_popc_peak(nclt_ctx* c, int iters, float* ms_out) {
     if (!c) return -1.0;

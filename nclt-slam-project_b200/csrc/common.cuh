@@ -29,6 +29,11 @@ struct nclt_ctx {
     size_t pinned_bytes = 0;
     // counts of kernel launches issued through this context (bench.py gpu_launches)
     unsigned long long launches = 0;
+    // optional timing of the dominant kernel (bench.py roofline): event pairs around every
+    // Hamming top-2 launch, summed by nclt_ctx_profile_read
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
 };
 
 struct nclt_lib {
@@ -71,6 +76,15 @@ static inline int nclt_fail(nclt_ctx* c, int code, const char* what, cudaError_t
     } while (0)
 
 int nclt_scratch_reserve(nclt_ctx* c, size_t bytes);
+static inline void nclt_prof_mark(nclt_ctx* c) {
+    if (!c->prof) return;
+    if (c->prof_used == c->prof_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->prof_ev.push_back(e);
+    }
+    cudaEventRecord(c->prof_ev[c->prof_used++], c->stream);
+}
 int nclt_pinned_reserve(nclt_ctx* c, size_t bytes);
 
 // ---- hamming.cu ----

@@ -315,9 +315,11 @@ int launch_hamming_top2(nclt_ctx* c, const MatchLaunch& m, uint32_t idx_offset) 
     int R = m.a_rows_max > 2 * TB ? 4 : (m.a_rows_max > TB ? 2 : 1);
     int achunks = (m.a_rows_max + TB * R - 1) / (TB * R);
     dim3 grid(n_items, p.nsplit, achunks);
+    nclt_prof_mark(c);
     if (R == 4) k_hamming_top2<4><<<grid, TB, 0, c->stream>>>(p);
     else if (R == 2) k_hamming_top2<2><<<grid, TB, 0, c->stream>>>(p);
     else k_hamming_top2<1><<<grid, TB, 0, c->stream>>>(p);
+    nclt_prof_mark(c);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;

@@ -1,0 +1,104 @@
+"""Batched repeat-time localisation: descriptors + keypoints of B frames in, one accepted
+anchor candidate per frame out (SURVEY.md section 8a rows a1-a7 in one device-resident pass).
+
+`localize_batch` takes host numpy arrays (copies inside the call); `DeviceLocalizer` keeps the
+inputs and outputs in HBM as torch tensors for the replay workloads of BASELINE.json configs
+2 and 4.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib as _c, ptr, as_c, LocalizeParams
+
+MODE_RATIO = 0       # checkpoint_a_selftest.py:68-71
+MODE_CROSSCHECK = 1  # visual_landmark_matcher.py:327
+
+
+def localize_batch(library, desc, pts2d, q_n=None, cand=None, params=None, per_item=False):
+    """desc u8[B,Nq,32], pts2d f32[B,Nq,2] -> dict(best_cand i32[B] (slot, -1 = none), n_inliers,
+    reproj, rvec f64[B,3], tvec f64[B,3], n_problems; with per_item=True also item_nmatch,
+    item_ok, item_ninl, item_err, item_rvec, item_tvec over [B,C])."""
+    ctx = library.ctx
+    prm = params or LocalizeParams()
+    desc = as_c(desc, np.uint8)
+    pts2d = as_c(pts2d, np.float32)
+    if desc.ndim == 2:
+        desc, pts2d = desc[None], pts2d[None]
+    B, Nq = desc.shape[0], desc.shape[1]
+    if pts2d.shape != (B, Nq, 2) or desc.shape[2] != 32:
+        raise ValueError(f'shape mismatch desc{desc.shape} pts2d{pts2d.shape}')
+    q_n = None if q_n is None else as_c(q_n, np.int32).reshape(B)
+    if cand is None:
+        Cn = library.n_keyframes
+    else:
+        cand = as_c(cand, np.int32).reshape(B, -1)
+        Cn = cand.shape[1]
+    out = {'best_cand': np.full(B, -1, dtype=np.int32), 'n_inliers': np.zeros(B, dtype=np.int32),
+           'reproj': np.zeros(B, dtype=np.float32), 'rvec': np.zeros((B, 3)), 'tvec': np.zeros((B, 3)),
+           'n_problems': 0}
+    item = {}
+    if per_item:
+        item = {'item_nmatch': np.zeros((B, Cn), dtype=np.int32), 'item_ok': np.zeros((B, Cn), dtype=np.uint8),
+                'item_ninl': np.zeros((B, Cn), dtype=np.int32), 'item_err': np.zeros((B, Cn), dtype=np.float32),
+                'item_rvec': np.zeros((B, Cn, 3)), 'item_tvec': np.zeros((B, Cn, 3))}
+    if B == 0 or Nq == 0 or Cn == 0:
+        out.update(item)
+        return out
+    nprob = C.c_int32(0)
+    ctx.check(_c.nclt_localize_batch(
+        ctx.h, library.h, ptr(desc), ptr(pts2d), ptr(q_n), B, Nq, ptr(cand), Cn, C.byref(prm),
+        ptr(out['best_cand']), ptr(out['n_inliers']), ptr(out['reproj']), ptr(out['rvec']), ptr(out['tvec']),
+        C.addressof(nprob), ptr(item.get('item_nmatch')), ptr(item.get('item_ok')), ptr(item.get('item_ninl')),
+        ptr(item.get('item_err')), ptr(item.get('item_rvec')), ptr(item.get('item_tvec'))))
+    out['n_problems'] = int(nprob.value)
+    out.update(item)
+    return out
+
+
+class DeviceLocalizer:
+    """Replay engine: per-frame results stay on the device (torch tensors); the C ABI runs on
+    torch's current stream so that CUDA events recorded through torch bracket the kernels."""
+
+    def __init__(self, library_arrays, device=0, params=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device('cuda', device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.ctx = _lib.Context(device, self.stream.cuda_stream)
+        from .library import LandmarkLibrary
+        descs, pts3 = library_arrays
+        self.library = LandmarkLibrary(descs, pts3, ctx=self.ctx)
+        self.params = params or LocalizeParams()
+        self._out = {}
+
+    def _buffers(self, B):
+        t = self.torch
+        o = self._out.get(B)
+        if o is None:
+            o = {'best_cand': t.empty(B, dtype=t.int32, device=self.device),
+                 'n_inliers': t.empty(B, dtype=t.int32, device=self.device),
+                 'reproj': t.empty(B, dtype=t.float32, device=self.device),
+                 'rvec': t.empty((B, 3), dtype=t.float64, device=self.device),
+                 'tvec': t.empty((B, 3), dtype=t.float64, device=self.device)}
+            self._out[B] = o
+        return o
+
+    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None):
+        """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors -> dict of CUDA tensors + n_problems."""
+        B, Nq = desc_dev.shape[0], desc_dev.shape[1]
+        Cn = n_cand if cand_dev is None else cand_dev.shape[1]
+        if Cn is None:
+            Cn = self.library.n_keyframes
+        o = self._buffers(B)
+        nprob = C.c_int32(0)
+        self.ctx.check(_c.nclt_localize_batch_dev(
+            self.ctx.h, self.library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(), None, B, Nq,
+            None if cand_dev is None else cand_dev.data_ptr(), Cn, C.byref(self.params),
+            o['best_cand'].data_ptr(), o['n_inliers'].data_ptr(), o['reproj'].data_ptr(), o['rvec'].data_ptr(),
+            o['tvec'].data_ptr(), C.addressof(nprob), None, None, None, None, None, None))
+        r = dict(o)
+        r['n_problems'] = int(nprob.value)
+        return r

@@ -1,0 +1,75 @@
+"""GPU parity of the whole repeat-time path (match -> gates -> PnP-RANSAC -> best candidate)
+against the CPU restatement of the reference loop (oracle/localize.py)."""
+import numpy as np
+import pytest
+
+from oracle import localize as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(data, lib, desc, pts2d, cand, mode, q_n=None):
+    from nclt_slam_project_b200.pipeline import localize_batch
+    from nclt_slam_project_b200._lib import LocalizeParams
+    out = localize_batch(lib, desc, pts2d, q_n, cand, LocalizeParams(mode=mode), per_item=True)
+    B = desc.shape[0]
+    n_pub = 0
+    for b in range(B):
+        nq = desc.shape[1] if q_n is None else int(q_n[b])
+        cands = list(range(len(data['landmarks']))) if cand is None else cand[b].tolist()
+        ref = ol.localize_frame(data['landmarks'], desc[b, :nq], pts2d[b, :nq], cands, mode)
+        assert out['best_cand'][b] == ref['best_slot'], (b, out['best_cand'][b], ref['best_slot'])
+        assert out['n_inliers'][b] == ref['n_in']
+        for c, it in enumerate(ref['items']):
+            assert out['item_nmatch'][b, c] == it['nmatch'], (b, c)
+            if it['nmatch'] >= 10:
+                assert bool(out['item_ok'][b, c]) == it['ok'], (b, c)
+                assert out['item_ninl'][b, c] == it['n_in'], (b, c)
+                if it['ok']:
+                    assert np.abs(out['item_rvec'][b, c] - it['rvec']).max() < 1e-4      # rad
+                    assert np.abs(out['item_tvec'][b, c] - it['tvec']).max() < 1e-3      # m
+                    assert abs(out['item_err'][b, c] - it['err']) < 1e-3
+        if ref['best_slot'] >= 0:
+            n_pub += 1
+            assert abs(out['reproj'][b] - ref['reproj']) < 1e-3
+            assert np.abs(out['rvec'][b] - ref['rvec']).max() < 1e-4
+            assert np.abs(out['tvec'][b] - ref['tvec']).max() < 1e-3
+    return n_pub, out
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_all_keyframes(ctx, mode):
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    data = synth.make_library(17, n_kf=12, n_desc=500, ragged=True)
+    lib = LandmarkLibrary.from_pkl_dict(data)
+    desc, pts2d, kstar, _ = synth.make_frame_batch(data, range(1700, 1706), n_desc=600, n_planted=250)
+    n_pub, out = _check(data, lib, desc, pts2d, None, mode)
+    assert n_pub >= 5
+    assert np.array_equal(out['best_cand'][out['best_cand'] >= 0], kstar[out['best_cand'] >= 0])
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_candidate_lists_and_short_frames(ctx, mode):
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    data = synth.make_library(19, n_kf=8, n_desc=400, ragged=True)
+    lib = LandmarkLibrary.from_pkl_dict(data)
+    desc, pts2d, kstar, _ = synth.make_frame_batch(data, range(1900, 1904), n_desc=500, n_planted=200)
+    cand = np.array([[kstar[0], 1, -1, 2, 3], [4, kstar[1], 5, -1, -1], [0, 1, 2, 3, 4],
+                     [-1, -1, -1, -1, -1]], dtype=np.int32)
+    q_n = np.array([500, 480, 500, 500], dtype=np.int32)
+    _check(data, lib, desc, pts2d, cand, mode, q_n)
+
+
+def test_two_identical_candidates_first_wins(ctx):
+    """a7: strict '>' on the inlier count -> the earliest candidate wins ties (matcher:379)."""
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    data = synth.make_library(23, n_kf=3, n_desc=300)
+    data['landmarks'].append(dict(data['landmarks'][1]))          # keyframe 3 == keyframe 1
+    lib = LandmarkLibrary.from_pkl_dict(data)
+    f = synth.make_frame(data, 5, k_star=1, n_desc=400, n_planted=150)
+    cand = np.array([[3, 1, 0]], dtype=np.int32)
+    n_pub, out = _check(data, lib, f['desc'][None], f['pts2d'][None], cand, 0)
+    assert n_pub == 1 and out['best_cand'][0] == 0
