@@ -271,7 +271,8 @@ def main():
     tp = os.path.join(ROOT, 'profiles', 'traffic_hamming.json')
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+            # ncu --set full capture (profiles/README.md), scaled from its batch to this one
+            traffic = json.load(open(tp)).get('dram_bytes_per_frame') * B
         except Exception:
             traffic = None
     roofline = {'bound': 'int-pipe (POPC)', 'achieved': achieved / 1e12, 'peak': popc_peak / 1e12,

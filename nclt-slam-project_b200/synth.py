@@ -166,7 +166,7 @@ def make_depth_frame(seed, pose, cyl_density=0.02, h=IMG_H, w=IMG_W, bad_frac=0.
     depth = z_ground
     # cylinders in camera-forward planar frame: forward f in [1,12], lateral l in [-6,6]
     n_cyl = rng.poisson(cyl_density * 12 * 12)
-    cyl_rng = np.random.default_rng((int(x * 10) * 73856093) ^ (int(y * 10) * 19349663) & 0x7FFFFFFF)
+    cyl_rng = np.random.default_rng(((int(x * 10) * 73856093) ^ (int(y * 10) * 19349663)) & 0x7FFFFFFF)
     for _ in range(n_cyl):
         f = cyl_rng.uniform(1.0, 12.0)
         l = cyl_rng.uniform(-6.0, 6.0)

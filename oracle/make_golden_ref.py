@@ -1,0 +1,146 @@
+"""TEST INFRASTRUCTURE - golden vectors produced by the REFERENCE'S OWN MODULES, imported
+unmodified from /root/reference under ROS stubs (build container only).
+
+  golden_map      tf_wall_clock_relay.TFRelay.depth_cb -> teach_run_depth_mapper.TeachDepthMapper.cb
+                  -> save(): point clouds, log-odds grid, PGM/YAML bytes on seeded synthetic depth
+  golden_selftest the candidate loop of checkpoint_a_selftest.run_matcher_self (lines 62-103) with
+                  the module's own imported constants, fed synthetic descriptors
+"""
+import io
+import os
+import tempfile
+
+import numpy as np
+
+from . import ros_stubs
+from nclt_slam_project_b200 import synth
+
+# a small grid keeps the fixture small; the CLI defaults are exercised by the format test
+MAP_CFG = dict(origin_x=-12.0, origin_y=-9.0, width_m=40.0, height_m=30.0, res=0.1)
+
+
+def _fake_image(depth):
+    from sensor_msgs.msg import Image
+    m = Image()
+    if depth.dtype == np.uint16:
+        m.encoding = '16UC1'
+    else:
+        m.encoding = '32FC1'
+    m.height, m.width = depth.shape
+    m.data = depth.tobytes()
+    return m
+
+
+def golden_map(out_dir, n_frames=24):
+    mods = ros_stubs.import_reference()
+    relay_mod, mapper_mod = mods['tf_wall_clock_relay'], mods['teach_run_depth_mapper']
+    relay = relay_mod.TFRelay(use_gt=True)
+    tmp = tempfile.mkdtemp()
+    prefix = os.path.join(tmp, 'teach_map')
+    mapper = mapper_mod.TeachDepthMapper(prefix, MAP_CFG['origin_x'], MAP_CFG['origin_y'], MAP_CFG['width_m'],
+                                         MAP_CFG['height_m'], MAP_CFG['res'])
+    rng = np.random.default_rng(3)
+    poses, depths, clouds, cloud_n, grids_after = [], [], [], [], []
+    x, y, yaw = -8.0, -5.0, 0.3
+    for f in range(n_frames):
+        x += 0.35 * np.cos(yaw)
+        y += 0.35 * np.sin(yaw)
+        yaw += rng.uniform(-0.05, 0.25)
+        if f == 5:
+            pose = (-30.0, 0.0, 0.0)            # sensor cell outside the grid: frame dropped
+        else:
+            pose = (x, y, yaw)
+        depth = synth.make_depth_frame(100 + f, pose, cyl_density=0.05)
+        if f == 7:
+            depth[:] = 0.0                      # empty cloud
+        if f == 9:
+            depth = (np.nan_to_num(depth, nan=0.0, posinf=0.0) * 1000.0).clip(0, 65535).astype(np.uint16)
+        tf = synth.camera_link_transform(*pose)
+        relay.depth_cb(_fake_image(depth))
+        pc = relay.pc_pub.sent[-1]
+        pts = np.frombuffer(pc.data, dtype=np.float32).reshape(-1, 3)
+        assert pc.point_step == 12 and pc.width == len(pts) and pc.header.frame_id == 'camera_link'
+        mapper.tf_buf.current = tf
+        mapper.cb(pc)
+        poses.append(tf)
+        if depth.dtype == np.uint16:
+            depth_u16 = depth.copy()
+        depths.append(depth.astype(np.float32))
+        clouds.append(pts.copy())
+        cloud_n.append(len(pts))
+        if f in (0, 3, n_frames - 1):
+            grids_after.append(mapper.grid.copy())
+    mapper.save()
+    pgm = open(prefix + '.pgm', 'rb').read()
+    yml = open(prefix + '.yaml', 'rb').read().replace(tmp.encode(), b'<TMP>')
+    nmax = max(cloud_n)
+    cl = np.zeros((n_frames, nmax, 3), dtype=np.float32)
+    for f, c in enumerate(clouds):
+        cl[f, :len(c)] = c
+    # depth frames as float32 metres; frame 9 was fed as 16UC1 millimetres (depth_u16)
+    np.savez_compressed(
+        os.path.join(out_dir, 'map_golden.npz'),
+        cfg=np.array([MAP_CFG['origin_x'], MAP_CFG['origin_y'], MAP_CFG['width_m'], MAP_CFG['height_m'], MAP_CFG['res']]),
+        tf=np.array(poses), depth=np.stack(depths).astype(np.float32), u16_frames=np.array([9], dtype=np.int32), depth_u16=depth_u16,
+        cloud=cl, cloud_n=np.array(cloud_n, dtype=np.int32),
+        grid_snap_frames=np.array([0, 3, n_frames - 1], dtype=np.int32), grid_snaps=np.stack(grids_after),
+        grid_final=mapper.grid.copy(), pgm=np.frombuffer(pgm, dtype=np.uint8), yaml=np.frombuffer(yml, dtype=np.uint8),
+        frames_integrated=np.int64(mapper.frames_integrated), total_points=np.int64(mapper.total_points_integrated),
+        skipped_empty=np.int64(mapper.frames_skipped_empty))
+    print('map_golden.npz frames_integrated', mapper.frames_integrated, 'pts', mapper.total_points_integrated,
+          'pgm bytes', len(pgm), 'clouds', cloud_n[:6])
+
+
+def golden_selftest(out_dir):
+    """Run the reference selftest's candidate loop (checkpoint_a_selftest.py:62-103) on synthetic
+    descriptors. run_matcher_self() itself starts from JPEG files (cv2.imread + ORB), which are not
+    shipped, so its loop body is executed here on the module's own imported names."""
+    mods = ros_stubs.import_reference()
+    st = mods['checkpoint_a_selftest']
+    import cv2
+    data = synth.make_library(77, n_kf=10, n_desc=400, ragged=True)
+    rows = []
+    descs, pts2, cands = [], [], []
+    for seed in range(6):
+        f = synth.make_frame(data, 7700 + seed, n_desc=500, n_planted=220)
+        cand_idx = [f['k_star'], (f['k_star'] + 1) % 10, (f['k_star'] + 5) % 10]
+        desc_curr, pts_curr_2d = f['desc'], f['pts2d']
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+        best = None
+        per = []
+        for li in cand_idx:
+            lm_t = data['landmarks'][li]
+            desc_t = lm_t['descriptors']
+            rec = [0, 0, 0, 0.0, 0, 0, 0, 0, 0, 0]
+            per.append(rec)
+            if desc_t is None or len(desc_t) < st.MIN_MATCHES:
+                continue
+            knn = bf.knnMatch(desc_curr, desc_t, k=2)
+            good = [m for m, n in knn if (m.distance < st.LOWE_RATIO * n.distance)]
+            rec[0] = len(good)
+            if len(good) < st.MIN_MATCHES:
+                continue
+            obj_pts = np.array([lm_t['keypoints_3d_cam'][m.trainIdx] for m in good], dtype=np.float32)
+            img_pts = np.array([pts_curr_2d[m.queryIdx] for m in good], dtype=np.float32)
+            ok, rvec, tvec, inliers = cv2.solvePnPRansac(
+                obj_pts, img_pts, st.K, st.DIST, iterationsCount=st.RANSAC_ITERATIONS,
+                reprojectionError=st.RANSAC_REPROJ_PX, flags=cv2.SOLVEPNP_ITERATIVE)
+            if not ok or inliers is None or len(inliers) < st.MIN_INLIERS:
+                continue
+            proj, _ = cv2.projectPoints(obj_pts[inliers[:, 0]], rvec, tvec, st.K, st.DIST)
+            err = float(np.linalg.norm(proj.reshape(-1, 2) - img_pts[inliers[:, 0]], axis=1).mean())
+            rec[1:] = [1, len(inliers), err] + rvec.ravel().tolist() + tvec.ravel().tolist()
+            if err > st.REPROJ_MAX_PX:
+                continue
+            if best is None or len(inliers) > best[1]:
+                best = (cand_idx.index(li), len(inliers))
+        rows.append((best[0] if best else -1, best[1] if best else 0, per))
+        descs.append(desc_curr)
+        pts2.append(pts_curr_2d)
+        cands.append(cand_idx)
+    np.savez_compressed(
+        os.path.join(out_dir, 'selftest_golden.npz'),
+        lib_seed=np.int64(77), desc=np.stack(descs), pts2d=np.stack(pts2), cand=np.array(cands, dtype=np.int32),
+        best_slot=np.array([r[0] for r in rows], dtype=np.int32), best_inl=np.array([r[1] for r in rows], dtype=np.int32),
+        items=np.array([r[2] for r in rows], dtype=np.float64))
+    print('selftest_golden.npz best slots', [r[0] for r in rows], 'inliers', [r[1] for r in rows])
