@@ -185,6 +185,44 @@ int nclt_localize_batch_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q
                             int32_t* out_item_nmatch, uint8_t* out_item_ok, int32_t* out_item_ninl,
                             float* out_item_err, double* out_item_rvec, double* out_item_tvec);
 
+/* ---- teach-time map builder ------------------------------------------------------------ */
+/* Log-odds occupancy grid of scripts/common/teach_run_depth_mapper.py (class TeachDepthMapper,
+ * :83-100): W = int(width_m/res) columns, H = int(height_m/res) rows, origin (origin_x, origin_y).
+ * The device grid holds exact integers in units of 0.2 (L_FREE -0.4 = -2, L_OCC +1.4 = +7,
+ * L_MIN/L_MAX +-5 = +-25); updates are applied in the reference's order (frame, ray, cell). */
+int nclt_occ_create(nclt_ctx* ctx, double origin_x, double origin_y, double res, int W, int H, nclt_occ** out);
+int nclt_occ_destroy(nclt_ctx* ctx, nclt_occ* occ);
+int nclt_occ_reset(nclt_ctx* ctx, nclt_occ* occ);
+
+/* replaces TFRelay.depth_cb (tf_wall_clock_relay.py:868-903) followed by TeachDepthMapper.cb
+ * (teach_run_depth_mapper.py:125-170) for F depth frames, processed in order.
+ * depth f32[F,Hd,Wd] metres (32FC1) or, with is_u16 != 0, u16[F,Hd,Wd] millimetres (16UC1);
+ * T f64[F,16] row-major map<-camera_link matrices (what _tf_to_matrix builds, mapper:64-80);
+ * fx,fy,cx,cy the relay intrinsics (relay:80-81). */
+int nclt_occ_integrate_depth(nclt_ctx* ctx, nclt_occ* occ, const void* depth, int is_u16, int F, int Hd, int Wd,
+                             const double* T, double fx, double fy, double cx, double cy);
+/* device pointers; optionally also returns the relay's point clouds: out_pts f32[F,pts_cap,3],
+ * out_pts_n i32[F] (NULL ok) */
+int nclt_occ_integrate_depth_dev(nclt_ctx* ctx, nclt_occ* occ, const void* depth, int is_u16, int F, int Hd,
+                                 int Wd, const double* T, double fx, double fy, double cx, double cy,
+                                 float* out_pts, int32_t* out_pts_n, int pts_cap);
+/* replaces TeachDepthMapper.cb(PointCloud2) alone: pts f32[F,Nmax,3] camera_link points
+ * (x,y,z FLOAT32 at offsets 0/4/8, point_step 12), n i32[F] points per cloud. */
+int nclt_occ_integrate_points(nclt_ctx* ctx, nclt_occ* occ, const float* pts, const int32_t* n, int F, int Nmax,
+                              const double* T);
+int nclt_occ_integrate_points_dev(nclt_ctx* ctx, nclt_occ* occ, const float* pts, const int32_t* n, int F,
+                                  int Nmax, const double* T);
+/* replaces TFRelay.depth_cb alone (the PointCloud2 payload, also consumed by Nav2's obstacle
+ * layer): out_pts f32[F,pts_cap,3] (z, -px, -py), out_n i32[F]. Host pointers. */
+int nclt_depth_to_points(nclt_ctx* ctx, const void* depth, int is_u16, int F, int Hd, int Wd, double fx,
+                         double fy, double cx, double cy, float* out_pts, int32_t* out_n, int pts_cap);
+/* read-back (any pointer may be NULL), host pointers: out_logodds f32[H,W] = TeachDepthMapper.grid
+ * (0.2 * units); out_pgm u8[H,W] = the P5 payload of save() (mapper:208-216: 205 unknown, 0
+ * occupied, 254 free, flipud); out_units i32[H,W]; out_counters i64[3] = frames_integrated,
+ * total_points_integrated, frames_skipped_empty (mapper:94-97). */
+int nclt_occ_read(nclt_ctx* ctx, nclt_occ* occ, float* out_logodds, uint8_t* out_pgm, int32_t* out_units,
+                  int64_t* out_counters);
+
 #ifdef __cplusplus
 }
 #endif

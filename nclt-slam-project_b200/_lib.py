@@ -89,6 +89,17 @@ for _n in ('nclt_localize_batch', 'nclt_localize_batch_dev'):
     _sig(_n, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _lp, *([_vp] * 12))
 
 
+_sig('nclt_occ_create', _i, _vp, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_vp))
+_sig('nclt_occ_destroy', _i, _vp, _vp)
+_sig('nclt_occ_reset', _i, _vp, _vp)
+_sig('nclt_occ_integrate_depth', _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _dbl, _dbl, _dbl, _dbl)
+_sig('nclt_occ_integrate_depth_dev', _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _i)
+_sig('nclt_occ_integrate_points', _i, _vp, _vp, _vp, _vp, _i, _i, _vp)
+_sig('nclt_occ_integrate_points_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _vp)
+_sig('nclt_depth_to_points', _i, _vp, _vp, _i, _i, _i, _i, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _i)
+_sig('nclt_occ_read', _i, _vp, _vp, _vp, _vp, _vp, _vp)
+
+
 def ptr(x):
     """Raw address of a numpy array / torch tensor / None / int."""
     if x is None:

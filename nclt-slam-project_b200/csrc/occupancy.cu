@@ -1,0 +1,587 @@
+// K6-K8: teach-time map builder - depth back-projection, ordered double compaction, Bresenham
+// free-space ray tracing and saturating log-odds, order-exact.
+//
+// Replaces:
+//   a10 relay depth_cb                      scripts/common/tf_wall_clock_relay.py:868-887
+//   a11 mapper transform + filters + [::4]  scripts/common/teach_run_depth_mapper.py:133-153
+//   a12 world_to_pix (truncation)           teach_run_depth_mapper.py:120-123
+//   a13 _bresenham_mark                     teach_run_depth_mapper.py:172-195
+//   a14 save (threshold, flipud)            teach_run_depth_mapper.py:208-216
+//
+// The reference updates a float32 log-odds grid sequentially, with clamps at +-5 that make the
+// result depend on the order of updates.  Here the grid holds exact integers in units of 0.2
+// (free -2, occupied +7, clamp +-25; thresholds: occupied <=> u >= 4, free <=> u <= -6), and
+// every update x -> clamp(x + a) is an element of the monoid {x -> min(max(x + s, lo), hi)},
+// closed under composition.  So:
+//   stage A (k_occ_frame, one CTA per frame, all SMs in parallel): build the frame's rays, count
+//     passes/hits per cell in a shared-memory window histogram (the privatised histogram), turn
+//     every touched cell into ONE composed map.  Cells that only saw passes or only hits have a
+//     closed form; cells that saw both get their exact interleaving from per-cell ray bitmaps.
+//   stage B (k_occ_apply, frames strictly in order): grid[cell] = map(grid[cell]).
+// The result equals the sequential reference update for update, ray by ray, frame by frame.
+#include "common.cuh"
+#include "scratch.cuh"
+
+#include <cfloat>
+#include <climits>
+
+namespace {
+
+constexpr int OT = 512;             // threads per frame CTA
+constexpr int MAX_RAYS = 8192;      // rays per frame handled by the fast path (depth mode: <= 4800)
+constexpr int BM_WORDS = MAX_RAYS / 32;
+constexpr int WIN_CAP = 40960;      // cells in the shared-memory window (bbox of one frame's rays)
+constexpr uint32_t OOB = 0xFFFFFFFFu;
+constexpr uint32_t MIXED = 0x80000000u;
+
+enum FrameStatus : int { FR_OK = 0, FR_EMPTY = 1, FR_NOHEIGHT = 2, FR_SENSOR_OOB = 3, FR_FALLBACK = 4 };
+
+struct FrameHdr {
+    int status;
+    int n_rays;      // len(pts_map) after [::4] (incl. out-of-grid endpoints)
+    int n_delta;
+    int r0, c0;
+    int pad[3];
+};
+
+struct OccGeom {
+    int GH, GW;
+    double ox, oy, res;
+};
+
+struct FrameIn {
+    // depth mode
+    const float* depth;       // [F][Hd][Wd] or null
+    const uint16_t* depth16;  // [F][Hd][Wd] or null
+    int Hd, Wd, step;
+    float fx, fy, cx, cy;
+    // point mode
+    const float* pts;         // [F][Nmax][3] or null
+    const int* pts_n;         // [F]
+    int Nmax;
+    const double* T;          // [F][16] row-major map <- camera_link
+};
+
+__device__ __forceinline__ int to_pix(double x, double origin, double res) { return (int)((x - origin) / res); }
+// one coordinate of T @ [p;1] in OpenBLAS dgemm's order: an FMA chain over k (verified bit-exact)
+__device__ __forceinline__ double xform(const double* t, double x, double y, double z) {
+    return fma(t[3], 1.0, fma(t[2], z, fma(t[1], y, t[0] * x)));
+}
+
+// sample `s` of frame `f` -> camera_link point; returns relay validity
+__device__ __forceinline__ bool sample_point(const FrameIn& in, int f, int s, int cols, float& X, float& Y, float& Z) {
+    if (in.pts) {
+        const float* p = in.pts + ((size_t)f * in.Nmax + s) * 3;
+        X = p[0]; Y = p[1]; Z = p[2];
+        return isfinite(X) && isfinite(Y) && isfinite(Z);      // _parse_pc2 finite filter
+    }
+    int v = (s / cols) * in.step, u = (s % cols) * in.step;
+    size_t off = ((size_t)f * in.Hd + v) * in.Wd + u;
+    float z = in.depth ? in.depth[off] : (float)in.depth16[off] / 1000.0f;
+    bool ok = (z > 0.3f) && (z < 10.0f) && isfinite(z);
+    float px = ((float)u - in.cx) / in.fx * z;      // float32, this order, no FMA (-fmad=false)
+    float py = ((float)v - in.cy) / in.fy * z;
+    X = z; Y = -px; Z = -py;
+    return ok;
+}
+
+// block-wide exclusive offset of `flag` in thread order; `base` advances by the block total
+__device__ __forceinline__ int block_rank(bool flag, int& base, int* s_warp) {
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, flag);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < OT / 32; ++w) {
+        int v = s_warp[w];
+        total += v;
+        if (w < warp) before += v;
+    }
+    int r = base + before + __popc(bal & ((1u << lane) - 1u));
+    base += total;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long pack_delta(int cell, int s, int lo, int hi) {
+    s = s > 50 ? 50 : (s < -50 ? -50 : s);     // |s| >= 50 already saturates on [-25, 25]
+    return ((unsigned long long)(unsigned)cell << 19) | ((unsigned long long)(s + 64) << 12) |
+           ((unsigned long long)(lo + 32) << 6) | (unsigned long long)(hi + 32);
+}
+
+template <typename F>
+__device__ __forceinline__ void bresenham(int r0, int c0, int r1, int c1, F&& visit) {
+    int dr = abs(r1 - r0), dc = abs(c1 - c0);
+    int sr = r0 < r1 ? 1 : -1, sc = c0 < c1 ? 1 : -1;
+    int err = dr - dc, r = r0, c = c0;
+    for (;;) {
+        bool end = (r == r1) && (c == c1);
+        visit(r, c, end);
+        if (end) return;
+        int e2 = 2 * err;
+        if (e2 > -dc) { err -= dc; r += sr; }
+        if (e2 < dr) { err += dr; c += sc; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage A
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OT) k_occ_frame(FrameIn in, OccGeom g, int F, FrameHdr* hdr,
+                                                  unsigned long long* delta /*[F][WIN_CAP]*/,
+                                                  uint32_t* rays_g /*[F][ray_cap]*/, int ray_cap,
+                                                  uint32_t* bitmaps /*[gridDim.x][MAX_RAYS][2][BM_WORDS]... see below*/,
+                                                  float* out_pts /*[F][cap][3] or null*/, int* out_pts_n, int pts_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                       // WIN_CAP
+    uint32_t* rays = win + WIN_CAP;                                              // MAX_RAYS
+    unsigned short* mixed_cell = reinterpret_cast<unsigned short*>(rays + MAX_RAYS);   // MAX_RAYS
+    __shared__ int s_warp[OT / 32];
+    __shared__ int s_bbox[4];
+    __shared__ int s_cnt[4];      // n_mixed, n_delta, overflow flag
+    __shared__ double sT[16];
+
+    const int tid = threadIdx.x;
+    for (int f = blockIdx.x; f < F; f += gridDim.x) {
+        __syncthreads();
+        if (tid < 16) sT[tid] = in.T[(size_t)f * 16 + tid];
+        if (tid == 0) {
+            s_bbox[0] = INT_MAX; s_bbox[1] = INT_MIN; s_bbox[2] = INT_MAX; s_bbox[3] = INT_MIN;
+            s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0;
+        }
+        __syncthreads();
+        const int cols = in.pts ? 1 : (in.Wd + in.step - 1) / in.step;
+        const int rows = in.pts ? 1 : (in.Hd + in.step - 1) / in.step;
+        const int n_samples = in.pts ? in.pts_n[f] : rows * cols;
+        const int r0 = to_pix(sT[7], g.oy, g.res), c0 = to_pix(sT[3], g.ox, g.res);
+        const bool sensor_ok = (0 <= r0 && r0 < g.GH && 0 <= c0 && c0 < g.GW);
+
+        // ---- a10/a11: points, filters, ordered double compaction, every 4th ---------------
+        int n_valid1 = 0, n_kept = 0;
+        bool overflow = false;
+        for (int s0 = 0; s0 < n_samples; s0 += OT) {
+            int s = s0 + tid;
+            float X = 0, Y = 0, Z = 0;
+            bool v1 = false;
+            if (s < n_samples) v1 = sample_point(in, f, s, cols, X, Y, Z);
+            int rank1 = block_rank(v1, n_valid1, s_warp);
+            if (v1 && out_pts && rank1 < pts_cap) {
+                float* o = out_pts + ((size_t)f * pts_cap + rank1) * 3;
+                o[0] = X; o[1] = Y; o[2] = Z;
+            }
+            bool v2 = false;
+            if (v1) {
+                double zm = xform(sT + 8, (double)X, (double)Y, (double)Z);
+                v2 = (zm > 0.2) && (zm < 2.0);
+            }
+            int k = block_rank(v2, n_kept, s_warp);
+            if (v2 && (k & 3) == 0) {
+                int ray = k >> 2;
+                double xm = xform(sT, (double)X, (double)Y, (double)Z);
+                double ym = xform(sT + 4, (double)X, (double)Y, (double)Z);
+                int c1 = to_pix(xm, g.ox, g.res), r1 = to_pix(ym, g.oy, g.res);
+                bool inb = (0 <= r1 && r1 < g.GH && 0 <= c1 && c1 < g.GW);
+                uint32_t packed = inb ? ((uint32_t)r1 << 16 | (uint32_t)c1) : OOB;
+                if (ray < MAX_RAYS) rays[ray] = packed;
+                if (ray < ray_cap) rays_g[(size_t)f * ray_cap + ray] = packed;
+                if (inb) {
+                    atomicMin(&s_bbox[0], r1); atomicMax(&s_bbox[1], r1);
+                    atomicMin(&s_bbox[2], c1); atomicMax(&s_bbox[3], c1);
+                }
+            }
+        }
+        if (out_pts_n && tid == 0) out_pts_n[f] = n_valid1;
+        const int n_rays = (n_kept + 3) >> 2;
+        if (n_rays > MAX_RAYS) overflow = true;
+        __syncthreads();
+
+        int status = FR_OK;
+        if (n_valid1 == 0) status = FR_EMPTY;
+        else if (n_kept == 0) status = FR_NOHEIGHT;
+        else if (!sensor_ok) status = FR_SENSOR_OOB;
+        int wr = 0, wc = 0, rmin = 0, cmin = 0;
+        if (status == FR_OK) {
+            rmin = min(s_bbox[0], r0); int rmax = max(s_bbox[1], r0);
+            cmin = min(s_bbox[2], c0); int cmax = max(s_bbox[3], c0);
+            wr = rmax - rmin + 1; wc = cmax - cmin + 1;
+            if (overflow || (long long)wr * wc > WIN_CAP || n_rays > ray_cap) status = FR_FALLBACK;
+        }
+        if (status != FR_OK) {
+            if (tid == 0) {
+                FrameHdr h{};
+                h.status = status; h.n_rays = n_rays; h.n_delta = 0; h.r0 = r0; h.c0 = c0;
+                hdr[f] = h;
+            }
+            continue;
+        }
+        const int ncell = wr * wc;
+        for (int i = tid; i < ncell; i += OT) win[i] = 0;
+        __syncthreads();
+
+        // ---- a13 pass 1: privatised pass/hit histogram in shared memory --------------------
+        for (int i = tid; i < n_rays; i += OT) {
+            uint32_t pk = rays[i];
+            if (pk == OOB) continue;
+            int r1 = (int)(pk >> 16), c1 = (int)(pk & 0xFFFF);
+            bresenham(r0, c0, r1, c1, [&](int r, int c, bool end) {
+                atomicAdd(&win[(r - rmin) * wc + (c - cmin)], end ? 0x10000u : 1u);
+            });
+        }
+        __syncthreads();
+
+        // ---- classify touched cells; pure cells get their closed-form map ------------------
+        unsigned long long* dl = delta + (size_t)f * WIN_CAP;
+        for (int i = tid; i < ncell; i += OT) {
+            uint32_t v = win[i];
+            if (v == 0) continue;
+            int nf = (int)(v & 0xFFFF), no = (int)(v >> 16);
+            int cell = (rmin + i / wc) * g.GW + (cmin + i % wc);
+            if (nf && no) {
+                int id = atomicAdd(&s_cnt[0], 1);
+                win[i] = MIXED | (uint32_t)id;
+                mixed_cell[id] = (unsigned short)i;
+            } else {
+                int pos = atomicAdd(&s_cnt[1], 1);
+                // only passes: x -> max(x - 2n, -25); only hits: x -> min(x + 7n, 25)
+                dl[pos] = nf ? pack_delta(cell, -2 * nf, -25, 25) : pack_delta(cell, 7 * no, -25, 25);
+            }
+        }
+        __syncthreads();
+        const int n_mixed = s_cnt[0];
+        if (n_mixed > 0) {
+            // ---- mixed cells: exact interleaving of passes and hits by ray index -------------
+            const int nw = (n_rays + 31) >> 5;
+            uint32_t* bm = bitmaps + (size_t)blockIdx.x * MAX_RAYS * 2 * BM_WORDS;   // [id][2][BM_WORDS]
+            for (int i = tid; i < n_mixed * 2 * BM_WORDS; i += OT) {
+                int w = i % BM_WORDS;
+                if (w < nw) bm[i] = 0;
+            }
+            __syncthreads();
+            for (int i = tid; i < n_rays; i += OT) {
+                uint32_t pk = rays[i];
+                if (pk == OOB) continue;
+                int r1 = (int)(pk >> 16), c1 = (int)(pk & 0xFFFF);
+                bresenham(r0, c0, r1, c1, [&](int r, int c, bool end) {
+                    uint32_t v = win[(r - rmin) * wc + (c - cmin)];
+                    if (v & MIXED) {
+                        uint32_t id = v & 0x7FFFFFFFu;
+                        atomicOr(&bm[((size_t)id * 2 + (end ? 1 : 0)) * BM_WORDS + (i >> 5)], 1u << (i & 31));
+                    }
+                });
+            }
+            __syncthreads();
+            for (int id = tid; id < n_mixed; id += OT) {
+                const uint32_t* pb = bm + (size_t)id * 2 * BM_WORDS;
+                const uint32_t* hb = pb + BM_WORDS;
+                int s = 0, lo = -1000000, hi = 1000000;
+                for (int w = 0; w < nw; ++w) {
+                    uint32_t p = pb[w], h = hb[w], m = p | h;
+                    while (m) {
+                        int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        int a = ((h >> b) & 1u) ? 7 : -2;
+                        s += a;
+                        lo = min(max(lo + a, -25), 25);
+                        hi = min(max(hi + a, -25), 25);
+                    }
+                }
+                int i = mixed_cell[id];
+                int cell = (rmin + i / wc) * g.GW + (cmin + i % wc);
+                int pos = atomicAdd(&s_cnt[1], 1);
+                dl[pos] = pack_delta(cell, s, lo, hi);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            FrameHdr h{};
+            h.status = FR_OK; h.n_rays = n_rays; h.n_delta = s_cnt[1]; h.r0 = r0; h.c0 = c0;
+            hdr[f] = h;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage B: frames strictly in order; cells of one frame are distinct -> parallel over cells
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_occ_apply(int* grid, OccGeom g, int F, const FrameHdr* hdr,
+                                                    const unsigned long long* delta, const uint32_t* rays_g,
+                                                    int ray_cap, long long* counters) {
+    const int tid = threadIdx.x;
+    long long integ = 0, pts = 0, empty = 0;
+    for (int f = 0; f < F; ++f) {
+        const FrameHdr h = hdr[f];
+        if (h.status == FR_EMPTY) { empty++; continue; }
+        if (h.status == FR_NOHEIGHT || h.status == FR_SENSOR_OOB) continue;
+        if (h.status == FR_FALLBACK) {
+            // exact sequential walk (window or ray count beyond the fast path's capacity)
+            if (tid == 0) {
+                int n = min(h.n_rays, ray_cap);
+                for (int i = 0; i < n; ++i) {
+                    uint32_t pk = rays_g[(size_t)f * ray_cap + i];
+                    if (pk == OOB) continue;
+                    bresenham(h.r0, h.c0, (int)(pk >> 16), (int)(pk & 0xFFFF), [&](int r, int c, bool end) {
+                        int* p = grid + (size_t)r * g.GW + c;
+                        *p = end ? min(*p + 7, 25) : max(*p - 2, -25);
+                    });
+                }
+            }
+        } else {
+            const unsigned long long* dl = delta + (size_t)f * WIN_CAP;
+            for (int i = tid; i < h.n_delta; i += blockDim.x) {
+                unsigned long long e = dl[i];
+                int cell = (int)(e >> 19);
+                int s = (int)((e >> 12) & 127) - 64, lo = (int)((e >> 6) & 63) - 32, hi = (int)(e & 63) - 32;
+                int x = grid[cell];
+                grid[cell] = min(max(x + s, lo), hi);
+            }
+        }
+        integ++;
+        pts += h.n_rays;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counters[0] += integ;
+        counters[1] += pts;
+        counters[2] += empty;
+    }
+}
+
+// a14: threshold + flipud ; and the float32 view of the grid
+__global__ void k_occ_render(const int* __restrict__ grid, int GH, int GW, unsigned char* img, float* logodds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= GH * GW) return;
+    int r = i / GW, c = i % GW;
+    int u = grid[i];
+    if (img) {
+        unsigned char v = 205;
+        if (u >= 4) v = 0;       // 0.2u > ln(0.65/0.35) = 0.619  <=>  u >= 4
+        if (u <= -6) v = 254;    // 0.2u < ln(0.25/0.75) = -1.0986 <=> u <= -6
+        img[(size_t)(GH - 1 - r) * GW + c] = v;
+    }
+    if (logodds) logodds[i] = (float)u * 0.2f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// handle + launchers
+// ---------------------------------------------------------------------------------------
+struct nclt_occ {
+    int device = 0;
+    OccGeom g{};
+    int* d_grid = nullptr;
+    long long* d_counters = nullptr;
+    uint32_t* d_bitmaps = nullptr;
+    int bitmap_ctas = 0;
+};
+
+static const size_t OCC_SMEM = (size_t)WIN_CAP * 4 + (size_t)MAX_RAYS * 4 + (size_t)MAX_RAYS * 2;
+
+extern "C" int nclt_occ_create(nclt_ctx* c, double origin_x, double origin_y, double res, int W, int H,
+                               nclt_occ** out) {
+    if (!c || !out || W <= 0 || H <= 0 || W > 65535 || H > 65535 || !(res > 0) || (long long)W * H > (1LL << 28))
+        return nclt_fail(c, NCLT_ERR_ARG, "occ_create args");
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    nclt_occ* o = new nclt_occ();
+    o->device = c->device;
+    o->g.GH = H; o->g.GW = W; o->g.ox = origin_x; o->g.oy = origin_y; o->g.res = res;
+    o->bitmap_ctas = c->sm_count;
+    cudaError_t e = cudaMalloc(&o->d_grid, (size_t)W * H * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_counters, 3 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_bitmaps, (size_t)o->bitmap_ctas * MAX_RAYS * 2 * BM_WORDS * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_grid, 0, (size_t)W * H * 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_counters, 0, 3 * sizeof(long long), c->stream);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_occ_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_SMEM);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        if (o->d_grid) cudaFree(o->d_grid);
+        if (o->d_counters) cudaFree(o->d_counters);
+        if (o->d_bitmaps) cudaFree(o->d_bitmaps);
+        delete o;
+        return nclt_fail(c, NCLT_ERR_CUDA, "occ_create", e);
+    }
+    *out = o;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_occ_destroy(nclt_ctx* c, nclt_occ* o) {
+    if (!o) return NCLT_OK;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(o->d_grid);
+    cudaFree(o->d_counters);
+    cudaFree(o->d_bitmaps);
+    delete o;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_occ_reset(nclt_ctx* c, nclt_occ* o) {
+    if (!c || !o) return NCLT_ERR_ARG;
+    cudaSetDevice(c->device);
+    CU_TRY(c, cudaMemsetAsync(o->d_grid, 0, (size_t)o->g.GW * o->g.GH * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(o->d_counters, 0, 3 * sizeof(long long), c->stream));
+    return NCLT_OK;
+}
+
+// shared driver: device pointers only
+static int occ_integrate_dev(nclt_ctx* c, nclt_occ* o, FrameIn in, int F, float* out_pts, int* out_pts_n,
+                             int pts_cap) {
+    if (F <= 0) return NCLT_OK;
+    cudaSetDevice(c->device);
+    int ray_cap;
+    if (in.pts) ray_cap = in.Nmax / 4 + 1;
+    else ray_cap = (((in.Hd + in.step - 1) / in.step) * ((in.Wd + in.step - 1) / in.step)) / 4 + 1;
+    ScratchScope scope(c);
+    int rc;
+    size_t need = pad256((size_t)F * sizeof(FrameHdr)) + pad256((size_t)F * WIN_CAP * 8) + pad256((size_t)F * ray_cap * 4);
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    FrameHdr* hdr = cv.take<FrameHdr>(F);
+    unsigned long long* delta = cv.take<unsigned long long>((size_t)F * WIN_CAP);
+    uint32_t* rays_g = cv.take<uint32_t>((size_t)F * ray_cap);
+    int grid = F < o->bitmap_ctas ? F : o->bitmap_ctas;
+    k_occ_frame<<<grid, OT, OCC_SMEM, c->stream>>>(in, o->g, F, hdr, delta, rays_g, ray_cap, o->d_bitmaps, out_pts,
+                                                   out_pts_n, pts_cap);
+    k_occ_apply<<<1, 1024, 0, c->stream>>>(o->d_grid, o->g, F, hdr, delta, rays_g, ray_cap, o->d_counters);
+    c->launches += 2;
+    CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}
+
+static int check_occ(nclt_ctx* c, nclt_occ* o) {
+    if (!c || !o) return nclt_fail(c, NCLT_ERR_ARG, "occ: null handle");
+    if (o->device != c->device) return nclt_fail(c, NCLT_ERR_ARG, "occ: grid lives on another device");
+    return NCLT_OK;
+}
+
+extern "C" int nclt_occ_integrate_depth_dev(nclt_ctx* c, nclt_occ* o, const void* depth, int is_u16, int F, int Hd,
+                                            int Wd, const double* T, double fx, double fy, double cx, double cy,
+                                            float* out_pts, int32_t* out_pts_n, int pts_cap) {
+    int rc = check_occ(c, o);
+    if (rc) return rc;
+    if (F < 0 || Hd <= 0 || Wd <= 0 || (F > 0 && (!depth || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_depth args");
+    FrameIn in{};
+    if (is_u16) in.depth16 = static_cast<const uint16_t*>(depth);
+    else in.depth = static_cast<const float*>(depth);
+    in.Hd = Hd; in.Wd = Wd; in.step = 4;          // step = 4 (tf_wall_clock_relay.py:876)
+    in.fx = (float)fx; in.fy = (float)fy; in.cx = (float)cx; in.cy = (float)cy;
+    in.T = T;
+    return occ_integrate_dev(c, o, in, F, out_pts, out_pts_n, pts_cap);
+}
+
+extern "C" int nclt_occ_integrate_points_dev(nclt_ctx* c, nclt_occ* o, const float* pts, const int32_t* n, int F,
+                                             int Nmax, const double* T) {
+    int rc = check_occ(c, o);
+    if (rc) return rc;
+    if (F < 0 || Nmax <= 0 || (F > 0 && (!pts || !n || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_points args");
+    FrameIn in{};
+    in.pts = pts; in.pts_n = n; in.Nmax = Nmax; in.step = 1; in.T = T;
+    return occ_integrate_dev(c, o, in, F, nullptr, nullptr, 0);
+}
+
+extern "C" int nclt_occ_integrate_depth(nclt_ctx* c, nclt_occ* o, const void* depth, int is_u16, int F, int Hd,
+                                        int Wd, const double* T, double fx, double fy, double cx, double cy) {
+    int rc = check_occ(c, o);
+    if (rc) return rc;
+    if (F < 0 || Hd <= 0 || Wd <= 0 || (F > 0 && (!depth || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_depth args");
+    if (F == 0) return NCLT_OK;
+    cudaSetDevice(c->device);
+    size_t px = (size_t)F * Hd * Wd, esz = is_u16 ? 2 : 4;
+    char* stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, pad256(px * esz) + pad256((size_t)F * 128));
+    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc depth staging", e);
+    double* dT = reinterpret_cast<double*>(stage + pad256(px * esz));
+    e = cudaMemcpyAsync(stage, depth, px * esz, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, (size_t)F * 128, cudaMemcpyHostToDevice, c->stream);
+    rc = e == cudaSuccess ? nclt_occ_integrate_depth_dev(c, o, stage, is_u16, F, Hd, Wd, dT, fx, fy, cx, cy, nullptr, nullptr, 0)
+                          : nclt_fail(c, NCLT_ERR_CUDA, "depth H2D", e);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+extern "C" int nclt_occ_integrate_points(nclt_ctx* c, nclt_occ* o, const float* pts, const int32_t* n, int F,
+                                         int Nmax, const double* T) {
+    int rc = check_occ(c, o);
+    if (rc) return rc;
+    if (F < 0 || Nmax <= 0 || (F > 0 && (!pts || !n || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_points args");
+    if (F == 0) return NCLT_OK;
+    cudaSetDevice(c->device);
+    size_t pb = (size_t)F * Nmax * 12;
+    char* stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, pad256(pb) + pad256((size_t)F * 4) + pad256((size_t)F * 128));
+    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc points staging", e);
+    int* dn = reinterpret_cast<int*>(stage + pad256(pb));
+    double* dT = reinterpret_cast<double*>(stage + pad256(pb) + pad256((size_t)F * 4));
+    e = cudaMemcpyAsync(stage, pts, pb, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, (size_t)F * 128, cudaMemcpyHostToDevice, c->stream);
+    rc = e == cudaSuccess ? nclt_occ_integrate_points_dev(c, o, reinterpret_cast<float*>(stage), dn, F, Nmax, dT)
+                          : nclt_fail(c, NCLT_ERR_CUDA, "points H2D", e);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    return rc;
+}
+
+// relay depth_cb alone: the PointCloud2 payload (the topic is also consumed by Nav2's obstacle layer)
+extern "C" int nclt_depth_to_points(nclt_ctx* c, const void* depth, int is_u16, int F, int Hd, int Wd, double fx,
+                                    double fy, double cx, double cy, float* out_pts, int32_t* out_n, int pts_cap) {
+    if (!c) return NCLT_ERR_ARG;
+    if (F < 0 || Hd <= 0 || Wd <= 0 || pts_cap <= 0 || (F > 0 && (!depth || !out_pts || !out_n)))
+        return nclt_fail(c, NCLT_ERR_ARG, "depth_to_points args");
+    if (F == 0) return NCLT_OK;
+    cudaSetDevice(c->device);
+    // a throw-away 1x1 grid: stage A alone produces the clouds
+    nclt_occ* o = nullptr;
+    int rc = nclt_occ_create(c, 0.0, 0.0, 1.0, 1, 1, &o);
+    if (rc) return rc;
+    size_t px = (size_t)F * Hd * Wd, esz = is_u16 ? 2 : 4;
+    char* stage = nullptr;
+    size_t ob = (size_t)F * pts_cap * 12;
+    cudaError_t e = cudaMalloc(&stage, pad256(px * esz) + pad256((size_t)F * 128) + pad256(ob) + pad256((size_t)F * 4));
+    if (e != cudaSuccess) { nclt_occ_destroy(c, o); return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc staging", e); }
+    double* dT = reinterpret_cast<double*>(stage + pad256(px * esz));
+    float* dp = reinterpret_cast<float*>(stage + pad256(px * esz) + pad256((size_t)F * 128));
+    int* dn = reinterpret_cast<int*>(reinterpret_cast<char*>(dp) + pad256(ob));
+    e = cudaMemcpyAsync(stage, depth, px * esz, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dT, 0, (size_t)F * 128, c->stream);
+    if (e == cudaSuccess)
+        rc = nclt_occ_integrate_depth_dev(c, o, stage, is_u16, F, Hd, Wd, dT, fx, fy, cx, cy, dp, dn, pts_cap);
+    else
+        rc = nclt_fail(c, NCLT_ERR_CUDA, "depth H2D", e);
+    if (rc == NCLT_OK) {
+        e = cudaMemcpyAsync(out_pts, dp, ob, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_n, dn, (size_t)F * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = nclt_fail(c, NCLT_ERR_CUDA, "points D2H", e);
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    nclt_occ_destroy(c, o);
+    return rc;
+}
+
+extern "C" int nclt_occ_read(nclt_ctx* c, nclt_occ* o, float* out_logodds, uint8_t* out_pgm, int32_t* out_units,
+                             int64_t* out_counters) {
+    int rc = check_occ(c, o);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    const size_t cells = (size_t)o->g.GW * o->g.GH;
+    ScratchScope scope(c);
+    if ((rc = nclt_scratch_reserve(c, pad256(cells * 4) + pad256(cells)))) return rc;
+    Carver cv(c);
+    float* d_lo = cv.take<float>(cells);
+    unsigned char* d_img = cv.take<unsigned char>(cells);
+    k_occ_render<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(o->d_grid, o->g.GH, o->g.GW,
+                                                                         out_pgm ? d_img : nullptr,
+                                                                         out_logodds ? d_lo : nullptr);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    if (out_logodds) CU_TRY(c, cudaMemcpyAsync(out_logodds, d_lo, cells * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_pgm) CU_TRY(c, cudaMemcpyAsync(out_pgm, d_img, cells, cudaMemcpyDeviceToHost, c->stream));
+    if (out_units) CU_TRY(c, cudaMemcpyAsync(out_units, o->d_grid, cells * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_counters)
+        CU_TRY(c, cudaMemcpyAsync(out_counters, o->d_counters, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
