@@ -1,0 +1,221 @@
+"""Host-side mirror of the repeat-time matcher node (scripts/common/visual_landmark_matcher.py)
+without rclpy: candidate selection (a9), the GPU candidate loop (a1-a7), pose composition (a8),
+consistency gate, covariance and the anchor_matches.csv log.
+
+The ROS node keeps its subscriptions, ORB extraction, pose-file reader and publisher; its
+`_tick` body from the candidate selection to the CSV line is what `LandmarkMatcher.tick`
+reproduces.  Module constants keep the reference's names because
+checkpoint_a_selftest.py:31-36 imports them by name.
+"""
+import math
+import os
+import pickle
+
+import numpy as np
+
+from ._lib import LocalizeParams, PnpParams
+from .library import LandmarkLibrary
+from .pipeline import localize_batch, MODE_CROSSCHECK, MODE_RATIO
+
+# --- constants of visual_landmark_matcher.py:46-89 ------------------------------------------
+FX, FY = 320.0, 320.0
+CX, CY = 320.0, 240.0
+K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], dtype=np.float32)
+DIST = np.zeros((4, 1), dtype=np.float32)
+CANDIDATE_RADIUS_M = 8.0
+MAX_CANDIDATES = 5
+HEADING_TOL_DEG = 90.0
+MIN_MATCHES = 10
+LOWE_RATIO = 0.80
+REPROJ_MAX_PX = 2.0
+RANSAC_REPROJ_PX = 3.0
+RANSAC_ITERATIONS = 200
+MIN_INLIERS = 10
+CONSISTENCY_M = 5.0
+TICK_HZ = 2.0
+
+CSV_HEADER = ('ts,vio_x,vio_y,candidates_tried,best_n_inliers,'
+              'best_reproj_err,anchor_x,anchor_y,outcome\n')
+
+
+def quat_to_rot(qx, qy, qz, qw):
+    """Unit quaternion -> rotation matrix (same element formulas as matcher:115-127)."""
+    xx, yy, zz = qx * qx, qy * qy, qz * qz
+    xy, xz, yz = qx * qy, qx * qz, qy * qz
+    wx, wy, wz = qw * qx, qw * qy, qw * qz
+    return np.array([[1 - 2 * (yy + zz), 2 * (xy - wz), 2 * (xz + wy)],
+                     [2 * (xy + wz), 1 - 2 * (xx + zz), 2 * (yz - wx)],
+                     [2 * (xz - wy), 2 * (yz + wx), 1 - 2 * (xx + yy)]], dtype=np.float64)
+
+
+def rot_to_quat(R):
+    """Rotation matrix -> (qx,qy,qz,qw), branch on the trace / largest diagonal like matcher:129-157."""
+    m00, m11, m22 = R[0, 0], R[1, 1], R[2, 2]
+    tr = m00 + m11 + m22
+    if tr > 0:
+        s = 0.5 / math.sqrt(tr + 1.0)
+        return ((R[2, 1] - R[1, 2]) * s, (R[0, 2] - R[2, 0]) * s, (R[1, 0] - R[0, 1]) * s, 0.25 / s)
+    if m00 > m11 and m00 > m22:
+        s = 2.0 * math.sqrt(1.0 + m00 - m11 - m22)
+        return (0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s, (R[2, 1] - R[1, 2]) / s)
+    if m11 > m22:
+        s = 2.0 * math.sqrt(1.0 + m11 - m00 - m22)
+        return ((R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s, (R[0, 2] - R[2, 0]) / s)
+    s = 2.0 * math.sqrt(1.0 + m22 - m00 - m11)
+    return ((R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s, (R[1, 0] - R[0, 1]) / s)
+
+
+def cam_world_to_base_world(cam_pose, base_to_cam_t, base_to_cam_R):
+    """Camera world pose -> base_link world pose (matcher:160-172)."""
+    R_wc = quat_to_rot(*cam_pose[3:7])
+    R_wb = R_wc @ np.asarray(base_to_cam_R).T
+    t_wb = np.array(cam_pose[:3], dtype=np.float64) - R_wb @ np.asarray(base_to_cam_t)
+    q = rot_to_quat(R_wb)
+    return (float(t_wb[0]), float(t_wb[1]), float(t_wb[2]), q[0], q[1], q[2], q[3])
+
+
+def rodrigues(rvec):
+    r = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = math.sqrt(float(r @ r))
+    if th < np.finfo(np.float64).eps:
+        return np.eye(3)
+    k = r / th
+    kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return math.cos(th) * np.eye(3) + (1 - math.cos(th)) * np.outer(k, k) + math.sin(th) * kx
+
+
+def compose_anchor(teach_pose, rvec, tvec, base_to_cam_t, base_to_cam_R):
+    """PnP result (teach camera in the current camera frame) -> current base_link pose in the
+    teach map (matcher:361-378)."""
+    R_teach_cur = rodrigues(rvec).T
+    t_teach_cur = -R_teach_cur @ np.asarray(tvec, dtype=np.float64).reshape(3)
+    R_world_teach = quat_to_rot(*teach_pose[3:7])
+    R_world_cur = R_world_teach @ R_teach_cur
+    t_world_cur = np.array(teach_pose[:3], dtype=np.float64) + R_world_teach @ t_teach_cur
+    q = rot_to_quat(R_world_cur)
+    cam_pose_world = (float(t_world_cur[0]), float(t_world_cur[1]), float(t_world_cur[2]), q[0], q[1], q[2], q[3])
+    return cam_world_to_base_world(cam_pose_world, base_to_cam_t, base_to_cam_R)
+
+
+def anchor_std(n_inliers):
+    """Inlier count -> anchor std (matcher:400-405)."""
+    if n_inliers >= 25:
+        return 0.05
+    if n_inliers >= 15:
+        return 0.05 + 0.15 * (25 - n_inliers) / 10.0
+    return 0.2
+
+
+def anchor_covariance(std):
+    cov = [0.0] * 36
+    cov[0] = std * std
+    cov[7] = std * std
+    cov[14] = 0.25
+    cov[21] = 0.05
+    cov[28] = 0.05
+    cov[35] = 0.05
+    return cov
+
+
+class LandmarkMatcher:
+    """`mode='crosscheck'` is the production node (matcher:318-380); `mode='ratio'` is the offline
+    validator's k=2 + Lowe variant (checkpoint_a_selftest.py:62-103, no heading gate, 5 nearest)."""
+
+    def __init__(self, pkl_path_or_dict, log_csv=None, mode='crosscheck', ctx=None):
+        if isinstance(pkl_path_or_dict, (str, os.PathLike)):
+            with open(pkl_path_or_dict, 'rb') as f:
+                data = pickle.load(f)
+        else:
+            data = pkl_path_or_dict
+        self.pkl_data = data
+        self.landmarks = data['landmarks']
+        self.base_to_cam_t = np.array(data['base_to_cam_translation'])
+        self.base_to_cam_R = np.array(data['base_to_cam_rot'])
+        self.xy = np.array([[lm['pose'][0], lm['pose'][1]] for lm in self.landmarks])
+        self.heading = np.array([self._lm_heading_rad(lm) for lm in self.landmarks])
+        self.mode = mode
+        self.library = LandmarkLibrary.from_pkl_dict(data, ctx=ctx)
+        self.params = LocalizeParams(
+            mode=MODE_CROSSCHECK if mode == 'crosscheck' else MODE_RATIO, ratio_num=4, ratio_den=5,
+            min_matches=MIN_MATCHES, min_inliers=MIN_INLIERS, reproj_max_px=REPROJ_MAX_PX,
+            pnp=PnpParams(FX, FY, CX, CY, RANSAC_ITERATIONS, RANSAC_REPROJ_PX, 0.99, 1))
+        self.n_attempts = 0
+        self.n_published = 0
+        self.last_anchor_ts = 0.0
+        self.log_csv = log_csv
+        if log_csv:
+            os.makedirs(os.path.dirname(log_csv), exist_ok=True)
+            with open(log_csv, 'w') as f:
+                f.write(CSV_HEADER)
+
+    def _lm_heading_rad(self, lm):
+        R_wb = quat_to_rot(*lm['pose'][3:7]) @ self.base_to_cam_R.T
+        fwd = R_wb @ np.array([1.0, 0.0, 0.0])
+        return math.atan2(fwd[1], fwd[0])
+
+    @staticmethod
+    def _heading_of(base_pose):
+        fwd = quat_to_rot(*base_pose[3:7]) @ np.array([1.0, 0.0, 0.0])
+        return math.atan2(fwd[1], fwd[0])
+
+    def select_candidates(self, base_pose):
+        """a9: <= MAX_CANDIDATES landmarks by VIO distance (matcher:293-302 / selftest:54-57)."""
+        d = np.linalg.norm(self.xy - np.array(base_pose[:2]), axis=1)
+        order = np.argsort(d)
+        if self.mode == 'ratio':
+            return [int(i) for i in order[:MAX_CANDIDATES] if d[i] < CANDIDATE_RADIUS_M]
+        cur = self._heading_of(base_pose)
+        dh = self.heading - cur
+        hdg_err = np.abs(np.arctan2(np.sin(dh), np.cos(dh)))
+        tol = math.radians(HEADING_TOL_DEG)
+        cand = [int(i) for i in order[:MAX_CANDIDATES * 3] if d[i] < CANDIDATE_RADIUS_M and hdg_err[i] < tol]
+        return cand[:MAX_CANDIDATES]
+
+    def _log(self, ts, vio_xy, n_tried, n_in, err, anchor_xy, outcome):
+        if not self.log_csv:
+            return
+        ax = anchor_xy[0] if anchor_xy else ''
+        ay = anchor_xy[1] if anchor_xy else ''
+        with open(self.log_csv, 'a') as f:
+            f.write(f'{ts:.3f},{vio_xy[0]:.3f},{vio_xy[1]:.3f},{n_tried},{n_in},{err},{ax},{ay},{outcome}\n')
+
+    def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0):
+        """One matcher tick from the ORB output onwards. Returns a dict with 'outcome' (the CSV
+        outcome string), and on publish 'anchor_pose', 'std', 'covariance', 'n_inliers',
+        'reproj_err', 'lm_idx'."""
+        self.n_attempts += 1
+        vio_xy = (base_pose[0], base_pose[1])
+        cand_idx = self.select_candidates(base_pose)
+        if desc_curr is None or len(desc_curr) < MIN_MATCHES:
+            self._log(ts, vio_xy, len(cand_idx), 0, '', None, 'curr_no_features')
+            return {'outcome': 'curr_no_features', 'candidates': cand_idx}
+        if not cand_idx:
+            self._log(ts, vio_xy, 0, 0, '', None, 'no_candidates')
+            return {'outcome': 'no_candidates', 'candidates': cand_idx}
+        cand = np.full((1, MAX_CANDIDATES), -1, dtype=np.int32)
+        cand[0, :len(cand_idx)] = cand_idx
+        out = localize_batch(self.library, np.asarray(desc_curr)[None], np.asarray(pts_curr_2d, dtype=np.float32)[None],
+                             None, cand, self.params)
+        slot = int(out['best_cand'][0])
+        if slot < 0:
+            self._log(ts, vio_xy, len(cand_idx), 0, '', None, 'no_pnp_accept')
+            return {'outcome': 'no_pnp_accept', 'candidates': cand_idx}
+        lm_idx = cand_idx[slot]
+        n_inliers = int(out['n_inliers'][0])
+        reproj_err = float(out['reproj'][0])
+        anchor_pose = compose_anchor(self.landmarks[lm_idx]['pose'], out['rvec'][0], out['tvec'][0],
+                                     self.base_to_cam_t, self.base_to_cam_R)
+        consistency_d = math.hypot(anchor_pose[0] - vio_xy[0], anchor_pose[1] - vio_xy[1])
+        res = {'candidates': cand_idx, 'anchor_pose': anchor_pose, 'n_inliers': n_inliers, 'reproj_err': reproj_err,
+               'lm_idx': lm_idx, 'shift': consistency_d}
+        if consistency_d > CONSISTENCY_M:
+            res['outcome'] = f'consistency_fail_{consistency_d:.1f}m'
+            self._log(ts, vio_xy, len(cand_idx), n_inliers, f'{reproj_err:.2f}', anchor_pose[:2], res['outcome'])
+            return res
+        std = anchor_std(n_inliers)
+        res.update(std=std, covariance=anchor_covariance(std),
+                   outcome=f'published_std{std:.2f}_shift{consistency_d:.1f}')
+        self.n_published += 1
+        self.last_anchor_ts = ts
+        self._log(ts, vio_xy, len(cand_idx), n_inliers, f'{reproj_err:.2f}', anchor_pose[:2], res['outcome'])
+        return res

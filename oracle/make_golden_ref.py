@@ -144,3 +144,79 @@ def golden_selftest(out_dir):
         best_slot=np.array([r[0] for r in rows], dtype=np.int32), best_inl=np.array([r[1] for r in rows], dtype=np.int32),
         items=np.array([r[2] for r in rows], dtype=np.float64))
     print('selftest_golden.npz best slots', [r[0] for r in rows], 'inliers', [r[1] for r in rows])
+
+
+def golden_tick(out_dir):
+    """The production node: VisualLandmarkMatcher._tick (visual_landmark_matcher.py:281-433), run
+    unmodified under ROS stubs with a stand-in ORB that returns synthetic keypoints/descriptors.
+    ACCUM_ENABLE is switched off for the run (the accumulation branch is dead in production,
+    matcher:78-89, and would mutate the landmark set between ticks)."""
+    import pickle
+    mods = ros_stubs.import_reference()
+    vm = mods['visual_landmark_matcher']
+    vm.ACCUM_ENABLE = False
+    data = synth.make_library(55, n_kf=40, n_desc=300, ragged=True, route_len_m=80.0)
+    tmp = tempfile.mkdtemp()
+    pkl = os.path.join(tmp, 'south_landmarks.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump(data, f)
+    csv = os.path.join(tmp, 'log', 'anchor_matches.csv')
+    node = vm.VisualLandmarkMatcher(pkl, csv)
+    node.last_rgb = np.zeros((480, 640, 3), dtype=np.uint8)
+    node.last_depth = np.full((480, 640), 2000, dtype=np.uint16)
+
+    class _Kp:
+        def __init__(self, pt):
+            self.pt = (float(pt[0]), float(pt[1]))
+
+    class _Orb:
+        def __init__(self):
+            self.next = None
+
+        def detectAndCompute(self, gray, mask):
+            d, p = self.next
+            return [_Kp(q) for q in p], d
+
+    node.orb = _Orb()
+    rng = np.random.default_rng(9)
+    ticks = []
+    kinds = ['ok', 'ok', 'far', 'few', 'random', 'shifted', 'ok', 'ok', 'ok', 'reverse']
+    for i, kind in enumerate(kinds):
+        k = int(rng.integers(3, 37))
+        fr = synth.make_frame(data, 5500 + i, k_star=k, n_desc=500, n_planted=(0 if kind == 'random' else 200))
+        lm = data['landmarks'][k]
+        bx, by = lm['pose'][0] - 0.35 + rng.normal(0, 0.3), lm['pose'][1] + rng.normal(0, 0.3)
+        yaw = rng.normal(0, 0.1)
+        if kind == 'far':
+            by += 40.0
+        if kind == 'shifted':
+            bx += 6.5
+        if kind == 'reverse':
+            yaw += np.pi
+        desc, pts = fr['desc'], fr['pts2d']
+        if kind == 'few':
+            desc, pts = desc[:6], pts[:6]
+        base_pose = (float(bx), float(by), 0.0, 0.0, 0.0, float(np.sin(yaw / 2)), float(np.cos(yaw / 2)))
+        node.orb.next = (desc, pts)
+        node._read_pose = (lambda bp=base_pose: bp)
+        n_before = len(node.anchor_pub.sent)
+        node._tick()
+        line = open(csv).read().strip().split('\n')[-1].split(',')
+        rec = {'kind': kind, 'base_pose': base_pose, 'csv': line[1:], 'published': len(node.anchor_pub.sent) > n_before}
+        if rec['published']:
+            m = node.anchor_pub.sent[-1]
+            p, o = m.pose.pose.position, m.pose.pose.orientation
+            rec['anchor'] = [p.x, p.y, p.z, o.x, o.y, o.z, o.w]
+            rec['cov'] = list(m.pose.covariance)
+        ticks.append((rec, desc, pts))
+    header = open(csv).read().split('\n')[0]
+    np.savez_compressed(
+        os.path.join(out_dir, 'tick_golden.npz'), lib_seed=np.int64(55), header=np.array(header),
+        kinds=np.array([t[0]['kind'] for t in ticks]), base_pose=np.array([t[0]['base_pose'] for t in ticks]),
+        csv=np.array([','.join(t[0]['csv']) for t in ticks]), published=np.array([t[0]['published'] for t in ticks]),
+        anchor=np.array([t[0].get('anchor', [0] * 7) for t in ticks], dtype=np.float64),
+        cov=np.array([t[0].get('cov', [0] * 36) for t in ticks], dtype=np.float64),
+        n_desc=np.array([len(t[1]) for t in ticks], dtype=np.int32),
+        desc=np.stack([np.pad(t[1], ((0, 500 - len(t[1])), (0, 0))) for t in ticks]),
+        pts2d=np.stack([np.pad(t[2], ((0, 500 - len(t[2])), (0, 0))) for t in ticks]))
+    print('tick_golden.npz', [t[0]['csv'][-1] for t in ticks])

@@ -1,0 +1,81 @@
+"""GPU parity of the host-side matcher mirror against the reference node itself:
+tests/golden/tick_golden.npz holds what VisualLandmarkMatcher._tick (run unmodified under ROS
+stubs, oracle/make_golden_ref.py) logged and published; selftest_golden.npz holds the candidate
+loop of checkpoint_a_selftest.py with the module's own constants."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_node_tick_against_reference(ctx, tmp_path):
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.matcher import LandmarkMatcher, CSV_HEADER
+    g = np.load(os.path.join(GD, 'tick_golden.npz'))
+    data = synth.make_library(int(g['lib_seed']), n_kf=40, n_desc=300, ragged=True, route_len_m=80.0)
+    csv = str(tmp_path / 'log' / 'anchor_matches.csv')
+    m = LandmarkMatcher(data, csv, mode='crosscheck')
+    assert CSV_HEADER.strip() == str(g['header'])
+    for i in range(len(g['kinds'])):
+        n = int(g['n_desc'][i])
+        r = m.tick(g['desc'][i, :n], g['pts2d'][i, :n], tuple(g['base_pose'][i]), ts=float(i))
+        ref = str(g['csv'][i]).split(',')
+        got = open(csv).read().strip().split('\n')[-1].split(',')[1:]
+        assert got[-1] == ref[-1], (i, got, ref)            # outcome string incl. std / shift
+        assert got[:4] == ref[:4], (i, got, ref)            # vio_x, vio_y, candidates_tried, best_n_inliers
+        assert got[4] == ref[4], (i, got, ref)              # best_reproj_err '%.2f'
+        if ref[5]:
+            assert abs(float(got[5]) - float(ref[5])) < 1e-3 and abs(float(got[6]) - float(ref[6])) < 1e-3
+        assert bool(g['published'][i]) == r['outcome'].startswith('published')
+        if g['published'][i]:
+            a = np.array(r['anchor_pose'])
+            assert np.abs(a[:3] - g['anchor'][i, :3]).max() < 1e-3           # 1 mm
+            assert np.abs(a[3:] - g['anchor'][i, 3:]).max() < 1e-4           # quaternion
+            assert np.allclose(r['covariance'], g['cov'][i], rtol=0, atol=1e-12)
+    assert m.n_published == int(g['published'].sum())
+
+
+def test_selftest_loop_against_reference(ctx):
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import localize_batch
+    from nclt_slam_project_b200._lib import LocalizeParams
+    g = np.load(os.path.join(GD, 'selftest_golden.npz'))
+    data = synth.make_library(int(g['lib_seed']), n_kf=10, n_desc=400, ragged=True)
+    lib = LandmarkLibrary.from_pkl_dict(data)
+    out = localize_batch(lib, g['desc'], g['pts2d'], None, g['cand'], LocalizeParams(mode=0), per_item=True)
+    assert np.array_equal(out['best_cand'], g['best_slot'])
+    assert np.array_equal(out['n_inliers'], g['best_inl'])
+    items = g['items']          # [B, C, 10] = nmatch, ok, n_inl, err, rvec3, tvec3
+    for b in range(items.shape[0]):
+        for c in range(items.shape[1]):
+            nm, ok, ninl, err = items[b, c, :4]
+            assert out['item_nmatch'][b, c] == int(nm)
+            if ok:
+                assert out['item_ok'][b, c] == 1 and out['item_ninl'][b, c] == int(ninl)
+                assert abs(out['item_err'][b, c] - err) < 1e-3
+                assert np.abs(out['item_rvec'][b, c] - items[b, c, 4:7]).max() < 1e-4
+                assert np.abs(out['item_tvec'][b, c] - items[b, c, 7:10]).max() < 1e-3
+
+
+def test_match_golden_from_cv2(ctx):
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    g = np.load(os.path.join(GD, 'match_golden.npz'))
+    for tag in ('full', 'ties'):
+        counts = g[f'{tag}_counts']
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        kfs = [g[f'{tag}_lib_desc'][offs[k]:offs[k + 1]] for k in range(len(counts))]
+        lib = LandmarkLibrary(kfs)
+        idx, dist = lib.knn2(g[f'{tag}_q'])
+        assert np.array_equal(idx, g[f'{tag}_knn_idx'])
+        assert np.array_equal(dist.astype(np.int32), g[f'{tag}_knn_dist'])
+        pairs, d, n = lib.cross(g[f'{tag}_q'])
+        rows = []
+        for b in range(2):
+            for k in range(len(counts)):
+                for i in range(n[b, k]):
+                    rows.append([b, k, pairs[b, k, i, 0], pairs[b, k, i, 1], int(d[b, k, i])])
+        assert np.array_equal(np.array(rows, dtype=np.int32), g[f'{tag}_cross'])
