@@ -43,6 +43,11 @@ int nclt_ctx_sync(nclt_ctx* ctx);
 const char* nclt_last_error(nclt_ctx* ctx);
 /* kernels launched through this context so far (bench.py's gpu_launches) */
 unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
+/* matching engine for the "every frame against every keyframe" ratio mode (cand == NULL):
+ * 0 = integer pipe (LOP3+POPC, the default), 1 = tcgen05 tensor cores (fp8 +-1 operands, fp16
+ * accumulators in TMEM, exact index recovery); both produce identical results. Candidate-list
+ * and crossCheck matching always use the integer pipe. */
+int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
 /* enable/disable CUDA-event timing of the dominant kernel (the Hamming top-2 launches) on this
  * context; nclt_ctx_profile_read synchronises, returns the summed device time and launch count
  * since the last read, and resets. Used by bench.py for the live roofline figure. */

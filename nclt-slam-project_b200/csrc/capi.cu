@@ -6,23 +6,60 @@
 #include <algorithm>
 #include <cstring>
 
+// Guarantee `bytes` of carve room after the current stack position. Nothing already carved moves:
+// if the current chunk is too small the stack continues in another (new or idle) chunk.
 int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
-    size_t need = c->scratch_off + bytes + 4096;
-    if (need <= c->scratch_bytes) return NCLT_OK;
-    if (c->scratch_off != 0) return nclt_fail(c, NCLT_ERR_STATE, "scratch grow while in use");
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->scratch) cudaFree(c->scratch);
-    c->scratch = nullptr;
-    c->scratch_bytes = 0;
-    size_t want = need + need / 4;
-    cudaError_t e = cudaMalloc(&c->scratch, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        want = need;
-        e = cudaMalloc(&c->scratch, want);
-        if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc scratch", e);
+    bytes += 4096;
+    if (c->scratch_chunk >= 0 && c->scratch_off + bytes <= c->scratch_bytes) return NCLT_OK;
+    const bool idle = c->scratch_chunk < 0 || (c->scratch_chunk == 0 && c->scratch_off == 0);
+    if (idle) {
+        // top-level call and nothing in use: consolidate into one chunk that fits
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        size_t total = bytes;
+        for (auto& ch : c->scratch_chunks) {
+            total = std::max(total, ch.second);
+            cudaFree(ch.first);
+        }
+        c->scratch_chunks.clear();
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+        c->scratch_chunk = -1;
+        c->scratch_off = 0;
+        size_t want = std::max(total, bytes + bytes / 4);
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc scratch", e);
+        }
+        c->scratch_chunks.emplace_back(p, want);
+        c->scratch_chunk = 0;
+        c->scratch = p;
+        c->scratch_bytes = want;
+        return NCLT_OK;
     }
+    // in use: continue in a later chunk (reuse an idle one if it is large enough)
+    for (int i = c->scratch_chunk + 1; i < (int)c->scratch_chunks.size(); ++i) {
+        if (c->scratch_chunks[i].second >= bytes) {
+            if (i != c->scratch_chunk + 1) std::swap(c->scratch_chunks[i], c->scratch_chunks[c->scratch_chunk + 1]);
+            c->scratch_chunk += 1;
+            c->scratch = c->scratch_chunks[c->scratch_chunk].first;
+            c->scratch_bytes = c->scratch_chunks[c->scratch_chunk].second;
+            c->scratch_off = 0;
+            return NCLT_OK;
+        }
+    }
+    void* p = nullptr;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc scratch chunk", e);
+    c->scratch_chunks.insert(c->scratch_chunks.begin() + c->scratch_chunk + 1, std::make_pair(p, want));
+    c->scratch_chunk += 1;
+    c->scratch = p;
     c->scratch_bytes = want;
+    c->scratch_off = 0;
     return NCLT_OK;
 }
 
@@ -71,7 +108,7 @@ extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
     if (!c) return NCLT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->scratch) cudaFree(c->scratch);
+    for (auto& ch : c->scratch_chunks) cudaFree(ch.first);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -87,6 +124,12 @@ extern "C" int nclt_ctx_sync(nclt_ctx* c) {
 
 extern "C" const char* nclt_last_error(nclt_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" unsigned long long nclt_ctx_launches(nclt_ctx* c) { return c ? c->launches : 0ull; }
+
+extern "C" int nclt_ctx_set_engine(nclt_ctx* c, int engine) {
+    if (!c || (engine != 0 && engine != 1)) return nclt_fail(c, NCLT_ERR_ARG, "engine must be 0 (integer pipe) or 1 (tensor cores)");
+    c->engine = engine;
+    return NCLT_OK;
+}
 
 extern "C" int nclt_ctx_profile(nclt_ctx* c, int enable) {
     if (!c) return NCLT_ERR_ARG;
@@ -222,6 +265,7 @@ extern "C" int nclt_lib_append(nclt_ctx* c, nclt_lib* L, const uint8_t* desc, co
 extern "C" int nclt_lib_destroy(nclt_ctx* c, nclt_lib* L) {
     if (!L) return NCLT_OK;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    nclt_tc_release(L);
     if (L->d_desc) cudaFree(L->d_desc);
     if (L->d_pts3d) cudaFree(L->d_pts3d);
     if (L->d_start) cudaFree(L->d_start);
@@ -285,6 +329,9 @@ extern "C" int nclt_match_ratio_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if ((rc = check_cand_null(c, L, cand, C))) return rc;
     if (num <= 0 || den <= 0 || !out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio args");
     if (B == 0) return NCLT_OK;
+    // every frame against every keyframe: the tensor-core path (tc_hamming.cu), same outputs
+    if (c->engine == 1 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30))
+        return tc_match_ratio_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, num, den, out_pairs, out_n);
     ScratchScope scope(c);
     size_t items = (size_t)B * C;
     if ((rc = nclt_scratch_reserve(c, pad256(items * Nq * sizeof(uint2))))) return rc;

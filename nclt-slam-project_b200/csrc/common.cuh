@@ -23,7 +23,9 @@ struct nclt_ctx {
     // grow-only device scratch
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
-    size_t scratch_off = 0;      // stack pointer inside one API call
+    size_t scratch_off = 0;      // stack pointer inside the current chunk
+    std::vector<std::pair<void*, size_t>> scratch_chunks;   // `scratch` = chunks[scratch_chunk].first
+    int scratch_chunk = -1;
     // pinned host staging for small result reads
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -31,6 +33,7 @@ struct nclt_ctx {
     unsigned long long launches = 0;
     // optional timing of the dominant kernel (bench.py roofline): event pairs around every
     // Hamming top-2 launch, summed by nclt_ctx_profile_read
+    int engine = 0;             // 0 = integer pipe (LOP3+POPC), 1 = tensor cores for all-keyframe ratio matching
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
@@ -48,6 +51,7 @@ struct nclt_lib {
     int* d_count = nullptr;      // [cap_kf] rows in keyframe
     std::vector<int> h_start, h_count;
     int max_count = 0;
+    void* tc_cache = nullptr;   // tensor-core operand images + tile table (tc_hamming.cu), built lazily
 };
 
 // A ragged set of 32-byte descriptors on the device.
@@ -110,6 +114,11 @@ int launch_cross_combine(nclt_ctx* c, const uint2* fwd_keys, const uint2* bwd_ke
 int launch_ratio_compact(nclt_ctx* c, const uint2* keys, const int* a_count, int a_stride_cnt, const int* cand,
                          int n_outer, int C, int a_rows_max, int num, int den, int2* out_pairs, int* out_n);
 double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
+
+// ---- tc_hamming.cu ----
+void nclt_tc_release(nclt_lib* L);
+int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
+                       int32_t* out_pairs, int32_t* out_n);
 
 // ---- pnp.cu ----
 struct PnpBuffers {

@@ -119,9 +119,8 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
     // pair rows per item: frame rows in ratio mode, teach rows in crossCheck mode
     const int Nrow = prm->mode == 0 ? Nq : (L->max_count > 0 ? L->max_count : 1);
     int rc;
-    // stage 1 scratch: pairs + counts + problem tables (+ what the match entry points carve)
-    size_t need1 = pad256(items * Nrow * 8) + 3 * pad256(items * 4) + 16384 +
-                   pad256(items * (size_t)Nrow * 8) + pad256(items * (size_t)Nq * 8);
+    // stage 1 scratch: pairs + counts + problem tables (the match entry points reserve their own)
+    size_t need1 = pad256(items * Nrow * 8) + 3 * pad256(items * 4) + 4096;
     if ((rc = nclt_scratch_reserve(c, need1))) return rc;
     Carver cv(c);
     int2* pairs = cv.take<int2>(items * Nrow);
@@ -154,31 +153,12 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
     float* p_err = nullptr;
     double *p_r = nullptr, *p_t = nullptr;
     if (P > 0) {
-        // stage 2 scratch is carved above stage 1 (the reserve may not move the buffer: it is
-        // in use) - so grow only if nothing else is needed; otherwise fall back to a fresh call
         const int iters = prm->pnp.iterations;
         size_t h = (size_t)P * iters;
         size_t need2 = pad256((size_t)P * Nrow * 12) + pad256((size_t)P * Nrow * 8) + 3 * pad256((size_t)P * 4) +
                        pad256((size_t)P * Nrow) + pad256((size_t)P) + 2 * pad256((size_t)P * 24) +
                        pad256(h * 20) + pad256(h * 48) + pad256(h * 4);
-        if (c->scratch_off + need2 + 4096 > c->scratch_bytes) {
-            // grow: everything carved so far must survive -> allocate a bigger buffer and copy
-            size_t want = c->scratch_off + need2 + 4096;
-            want += want / 4;
-            void* nb = nullptr;
-            cudaError_t e = cudaMalloc(&nb, want);
-            if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc scratch (pnp stage)", e);
-            CU_TRY(c, cudaMemcpyAsync(nb, c->scratch, c->scratch_off, cudaMemcpyDeviceToDevice, c->stream));
-            CU_TRY(c, cudaStreamSynchronize(c->stream));
-            ptrdiff_t delta = static_cast<char*>(nb) - static_cast<char*>(c->scratch);
-            cudaFree(c->scratch);
-            c->scratch = nb;
-            c->scratch_bytes = want;
-            pairs = reinterpret_cast<int2*>(reinterpret_cast<char*>(pairs) + delta);
-            if (!out_item_nmatch) n_pairs = reinterpret_cast<int*>(reinterpret_cast<char*>(n_pairs) + delta);
-            prob_item = reinterpret_cast<int*>(reinterpret_cast<char*>(prob_item) + delta);
-            item_prob = reinterpret_cast<int*>(reinterpret_cast<char*>(item_prob) + delta);
-        }
+        if ((rc = nclt_scratch_reserve(c, need2))) return rc;   // never moves what is already carved
         Carver cv2(c);
         float* obj = cv2.take<float>((size_t)P * Nrow * 3);
         float* img = cv2.take<float>((size_t)P * Nrow * 2);

@@ -1,25 +1,33 @@
-// Per-context device scratch: one grow-only buffer carved as a stack inside one API call.
+// Per-context device scratch: a stack carved inside one API call, backed by a list of chunks so
+// that a nested call can always get more memory without moving what is already carved.
 #pragma once
 #include "common.cuh"
 
 struct Carver {
     nclt_ctx* c;
-    size_t off;
-    explicit Carver(nclt_ctx* ctx) : c(ctx), off(ctx->scratch_off) {}
+    explicit Carver(nclt_ctx* ctx) : c(ctx) {}
     template <typename T>
     T* take(size_t n) {
         size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
-        T* p = reinterpret_cast<T*>(static_cast<char*>(c->scratch) + off);
-        off += bytes;
-        c->scratch_off = off;
+        // nclt_scratch_reserve() guaranteed room in the current chunk for everything carved after it
+        T* p = reinterpret_cast<T*>(static_cast<char*>(c->scratch) + c->scratch_off);
+        c->scratch_off += bytes;
         return p;
     }
 };
 static inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
-struct ScratchScope {   // resets the stack when the outermost API call returns
+struct ScratchScope {   // restores the stack when the API call returns
     nclt_ctx* c;
-    size_t saved;
-    explicit ScratchScope(nclt_ctx* ctx) : c(ctx), saved(ctx->scratch_off) {}
-    ~ScratchScope() { c->scratch_off = saved; }
+    size_t saved_off;
+    int saved_chunk;
+    explicit ScratchScope(nclt_ctx* ctx) : c(ctx), saved_off(ctx->scratch_off), saved_chunk(ctx->scratch_chunk) {}
+    ~ScratchScope() {
+        c->scratch_off = saved_off;
+        c->scratch_chunk = saved_chunk;
+        if (saved_chunk >= 0 && saved_chunk < (int)c->scratch_chunks.size()) {
+            c->scratch = c->scratch_chunks[saved_chunk].first;
+            c->scratch_bytes = c->scratch_chunks[saved_chunk].second;
+        }
+    }
 };

@@ -1,0 +1,503 @@
+// Tensor-core Hamming top-2 for the "every frame against every keyframe" replay workloads
+// (BASELINE.json configs 1, 2, 4; checkpoint_a_selftest.py:68-71 semantics per keyframe).
+//
+// The integer-pipe kernel (hamming.cu) sits at 99 % of the POPC roofline (2 comparisons/clk/SM).
+// sm_100a has no native 1-bit MMA (SURVEY finding 6), so distances go through tcgen05 as
+//     x . y = 256 - 2 * Hamming(a, b),   x, y in {+1,-1}^256 stored as fp8 e4m3,
+// with fp16 accumulators in TMEM (exact: |sum| <= 256).  Measured building blocks (tools/tcbench.py):
+// 32 comparisons/clk/SM of MMA at N = 256, packed 16-bit TMEM loads almost free, half2 top-2 tracking
+// at 1.5 ALU ops per comparison.
+//
+// Only VALUES (best, second best) per (query, keyframe) come out of this kernel: the Lowe ratio test
+// needs nothing else, and the train index of the (rare) survivors is recovered exactly, lowest index
+// first, by an integer re-scan of that one keyframe (k_tc_ratio_recover).  Results are bit-identical
+// to the integer path (tests/test_tc_match_gpu.py).
+//
+// Kernel k_tc_top2: persistent, warp specialised, one CTA per SM:
+//   warps 0-7  epilogue: TMEM -> registers (tcgen05.ld .pack::16b), half2 running top-2 per row;
+//              warp w owns TMEM lane quadrant w%4 and column half w/4
+//   warp 8     producer: 1-D TMA bulk copies of pre-expanded operand tile images
+//   warp 9     MMA issuer: 8 x tcgen05.mma (K = 32 B each) per 128 x N x 256 tile step
+// A work item = MA (<= 3) resident 128-row query tiles x a contiguous range of library tiles.
+#include "common.cuh"
+#include "scratch.cuh"
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <cuda_fp16.h>
+#include <vector>
+
+namespace {
+
+constexpr int MA = 3;                    // resident query tiles per work item
+constexpr int A_TILE_BYTES = 128 * 256;  // 32 KB
+constexpr int B_STAGE_BYTES = 256 * 256; // 64 KB
+constexpr int NSTAGE = 2;
+constexpr int TC_THREADS = 320;
+constexpr uint32_t NEG_INF2 = 0xFC00FC00u;   // half2(-inf, -inf)
+__device__ __forceinline__ __half2 neg_inf2() {
+    uint32_t v = 0xFC00FC00u;
+    return *reinterpret_cast<__half2*>(&v);
+}
+
+struct LibTile {
+    uint32_t img_off256;   // byte offset / 256 into the library image buffer
+    uint16_t n;            // rows in the tile image (multiple of 16, <= 256)
+    uint16_t n_valid;      // real descriptor rows (<= n)
+    int kf;                // keyframe id
+    int last_of_kf;        // 1 if this is the keyframe's last tile
+};
+
+// ---- operand expansion -------------------------------------------------------------------
+// rows: 32-byte descriptors; tile t covers rows [t*128, t*128+128) -> 32 KB image
+__global__ void k_expand_queries(const uint32_t* __restrict__ desc, long long n_rows, uint8_t* img) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, chunk)
+    long long total_rows = ((n_rows + 127) / 128) * 128;
+    if (i >= total_rows * 16) return;
+    long long row = i >> 4;
+    int c = (int)(i & 15);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < n_rows) {
+        uint32_t w = desc[row * 8 + (c >> 1)];
+        v = tc::expand16((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+    }
+    long long tile = row >> 7;
+    int r = (int)(row & 127);
+    *reinterpret_cast<uint4*>(img + tile * A_TILE_BYTES + tc::image_offset(128, r, c * 16)) = v;
+}
+
+__global__ void k_expand_library(const uint32_t* __restrict__ desc, const LibTile* __restrict__ tiles,
+                                 const int* __restrict__ tile_row0, int n_tiles, uint8_t* img) {
+    int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    const LibTile lt = tiles[t];
+    const long long row0 = tile_row0[t];
+    uint8_t* dst = img + (size_t)lt.img_off256 * 256;
+    for (int i = threadIdx.x; i < lt.n * 16; i += blockDim.x) {
+        int r = i >> 4, c = i & 15;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < lt.n_valid) {
+            uint32_t w = desc[(row0 + r) * 8 + (c >> 1)];
+            v = tc::expand16((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+        }
+        *reinterpret_cast<uint4*>(dst + tc::image_offset(lt.n, r, c * 16)) = v;
+    }
+}
+
+// ---- main kernel ---------------------------------------------------------------------------
+struct TcParams {
+    const uint8_t* q_img;      // [n_mtiles][32 KB]
+    const uint8_t* lib_img;
+    const LibTile* tiles;
+    int n_mtiles;
+    int n_groups;              // ceil(n_mtiles / MA)
+    int n_splits;
+    const int* split_tile;     // [n_splits + 1] tile ranges (aligned to keyframes)
+    long long rows_total;      // valid query rows (B * Nq)
+    uint32_t* out;             // [n_kf][rows_pad] : d1 | d2 << 16
+    long long rows_pad;        // n_mtiles * 128
+};
+
+__device__ __forceinline__ void half2_top2(uint32_t raw, __half2& M1, __half2& M2) {
+    __half2 v = *reinterpret_cast<__half2*>(&raw);
+    __half2 lo = __hmin2(M1, v);
+    M1 = __hmax2(M1, v);
+    M2 = __hmax2(M2, lo);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                                  // MA x 32 KB
+    uint8_t* sB = smem + MA * A_TILE_BYTES;              // NSTAGE x 64 KB
+    uint8_t* tail = sB + NSTAGE * B_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // 10 barriers
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;      // [2]
+    uint64_t* b_empty = bars + 4;     // [2]
+    uint64_t* acc_full = bars + 6;    // [2]
+    uint64_t* acc_empty = bars + 8;   // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 10);
+    uint32_t* xchg = s_tmem + 2;      // [4][32]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(a_full, 1);
+        tc::mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&b_empty[s], 1);
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], 8);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(s_tmem, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const int n_items = p.n_groups * p.n_splits;
+
+    if (warp == 8) {
+        // =========================== producer ===========================
+        if (lane == 0) {
+            uint32_t it_cnt = 0, bt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+                const int split = item / p.n_groups, group = item % p.n_groups;
+                const int m0 = group * MA;
+                const int ma = min(MA, p.n_mtiles - m0);
+                tc::mbar_wait(a_empty, (it_cnt & 1) ^ 1);
+                tc::mbar_expect_tx(a_full, (uint32_t)ma * A_TILE_BYTES);
+                for (int m = 0; m < ma; ++m)
+                    tc::bulk_g2s(sA + m * A_TILE_BYTES, p.q_img + (size_t)(m0 + m) * A_TILE_BYTES, A_TILE_BYTES, a_full);
+                for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t, ++bt) {
+                    const int s = bt & 1;
+                    const LibTile lt = p.tiles[t];
+                    tc::mbar_wait(&b_empty[s], ((bt >> 1) & 1) ^ 1);
+                    const uint32_t bytes = (uint32_t)lt.n * 256u;
+                    tc::mbar_expect_tx(&b_full[s], bytes);
+                    tc::bulk_g2s(sB + s * B_STAGE_BYTES, p.lib_img + (size_t)lt.img_off256 * 256, bytes, &b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t it_cnt = 0, bt = 0, st = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+                const int split = item / p.n_groups, group = item % p.n_groups;
+                const int ma = min(MA, p.n_mtiles - group * MA);
+                tc::mbar_wait(a_full, it_cnt & 1);
+                for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t, ++bt) {
+                    const int s = bt & 1;
+                    const int n = p.tiles[t].n;
+                    tc::mbar_wait(&b_full[s], (bt >> 1) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t idesc = tc::idesc_f8(128, n, 0);
+                    const uint32_t lboB = (uint32_t)n * 16u;
+                    const uint32_t bbase = tc::smem_u32(sB + s * B_STAGE_BYTES);
+                    for (int m = 0; m < ma; ++m, ++st) {
+                        const int buf = st & 1;
+                        tc::mbar_wait(&acc_empty[buf], ((st >> 1) & 1) ^ 1);
+                        tc::tc_fence_after();
+                        const uint32_t abase = tc::smem_u32(sA + m * A_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            uint64_t da = tc::smem_desc(abase + k * 4096u, 2048u, 128u);
+                            uint64_t db = tc::smem_desc(bbase + k * 2u * lboB, lboB, 128u);
+                            tc::mma_f8(tmem + buf * 256, da, db, idesc, k > 0 ? 1u : 0u);
+                        }
+                        tc::mma_commit(&acc_full[buf]);
+                    }
+                    tc::mma_commit(&b_empty[s]);       // stage reusable once these MMAs have read it
+                }
+                tc::mma_commit(a_empty);
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-7) ===========================
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        uint32_t st = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int split = item / p.n_groups, group = item % p.n_groups;
+            const int m0 = group * MA;
+            const int ma = min(MA, p.n_mtiles - m0);
+            __half2 M1[MA], M2[MA];
+#pragma unroll
+            for (int m = 0; m < MA; ++m) {
+                M1[m] = neg_inf2();
+                M2[m] = M1[m];
+            }
+            for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
+                const LibTile lt = p.tiles[t];
+                const int c_lo = half * 128;
+                const int nv = lt.n_valid;
+#pragma unroll
+                for (int m = 0; m < MA; ++m) {
+                    if (m >= ma) break;
+                    const int buf = st & 1;
+                    tc::mbar_wait(&acc_full[buf], (st >> 1) & 1);
+                    tc::tc_fence_after();
+                    ++st;
+                    if (c_lo < nv) {
+                        uint32_t r0[32], r1[32];
+                        const uint32_t taddr = tmem + buf * 256 + lane_base + (uint32_t)c_lo;
+                        const bool second = c_lo + 64 < nv;
+                        tc::tmem_ld32_pack16(taddr, r0);
+                        if (second) tc::tmem_ld32_pack16(taddr + 64, r1);
+                        tc::tmem_wait_ld();
+                        if (c_lo + 64 <= nv) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) half2_top2(r0[j], M1[m], M2[m]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                int c = c_lo + 2 * j;
+                                uint32_t v = r0[j];
+                                if (c + 1 >= nv) v = (c >= nv) ? NEG_INF2 : ((v & 0xFFFFu) | 0xFC000000u);
+                                half2_top2(v, M1[m], M2[m]);
+                            }
+                        }
+                        if (second) {
+                            if (c_lo + 128 <= nv) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) half2_top2(r1[j], M1[m], M2[m]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    int c = c_lo + 64 + 2 * j;
+                                    uint32_t v = r1[j];
+                                    if (c + 1 >= nv) v = (c >= nv) ? NEG_INF2 : ((v & 0xFFFFu) | 0xFC000000u);
+                                    half2_top2(v, M1[m], M2[m]);
+                                }
+                            }
+                        }
+                    }
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                }
+                if (lt.last_of_kf) {
+                    // ---- keyframe finished: merge even/odd lanes, the two column halves, write (d1,d2)
+#pragma unroll
+                    for (int m = 0; m < MA; ++m) {
+                        if (m >= ma) break;
+                        float2 a = __half22float2(M1[m]), b = __half22float2(M2[m]);
+                        float f1 = fmaxf(a.x, a.y);
+                        float f2 = fmaxf(fminf(a.x, a.y), a.x >= a.y ? b.x : b.y);
+                        if (half == 1) {
+                            __half2 pk = __floats2half2_rn(f1, f2);
+                            xchg[quad * 32 + lane] = *reinterpret_cast<uint32_t*>(&pk);
+                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                        if (half == 0) {
+                            uint32_t raw = xchg[quad * 32 + lane];
+                            float2 o = __half22float2(*reinterpret_cast<__half2*>(&raw));
+                            float g1 = fmaxf(f1, o.x);
+                            float g2 = fmaxf(fminf(f1, o.x), fmaxf(f2, o.y));
+                            long long row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                            uint32_t d1 = (uint32_t)((256.f - g1) * 0.5f);
+                            uint32_t d2 = g2 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g2) * 0.5f);
+                            if (g1 < -300.f) d1 = 0xFFFFu;
+                            p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);
+                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                        M1[m] = neg_inf2();
+                        M2[m] = M1[m];
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- ratio test + exact index recovery --------------------------------------------------------
+// One CTA per (frame, keyframe): Lowe ratio on the value pairs, ordered compaction of the passing
+// query rows, then, per passer, the LOWEST train row whose distance equals d1 (integer re-scan).
+__global__ void __launch_bounds__(256) k_tc_ratio_recover(const uint32_t* __restrict__ d12, long long rows_pad, int Nq,
+                                                          const int* __restrict__ q_n, int n_kf, int num, int den,
+                                                          const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
+                                                          const int* __restrict__ kf_start, const int* __restrict__ kf_count,
+                                                          int2* out_pairs, int* out_n) {
+    __shared__ int s_warp[8];
+    __shared__ int s_list[1024];
+    __shared__ unsigned short s_d1[1024];
+    const int item = blockIdx.x;
+    const int b = item / n_kf, kf = item % n_kf;
+    const int nq = q_n ? q_n[b] : Nq;
+    const int nt = kf_count[kf];
+    const uint32_t* src = d12 + (size_t)kf * rows_pad + (size_t)b * Nq;
+    int2* dst = out_pairs + (size_t)item * Nq;
+    int total = 0;
+    for (int q0 = 0; q0 < nq; q0 += 1024) {
+        int base = 0;
+        // ordered compaction of up to 1024 rows (4 per thread, row-major order)
+        for (int sub = 0; sub < 4; ++sub) {
+            int q = q0 + sub * 256 + threadIdx.x;
+            bool keep = false;
+            uint32_t v = 0;
+            if (q < nq && nt >= 2) {
+                v = src[q];
+                uint32_t d1 = v & 0xFFFFu, d2 = v >> 16;
+                keep = d2 != 0xFFFFu && d1 != 0xFFFFu && (uint32_t)den * d1 < (uint32_t)num * d2;
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { int c = s_warp[w]; tot += c; if (w < warp) before += c; }
+            if (keep) {
+                int slot = base + before + __popc(bal & ((1u << lane) - 1u));
+                s_list[slot] = q;
+                s_d1[slot] = (unsigned short)(v & 0xFFFFu);
+            }
+            base += tot;
+            __syncthreads();
+        }
+        // recovery: one warp per passer
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint4* trows = lib_desc + (size_t)kf_start[kf] * 2;
+        for (int i = warp; i < base; i += 8) {
+            const int q = s_list[i];
+            const uint32_t d1 = s_d1[i];
+            const uint4* qa = q_desc + ((size_t)b * Nq + q) * 2;
+            const uint4 a0 = __ldg(qa), a1 = __ldg(qa + 1);
+            int found = -1;
+            for (int j0 = 0; j0 < nt && found < 0; j0 += 32) {
+                int j = j0 + lane;
+                bool hit = false;
+                if (j < nt) {
+                    const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
+                    uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
+                                 __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
+                    hit = d == d1;
+                }
+                unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (m) found = j0 + __ffs(m) - 1;
+            }
+            if (lane == 0) dst[total + i] = make_int2(q, found);
+        }
+        total += base;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_n[item] = total;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// host side: library image cache + launch
+// ---------------------------------------------------------------------------------------
+struct TcLibCache {
+    int built_for_kf = -1, built_for_desc = -1;
+    uint8_t* d_img = nullptr;
+    LibTile* d_tiles = nullptr;
+    int n_tiles = 0;
+    std::vector<int> kf_first_tile;   // [n_kf + 1]
+};
+
+static void tc_cache_free(TcLibCache* cch) {
+    if (!cch) return;
+    if (cch->d_img) cudaFree(cch->d_img);
+    if (cch->d_tiles) cudaFree(cch->d_tiles);
+    cch->d_img = nullptr;
+    cch->d_tiles = nullptr;
+}
+
+void nclt_tc_release(nclt_lib* L) {
+    if (L && L->tc_cache) {
+        tc_cache_free(static_cast<TcLibCache*>(L->tc_cache));
+        delete static_cast<TcLibCache*>(L->tc_cache);
+        L->tc_cache = nullptr;
+    }
+}
+
+static int tc_build_library(nclt_ctx* c, nclt_lib* L) {
+    TcLibCache* cch = static_cast<TcLibCache*>(L->tc_cache);
+    if (!cch) {
+        cch = new TcLibCache();
+        L->tc_cache = cch;
+    }
+    if (cch->built_for_kf == L->n_kf && cch->built_for_desc == L->n_desc) return NCLT_OK;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    tc_cache_free(cch);
+    std::vector<LibTile> tiles;
+    std::vector<int> row0;
+    cch->kf_first_tile.assign(L->n_kf + 1, 0);
+    size_t off256 = 0;
+    for (int k = 0; k < L->n_kf; ++k) {
+        cch->kf_first_tile[k] = (int)tiles.size();
+        int cnt = L->h_count[k], start = L->h_start[k];
+        if (cnt == 0) {   // an empty keyframe still owns one (all-padding) tile so that it gets an output row
+            LibTile t{(uint32_t)off256, 16, 0, k, 1};
+            tiles.push_back(t);
+            row0.push_back(start);
+            off256 += 16;
+            continue;
+        }
+        for (int r = 0; r < cnt; r += 256) {
+            int nv = std::min(256, cnt - r);
+            int n = (nv + 15) & ~15;
+            LibTile t{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, k, r + 256 >= cnt ? 1 : 0};
+            tiles.push_back(t);
+            row0.push_back(start + r);
+            off256 += (size_t)n;     // n * 256 bytes / 256
+        }
+    }
+    cch->kf_first_tile[L->n_kf] = (int)tiles.size();
+    cch->n_tiles = (int)tiles.size();
+    if (cch->n_tiles == 0) { cch->built_for_kf = L->n_kf; cch->built_for_desc = L->n_desc; return NCLT_OK; }
+    int* d_row0 = nullptr;
+    CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
+    CU_TRY(c, cudaMalloc(&cch->d_tiles, tiles.size() * sizeof(LibTile)));
+    CU_TRY(c, cudaMalloc(&d_row0, row0.size() * sizeof(int)));
+    CU_TRY(c, cudaMemcpyAsync(cch->d_tiles, tiles.data(), tiles.size() * sizeof(LibTile), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d_row0, row0.data(), row0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_expand_library<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
+                                                          cch->n_tiles, cch->d_img);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_row0);
+    cch->built_for_kf = L->n_kf;
+    cch->built_for_desc = L->n_desc;
+    return NCLT_OK;
+}
+
+// all keyframes, every frame: knn2 + Lowe ratio via tensor cores. Same outputs as the integer path.
+int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
+                       int32_t* out_pairs, int32_t* out_n) {
+    int rc;
+    if ((rc = tc_build_library(c, L))) return rc;
+    TcLibCache* cch = static_cast<TcLibCache*>(L->tc_cache);
+    const int n_kf = L->n_kf;
+    if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
+    const long long rows = (long long)B * Nq;
+    const int n_mtiles = (int)((rows + 127) / 128);
+    const long long rows_pad = (long long)n_mtiles * 128;
+    const int n_groups = (n_mtiles + MA - 1) / MA;
+    // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
+    int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 6 + n_groups - 1) / n_groups));
+    std::vector<int> split_tile(n_splits + 1);
+    for (int s = 0; s <= n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / n_splits];
+
+    ScratchScope scope(c);
+    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4) + pad256((n_splits + 1) * 4);
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * A_TILE_BYTES);
+    uint32_t* d12 = cv.take<uint32_t>((size_t)n_kf * rows_pad);
+    int* d_split = cv.take<int>(n_splits + 1);
+    CU_TRY(c, cudaMemcpyAsync(d_split, split_tile.data(), (n_splits + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    {
+        long long threads = rows_pad * 16;
+        k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
+        c->launches++;
+    }
+    TcParams p;
+    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = n_mtiles; p.n_groups = n_groups;
+    p.n_splits = n_splits; p.split_tile = d_split; p.rows_total = rows; p.out = d12; p.rows_pad = rows_pad;
+    const size_t smem = (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
+    CU_TRY(c, cudaFuncSetAttribute(k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(c->sm_count, n_groups * n_splits);
+    nclt_prof_mark(c);
+    k_tc_top2<<<grid, TC_THREADS, smem, c->stream>>>(p);
+    nclt_prof_mark(c);
+    c->launches++;
+    k_tc_ratio_recover<<<B * n_kf, 256, 0, c->stream>>>(d12, rows_pad, Nq, q_n, n_kf, num, den,
+                                                        reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start, L->d_count,
+                                                        reinterpret_cast<int2*>(out_pairs), out_n);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}

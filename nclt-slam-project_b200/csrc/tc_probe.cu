@@ -1,0 +1,217 @@
+// Diagnostic: one tcgen05 tile (M = 128 queries x N train rows x K = 256 bits) end to end -
+// validates the operand image layout, the shared-memory / instruction descriptors, the TMEM
+// accumulator layout (f16 and f32) and the packed 16-bit TMEM load against a NumPy popcount
+// (tests/test_tc_gpu.py), and times the building blocks of the tensor-core Hamming path
+// (MMA issue rate, TMEM read rate, half2 min/max rate) for DESIGN.md.
+#include "common.cuh"
+#include "scratch.cuh"
+#include "tc_common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace {
+
+__global__ void __launch_bounds__(128) k_tc_probe(const uint32_t* __restrict__ a_bits /*[128][8]*/,
+                                                  const uint32_t* __restrict__ b_bits /*[N][8]*/, int N, int c_fmt,
+                                                  int ld_mode, uint32_t* out /*[128][N]*/) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                 // 128 x 256 B
+    uint8_t* sB = smem + 32768;         // N x 256 B
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // bits -> fp8 image (generic proxy writes)
+    for (int i = tid; i < 128 * 16; i += 128) {
+        int r = i >> 4, c = i & 15;
+        uint32_t w = a_bits[r * 8 + (c >> 1)];
+        uint32_t bits16 = (c & 1) ? (w >> 16) : (w & 0xFFFFu);
+        *reinterpret_cast<uint4*>(sA + tc::image_offset(128, r, c * 16)) = tc::expand16(bits16);
+    }
+    for (int i = tid; i < N * 16; i += 128) {
+        int r = i >> 4, c = i & 15;
+        uint32_t w = b_bits[r * 8 + (c >> 1)];
+        uint32_t bits16 = (c & 1) ? (w >> 16) : (w & 0xFFFFu);
+        *reinterpret_cast<uint4*>(sB + tc::image_offset(N, r, c * 16)) = tc::expand16(bits16);
+    }
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        tc::mbar_init(&s_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(&s_tmem, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (tid == 0) {
+        const uint32_t idesc = tc::idesc_f8(128, N, c_fmt);
+        const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+        for (int k = 0; k < 8; ++k) {
+            uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+            uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+            tc::mma_f8(tmem, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&s_bar);
+    }
+    tc::mbar_wait(&s_bar, 0);
+    tc::tc_fence_after();
+
+    // dump: lane quadrant of this warp, all columns (raw 32-bit cells, or packed pairs)
+    const uint32_t row = warp * 32 + lane;
+    const int ncols = ld_mode == 1 ? N / 2 : N;      // packed: one register per 2 columns
+    for (int c0 = 0; c0 < N; c0 += (ld_mode == 1 ? 64 : 32)) {
+        uint32_t r[32];
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        if (ld_mode == 1) tc::tmem_ld32_pack16(taddr, r);
+        else tc::tmem_ld32(taddr, r);
+        tc::tmem_wait_ld();
+        int o0 = ld_mode == 1 ? c0 / 2 : c0;
+        for (int j = 0; j < 32; ++j)
+            if (o0 + j < ncols) out[(size_t)row * ncols + o0 + j] = r[j];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- micro-benchmarks -------------------------------------------------------------------------
+// mode 0: back-to-back MMAs (M=128, N, K=32) on resident smem tiles, `iters` x 8 k-steps
+// mode 1: + every warp reads the accumulator tile back with packed 16-bit loads (no math)
+// mode 2: + half2 top-2 max tracking on what was read
+__global__ void __launch_bounds__(192) k_tc_bench(int N, int iters, int mode, float* sink, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 32768;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (32768 + N * 256) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x38383838u, 0xB838B838u, 0x3838B8B8u, 0xB8B83838u);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 128); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    long long t0 = clock64();
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_f8(128, N, 0);
+            const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+            for (int it = 0; it < iters; ++it) {
+                int buf = it & 1;
+                if (mode > 0 && it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                for (int k = 0; k < 8; ++k) {
+                    uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+                    uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+                    tc::mma_f8(tmem + buf * 256, da, db, idesc, k > 0 ? 1u : 0u);
+                }
+                tc::mma_commit(&s_full[buf]);
+            }
+        }
+    } else if (warp < 4) {
+        __half2 m1 = __float2half2_rn(-1000.f), m2 = m1;
+        uint32_t acc = 0;
+        for (int it = 0; it < iters; ++it) {
+            int buf = it & 1;
+            tc::mbar_wait(&s_full[buf], (it >> 1) & 1);
+            tc::tc_fence_after();
+            if (mode > 0) {
+                for (int c0 = 0; c0 < N; c0 += 64) {
+                    uint32_t r[32];
+                    tc::tmem_ld32_pack16(tmem + buf * 256 + ((uint32_t)(warp * 32) << 16) + c0, r);
+                    tc::tmem_wait_ld();
+                    if (mode == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            __half2 v = *reinterpret_cast<__half2*>(&r[j]);
+                            __half2 lo = __hmin2(m1, v);
+                            m1 = __hmax2(m1, v);
+                            m2 = __hmax2(m2, lo);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc ^= r[j];
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&s_empty[buf]);
+            }
+        }
+        float2 f1 = __half22float2(m1), f2 = __half22float2(m2);
+        if (f1.x + f1.y + f2.x + f2.y + (float)acc == 12345.f) sink[tid] = 1.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int nclt_tc_probe(nclt_ctx* c, const uint8_t* a_desc, const uint8_t* b_desc, int N, int c_fmt, int ld_mode,
+                             uint32_t* out) {
+    if (!c || !a_desc || !b_desc || !out || N < 16 || N > 256 || (N % 16)) return nclt_fail(c, NCLT_ERR_ARG, "tc_probe args");
+    cudaSetDevice(c->device);
+    ScratchScope scope(c);
+    int rc;
+    size_t out_elems = (size_t)128 * (ld_mode == 1 ? N / 2 : N);
+    if ((rc = nclt_scratch_reserve(c, pad256(128 * 32) + pad256((size_t)N * 32) + pad256(out_elems * 4)))) return rc;
+    Carver cv(c);
+    uint32_t* da = cv.take<uint32_t>(128 * 8);
+    uint32_t* db = cv.take<uint32_t>((size_t)N * 8);
+    uint32_t* dout = cv.take<uint32_t>(out_elems);
+    CU_TRY(c, cudaMemcpyAsync(da, a_desc, 128 * 32, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(db, b_desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
+    size_t smem = 32768 + (size_t)N * 256;
+    CU_TRY(c, cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_probe<<<1, 128, smem, c->stream>>>(da, db, N, c_fmt, ld_mode, dout);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+// returns comparisons (pairs) per second over the whole GPU for the chosen mode
+extern "C" double nclt_tc_bench(nclt_ctx* c, int N, int iters, int mode, double* cycles_per_tile) {
+    if (!c || N < 16 || N > 256 || (N % 16) || iters < 4) return -1.0;
+    cudaSetDevice(c->device);
+    float* sink = nullptr;
+    long long* cyc = nullptr;
+    int blocks = c->sm_count;
+    if (cudaMalloc(&sink, 192 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
+    size_t smem = 32768 + (size_t)N * 256;
+    cudaFuncSetAttribute(k_tc_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_tc_bench<<<blocks, 192, smem, c->stream>>>(N, 8, mode, sink, cyc);
+    cudaEventRecord(e0, c->stream);
+    k_tc_bench<<<blocks, 192, smem, c->stream>>>(N, iters, mode, sink, cyc);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    if (cycles_per_tile) *cycles_per_tile = (double)h / iters;
+    c->launches += 2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench", e); return -1.0; }
+    return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
+}
