@@ -52,54 +52,64 @@ def make_inputs(n_frames, seed0, lib=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  In-process NVML
+    (nvidia_ml_py) in a background thread: spawning `nvidia-smi -lms` was measured to stall CUDA calls
+    of this process for up to ~0.9 s per poll, which corrupts short steps; NVML queries do not."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period_s=0.05):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = self.idx
+            if vis:
+                try:
+                    phys = int(vis.split(',')[self.idx])
+                except Exception:
+                    phys = self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.stop_flag.wait(self.period)
+            pynvml.nvmlShutdown()
+        except Exception as e:      # keep the bench alive; the JSON says why there are no samples
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.idx)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        t0 = time.time()                      # NVML initialisation must be over before anything is timed
+        while not self.sm and self.err is None and time.time() - t0 < 5.0:
+            time.sleep(0.01)
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped."""
+        self.sm, self.mx = [], []
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        out = {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+               'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'NVML in-process, 50 ms period'}
+        if self.err:
+            out['error'] = self.err
+        return out
 
 
 def cpu_reference_frames(lib, desc, pts2d, n_frames):
@@ -153,10 +163,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
+    ap.add_argument('--engine', default='tensor', choices=['int', 'tensor'],
+                    help='matching engine: integer pipe (LOP3+POPC) or tcgen05 tensor cores (identical results)')
     ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
     ap.add_argument('--ref-frames-per-step', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -192,6 +204,7 @@ def main():
     lms = lib['landmarks']
     eng = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
                           device=local_rank, params=LocalizeParams(mode=0))
+    eng.ctx.set_engine(args.engine)
     d_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
     d_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -202,6 +215,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up stalls CUDA calls for tens
+    # of milliseconds and must not land inside the timed region; it then samples warm-up + timed steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
     for w in range(max(args.warmup, 3)):
         out = eng.run(d_desc[w % n_batches], d_pts[w % n_batches])
     torch.cuda.synchronize()
@@ -211,13 +229,12 @@ def main():
     log(f'[rank {rank}] warm-up ok: {acc_rate * 100:.1f}% of frames localised to their planted keyframe; '
         f'{out["n_problems"]} PnP problems in the last batch')
 
-    sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     eng.ctx.profile(True)
     eng.ctx.profile_read()
     barrier()
     launches0 = eng.ctx.launches
-    sampler.start()
+    sampler.mark()
     n_prob = 0
     for s in range(args.steps):
         flush.zero_()                                   # evict L2 between timed steps (outside the events)
@@ -230,7 +247,9 @@ def main():
     launches = eng.ctx.launches - launches0
     k_ms, k_n = eng.ctx.profile_read()
     eng.ctx.profile(False)
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    log(f'[rank {rank}] step ms: ' + ' '.join(f'{x:.2f}' for x in step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -241,7 +260,7 @@ def main():
     h_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
     h_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
     prm = LocalizeParams(mode=0)
-    for w in range(2):
+    for w in range(3):
         localize_batch(eng.library, h_desc[w % n_batches].numpy(), h_pts[w % n_batches].numpy(), params=prm)
     barrier()
     t0 = time.perf_counter()
@@ -264,24 +283,43 @@ def main():
     # ---- roofline of the dominant kernel ----------------------------------------------------
     popc_peak, _ = eng.ctx.popc_peak(8192)
     cmp_per_launch = float(B) * N_KF * N_QUERY * N_DESC
-    popc_per_launch = cmp_per_launch * 8.0               # 8 POPC32 per 256-bit comparison
     k_avg_s = (k_ms / max(k_n, 1)) * 1e-3
-    achieved = popc_per_launch / k_avg_s if k_avg_s > 0 else 0.0
+    cmp_per_s = cmp_per_launch / k_avg_s if k_avg_s > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'traffic_hamming.json')
+    tp = os.path.join(ROOT, 'profiles', 'traffic_tc.json' if args.engine == 'tensor' else 'traffic_hamming.json')
     if os.path.exists(tp):
         try:
             # ncu --set full capture (profiles/README.md), scaled from its batch to this one
             traffic = json.load(open(tp)).get('dram_bytes_per_frame') * B
         except Exception:
             traffic = None
-    roofline = {'bound': 'int-pipe (POPC)', 'achieved': achieved / 1e12, 'peak': popc_peak / 1e12,
-                'unit': 'Tpopc32/s', 'frac': achieved / popc_peak, 'traffic': traffic,
-                'kernel': 'k_hamming_top2<4>', 'kernel_ms_per_launch': k_avg_s * 1e3, 'kernel_launches': k_n,
-                'kernel_share_of_step': k_ms / total_ms if total_ms > 0 else None,
-                'hamming_cmp_per_s': cmp_per_launch / k_avg_s if k_avg_s > 0 else 0.0,
-                'peak_source': 'register-only POPC probe (nclt_popc_peak) on this GPU in this run; '
-                               'MEASURED_PEAKS.json carries no integer-pipe figure'}
+    common = {'traffic': traffic, 'kernel_ms_per_launch': k_avg_s * 1e3, 'kernel_launches': k_n,
+              'kernel_share_of_step': k_ms / total_ms if total_ms > 0 else None, 'hamming_cmp_per_s': cmp_per_s,
+              'popc_pipe_ceiling_cmp_per_s': popc_peak / 8.0,
+              'vs_popc_pipe_ceiling': cmp_per_s / (popc_peak / 8.0)}
+    if args.engine == 'int':
+        # 8 POPC32 per 256-bit comparison; peak from the register-only probe in this run
+        achieved = cmp_per_s * 8.0
+        roofline = {'bound': 'int-pipe (POPC)', 'achieved': achieved / 1e12, 'peak': popc_peak / 1e12,
+                    'unit': 'Tpopc32/s', 'frac': achieved / popc_peak, 'kernel': 'k_hamming_top2<4>',
+                    'peak_source': 'register-only POPC probe (nclt_popc_peak) on this GPU in this run; '
+                                   'MEASURED_PEAKS.json carries no integer-pipe figure'}
+    else:
+        # 256 MACs = 512 flop per comparison on the fp8 tensor path; fp8 dense peak = 2 x the measured
+        # cuBLAS bf16 figure (sustained: the kernel is timed inside a long step)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        bf16 = peaks.get('bf16_tflops_sustained')
+        src = 'MEASURED_PEAKS.json bf16_tflops_sustained x 2 (fp8 runs at twice the bf16 MMA rate)'
+        if not bf16:
+            bf16, src = 1400.0, 'fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) x 2 for fp8'
+        achieved = cmp_per_s * 512.0 / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': 2.0 * bf16, 'unit': 'TFLOP/s (fp8)',
+                    'frac': achieved / (2.0 * bf16), 'kernel': 'k_tc_top2', 'peak_source': src}
+    roofline.update(common)
 
     # ---- CPU baseline (rank 0, bounded sample) ----------------------------------------------
     cpu = None
@@ -301,7 +339,7 @@ def main():
         'config': {'workload': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
                                'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
                    'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY,
-                   'frames_per_step_per_gpu': B, 'sharding': f'frames x {world} GPUs, library replicated, no collective',
+                   'frames_per_step_per_gpu': B, 'engine': args.engine, 'sharding': f'frames x {world} GPUs, library replicated, no collective',
                    'cache': 'L2 flushed (256 MB write) between timed steps; per-step CUDA events',
                    'pnp_problems_per_step': n_prob / args.steps, 'localised_to_planted_keyframe': acc_rate},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},

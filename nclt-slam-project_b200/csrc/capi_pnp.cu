@@ -15,7 +15,7 @@ static int check_pnp(nclt_ctx* c, const void* obj, const void* img, const void* 
 
 static size_t pnp_buf_bytes(int P, int iters) {
     size_t h = (size_t)P * iters;
-    return pad256(h * 5 * sizeof(int)) + pad256(h * 6 * sizeof(double)) + pad256(h * sizeof(int));
+    return pad256(h * 5 * sizeof(int)) + pad256(h * 6 * sizeof(double)) + pad256(h * sizeof(int)) + pad256((size_t)P * 16);
 }
 static PnpBuffers carve_pnp(Carver& cv, int P, int iters) {
     size_t h = (size_t)P * iters;
@@ -23,6 +23,7 @@ static PnpBuffers carve_pnp(Carver& cv, int P, int iters) {
     b.sets = cv.take<int>(h * 5);
     b.models = cv.take<double>(h * 6);
     b.counts = cv.take<int>(h);
+    b.state = cv.take<int>((size_t)P * 4);
     return b;
 }
 
@@ -111,7 +112,7 @@ extern "C" int nclt_pnp_score(nclt_ctx* c, const float* obj, const float* img, c
     float* d_img = cv.take<float>(pts * 2);
     int* d_n = cv.take<int>(P);
     double* d_models = cv.take<double>(h * 6);
-    PnpBuffers buf{nullptr, nullptr, cv.take<int>(h)};
+    PnpBuffers buf{nullptr, nullptr, cv.take<int>(h), nullptr};
     cudaStream_t s = c->stream;
     CU_TRY(c, cudaMemcpyAsync(d_obj, obj, pts * 12, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaMemcpyAsync(d_img, img, pts * 8, cudaMemcpyHostToDevice, s));

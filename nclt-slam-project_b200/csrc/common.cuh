@@ -125,6 +125,7 @@ struct PnpBuffers {
     int* sets;         // [P][iters][5]
     double* models;    // [P][iters][6]
     int* counts;       // [P][iters]
+    int* state;        // [P][4] replay state: cursor, best, max_good, niters
 };
 int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, int Nmax,
                const nclt_pnp_params* prm, const PnpBuffers& buf, const double* models_override,

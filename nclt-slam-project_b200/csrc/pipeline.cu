@@ -157,7 +157,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         size_t h = (size_t)P * iters;
         size_t need2 = pad256((size_t)P * Nrow * 12) + pad256((size_t)P * Nrow * 8) + 3 * pad256((size_t)P * 4) +
                        pad256((size_t)P * Nrow) + pad256((size_t)P) + 2 * pad256((size_t)P * 24) +
-                       pad256(h * 20) + pad256(h * 48) + pad256(h * 4);
+                       pad256(h * 20) + pad256(h * 48) + pad256(h * 4) + pad256((size_t)P * 16);
         if ((rc = nclt_scratch_reserve(c, need2))) return rc;   // never moves what is already carved
         Carver cv2(c);
         float* obj = cv2.take<float>((size_t)P * Nrow * 3);
@@ -173,6 +173,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         buf.sets = cv2.take<int>(h * 5);
         buf.models = cv2.take<double>(h * 6);
         buf.counts = cv2.take<int>(h);
+        buf.state = cv2.take<int>((size_t)P * 4);
         k_gather_problems<<<P, 256, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
                                                     L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow);
         c->launches++;

@@ -60,10 +60,18 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
     }
 }
 
-__global__ void __launch_bounds__(64) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= v.P * v.iters) return;
-    int p = g / v.iters;
+// Per-problem RANSAC replay state: {cursor, best, max_good, niters}. Hypotheses are evaluated in
+// rounds of `it_cnt` iterations; iterations OpenCV's loop would never reach (it >= niters, which
+// shrinks as soon as a good model appears) are skipped.
+__global__ void __launch_bounds__(64) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
+                                                 int it_lo, int it_cnt, const int* __restrict__ state) {
+    int gg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gg >= v.P * it_cnt) return;
+    int p = gg / it_cnt;
+    int it = it_lo + gg % it_cnt;
+    if (it >= v.iters) return;
+    if (state && it >= state[4 * p + 3]) return;
+    int g = p * v.iters + it;
     int n = v.n[p];
     double* out = models + (size_t)g * 6;
     if (n < 5) {
@@ -108,11 +116,16 @@ __device__ __forceinline__ float reproj_err2(const double* R, const double* t, d
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_pnp_score(PnpView v, const double* __restrict__ models, int* counts) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(256) k_pnp_score(PnpView v, const double* __restrict__ models, int* counts, int it_lo,
+                                                   int it_cnt, const int* __restrict__ state) {
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (warp >= v.P * v.iters) return;
-    int p = warp / v.iters;
+    if (gw >= v.P * it_cnt) return;
+    int p = gw / it_cnt;
+    int it = it_lo + gw % it_cnt;
+    if (it >= v.iters) return;
+    if (state && it >= state[4 * p + 3]) return;
+    int warp = p * v.iters + it;
     int n = v.n[p];
     if (n < 5) {
         if (lane == 0) counts[warp] = 0;
@@ -250,8 +263,41 @@ struct PnpOut {
     int* niters;             // [P] or null
 };
 
+// sequential part of RANSACPointSetRegistrator::run over the counts of one round: strict > on
+// max(best, 4), niters shrinking in place. One thread per problem.
+__global__ void k_pnp_replay(PnpView v, const int* __restrict__ counts, int* state, int it_hi) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= v.P) return;
+    int n = v.n[p];
+    int cursor = state[4 * p], best = state[4 * p + 1], max_good = state[4 * p + 2], niters = state[4 * p + 3];
+    if (n == 5) {
+        best = 0; max_good = 5; cursor = niters;
+    } else if (n > 5) {
+        const int* cnt = counts + (size_t)p * v.iters;
+        int hi = it_hi < niters ? it_hi : niters;
+        for (; cursor < hi; cursor++) {
+            int good = cnt[cursor];
+            if (good > (max_good > 4 ? max_good : 4)) {
+                max_good = good;
+                best = cursor;
+                niters = ransac_update_niters(v.conf, (double)(n - good) / n, 5, niters);
+                hi = it_hi < niters ? it_hi : niters;
+            }
+        }
+    } else {
+        cursor = niters;
+    }
+    state[4 * p] = cursor; state[4 * p + 1] = best; state[4 * p + 2] = max_good; state[4 * p + 3] = niters;
+}
+
+__global__ void k_pnp_state_init(int P, int iters, int* state) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    state[4 * p] = 0; state[4 * p + 1] = -1; state[4 * p + 2] = 0; state[4 * p + 3] = iters > 1 ? iters : 1;
+}
+
 __global__ void __launch_bounds__(128) k_pnp_finish(PnpView v, const double* __restrict__ models,
-                                                    const int* __restrict__ counts, PnpOut o) {
+                                                    const int* __restrict__ state, PnpOut o) {
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= v.P) return;
@@ -259,28 +305,7 @@ __global__ void __launch_bounds__(128) k_pnp_finish(PnpView v, const double* __r
     const float* obj = v.obj + (size_t)p * v.Nmax * 3;
     const float* img = v.img + (size_t)p * v.Nmax * 2;
     unsigned char* mask = o.mask + (size_t)p * v.Nmax;
-
-    // --- replay of RANSACPointSetRegistrator::run over the per-iteration counts ----------
-    int best = -1, max_good = 0, niters = v.iters > 1 ? v.iters : 1;
-    if (n == 5) {
-        best = 0;
-        max_good = 5;
-    } else if (n > 5) {
-        if (lane == 0) {
-            const int* cnt = counts + (size_t)p * v.iters;
-            for (int it = 0; it < niters; it++) {
-                int good = cnt[it];
-                if (good > (max_good > 4 ? max_good : 4)) {
-                    max_good = good;
-                    best = it;
-                    niters = ransac_update_niters(v.conf, (double)(n - good) / n, 5, niters);
-                }
-            }
-        }
-        best = __shfl_sync(0xFFFFFFFFu, best, 0);
-        max_good = __shfl_sync(0xFFFFFFFFu, max_good, 0);
-        niters = __shfl_sync(0xFFFFFFFFu, niters, 0);
-    }
+    const int best = state[4 * p + 1], max_good = state[4 * p + 2], niters = state[4 * p + 3];
     if (lane == 0) {
         if (o.best_iter) o.best_iter[p] = best;
         if (o.niters) o.niters[p] = niters;
@@ -408,21 +433,33 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     v.conf = prm->confidence;
     v.refine = prm->refine;
     const double* models = models_override ? models_override : buf.models;
-    if (!models_override) {
-        k_pnp_sets<<<(P + 63) / 64, 64, 0, c->stream>>>(v, buf.sets);
-        int total = P * v.iters;
-        k_pnp_hypo<<<(total + 63) / 64, 64, 0, c->stream>>>(v, buf.sets, buf.models);
-        c->launches += 2;
+    if (score_only) {
+        // staged parity (ii): score every caller-supplied hypothesis
+        long long threads = (long long)P * v.iters * 32;
+        k_pnp_score<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(v, models, buf.counts, 0, v.iters, nullptr);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        return NCLT_OK;
+    }
+    // counts of iterations that are never reached stay -1 (debug output)
+    CU_TRY(c, cudaMemsetAsync(buf.counts, 0xFF, (size_t)P * v.iters * sizeof(int), c->stream));
+    k_pnp_sets<<<(P + 63) / 64, 64, 0, c->stream>>>(v, buf.sets);
+    k_pnp_state_init<<<(P + 127) / 128, 128, 0, c->stream>>>(P, v.iters, buf.state);
+    c->launches += 2;
+    const int ROUND = 32;
+    for (int lo = 0; lo < v.iters; lo += ROUND) {
+        int cnt = v.iters - lo < ROUND ? v.iters - lo : ROUND;
+        int total = P * cnt;
+        k_pnp_hypo<<<(total + 63) / 64, 64, 0, c->stream>>>(v, buf.sets, buf.models, lo, cnt, buf.state);
+        long long threads = (long long)total * 32;
+        k_pnp_score<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
+        k_pnp_replay<<<(P + 127) / 128, 128, 0, c->stream>>>(v, buf.counts, buf.state, lo + cnt);
+        c->launches += 3;
     }
     {
-        long long threads = (long long)P * v.iters * 32;
-        k_pnp_score<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(v, models, buf.counts);
-        c->launches++;
-    }
-    if (!score_only) {
         PnpOut o{ok, rvec, tvec, n_inl, mask, mean_err, best_iter, niters};
         long long threads = (long long)P * 32;
-        k_pnp_finish<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, o);
+        k_pnp_finish<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.state, o);
         c->launches++;
     }
     CU_TRY(c, cudaGetLastError());

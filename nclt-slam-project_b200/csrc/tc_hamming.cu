@@ -467,7 +467,8 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     const long long rows_pad = (long long)n_mtiles * 128;
     const int n_groups = (n_mtiles + MA - 1) / MA;
     // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
-    int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 6 + n_groups - 1) / n_groups));
+    // >= ~24 items per SM so that the last (partial) wave of the static round-robin costs a few percent
+    int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 24 + n_groups - 1) / n_groups));
     std::vector<int> split_tile(n_splits + 1);
     for (int s = 0; s <= n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / n_splits];
 
