@@ -43,6 +43,10 @@ int nclt_ctx_sync(nclt_ctx* ctx);
 const char* nclt_last_error(nclt_ctx* ctx);
 /* kernels launched through this context so far (bench.py's gpu_launches) */
 unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
+/* asynchronous nclt_localize_batch_dev calls (out_n_problems == NULL) size their PnP buffers for
+ * max(4*B, 1024) problems per batch; returns how many problems were dropped since the last reset
+ * (>= 0; synchronises the stream). A caller that sees > 0 re-runs those batches synchronously. */
+int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
 /* matching engine for the "every frame against every keyframe" ratio mode (cand == NULL):
  * 0 = integer pipe (LOP3+POPC, the default), 1 = tcgen05 tensor cores (fp8 +-1 operands, fp16
  * accumulators in TMEM, exact index recovery); both produce identical results. Candidate-list
@@ -171,7 +175,8 @@ typedef struct nclt_localize_params {
  * q u8[B,Nq,32], q_pts2d f32[B,Nq,2] keypoint pixel coordinates, q_n/cand as for nclt_match_*.
  * Per frame: out_best_cand i32[B] winning candidate SLOT (-1 = none accepted), out_n_inliers i32[B],
  * out_reproj f32[B], out_rvec/out_tvec f64[B,3] (teach camera in the current camera frame, as
- * solvePnPRansac returns it).  out_n_problems: HOST int, PnP problems solved (NULL ok).
+ * solvePnPRansac returns it).  out_n_problems: HOST int, PnP problems solved; passing NULL to the
+ * _dev variant selects the fully asynchronous mode (no host synchronisation, see nclt_ctx_overflow).
  * Optional per (frame, candidate) outputs (NULL ok): out_item_nmatch i32[B,C] matches after the
  * ratio / crossCheck filter, out_item_ok u8[B,C], out_item_ninl i32[B,C], out_item_err f32[B,C],
  * out_item_rvec/out_item_tvec f64[B,C,3] (valid where nmatch >= min_matches). */

@@ -41,6 +41,7 @@ _sig('nclt_ctx_sync', _i, _vp)
 _sig('nclt_last_error', C.c_char_p, _vp)
 _sig('nclt_ctx_launches', C.c_ulonglong, _vp)
 _sig('nclt_ctx_set_engine', _i, _vp, _i)
+_sig('nclt_ctx_overflow', _i, _vp, _i)
 _sig('nclt_ctx_profile', _i, _vp, _i)
 _sig('nclt_ctx_profile_read', _i, _vp, C.POINTER(_dbl), C.POINTER(_i))
 _sig('nclt_popc_peak', _dbl, _vp, _i, C.POINTER(C.c_float))
@@ -148,6 +149,13 @@ class Context:
         """'int' (LOP3+POPC) or 'tensor' (tcgen05) for all-keyframe ratio matching; same results."""
         code = {'int': 0, 'tensor': 1, 0: 0, 1: 1}[engine]
         self.check(lib.nclt_ctx_set_engine(self.h, code))
+
+    def overflow(self, reset=True):
+        """PnP problems dropped by asynchronous localisation calls since the last reset."""
+        v = lib.nclt_ctx_overflow(self.h, 1 if reset else 0)
+        if v < 0:
+            raise NcltError('nclt_ctx_overflow failed')
+        return v
 
     def profile(self, enable=True):
         self.check(lib.nclt_ctx_profile(self.h, 1 if enable else 0))

@@ -15,9 +15,9 @@ int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
     if (idle) {
         // top-level call and nothing in use: consolidate into one chunk that fits
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        size_t total = bytes;
+        size_t total = 0;      // the sum: what used to need several chunks then fits one
         for (auto& ch : c->scratch_chunks) {
-            total = std::max(total, ch.second);
+            total += ch.second;
             cudaFree(ch.first);
         }
         c->scratch_chunks.clear();
@@ -111,6 +111,7 @@ extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
     for (auto& ch : c->scratch_chunks) cudaFree(ch.first);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    if (c->d_overflow) cudaFree(c->d_overflow);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return NCLT_OK;
@@ -124,6 +125,17 @@ extern "C" int nclt_ctx_sync(nclt_ctx* c) {
 
 extern "C" const char* nclt_last_error(nclt_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" unsigned long long nclt_ctx_launches(nclt_ctx* c) { return c ? c->launches : 0ull; }
+
+extern "C" int nclt_ctx_overflow(nclt_ctx* c, int reset) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!c->d_overflow) return 0;
+    cudaSetDevice(c->device);
+    int v = 0;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return NCLT_ERR_CUDA;
+    if (cudaMemcpy(&v, c->d_overflow, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return NCLT_ERR_CUDA;
+    if (reset) cudaMemset(c->d_overflow, 0, 4);
+    return v;
+}
 
 extern "C" int nclt_ctx_set_engine(nclt_ctx* c, int engine) {
     if (!c || (engine != 0 && engine != 1)) return nclt_fail(c, NCLT_ERR_ARG, "engine must be 0 (integer pipe) or 1 (tensor cores)");

@@ -40,7 +40,7 @@ extern "C" int nclt_pnp_ransac_dev(nclt_ctx* c, const float* obj, const float* i
     Carver cv(c);
     PnpBuffers buf = carve_pnp(cv, P, prm->iterations);
     uint8_t* mask = out_mask ? out_mask : cv.take<uint8_t>((size_t)P * Nmax);
-    return launch_pnp(c, obj, img, n, P, Nmax, prm, buf, nullptr, out_ok, out_rvec, out_tvec, out_n_inliers, mask,
+    return launch_pnp(c, obj, img, n, P, nullptr, Nmax, prm, buf, nullptr, out_ok, out_rvec, out_tvec, out_n_inliers, mask,
                       out_mean_err, nullptr, nullptr, false);
 }
 
@@ -76,7 +76,7 @@ extern "C" int nclt_pnp_ransac(nclt_ctx* c, const float* obj, const float* img, 
     CU_TRY(c, cudaMemcpyAsync(d_obj, obj, pts * 12, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaMemcpyAsync(d_img, img, pts * 8, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaMemcpyAsync(d_n, n, (size_t)P * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = launch_pnp(c, d_obj, d_img, d_n, P, Nmax, prm, buf, nullptr, d_ok, d_r, d_t, d_ninl, d_mask, d_err,
+    if ((rc = launch_pnp(c, d_obj, d_img, d_n, P, nullptr, Nmax, prm, buf, nullptr, d_ok, d_r, d_t, d_ninl, d_mask, d_err,
                          d_best, d_nit, false)))
         return rc;
     size_t h = (size_t)P * iters;
@@ -118,7 +118,7 @@ extern "C" int nclt_pnp_score(nclt_ctx* c, const float* obj, const float* img, c
     CU_TRY(c, cudaMemcpyAsync(d_img, img, pts * 8, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaMemcpyAsync(d_n, n, (size_t)P * 4, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaMemcpyAsync(d_models, models, h * 48, cudaMemcpyHostToDevice, s));
-    if ((rc = launch_pnp(c, d_obj, d_img, d_n, P, Nmax, prm, buf, d_models, nullptr, nullptr, nullptr, nullptr,
+    if ((rc = launch_pnp(c, d_obj, d_img, d_n, P, nullptr, Nmax, prm, buf, d_models, nullptr, nullptr, nullptr, nullptr,
                          nullptr, nullptr, nullptr, nullptr, true)))
         return rc;
     CU_TRY(c, cudaMemcpyAsync(out_counts, buf.counts, h * 4, cudaMemcpyDeviceToHost, s));

@@ -37,6 +37,8 @@ struct nclt_ctx {
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
+    // async pipeline: PnP problems dropped because a batch produced more than its problem capacity
+    int* d_overflow = nullptr;
 };
 
 struct nclt_lib {
@@ -127,7 +129,7 @@ struct PnpBuffers {
     int* counts;       // [P][iters]
     int* state;        // [P][4] replay state: cursor, best, max_good, niters
 };
-int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, int Nmax,
+int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, const int* P_dev, int Nmax,
                const nclt_pnp_params* prm, const PnpBuffers& buf, const double* models_override,
                unsigned char* ok, double* rvec, double* tvec, int* n_inl, unsigned char* mask, float* mean_err,
                int* best_iter, int* niters, bool score_only);

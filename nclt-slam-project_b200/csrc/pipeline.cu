@@ -7,17 +7,22 @@
 #include "common.cuh"
 #include "scratch.cuh"
 
+#include <algorithm>
+
 namespace {
 
 // items with enough matches become PnP problems (order irrelevant: problems are independent)
+// `cap`: problem capacity of the buffers (asynchronous mode); what does not fit is counted in
+// `overflow` (the caller re-runs such a batch synchronously - parity is never silently lost).
 __global__ void k_select_problems(const int* __restrict__ n_pairs, int n_items, int min_matches, int* prob_item,
-                                  int* item_prob, int* count) {
+                                  int* item_prob, int* count, int cap, int* overflow) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     int slot = -1;
     if (n_pairs[i] >= min_matches) {
         slot = atomicAdd(count, 1);
-        prob_item[slot] = i;
+        if (slot < cap) prob_item[slot] = i;
+        else { slot = -1; if (overflow) atomicAdd(overflow, 1); }
     }
     item_prob[i] = slot;
 }
@@ -29,8 +34,10 @@ __global__ void __launch_bounds__(256) k_gather_problems(const int* __restrict__
                                                          const int* __restrict__ kf_start,
                                                          const float* __restrict__ pts3d,
                                                          const float* __restrict__ pts2d, int Nq, float* obj,
-                                                         float* img, int* n_out, int Nmax) {
+                                                         float* img, int* n_out, int Nmax,
+                                                         const int* __restrict__ count) {
     const int p = blockIdx.x;
+    if (p >= *count) return;
     const int item = prob_item[p];
     const int b = item / C;
     const int kf = cand ? cand[item] : item % C;
@@ -137,16 +144,30 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
     }
     if (rc) return rc;
     CU_TRY(c, cudaMemsetAsync(d_count, 0, 4, c->stream));
-    k_select_problems<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(n_pairs, (int)items, prm->min_matches,
-                                                                             prob_item, item_prob, d_count);
-    c->launches++;
-    // the number of PnP problems is data dependent: one 4-byte read-back per batch
+    // The number of PnP problems is data dependent.  Synchronous mode (out_n_problems given): one
+    // 4-byte read-back, buffers sized exactly.  Asynchronous mode (out_n_problems == NULL): no host
+    // sync at all - buffers sized for `cap` problems, kernels read the count on the device, and a
+    // per-context overflow counter (nclt_ctx_overflow) reports batches that needed more.
+    const bool async_mode = out_n_problems_host == nullptr;
     int P = 0;
-    if ((rc = nclt_pinned_reserve(c, 64))) return rc;
-    CU_TRY(c, cudaMemcpyAsync(c->pinned, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    P = *static_cast<int*>(c->pinned);
-    if (out_n_problems_host) *out_n_problems_host = P;
+    if (async_mode) {
+        P = (int)std::min<size_t>(items, std::max<size_t>((size_t)B * 4, 1024));
+        if (!c->d_overflow) {
+            CU_TRY(c, cudaMalloc(&c->d_overflow, 4));
+            CU_TRY(c, cudaMemsetAsync(c->d_overflow, 0, 4, c->stream));
+        }
+    }
+    k_select_problems<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(
+        n_pairs, (int)items, prm->min_matches, prob_item, item_prob, d_count, async_mode ? P : (int)items,
+        async_mode ? c->d_overflow : nullptr);
+    c->launches++;
+    if (!async_mode) {
+        if ((rc = nclt_pinned_reserve(c, 64))) return rc;
+        CU_TRY(c, cudaMemcpyAsync(c->pinned, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        P = *static_cast<int*>(c->pinned);
+        *out_n_problems_host = P;
+    }
 
     unsigned char* p_ok = nullptr;
     int* p_inl = nullptr;
@@ -175,10 +196,10 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         buf.counts = cv2.take<int>(h);
         buf.state = cv2.take<int>((size_t)P * 4);
         k_gather_problems<<<P, 256, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
-                                                    L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow);
+                                                    L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow, d_count);
         c->launches++;
-        if ((rc = launch_pnp(c, obj, img, pn, P, Nrow, &prm->pnp, buf, nullptr, p_ok, p_r, p_t, p_inl, mask, p_err,
-                             nullptr, nullptr, false)))
+        if ((rc = launch_pnp(c, obj, img, pn, P, async_mode ? d_count : nullptr, Nrow, &prm->pnp, buf, nullptr, p_ok,
+                             p_r, p_t, p_inl, mask, p_err, nullptr, nullptr, false)))
             return rc;
     }
     k_reduce_frames<<<(B + 127) / 128, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t,

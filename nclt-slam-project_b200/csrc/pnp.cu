@@ -22,13 +22,16 @@ struct PnpView {
     const float* obj;   // [P][Nmax][3]
     const float* img;   // [P][Nmax][2]
     const int* n;       // [P]
-    int P, Nmax;
+    int P, Nmax;          // P = problems the buffers are sized for
+    const int* P_dev;     // optional device-side problem count (async pipeline): effective P = min(*P_dev, P)
     double fx, fy, cx, cy;
     int iters;
     float thr2;
     double conf;
     int refine;
 };
+
+__device__ __forceinline__ int eff_P(const PnpView& v) { return v.P_dev ? min(*v.P_dev, v.P) : v.P; }
 
 __device__ __forceinline__ uint32_t mwc_next(uint64_t& st) {
     st = (uint64_t)(uint32_t)st * 4164903690ull + (uint32_t)(st >> 32);
@@ -37,7 +40,7 @@ __device__ __forceinline__ uint32_t mwc_next(uint64_t& st) {
 
 __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= v.P) return;
+    if (p >= eff_P(v)) return;
     int n = v.n[p];
     int* out = sets + (size_t)p * v.iters * 5;
     if (n <= 5) {
@@ -66,7 +69,7 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
 __global__ void __launch_bounds__(64) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
                                                  int it_lo, int it_cnt, const int* __restrict__ state) {
     int gg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gg >= v.P * it_cnt) return;
+    if (gg >= eff_P(v) * it_cnt) return;
     int p = gg / it_cnt;
     int it = it_lo + gg % it_cnt;
     if (it >= v.iters) return;
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(256) k_pnp_score(PnpView v, const double* __re
                                                    int it_cnt, const int* __restrict__ state) {
     int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (gw >= v.P * it_cnt) return;
+    if (gw >= eff_P(v) * it_cnt) return;
     int p = gw / it_cnt;
     int it = it_lo + gw % it_cnt;
     if (it >= v.iters) return;
@@ -267,7 +270,7 @@ struct PnpOut {
 // max(best, 4), niters shrinking in place. One thread per problem.
 __global__ void k_pnp_replay(PnpView v, const int* __restrict__ counts, int* state, int it_hi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= v.P) return;
+    if (p >= eff_P(v)) return;
     int n = v.n[p];
     int cursor = state[4 * p], best = state[4 * p + 1], max_good = state[4 * p + 2], niters = state[4 * p + 3];
     if (n == 5) {
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128) k_pnp_finish(PnpView v, const double* __r
                                                     const int* __restrict__ state, PnpOut o) {
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (p >= v.P) return;
+    if (p >= eff_P(v)) return;
     const int n = v.n[p];
     const float* obj = v.obj + (size_t)p * v.Nmax * 3;
     const float* img = v.img + (size_t)p * v.Nmax * 2;
@@ -420,13 +423,13 @@ __global__ void k_project_points(const float* __restrict__ obj, int n, double r0
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, int Nmax,
+int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, int P, const int* P_dev, int Nmax,
                const nclt_pnp_params* prm, const PnpBuffers& buf, const double* models_override,
                unsigned char* ok, double* rvec, double* tvec, int* n_inl, unsigned char* mask, float* mean_err,
                int* best_iter, int* niters, bool score_only) {
     if (P <= 0) return NCLT_OK;
     PnpView v;
-    v.obj = obj; v.img = img; v.n = n; v.P = P; v.Nmax = Nmax;
+    v.obj = obj; v.img = img; v.n = n; v.P = P; v.P_dev = P_dev; v.Nmax = Nmax;
     v.fx = prm->fx; v.fy = prm->fy; v.cx = prm->cx; v.cy = prm->cy;
     v.iters = prm->iterations;
     v.thr2 = prm->reproj_error * prm->reproj_error;

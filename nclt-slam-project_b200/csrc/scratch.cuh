@@ -23,11 +23,14 @@ struct ScratchScope {   // restores the stack when the API call returns
     int saved_chunk;
     explicit ScratchScope(nclt_ctx* ctx) : c(ctx), saved_off(ctx->scratch_off), saved_chunk(ctx->scratch_chunk) {}
     ~ScratchScope() {
+        // a scope opened before the first chunk existed (saved_chunk == -1) returns to chunk 0, offset 0:
+        // restoring -1 would make every later top-level call look "idle and too small" and re-allocate
+        int chunk = saved_chunk >= 0 ? saved_chunk : (c->scratch_chunks.empty() ? -1 : 0);
         c->scratch_off = saved_off;
-        c->scratch_chunk = saved_chunk;
-        if (saved_chunk >= 0 && saved_chunk < (int)c->scratch_chunks.size()) {
-            c->scratch = c->scratch_chunks[saved_chunk].first;
-            c->scratch_bytes = c->scratch_chunks[saved_chunk].second;
+        c->scratch_chunk = chunk;
+        if (chunk >= 0 && chunk < (int)c->scratch_chunks.size()) {
+            c->scratch = c->scratch_chunks[chunk].first;
+            c->scratch_bytes = c->scratch_chunks[chunk].second;
         }
     }
 };

@@ -98,11 +98,15 @@ struct TcParams {
     long long rows_pad;        // n_mtiles * 128
 };
 
-__device__ __forceinline__ void half2_top2(uint32_t raw, __half2& M1, __half2& M2) {
-    __half2 v = *reinterpret_cast<__half2*>(&raw);
-    __half2 lo = __hmin2(M1, v);
-    M1 = __hmax2(M1, v);
-    M2 = __hmax2(M2, lo);
+// Epilogue primitive. Exact running top-2 costs 3 half2 min/max per register and made the
+// epilogue (ALU pipe) the bottleneck at 75 % tensor utilisation. Instead each thread keeps the
+// plain maximum of two DISJOINT column subsets (even / odd registers); with the two half2 lanes
+// and the two column-half warps that is 8 disjoint subsets per (row, keyframe).  Their largest
+// value is the exact best; their second largest is a LOWER bound of the second-best accumulator,
+// i.e. an UPPER bound d2_bound >= d2 of the second-best distance.  The ratio test can only pass
+// if 5*d1 < 4*d2_bound; those rare rows are then re-evaluated exactly (k_tc_ratio_recover).
+__device__ __forceinline__ void half2_max(uint32_t raw, __half2& M) {
+    M = __hmax2(M, *reinterpret_cast<__half2*>(&raw));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
@@ -233,27 +237,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
                         tc::tmem_wait_ld();
                         if (c_lo + 64 <= nv) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) half2_top2(r0[j], M1[m], M2[m]);
+                            for (int j = 0; j < 32; ++j) half2_max(r0[j], (j & 1) ? M2[m] : M1[m]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 int c = c_lo + 2 * j;
                                 uint32_t v = r0[j];
                                 if (c + 1 >= nv) v = (c >= nv) ? NEG_INF2 : ((v & 0xFFFFu) | 0xFC000000u);
-                                half2_top2(v, M1[m], M2[m]);
+                                half2_max(v, (j & 1) ? M2[m] : M1[m]);
                             }
                         }
                         if (second) {
                             if (c_lo + 128 <= nv) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) half2_top2(r1[j], M1[m], M2[m]);
+                                for (int j = 0; j < 32; ++j) half2_max(r1[j], (j & 1) ? M2[m] : M1[m]);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
                                     int c = c_lo + 64 + 2 * j;
                                     uint32_t v = r1[j];
                                     if (c + 1 >= nv) v = (c >= nv) ? NEG_INF2 : ((v & 0xFFFFu) | 0xFC000000u);
-                                    half2_top2(v, M1[m], M2[m]);
+                                    half2_max(v, (j & 1) ? M2[m] : M1[m]);
                                 }
                             }
                         }
@@ -268,8 +272,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
                     for (int m = 0; m < MA; ++m) {
                         if (m >= ma) break;
                         float2 a = __half22float2(M1[m]), b = __half22float2(M2[m]);
-                        float f1 = fmaxf(a.x, a.y);
-                        float f2 = fmaxf(fminf(a.x, a.y), a.x >= a.y ? b.x : b.y);
+                        // top-2 of the four subset maxima {a.x, a.y, b.x, b.y}
+                        float h1 = fmaxf(a.x, a.y), l1 = fminf(a.x, a.y);
+                        float h2 = fmaxf(b.x, b.y), l2 = fminf(b.x, b.y);
+                        float f1 = fmaxf(h1, h2);
+                        float f2 = fmaxf(fminf(h1, h2), h1 >= h2 ? l1 : l2);
                         if (half == 1) {
                             __half2 pk = __floats2half2_rn(f1, f2);
                             xchg[quad * 32 + lane] = *reinterpret_cast<uint32_t*>(&pk);
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
                             uint32_t d1 = (uint32_t)((256.f - g1) * 0.5f);
                             uint32_t d2 = g2 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g2) * 0.5f);
                             if (g1 < -300.f) d1 = 0xFFFFu;
-                            p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);
+                            p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);   // (exact d1, upper bound of d2)
                         }
                         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
                         M1[m] = neg_inf2();
@@ -299,9 +306,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-// ---- ratio test + exact index recovery --------------------------------------------------------
-// One CTA per (frame, keyframe): Lowe ratio on the value pairs, ordered compaction of the passing
-// query rows, then, per passer, the LOWEST train row whose distance equals d1 (integer re-scan).
+// ---- candidate filter + exact verification ----------------------------------------------------
+// One CTA per (frame, keyframe).  Phase 1: rows whose (exact d1, upper bound of d2) could pass the
+// Lowe ratio become candidates (ordered).  Phase 2: one warp per candidate re-scans the keyframe on
+// the integer pipe: exact best (lowest train row on ties) and exact second-best distance, then the
+// exact ratio test.  Phase 3: ordered compaction of the verified rows -> (queryIdx, trainIdx).
 __global__ void __launch_bounds__(256) k_tc_ratio_recover(const uint32_t* __restrict__ d12, long long rows_pad, int Nq,
                                                           const int* __restrict__ q_n, int n_kf, int num, int den,
                                                           const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
@@ -309,66 +318,81 @@ __global__ void __launch_bounds__(256) k_tc_ratio_recover(const uint32_t* __rest
                                                           int2* out_pairs, int* out_n) {
     __shared__ int s_warp[8];
     __shared__ int s_list[1024];
-    __shared__ unsigned short s_d1[1024];
+    __shared__ int s_idx[1024];      // verified train row, or -1
     const int item = blockIdx.x;
     const int b = item / n_kf, kf = item % n_kf;
     const int nq = q_n ? q_n[b] : Nq;
     const int nt = kf_count[kf];
     const uint32_t* src = d12 + (size_t)kf * rows_pad + (size_t)b * Nq;
     int2* dst = out_pairs + (size_t)item * Nq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int total = 0;
     for (int q0 = 0; q0 < nq; q0 += 1024) {
+        // ---- phase 1: ordered candidate list of up to 1024 rows ----
         int base = 0;
-        // ordered compaction of up to 1024 rows (4 per thread, row-major order)
         for (int sub = 0; sub < 4; ++sub) {
             int q = q0 + sub * 256 + threadIdx.x;
             bool keep = false;
-            uint32_t v = 0;
             if (q < nq && nt >= 2) {
-                v = src[q];
-                uint32_t d1 = v & 0xFFFFu, d2 = v >> 16;
-                keep = d2 != 0xFFFFu && d1 != 0xFFFFu && (uint32_t)den * d1 < (uint32_t)num * d2;
+                uint32_t v = src[q];
+                uint32_t d1 = v & 0xFFFFu, d2b = v >> 16;
+                keep = d1 != 0xFFFFu && (d2b == 0xFFFFu || (uint32_t)den * d1 < (uint32_t)num * d2b);
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             if (lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
             int before = 0, tot = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { int c = s_warp[w]; tot += c; if (w < warp) before += c; }
-            if (keep) {
-                int slot = base + before + __popc(bal & ((1u << lane) - 1u));
-                s_list[slot] = q;
-                s_d1[slot] = (unsigned short)(v & 0xFFFFu);
-            }
+            if (keep) s_list[base + before + __popc(bal & ((1u << lane) - 1u))] = q;
             base += tot;
             __syncthreads();
         }
-        // recovery: one warp per passer
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // ---- phase 2: exact top-2 of each candidate against the keyframe (integer pipe) ----
         const uint4* trows = lib_desc + (size_t)kf_start[kf] * 2;
         for (int i = warp; i < base; i += 8) {
             const int q = s_list[i];
-            const uint32_t d1 = s_d1[i];
             const uint4* qa = q_desc + ((size_t)b * Nq + q) * 2;
             const uint4 a0 = __ldg(qa), a1 = __ldg(qa + 1);
-            int found = -1;
-            for (int j0 = 0; j0 < nt && found < 0; j0 += 32) {
-                int j = j0 + lane;
-                bool hit = false;
-                if (j < nt) {
-                    const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
-                    uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
-                                 __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
-                    hit = d == d1;
-                }
-                unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-                if (m) found = j0 + __ffs(m) - 1;
+            uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;      // keys: dist << 16 | train row
+            for (int j = lane; j < nt; j += 32) {
+                const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
+                uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
+                             __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
+                uint32_t key = (d << 16) | (uint32_t)j;
+                uint32_t mx = max(m1, key);
+                m1 = min(m1, key);
+                m2 = min(m2, mx);
             }
-            if (lane == 0) dst[total + i] = make_int2(q, found);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+                uint32_t lo = min(m1, o1), hi = max(m1, o1);
+                m2 = min(min(m2, o2), hi);
+                m1 = lo;
+            }
+            if (lane == 0) {
+                uint32_t d1 = m1 >> 16, d2 = m2 >> 16;
+                bool pass = m2 != 0xFFFFFFFFu && (uint32_t)den * d1 < (uint32_t)num * d2;
+                s_idx[i] = pass ? (int)(m1 & 0xFFFFu) : -1;
+            }
         }
-        total += base;
         __syncthreads();
+        // ---- phase 3: ordered compaction of the verified candidates ----
+        for (int i0 = 0; i0 < base; i0 += 256) {
+            int i = i0 + threadIdx.x;
+            int ti = i < base ? s_idx[i] : -1;
+            bool keep = ti >= 0;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { int c = s_warp[w]; tot += c; if (w < warp) before += c; }
+            if (keep) dst[total + before + __popc(bal & ((1u << lane) - 1u))] = make_int2(s_list[i], ti);
+            total += tot;
+            __syncthreads();
+        }
     }
     if (threadIdx.x == 0) out_n[item] = total;
 }
@@ -384,14 +408,21 @@ struct TcLibCache {
     LibTile* d_tiles = nullptr;
     int n_tiles = 0;
     std::vector<int> kf_first_tile;   // [n_kf + 1]
+    // work split table cached on the device (keeps the steady-state call free of host->device copies,
+    // so that a whole localisation step can be captured into a CUDA graph)
+    int* d_split = nullptr;
+    int split_groups = -1, split_n = 0;
 };
 
 static void tc_cache_free(TcLibCache* cch) {
     if (!cch) return;
     if (cch->d_img) cudaFree(cch->d_img);
     if (cch->d_tiles) cudaFree(cch->d_tiles);
+    if (cch->d_split) cudaFree(cch->d_split);
     cch->d_img = nullptr;
     cch->d_tiles = nullptr;
+    cch->d_split = nullptr;
+    cch->split_groups = -1;
 }
 
 void nclt_tc_release(nclt_lib* L) {
@@ -469,17 +500,25 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
     // >= ~24 items per SM so that the last (partial) wave of the static round-robin costs a few percent
     int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 24 + n_groups - 1) / n_groups));
-    std::vector<int> split_tile(n_splits + 1);
-    for (int s = 0; s <= n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / n_splits];
+    if (cch->split_groups != n_groups || cch->split_n != n_splits) {
+        std::vector<int> split_tile(n_splits + 1);
+        for (int s = 0; s <= n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / n_splits];
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (cch->d_split) cudaFree(cch->d_split);
+        cch->d_split = nullptr;
+        CU_TRY(c, cudaMalloc(&cch->d_split, (n_splits + 1) * sizeof(int)));
+        CU_TRY(c, cudaMemcpy(cch->d_split, split_tile.data(), (n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        cch->split_groups = n_groups;
+        cch->split_n = n_splits;
+    }
+    int* d_split = cch->d_split;
 
     ScratchScope scope(c);
-    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4) + pad256((n_splits + 1) * 4);
+    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4);
     if ((rc = nclt_scratch_reserve(c, need))) return rc;
     Carver cv(c);
     uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * A_TILE_BYTES);
     uint32_t* d12 = cv.take<uint32_t>((size_t)n_kf * rows_pad);
-    int* d_split = cv.take<int>(n_splits + 1);
-    CU_TRY(c, cudaMemcpyAsync(d_split, split_tile.data(), (n_splits + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     {
         long long threads = rows_pad * 16;
         k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);

@@ -82,7 +82,9 @@ class ShardedLibrary:
         lo, hi, off = self.ranges[self.rank]
         self.row_offset = off
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
-        self.ctx = _lib.Context(self.device.index, torch.cuda.current_stream(self.device).cuda_stream)
+        # one torch stream shared by the C-ABI kernels and the NCCL collective (stream-ordered)
+        self.stream = torch.cuda.Stream(self.device)
+        self.ctx = _lib.Context(self.device.index, self.stream.cuda_stream)
         self.local = LandmarkLibrary(descriptors[lo:hi], None if points3d is None else points3d[lo:hi], ctx=self.ctx)
         self.kf_cum = np.concatenate([[0], np.cumsum(counts)])
 
@@ -92,6 +94,15 @@ class ShardedLibrary:
         from ._lib import lib as _c
         t = self.torch
         B, Nq = desc_dev.shape[0], desc_dev.shape[1]
+        self.stream.wait_stream(t.cuda.current_stream(self.device))      # inputs produced on the caller's stream
+        with t.cuda.stream(self.stream):
+            out = self._flat_top2(desc_dev, B, Nq)
+        t.cuda.current_stream(self.device).wait_stream(self.stream)
+        return out
+
+    def _flat_top2(self, desc_dev, B, Nq):
+        from ._lib import lib as _c
+        t = self.torch
         keys = t.empty((B, Nq, 2), dtype=t.int32, device=self.device)     # u32 payload
         self.ctx.check(_c.nclt_match_flat2_dev(self.ctx.h, self.local.h, desc_dev.data_ptr(), None, B, Nq,
                                                self.row_offset, keys.data_ptr()))

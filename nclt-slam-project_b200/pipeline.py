@@ -66,7 +66,10 @@ class DeviceLocalizer:
         self.torch = torch
         self.device = torch.device('cuda', device)
         torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.current_stream(self.device)
+        # a dedicated torch stream whose handle the C ABI launches on: torch events / copies issued
+        # under `with torch.cuda.stream(self.stream)` are ordered with the kernels.  (Handle 0, the
+        # legacy default stream, would make the context create a private stream instead.)
+        self.stream = torch.cuda.Stream(self.device)
         self.ctx = _lib.Context(device, self.stream.cuda_stream)
         from .library import LandmarkLibrary
         descs, pts3 = library_arrays
@@ -86,8 +89,9 @@ class DeviceLocalizer:
             self._out[B] = o
         return o
 
-    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None):
-        """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors -> dict of CUDA tensors + n_problems."""
+    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True):
+        """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors -> dict of CUDA tensors + n_problems.
+        sync_count=False: fully asynchronous (no host sync; n_problems = -1; check ctx.overflow())."""
         B, Nq = desc_dev.shape[0], desc_dev.shape[1]
         Cn = n_cand if cand_dev is None else cand_dev.shape[1]
         if Cn is None:
@@ -98,7 +102,21 @@ class DeviceLocalizer:
             self.ctx.h, self.library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(), None, B, Nq,
             None if cand_dev is None else cand_dev.data_ptr(), Cn, C.byref(self.params),
             o['best_cand'].data_ptr(), o['n_inliers'].data_ptr(), o['reproj'].data_ptr(), o['rvec'].data_ptr(),
-            o['tvec'].data_ptr(), C.addressof(nprob), None, None, None, None, None, None))
+            o['tvec'].data_ptr(), C.addressof(nprob) if sync_count else None, None, None, None, None, None, None))
         r = dict(o)
-        r['n_problems'] = int(nprob.value)
+        r['n_problems'] = int(nprob.value) if sync_count else -1
         return r
+
+    def capture(self, desc_dev, pts2d_dev):
+        """Capture one fully asynchronous localisation step on (desc_dev, pts2d_dev) into a CUDA graph
+        (launch-bound inner loop: ~30 kernels per step).  Returns the torch.cuda.CUDAGraph; replay with
+        `.replay()` on any stream.  The step must have run once before (buffers allocated)."""
+        t = self.torch
+        self.run(desc_dev, pts2d_dev, sync_count=False)       # make sure every lazy allocation exists
+        t.cuda.synchronize(self.device)
+        g = t.cuda.CUDAGraph()
+        # 'relaxed': the C ABI makes runtime calls that are not stream operations (cudaSetDevice,
+        # cudaFuncSetAttribute, cudaGetLastError) - harmless, but rejected by the default 'global' mode
+        with t.cuda.graph(g, stream=self.stream, capture_error_mode='relaxed'):
+            self.run(desc_dev, pts2d_dev, sync_count=False)
+        return g
