@@ -234,9 +234,15 @@ extern "C" int nclt_localize_batch(nclt_ctx* c, const nclt_lib* L, const uint8_t
     size_t in_bytes = pad256((size_t)B * Nq * 32) + pad256((size_t)B * Nq * 8) + pad256((size_t)B * 4) + pad256(items * 4);
     size_t out_bytes = 2 * pad256((size_t)B * 4) + pad256((size_t)B * 4) + 2 * pad256((size_t)B * 24) +
                        2 * pad256(items * 4) + pad256(items) + pad256(items * 4) + 2 * pad256(items * 24);
-    char* stage = nullptr;
-    cudaError_t e = cudaMalloc(&stage, in_bytes + out_bytes);
-    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc localize staging", e);
+    // staging comes from the context scratch (chunked: the nested device call can still grow it);
+    // no cudaMalloc/cudaFree per call - both synchronise the device
+    ScratchScope scope(c);
+    {
+        int rc0 = nclt_scratch_reserve(c, in_bytes + out_bytes + 8192);
+        if (rc0) return rc0;
+    }
+    Carver cvs(c);
+    char* stage = cvs.take<char>(in_bytes + out_bytes + 4096);
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = stage + off; off += pad256(bytes); return p; };
     uint8_t* d_q = (uint8_t*)take((size_t)B * Nq * 32);
@@ -282,7 +288,6 @@ extern "C" int nclt_localize_batch(nclt_ctx* c, const nclt_lib* L, const uint8_t
     LOC_TRY(cudaStreamSynchronize(s));
 done:
     cudaStreamSynchronize(s);
-    cudaFree(stage);
     return rc;
 #undef LOC_TRY
 }
