@@ -187,6 +187,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line only)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():

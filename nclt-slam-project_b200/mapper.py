@@ -179,3 +179,13 @@ class TeachDepthMapper:
             self.close()
         except Exception:
             pass
+
+
+def integrate_depth_device(mapper, depth_dev, T_dev, fx=320.0, fy=320.0, cx=320.0, cy=240.0):
+    """Device-resident variant for replay workloads: depth_dev f32|u16 [F,H,W] and T_dev f64[F,4,4] are
+    CUDA tensors already in HBM; enqueues on the mapper's context stream and returns."""
+    import torch
+    is_u16 = depth_dev.dtype in (torch.uint16, torch.int16)
+    F, H, W = depth_dev.shape
+    mapper.ctx.check(_c.nclt_occ_integrate_depth_dev(mapper.ctx.h, mapper.h, depth_dev.data_ptr(), int(is_u16), F, H, W,
+                                                     T_dev.data_ptr(), fx, fy, cx, cy, None, None, 0))

@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Teach-map build throughput (BASELINE.json configs[2]): 640x480 depth frames back-projected and
+ray-traced into the 1950x900 @ 0.1 m log-odds grid along a boustrophedon path.
+
+Prints one JSON object: GPU frames/s with the frames resident in HBM, the algorithmic depth bytes/s
+against the measured HBM peak (1 228 800 B + 128 B per frame), rays/s and ordered cell
+updates/s, the host-pointer (end to end) rate, and the CPU oracle port on a bounded sample.
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--frames', type=int, default=2048)
+    ap.add_argument('--distinct', type=int, default=48)
+    ap.add_argument('--batch', type=int, default=512)
+    ap.add_argument('--cpu-frames', type=int, default=200)
+    args = ap.parse_args()
+    import torch
+    import nclt_slam_project_b200  # noqa
+    from nclt_slam_project_b200 import synth, _lib
+    from nclt_slam_project_b200.mapper import TeachDepthMapper, integrate_depth_device, tf_to_matrix
+    from oracle import occupancy as oo
+    cfg = (-110.0, -45.0, 195.0, 90.0, 0.1)
+    poses = synth.boustrophedon_path(args.frames, step_m=0.05)
+    t0 = time.time()
+    distinct = np.stack([synth.make_depth_frame(3000 + i, poses[i], cyl_density=0.05) for i in range(args.distinct)])
+    depth = distinct[np.arange(args.frames) % args.distinct]
+    tfs = [synth.camera_link_transform(*p) for p in poses]
+    T = np.stack([tf_to_matrix(*t) for t in tfs])
+    print(f'generated {args.frames} frames ({args.distinct} distinct) in {time.time()-t0:.1f}s', file=sys.stderr)
+
+    dev = torch.device('cuda', 0)
+    stream = torch.cuda.Stream(dev)
+    ctx = _lib.Context(0, stream.cuda_stream)
+    m = TeachDepthMapper('/tmp/bench_map', *cfg, ctx=ctx)
+    d_depth = torch.from_numpy(depth).to(dev)
+    d_T = torch.from_numpy(T).to(dev)
+    torch.cuda.synchronize()
+    B = args.batch
+    # warm-up + correctness on the first batch against the sequential oracle
+    n_chk = min(args.cpu_frames, B)
+    integrate_depth_device(m, d_depth[:n_chk], d_T[:n_chk]); ctx.sync()
+    ref = oo.OracleMapperInt(*cfg)
+    rays = 0
+    t0 = time.perf_counter()
+    for f in range(min(args.cpu_frames, B)):
+        ref.cb(oo.depth_to_points(depth[f]), tfs[f])
+    cpu_s = time.perf_counter() - t0
+    n_cpu = min(args.cpu_frames, B)
+    rays = ref.total_points_integrated
+    assert np.array_equal(m.units, ref.grid), 'GPU grid differs from the sequential oracle'
+    integrate_depth_device(m, d_depth[:B], d_T[:B]); ctx.sync()       # warm-up at the timed batch size
+    m.reset(); ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for s in range(0, args.frames, B):
+            integrate_depth_device(m, d_depth[s:s + B], d_T[s:s + B])
+        e1.record(stream)
+    torch.cuda.synchronize()
+    gpu_s = e0.elapsed_time(e1) * 1e-3
+    total_rays = m.total_points_integrated
+    touched = int((m.units != 0).sum())
+    m.reset(); ctx.sync()
+    t0 = time.perf_counter()
+    for s in range(0, args.frames, B):
+        m.integrate_depth(depth[s:s + B], T[s:s + B])
+    e2e_s = time.perf_counter() - t0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    alg_bytes = args.frames * (480 * 640 * 4 + 128)
+    out = {
+        'metric': 'teach-map frames/s (depth back-projection + ordered Bresenham log-odds)',
+        'frames': args.frames, 'grid': '1950x900 @ 0.1 m', 'batch': B,
+        'gpu_frames_per_s': args.frames / gpu_s, 'gpu_ms_per_frame': 1e3 * gpu_s / args.frames,
+        'e2e_frames_per_s': args.frames / e2e_s, 'e2e_h2d_bytes_per_frame': 480 * 640 * 4 + 128,
+        'rays_per_s': total_rays / gpu_s, 'rays_per_frame': total_rays / args.frames,
+        'roofline': {'bound': 'hbm', 'achieved': alg_bytes / gpu_s / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                     'frac': alg_bytes / gpu_s / 1e9 / hbm,
+                     'note': 'algorithmic bytes = full 640x480 f32 frame + pose (SURVEY 8d); the reference-faithful path '
+                             'samples every 4th pixel of every 4th row and is bound by ordered cell updates, not HBM'},
+        'grid_cells_touched': touched,
+        'cpu_baseline': {'value': n_cpu / cpu_s, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+                         'sample': f'{n_cpu} frames, C oracle (oracle/occupancy.c, sequential float-free integer model); '
+                                   'the reference itself is a pure-Python loop measured at ~20 frames/s (BASELINE.md section 2)'},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
