@@ -1,0 +1,77 @@
+"""GPU: BASELINE.json full sizes (400 keyframes x 1000 descriptors, 1000-descriptor frames) through
+size-independent properties - the oracle would take minutes here, so: engine equivalence (tensor ==
+integer, the integer engine being oracle-checked at small sizes), planted-keyframe recovery,
+determinism / idempotence, invariance under keyframe permutation, and a spot check of single
+(frame, keyframe) pairs against the NumPy oracle."""
+import numpy as np
+import pytest
+
+from oracle import hamming as oh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def full():
+    from nclt_slam_project_b200 import synth
+    data = synth.make_library(20261018, n_kf=400, n_desc=1000)
+    desc, pts2d, kstar, _ = synth.make_frame_batch(data, range(9000, 9006), n_desc=1000, n_planted=500)
+    return data, desc, pts2d, kstar
+
+
+def _localize(data, desc, pts2d, engine, order=None, per_item=False):
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import localize_batch
+    lms = data['landmarks'] if order is None else [data['landmarks'][i] for i in order]
+    c = _lib.Context(0)
+    c.set_engine(engine)
+    lib = LandmarkLibrary([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms], ctx=c)
+    out = localize_batch(lib, desc, pts2d, per_item=per_item)
+    lib.close()
+    c.close()
+    return out
+
+
+def test_engines_agree_and_find_planted_keyframe(full):
+    data, desc, pts2d, kstar = full
+    a = _localize(data, desc, pts2d, 'int', per_item=True)
+    b = _localize(data, desc, pts2d, 'tensor', per_item=True)
+    for k in ('best_cand', 'n_inliers', 'item_nmatch', 'item_ok', 'item_ninl'):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a['rvec'], b['rvec']) and np.array_equal(a['tvec'], b['tvec'])
+    assert np.array_equal(b['best_cand'], kstar)                  # exactly the planted keyframe wins
+    nm = b['item_nmatch'].copy()
+    nm[np.arange(len(kstar)), kstar] = 0
+    assert nm.max() < 10                                          # no other keyframe reaches MIN_MATCHES
+    assert (b['n_inliers'] > 200).all()
+
+
+def test_idempotent_and_permutation_invariant(full):
+    data, desc, pts2d, kstar = full
+    a = _localize(data, desc, pts2d, 'tensor')
+    b = _localize(data, desc, pts2d, 'tensor')
+    for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
+        assert np.array_equal(a[k], b[k]), k                      # bitwise reproducible
+    perm = np.random.default_rng(1).permutation(400)
+    c = _localize(data, desc, pts2d, 'tensor', order=perm)
+    assert np.array_equal(perm[c['best_cand']], a['best_cand'])
+    assert np.array_equal(c['n_inliers'], a['n_inliers']) and np.array_equal(c['rvec'], a['rvec'])
+
+
+def test_spot_check_pairs_against_oracle(full):
+    data, desc, pts2d, kstar = full
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    for engine in ('int', 'tensor'):
+        c = _lib.Context(0)
+        c.set_engine(engine)
+        lib = LandmarkLibrary.from_pkl_dict(data, ctx=c)
+        pairs, n = lib.ratio(desc[:2])
+        for b in range(2):
+            for k in (int(kstar[b]), 0, 399, 123):
+                qi, ti, _ = oh.knn2_ratio(desc[b], data['landmarks'][k]['descriptors'])
+                assert n[b, k] == len(qi)
+                assert np.array_equal(pairs[b, k, :len(qi), 0], qi) and np.array_equal(pairs[b, k, :len(qi), 1], ti)
+        lib.close()
+        c.close()
