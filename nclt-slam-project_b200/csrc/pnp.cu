@@ -66,7 +66,7 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
 // Per-problem RANSAC replay state: {cursor, best, max_good, niters}. Hypotheses are evaluated in
 // rounds of `it_cnt` iterations; iterations OpenCV's loop would never reach (it >= niters, which
 // shrinks as soon as a good model appears) are skipped.
-__global__ void __launch_bounds__(64) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
+__global__ void __launch_bounds__(32) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
                                                  int it_lo, int it_cnt, const int* __restrict__ state) {
     int gg = blockIdx.x * blockDim.x + threadIdx.x;
     if (gg >= eff_P(v) * it_cnt) return;
@@ -119,7 +119,7 @@ __device__ __forceinline__ float reproj_err2(const double* R, const double* t, d
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_pnp_score(PnpView v, const double* __restrict__ models, int* counts, int it_lo,
+__global__ void __launch_bounds__(128) k_pnp_score(PnpView v, const double* __restrict__ models, int* counts, int it_lo,
                                                    int it_cnt, const int* __restrict__ state) {
     int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -299,7 +299,7 @@ __global__ void k_pnp_state_init(int P, int iters, int* state) {
     state[4 * p] = 0; state[4 * p + 1] = -1; state[4 * p + 2] = 0; state[4 * p + 3] = iters > 1 ? iters : 1;
 }
 
-__global__ void __launch_bounds__(128) k_pnp_finish(PnpView v, const double* __restrict__ models,
+__global__ void __launch_bounds__(32) k_pnp_finish(PnpView v, const double* __restrict__ models,
                                                     const int* __restrict__ state, PnpOut o) {
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -439,7 +439,7 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     if (score_only) {
         // staged parity (ii): score every caller-supplied hypothesis
         long long threads = (long long)P * v.iters * 32;
-        k_pnp_score<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(v, models, buf.counts, 0, v.iters, nullptr);
+        k_pnp_score<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, 0, v.iters, nullptr);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return NCLT_OK;
@@ -449,20 +449,22 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     k_pnp_sets<<<(P + 63) / 64, 64, 0, c->stream>>>(v, buf.sets);
     k_pnp_state_init<<<(P + 127) / 128, 128, 0, c->stream>>>(P, v.iters, buf.state);
     c->launches += 2;
-    const int ROUND = 32;
+    // rounds of 64 hypotheses: with >= 55 % inliers OpenCV's loop stops before iteration 64, so one round
+    // (one EPnP latency, ~0.6 ms) is all that does work; later rounds exit at once
+    const int ROUND = 64;
     for (int lo = 0; lo < v.iters; lo += ROUND) {
         int cnt = v.iters - lo < ROUND ? v.iters - lo : ROUND;
         int total = P * cnt;
-        k_pnp_hypo<<<(total + 63) / 64, 64, 0, c->stream>>>(v, buf.sets, buf.models, lo, cnt, buf.state);
+        k_pnp_hypo<<<(total + 31) / 32, 32, 0, c->stream>>>(v, buf.sets, buf.models, lo, cnt, buf.state);
         long long threads = (long long)total * 32;
-        k_pnp_score<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
+        k_pnp_score<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
         k_pnp_replay<<<(P + 127) / 128, 128, 0, c->stream>>>(v, buf.counts, buf.state, lo + cnt);
         c->launches += 3;
     }
     {
         PnpOut o{ok, rvec, tvec, n_inl, mask, mean_err, best_iter, niters};
         long long threads = (long long)P * 32;
-        k_pnp_finish<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.state, o);
+        k_pnp_finish<<<(unsigned)((threads + 31) / 32), 32, 0, c->stream>>>(v, models, buf.state, o);
         c->launches++;
     }
     CU_TRY(c, cudaGetLastError());

@@ -307,94 +307,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
 }
 
 // ---- candidate filter + exact verification ----------------------------------------------------
-// One CTA per (frame, keyframe).  Phase 1: rows whose (exact d1, upper bound of d2) could pass the
-// Lowe ratio become candidates (ordered).  Phase 2: one warp per candidate re-scans the keyframe on
-// the integer pipe: exact best (lowest train row on ties) and exact second-best distance, then the
-// exact ratio test.  Phase 3: ordered compaction of the verified rows -> (queryIdx, trainIdx).
-__global__ void __launch_bounds__(256) k_tc_ratio_recover(const uint32_t* __restrict__ d12, long long rows_pad, int Nq,
-                                                          const int* __restrict__ q_n, int n_kf, int num, int den,
-                                                          const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
-                                                          const int* __restrict__ kf_start, const int* __restrict__ kf_count,
-                                                          int2* out_pairs, int* out_n) {
-    __shared__ int s_warp[8];
-    __shared__ int s_list[1024];
-    __shared__ int s_idx[1024];      // verified train row, or -1
-    const int item = blockIdx.x;
+// Rows whose (exact d1, upper bound of d2) could pass the Lowe ratio are candidates; each is then
+// re-evaluated exactly on the integer pipe.  Three small kernels, no shared memory beyond a few ints,
+// < 10 K registers per CTA (they can co-reside with a k_tc_top2 CTA of the next batch):
+//   k_tc_candidates  one warp per (frame, keyframe): ordered candidate list written into the item's
+//                    slice of out_pairs as (query, -1); a global work list gets one entry per candidate
+//   k_tc_verify      one warp per work-list entry: exact best (lowest train row on ties) and exact
+//                    second-best distance over the keyframe, exact ratio test -> train row or -1
+//   k_tc_compact     one warp per item that had candidates: drops the -1 entries, keeps query order
+struct WorkItem { int item; int slot; };
+
+__global__ void __launch_bounds__(128) k_tc_candidates(const uint32_t* __restrict__ d12, long long rows_pad, int Nq,
+                                                       const int* __restrict__ q_n, int n_kf, int n_items, int num, int den,
+                                                       const int* __restrict__ kf_count, int2* out_pairs, int* out_n,
+                                                       WorkItem* work, int* work_count, int work_cap) {
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= n_items) return;
     const int b = item / n_kf, kf = item % n_kf;
     const int nq = q_n ? q_n[b] : Nq;
     const int nt = kf_count[kf];
     const uint32_t* src = d12 + (size_t)kf * rows_pad + (size_t)b * Nq;
     int2* dst = out_pairs + (size_t)item * Nq;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int total = 0;
-    for (int q0 = 0; q0 < nq; q0 += 1024) {
-        // ---- phase 1: ordered candidate list of up to 1024 rows ----
-        int base = 0;
-        for (int sub = 0; sub < 4; ++sub) {
-            int q = q0 + sub * 256 + threadIdx.x;
-            bool keep = false;
-            if (q < nq && nt >= 2) {
+    int cnt = 0;
+    if (nt >= 2) {
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            bool cand = false;
+            if (q < nq) {
                 uint32_t v = src[q];
                 uint32_t d1 = v & 0xFFFFu, d2b = v >> 16;
-                keep = d1 != 0xFFFFu && (d2b == 0xFFFFu || (uint32_t)den * d1 < (uint32_t)num * d2b);
+                cand = d1 != 0xFFFFu && (d2b == 0xFFFFu || (uint32_t)den * d1 < (uint32_t)num * d2b);
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            if (lane == 0) s_warp[warp] = __popc(bal);
-            __syncthreads();
-            int before = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { int c = s_warp[w]; tot += c; if (w < warp) before += c; }
-            if (keep) s_list[base + before + __popc(bal & ((1u << lane) - 1u))] = q;
-            base += tot;
-            __syncthreads();
-        }
-        // ---- phase 2: exact top-2 of each candidate against the keyframe (integer pipe) ----
-        const uint4* trows = lib_desc + (size_t)kf_start[kf] * 2;
-        for (int i = warp; i < base; i += 8) {
-            const int q = s_list[i];
-            const uint4* qa = q_desc + ((size_t)b * Nq + q) * 2;
-            const uint4 a0 = __ldg(qa), a1 = __ldg(qa + 1);
-            uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;      // keys: dist << 16 | train row
-            for (int j = lane; j < nt; j += 32) {
-                const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
-                uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
-                             __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
-                uint32_t key = (d << 16) | (uint32_t)j;
-                uint32_t mx = max(m1, key);
-                m1 = min(m1, key);
-                m2 = min(m2, mx);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
+            if (m) {
+                const int n = __popc(m);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(work_count, n);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (cand) {
+                    const int r = __popc(m & ((1u << lane) - 1u));
+                    dst[cnt + r] = make_int2(q, -1);
+                    if (base + r < work_cap) work[base + r] = WorkItem{item, cnt + r};
+                }
+                cnt += n;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
-                uint32_t lo = min(m1, o1), hi = max(m1, o1);
-                m2 = min(min(m2, o2), hi);
-                m1 = lo;
-            }
-            if (lane == 0) {
-                uint32_t d1 = m1 >> 16, d2 = m2 >> 16;
-                bool pass = m2 != 0xFFFFFFFFu && (uint32_t)den * d1 < (uint32_t)num * d2;
-                s_idx[i] = pass ? (int)(m1 & 0xFFFFu) : -1;
-            }
-        }
-        __syncthreads();
-        // ---- phase 3: ordered compaction of the verified candidates ----
-        for (int i0 = 0; i0 < base; i0 += 256) {
-            int i = i0 + threadIdx.x;
-            int ti = i < base ? s_idx[i] : -1;
-            bool keep = ti >= 0;
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            if (lane == 0) s_warp[warp] = __popc(bal);
-            __syncthreads();
-            int before = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { int c = s_warp[w]; tot += c; if (w < warp) before += c; }
-            if (keep) dst[total + before + __popc(bal & ((1u << lane) - 1u))] = make_int2(s_list[i], ti);
-            total += tot;
-            __syncthreads();
         }
     }
-    if (threadIdx.x == 0) out_n[item] = total;
+    if (lane == 0) out_n[item] = cnt;      // candidates for now; k_tc_compact turns it into verified pairs
+}
+
+__global__ void __launch_bounds__(128) k_tc_verify(const WorkItem* __restrict__ work, const int* __restrict__ work_count,
+                                                   int work_cap, int Nq, int n_kf, int num, int den,
+                                                   const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
+                                                   const int* __restrict__ kf_start, const int* __restrict__ kf_count,
+                                                   int2* out_pairs) {
+    const int lane = threadIdx.x & 31;
+    const int n_work = min(*work_count, work_cap);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += warps) {
+        const WorkItem wi = work[w];
+        const int b = wi.item / n_kf, kf = wi.item % n_kf;
+        int2* slot = out_pairs + (size_t)wi.item * Nq + wi.slot;
+        const int qq = slot->x;
+        const int nt = kf_count[kf];
+        const uint4* trows = lib_desc + (size_t)kf_start[kf] * 2;
+        const uint4* qa = q_desc + ((size_t)b * Nq + qq) * 2;
+        const uint4 a0 = __ldg(qa), a1 = __ldg(qa + 1);
+        uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;      // keys: dist << 16 | train row
+        for (int j = lane; j < nt; j += 32) {
+            const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
+            uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
+                         __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
+            uint32_t key = (d << 16) | (uint32_t)j;
+            uint32_t mx = max(m1, key);
+            m1 = min(m1, key);
+            m2 = min(m2, mx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+            uint32_t lo = min(m1, o1), hi = max(m1, o1);
+            m2 = min(min(m2, o2), hi);
+            m1 = lo;
+        }
+        const bool pass = m2 != 0xFFFFFFFFu && (uint32_t)den * (m1 >> 16) < (uint32_t)num * (m2 >> 16);
+        if (lane == 0) slot->y = pass ? (int)(m1 & 0xFFFFu) : -1;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_tc_compact(int n_items, int Nq, int2* out_pairs, int* out_n) {
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const int n = out_n[item];
+    if (n == 0) return;
+    int2* dst = out_pairs + (size_t)item * Nq;
+    int kept = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        int2 e = make_int2(0, -1);
+        if (i < n) e = dst[i];
+        const bool keep = e.y >= 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        __syncwarp();
+        if (keep) dst[kept + __popc(m & ((1u << lane) - 1u))] = e;      // kept + rank <= i: never ahead of unread data
+        __syncwarp();
+        kept += __popc(m);
+    }
+    if (lane == 0) out_n[item] = kept;
 }
 
 }  // namespace
@@ -514,11 +535,17 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     int* d_split = cch->d_split;
 
     ScratchScope scope(c);
-    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4);
+    // candidate work list: every (query, keyframe) pair may be a candidate in the worst case
+    const long long all_pairs = rows * (long long)n_kf;
+    const int work_cap = (int)std::min<long long>(all_pairs, 1LL << 28);
+    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4) +
+                  pad256((size_t)work_cap * sizeof(WorkItem)) + 256;
     if ((rc = nclt_scratch_reserve(c, need))) return rc;
     Carver cv(c);
     uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * A_TILE_BYTES);
     uint32_t* d12 = cv.take<uint32_t>((size_t)n_kf * rows_pad);
+    WorkItem* work = cv.take<WorkItem>((size_t)work_cap);
+    int* work_count = cv.take<int>(1);
     {
         long long threads = rows_pad * 16;
         k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
@@ -531,13 +558,42 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     CU_TRY(c, cudaFuncSetAttribute(k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(c->sm_count, n_groups * n_splits);
     nclt_prof_mark(c);
-    k_tc_top2<<<grid, TC_THREADS, smem, c->stream>>>(p);
+    {
+        // Highest launch priority: when two engines alternate (PipelinedLocalizer) this kernel's CTAs must be
+        // placed before the small tail CTAs of the previous batch (each of which would otherwise pin some of
+        // the 224 KB of shared memory a k_tc_top2 CTA needs and delay it).
+        static int prio_hi = 1 << 30;
+        if (prio_hi == (1 << 30)) {
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            prio_hi = greatest;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributePriority;
+        attr[0].val.priority = prio_hi;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CU_TRY(c, cudaLaunchKernelEx(&cfg, k_tc_top2, p));
+    }
     nclt_prof_mark(c);
     c->launches++;
-    k_tc_ratio_recover<<<B * n_kf, 256, 0, c->stream>>>(d12, rows_pad, Nq, q_n, n_kf, num, den,
-                                                        reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start, L->d_count,
-                                                        reinterpret_cast<int2*>(out_pairs), out_n);
-    c->launches++;
+    {
+        const int n_items = B * n_kf;
+        const unsigned blocks = (unsigned)(((long long)n_items * 32 + 127) / 128);
+        CU_TRY(c, cudaMemsetAsync(work_count, 0, 4, c->stream));
+        k_tc_candidates<<<blocks, 128, 0, c->stream>>>(d12, rows_pad, Nq, q_n, n_kf, n_items, num, den, L->d_count,
+                                                      reinterpret_cast<int2*>(out_pairs), out_n, work, work_count, work_cap);
+        k_tc_verify<<<c->sm_count * 16, 128, 0, c->stream>>>(work, work_count, work_cap, Nq, n_kf, num, den,
+                                                            reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start,
+                                                            L->d_count, reinterpret_cast<int2*>(out_pairs));
+        k_tc_compact<<<blocks, 128, 0, c->stream>>>(n_items, Nq, reinterpret_cast<int2*>(out_pairs), out_n);
+        c->launches += 3;
+    }
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
 }

@@ -120,3 +120,30 @@ class DeviceLocalizer:
         with t.cuda.graph(g, stream=self.stream, capture_error_mode='relaxed'):
             self.run(desc_dev, pts2d_dev, sync_count=False)
         return g
+
+
+class PipelinedLocalizer:
+    """Replay engine for BASELINE configs 2/4: two DeviceLocalizers (own CUDA stream and scratch each)
+    take the batches alternately.  The matching kernel of batch i+1 owns the SMs' shared memory, but the
+    tail of batch i (candidate verification, PnP rounds, LM refinement - small-register, no-smem CTAs on
+    the FP64 / integer pipes) co-resides with it, so the tail is hidden behind the next batch's matching.
+    Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
+
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor'):
+        self.engines = [DeviceLocalizer(library_arrays, device, params) for _ in range(2)]
+        for e in self.engines:
+            e.ctx.set_engine(engine)
+        self.k = 0
+
+    def submit(self, desc_dev, pts2d_dev):
+        """Enqueue one batch (fully asynchronous). Returns (engine, result dict of CUDA tensors)."""
+        e = self.engines[self.k & 1]
+        self.k += 1
+        return e, e.run(desc_dev, pts2d_dev, sync_count=False)
+
+    def synchronize(self):
+        for e in self.engines:
+            e.ctx.sync()
+
+    def overflow(self):
+        return sum(e.ctx.overflow() for e in self.engines)
