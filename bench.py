@@ -175,6 +175,7 @@ def main():
     ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
     ap.add_argument('--ref-frames-per-step', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--engines', type=int, default=2, help='alternating engines (streams) in the pipelined mode')
     ap.add_argument('--no-pipeline', action='store_true', help='one engine/stream instead of two alternating ones')
     ap.add_argument('--no-graph', action='store_true', help='direct launches instead of CUDA graph replay')
     args = ap.parse_args()
@@ -261,12 +262,12 @@ def main():
     # stream and scratch take the steps alternately, so the tail of step i (verification, PnP) overlaps
     # the matching kernel of step i+1; the K steps are then bracketed by one pair of events.
     engines = [eng]
-    if not args.no_pipeline:
+    for k in range(1, 1 if args.no_pipeline else max(args.engines, 1)):
         eng2 = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
                                device=local_rank, params=LocalizeParams(mode=0))
         eng2.ctx.set_engine(args.engine)
         for w in range(3):
-            eng2.run(d_desc[1 % n_batches], d_pts[1 % n_batches])
+            eng2.run(d_desc[k % n_batches], d_pts[k % n_batches])
         engines.append(eng2)
     n_eng = len(engines)
     step_graph = [None] * n_eng

@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <vector>
 
@@ -557,6 +558,10 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     const size_t smem = (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
     CU_TRY(c, cudaFuncSetAttribute(k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(c->sm_count, n_groups * n_splits);
+    if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
+        int g = atoi(env);
+        if (g > 0) grid = std::min(grid, g);
+    }
     nclt_prof_mark(c);
     {
         // Highest launch priority: when two engines alternate (PipelinedLocalizer) this kernel's CTAs must be

@@ -215,3 +215,230 @@ extern "C" double nclt_tc_bench(nclt_ctx* c, int N, int iters, int mode, double*
     if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench", e); return -1.0; }
     return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
 }
+
+// =========================================================================================
+// kind::mxf4 (block-scaled fp4, K = 64 per instruction) probe: +-1.0 as e2m1 nibbles (0x2 / 0xA),
+// all scale factors = 1.0 (UE8M0 0x7F, a TMEM region filled with 0x7F7F7F7F so that the SF layout
+// does not matter), f32 accumulators.  Same check: accumulator == 256 - 2 * Hamming.
+// =========================================================================================
+namespace {
+
+__device__ __forceinline__ uint2 expand16_fp4(uint32_t bits16) {
+    // 16 descriptor bits -> 16 e2m1 nibbles = 8 bytes; bit t -> nibble t (low nibble first)
+    uint32_t w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t b = (bits16 >> (8 * i)) & 0xFFu, s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s |= ((b >> t) & 1u) << (4 * t + 3);
+        w[i] = 0x22222222u | s;
+    }
+    return make_uint2(w[0], w[1]);
+}
+__device__ __forceinline__ uint32_t image_offset4(int rows, int r, int kb) {   // kb = byte index (2 elements per byte)
+    return (uint32_t)(kb >> 4) * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kb & 15);
+}
+__host__ __device__ constexpr uint32_t idesc_mxf4(int M, int N) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc, uint32_t sfa,
+                                         uint32_t sfb) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32_const(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+        "r"(v)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restrict__ a_bits, const uint32_t* __restrict__ b_bits,
+                                                       int N, uint32_t* out /*[128][N] f32 bits*/) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;              // 128 x 128 B
+    uint8_t* sB = smem + 16384;      // N x 128 B
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 128 * 16; i += 128) {
+        int r = i >> 4, c = i & 15;           // c = 16-bit group -> 8 bytes at byte offset c*8
+        uint32_t w = a_bits[r * 8 + (c >> 1)];
+        *reinterpret_cast<uint2*>(sA + image_offset4(128, r, c * 8)) = expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+    }
+    for (int i = tid; i < N * 16; i += 128) {
+        int r = i >> 4, c = i & 15;
+        uint32_t w = b_bits[r * 8 + (c >> 1)];
+        *reinterpret_cast<uint2*>(sB + image_offset4(N, r, c * 8)) = expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+    }
+    tc::fence_proxy_async();
+    if (tid == 0) { tc::mbar_init(&s_bar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + 480u, 0x7F7F7F7Fu);    // scale factors = 1.0 everywhere
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = idesc_mxf4(128, N);
+        const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+        for (int k = 0; k < 4; ++k) {
+            uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+            uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+            mma_mxf4(tmem, da, db, idesc, k > 0 ? 1u : 0u, tmem + 480u, tmem + 496u);
+        }
+        tc::mma_commit(&s_bar);
+    }
+    tc::mbar_wait(&s_bar, 0);
+    tc::tc_fence_after();
+    const uint32_t row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tc::tmem_wait_ld();
+        for (int j = 0; j < 32; ++j)
+            if (c0 + j < N) out[(size_t)row * N + c0 + j] = r[j];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// MMA-only / MMA + f32 max epilogue rate of the mxf4 path (mode 0 / 1)
+__global__ void __launch_bounds__(320) k_tc_bench_mxf4(int N, int iters, int mode, float* sink, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 16384;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (16384 + N * 128) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x2A2A2A2Au, 0xA2A2A2A2u, 0x22AA22AAu, 0xAA22AA22u);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 8); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp < 4) tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + 480u, 0x7F7F7F7Fu);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    long long t0 = clock64();
+    if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_mxf4(128, N);
+            const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+            for (int it = 0; it < iters; ++it) {
+                int buf = it & 1;
+                if (mode > 0 && it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+                    uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+                    mma_mxf4(tmem + buf * 240, da, db, idesc, k > 0 ? 1u : 0u, tmem + 480u, tmem + 496u);
+                }
+                tc::mma_commit(&s_full[buf]);
+            }
+        }
+    } else if (warp < 8) {
+        const int quad = warp & 3, half = warp >> 2;
+        float m0 = -1e30f, m1 = -1e30f;
+        for (int it = 0; it < iters; ++it) {
+            int buf = it & 1;
+            tc::mbar_wait(&s_full[buf], (it >> 1) & 1);
+            tc::tc_fence_after();
+            if (mode > 0) {
+                const int c_lo = half * (N / 2);
+                for (int c0 = 0; c0 + 32 <= N / 2; c0 += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(tmem + buf * 240 + ((uint32_t)(quad * 32) << 16) + c_lo + c0, r);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        m0 = fmaxf(m0, __uint_as_float(r[j]));
+                        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s_empty[buf]);
+            }
+        }
+        if (m0 + m1 == 12345.f) sink[tid] = 1.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int nclt_tc_probe_mxf4(nclt_ctx* c, const uint8_t* a_desc, const uint8_t* b_desc, int N, uint32_t* out) {
+    if (!c || !a_desc || !b_desc || !out || N < 16 || N > 240 || (N % 16)) return nclt_fail(c, NCLT_ERR_ARG, "tc_probe_mxf4 args");
+    cudaSetDevice(c->device);
+    ScratchScope scope(c);
+    int rc;
+    size_t out_elems = (size_t)128 * N;
+    if ((rc = nclt_scratch_reserve(c, pad256(128 * 32) + pad256((size_t)N * 32) + pad256(out_elems * 4)))) return rc;
+    Carver cv(c);
+    uint32_t* da = cv.take<uint32_t>(128 * 8);
+    uint32_t* db = cv.take<uint32_t>((size_t)N * 8);
+    uint32_t* dout = cv.take<uint32_t>(out_elems);
+    CU_TRY(c, cudaMemcpyAsync(da, a_desc, 128 * 32, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(db, b_desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
+    size_t smem = 16384 + (size_t)N * 128;
+    CU_TRY(c, cudaFuncSetAttribute(k_tc_probe_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_probe_mxf4<<<1, 128, smem, c->stream>>>(da, db, N, dout);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, double* cycles_per_tile) {
+    if (!c || N < 16 || N > 240 || (N % 16) || iters < 4) return -1.0;
+    cudaSetDevice(c->device);
+    float* sink = nullptr;
+    long long* cyc = nullptr;
+    int blocks = c->sm_count;
+    if (cudaMalloc(&sink, 320 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
+    size_t smem = 16384 + (size_t)N * 128;
+    cudaFuncSetAttribute(k_tc_bench_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_tc_bench_mxf4<<<blocks, 320, smem, c->stream>>>(N, 8, mode, sink, cyc);
+    cudaEventRecord(e0, c->stream);
+    k_tc_bench_mxf4<<<blocks, 320, smem, c->stream>>>(N, iters, mode, sink, cyc);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    if (cycles_per_tile) *cycles_per_tile = (double)h / iters;
+    c->launches += 2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mxf4", e); return -1.0; }
+    return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
+}
