@@ -170,7 +170,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
-    ap.add_argument('--engine', default='tensor', choices=['int', 'tensor'],
+    ap.add_argument('--engine', default='tensor', choices=['int', 'tensor', 'tensor4'],
                     help='matching engine: integer pipe (LOP3+POPC) or tcgen05 tensor cores (identical results)')
     ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
     ap.add_argument('--ref-frames-per-step', type=int, default=2)

@@ -147,7 +147,7 @@ class Context:
 
     def set_engine(self, engine):
         """'int' (LOP3+POPC) or 'tensor' (tcgen05) for all-keyframe ratio matching; same results."""
-        code = {'int': 0, 'tensor': 1, 0: 0, 1: 1}[engine]
+        code = {'int': 0, 'tensor': 1, 'tensor8': 1, 'tensor4': 2, 0: 0, 1: 1, 2: 2}[engine]
         self.check(lib.nclt_ctx_set_engine(self.h, code))
 
     def overflow(self, reset=True):

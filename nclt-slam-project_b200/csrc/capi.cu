@@ -112,6 +112,7 @@ extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->d_tc_clk) cudaFree(c->d_tc_clk);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return NCLT_OK;
@@ -138,7 +139,7 @@ extern "C" int nclt_ctx_overflow(nclt_ctx* c, int reset) {
 }
 
 extern "C" int nclt_ctx_set_engine(nclt_ctx* c, int engine) {
-    if (!c || (engine != 0 && engine != 1)) return nclt_fail(c, NCLT_ERR_ARG, "engine must be 0 (integer pipe) or 1 (tensor cores)");
+    if (!c || engine < 0 || engine > 2) return nclt_fail(c, NCLT_ERR_ARG, "engine must be 0 (integer pipe), 1 (tensor cores, fp8) or 2 (tensor cores, block-scaled fp4)");
     c->engine = engine;
     return NCLT_OK;
 }
@@ -342,8 +343,8 @@ extern "C" int nclt_match_ratio_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if (num <= 0 || den <= 0 || !out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio args");
     if (B == 0) return NCLT_OK;
     // every frame against every keyframe: the tensor-core path (tc_hamming.cu), same outputs
-    if (c->engine == 1 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30))
-        return tc_match_ratio_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, num, den, out_pairs, out_n);
+    if (c->engine >= 1 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30))
+        return tc_match_ratio_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, num, den, out_pairs, out_n, c->engine == 2);
     ScratchScope scope(c);
     size_t items = (size_t)B * C;
     if ((rc = nclt_scratch_reserve(c, pad256(items * Nq * sizeof(uint2))))) return rc;

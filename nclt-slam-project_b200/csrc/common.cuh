@@ -33,12 +33,13 @@ struct nclt_ctx {
     unsigned long long launches = 0;
     // optional timing of the dominant kernel (bench.py roofline): event pairs around every
     // Hamming top-2 launch, summed by nclt_ctx_profile_read
-    int engine = 0;             // 0 = integer pipe (LOP3+POPC), 1 = tensor cores for all-keyframe ratio matching
+    int engine = 0;             // 0 = integer pipe (LOP3+POPC), 1 / 2 = tensor cores (fp8 / block-scaled fp4) for all-keyframe ratio matching
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     // async pipeline: PnP problems dropped because a batch produced more than its problem capacity
     int* d_overflow = nullptr;
+    unsigned long long* d_tc_clk = nullptr;   // tensor-kernel clock diagnostics (profile mode)
 };
 
 struct nclt_lib {
@@ -54,6 +55,7 @@ struct nclt_lib {
     std::vector<int> h_start, h_count;
     int max_count = 0;
     void* tc_cache = nullptr;   // tensor-core operand images + tile table (tc_hamming.cu), built lazily
+    void* tc4_cache = nullptr;  // same for the block-scaled fp4 flavour
 };
 
 // A ragged set of 32-byte descriptors on the device.
@@ -120,7 +122,7 @@ double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
 // ---- tc_hamming.cu ----
 void nclt_tc_release(nclt_lib* L);
 int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
-                       int32_t* out_pairs, int32_t* out_n);
+                       int32_t* out_pairs, int32_t* out_n, bool fp4);
 
 // ---- pnp.cu ----
 struct PnpBuffers {

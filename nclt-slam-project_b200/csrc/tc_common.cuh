@@ -121,6 +121,103 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_pack16(uint32_t taddr, uint32_t* r) {   // 32 columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t* r) {    // 16 columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_pack16(uint32_t taddr, uint32_t* r) {    // 8 columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {   // 16 columns, 32-bit cells
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {    // 8 columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// registers -> TMEM, one constant into 8 / 16 / 32 / 64 consecutive columns of this warp's 32 lanes (no wait)
+#define NCLT_R8 "%1,%1,%1,%1,%1,%1,%1,%1"
+#define NCLT_R16 NCLT_R8 "," NCLT_R8
+#define NCLT_R32 NCLT_R16 "," NCLT_R16
+#define NCLT_R64 NCLT_R32 "," NCLT_R32
+__device__ __forceinline__ void tmem_st8_const(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {" NCLT_R8 "};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_const(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {" NCLT_R16 "};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st32_const(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {" NCLT_R32 "};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st64_const(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {" NCLT_R64 "};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- kind::mxf4 (block-scaled fp4, K = 64 per instruction, f32 accumulators) ------------------------------
+// +-1.0 as e2m1 nibbles (0x2 / 0xA); every scale factor is UE8M0 0x7F = 1.0 (a TMEM region filled with
+// 0x7F7F7F7F, so the scale-factor layout does not matter).
+// 16 descriptor bits -> 16 nibbles = 8 bytes; bit t -> nibble t (low nibble first; A and B agree, which is all a dot product needs)
+__device__ __forceinline__ uint2 expand16_fp4(uint32_t bits16) {
+    uint32_t w[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t b = (bits16 >> (8 * i)) & 0xFFu, s = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s |= ((b >> t) & 1u) << (4 * t + 3);
+        w[i] = 0x22222222u | s;
+    }
+    return make_uint2(w[0], w[1]);
+}
+// byte offset of (row r, byte kb of its 128-byte fp4 row) inside a K-major no-swizzle tile image of `rows` rows
+__host__ __device__ __forceinline__ uint32_t image_offset4(int rows, int r, int kb) {
+    return (uint32_t)(kb >> 4) * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kb & 15);
+}
+// block-scaled instruction descriptor: a/b format E2M1 (1) at bits 7 / 10, N>>3 at 17, scale format UE8M0 at 23,
+// M>>4 at 24, scale-factor ids 0
+__host__ __device__ constexpr uint32_t idesc_mxf4(int M, int N) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc, uint32_t sfa,
+                                         uint32_t sfb) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+// Accumulators are pre-loaded with 1.5 * 2^23 + 0x4000 (f32 bits 0x4B404000): the exact integer sum
+// 256 - 2H then sits in the low mantissa bits, so the LOW 16 bits of the f32 cell are 0x4100 - 2H, a positive
+// normal fp16 bit pattern that is monotone in -H: .pack::16b loads + half2 max work exactly as on fp16 accumulators.
+constexpr uint32_t MX_MAGIC = 0x4B404000u;
+constexpr uint32_t MX_ZERO16 = 0x4100u;      // low 16 bits at H = 0
+
 // byte offset of element (row r, k-byte k) inside a tile image of `rows` rows
 __host__ __device__ __forceinline__ uint32_t image_offset(int rows, int r, int k) {
     return (uint32_t)(k >> 4) * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 15);

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_fp16.h>
 #include <vector>
 
@@ -97,6 +98,7 @@ struct TcParams {
     long long rows_total;      // valid query rows (B * Nq)
     uint32_t* out;             // [n_kf][rows_pad] : d1 | d2 << 16
     long long rows_pad;        // n_mtiles * 128
+    unsigned long long* clk;   // diagnostics: [0] max SM cycles, [1] max globaltimer ns of a CTA (nclt_ctx_tc_clock)
 };
 
 // Epilogue primitive. Exact running top-2 costs 3 half2 min/max per register and made the
@@ -146,6 +148,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
     tc::tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const int n_items = p.n_groups * p.n_splits;
+    const long long clk0 = clock64();
+    unsigned long long ns0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
 
     if (warp == 8) {
         // =========================== producer ===========================
@@ -304,6 +309,305 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (tid == 0 && p.clk) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicMax(p.clk, (unsigned long long)(clock64() - clk0));
+        atomicMax(p.clk + 1, ns1 - ns0);
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ==============================================================================================
+// Block-scaled fp4 flavour (kind::mxf4, K = 64 per instruction): twice the MMA rate of fp8
+// (64 comparisons/clk/SM at N = 240, tools/mxf4_probe.py), +-1.0 as e2m1 nibbles, all scale factors
+// 1.0, f32 accumulators (the only accumulator type of the block-scaled kinds; exact: |sum| <= 256).
+// The epilogue now reads 32-bit cells, so the TMEM read port (64 cells/clk/SM) is the binding limit:
+// plain three-input f32 maxima (FMNMX3) into 4 disjoint column subsets per thread - with the two
+// column-half warps 8 subsets per (row, keyframe), the same (exact d1, upper bound of d2) contract as
+// the fp8 kernel.  Operand images are half the size (128 B per descriptor): 4 resident query tiles
+// (64 KB) + 3 library stages (3 x 30 KB) leave > 60 KB of shared memory per SM to co-resident kernels.
+// TMEM: accumulator buffers at columns 0 and 240, scale factors at 480..511.
+// ==============================================================================================
+constexpr int MA4 = 4;
+constexpr int A4_TILE_BYTES = 128 * 128;        // 16 KB
+constexpr int B4_ROWS = 240;
+constexpr int B4_STAGE_BYTES = B4_ROWS * 128;   // 30 KB
+constexpr int NSTAGE4 = 3;
+constexpr uint32_t SF_COL = 480;
+
+__global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n_rows, uint8_t* img) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, 16-bit group)
+    long long total_rows = ((n_rows + 127) / 128) * 128;
+    if (i >= total_rows * 16) return;
+    long long row = i >> 4;
+    int c = (int)(i & 15);
+    uint2 v = make_uint2(0, 0);
+    if (row < n_rows) {
+        uint32_t w = desc[row * 8 + (c >> 1)];
+        v = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+    }
+    long long tile = row >> 7;
+    int r = (int)(row & 127);
+    *reinterpret_cast<uint2*>(img + tile * A4_TILE_BYTES + tc::image_offset4(128, r, c * 8)) = v;
+}
+
+__global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile* __restrict__ tiles,
+                                  const int* __restrict__ tile_row0, int n_tiles, uint8_t* img) {
+    int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    const LibTile lt = tiles[t];
+    const long long row0 = tile_row0[t];
+    uint8_t* dst = img + (size_t)lt.img_off256 * 256;
+    for (int i = threadIdx.x; i < lt.n * 16; i += blockDim.x) {
+        int r = i >> 4, c = i & 15;
+        uint2 v = make_uint2(0, 0);
+        if (r < lt.n_valid) {
+            uint32_t w = desc[(row0 + r) * 8 + (c >> 1)];
+            v = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+        }
+        *reinterpret_cast<uint2*>(dst + tc::image_offset4(lt.n, r, c * 8)) = v;
+    }
+}
+
+// W accumulator cells of one row -> running maxima of 4 disjoint column subsets
+template <int W>
+__device__ __forceinline__ void max_piece(const uint32_t (&r)[W], float (&M)[4]) {
+#pragma unroll
+    for (int j = 0; j < W; j += 2) M[(j >> 1) & 3] = tc::fmax3(M[(j >> 1) & 3], __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+}
+// Padding columns [valid, cnt) of a keyframe's last tile are overwritten with -inf IN TMEM before the loads, so
+// that the epilogue has a single (unmasked) code path: one copy of the hot loop instead of two per piece.
+__device__ __forceinline__ void premask_padding(uint32_t ta, int valid, int cnt) {
+    int c = valid;
+    while (c < cnt) {
+        if ((c & 7) == 0 && c + 8 <= cnt) {
+            tc::tmem_st8_const(ta + (uint32_t)c, 0xFF800000u);
+            c += 8;
+        } else {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + (uint32_t)c), "r"(0xFF800000u) : "memory");
+            c += 1;
+        }
+    }
+    tc::tmem_wait_st();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                                   // MA4 x 16 KB
+    uint8_t* sB = smem + MA4 * A4_TILE_BYTES;             // NSTAGE4 x 30 KB
+    uint8_t* tail = sB + NSTAGE4 * B4_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;      // [3]
+    uint64_t* b_empty = bars + 5;     // [3]
+    uint64_t* acc_full = bars + 8;    // [2]
+    uint64_t* acc_empty = bars + 10;  // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+    float2* xchg = reinterpret_cast<float2*>(bars + 14);   // [4 quadrants][MA4][32 lanes]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(a_full, 1);
+        tc::mbar_init(a_empty, 1);
+        for (int s = 0; s < NSTAGE4; ++s) {
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], 8);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(s_tmem, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    if (warp < 4) {      // every scale factor = 2^0
+        tc::tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + SF_COL, 0x7F7F7F7Fu);
+        tc::tmem_wait_st();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const int n_items = p.n_groups * p.n_splits;
+    const long long clk0 = clock64();
+    unsigned long long ns0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+
+    if (warp == 8) {
+        // =========================== producer ===========================
+        if (lane == 0) {
+            uint32_t it_cnt = 0, s = 0, ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+                const int split = item / p.n_groups, group = item % p.n_groups;
+                const int m0 = group * MA4;
+                const int ma = min(MA4, p.n_mtiles - m0);
+                tc::mbar_wait(a_empty, (it_cnt & 1) ^ 1);
+                tc::mbar_expect_tx(a_full, (uint32_t)ma * A4_TILE_BYTES);
+                for (int m = 0; m < ma; ++m)
+                    tc::bulk_g2s(sA + m * A4_TILE_BYTES, p.q_img + (size_t)(m0 + m) * A4_TILE_BYTES, A4_TILE_BYTES, a_full);
+                for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
+                    const LibTile lt = p.tiles[t];
+                    tc::mbar_wait(&b_empty[s], ph ^ 1);
+                    const uint32_t bytes = (uint32_t)lt.n * 128u;
+                    tc::mbar_expect_tx(&b_full[s], bytes);
+                    tc::bulk_g2s(sB + s * B4_STAGE_BYTES, p.lib_img + (size_t)lt.img_off256 * 256, bytes, &b_full[s]);
+                    if (++s == NSTAGE4) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t it_cnt = 0, s = 0, ph = 0, st = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+                const int split = item / p.n_groups, group = item % p.n_groups;
+                const int ma = min(MA4, p.n_mtiles - group * MA4);
+                tc::mbar_wait(a_full, it_cnt & 1);
+                for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
+                    const int n = p.tiles[t].n;
+                    tc::mbar_wait(&b_full[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t idesc = tc::idesc_mxf4(128, n);
+                    const uint32_t lboB = (uint32_t)n * 16u;
+                    const uint32_t bbase = tc::smem_u32(sB + s * B4_STAGE_BYTES);
+                    for (int m = 0; m < ma; ++m, ++st) {
+                        const int buf = st & 1;
+                        tc::mbar_wait(&acc_empty[buf], ((st >> 1) & 1) ^ 1);
+                        tc::tc_fence_after();
+                        const uint32_t abase = tc::smem_u32(sA + m * A4_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint64_t da = tc::smem_desc(abase + k * 4096u, 2048u, 128u);
+                            uint64_t db = tc::smem_desc(bbase + k * 2u * lboB, lboB, 128u);
+                            tc::mma_mxf4(tmem + buf * B4_ROWS, da, db, idesc, k > 0 ? 1u : 0u, tmem + SF_COL, tmem + SF_COL + 16u);
+                        }
+                        tc::mma_commit(&acc_full[buf]);
+                    }
+                    tc::mma_commit(&b_empty[s]);
+                    if (++s == NSTAGE4) { s = 0; ph ^= 1; }
+                }
+                tc::mma_commit(a_empty);
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 0-7) ===========================
+        // warp w: TMEM lane quadrant w % 4, column half w / 4 (<= 120 columns = up to 5 loads in flight, one wait)
+        const int quad = warp & 3, part = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        uint32_t st = 0;
+#ifdef NCLT_TC_TIMING
+        long long tt_acc[5] = {0, 0, 0, 0, 0}, tt_last = clock64();
+#define TT(i) { long long now_ = clock64(); tt_acc[i] += now_ - tt_last; tt_last = now_; }
+#else
+#define TT(i)
+#endif
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int split = item / p.n_groups, group = item % p.n_groups;
+            const int m0 = group * MA4;
+            const int ma = min(MA4, p.n_mtiles - m0);
+            float M[MA4][4];
+#pragma unroll
+            for (int m = 0; m < MA4; ++m)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) M[m][k] = -INFINITY;
+            const int t_end = p.split_tile[split + 1];
+            LibTile nxt = p.tiles[p.split_tile[split]];
+            for (int t = p.split_tile[split]; t < t_end; ++t) {
+                const LibTile lt = nxt;
+                nxt = p.tiles[t + 1];                         // prefetch (the table carries one sentinel entry)
+                const int cnt = lt.n >> 1;                    // columns of this warp: multiple of 8, <= 120
+                const int c_lo = part * cnt;
+                const int valid = min(max((int)lt.n_valid - c_lo, 0), cnt);
+                const int o16 = cnt & ~31, o8 = cnt & ~15;
+#pragma unroll
+                for (int m = 0; m < MA4; ++m) {
+                    if (m >= ma) break;
+                    const int buf = st & 1;
+                    TT(0);
+                    tc::mbar_wait(&acc_full[buf], (st >> 1) & 1);
+                    tc::tc_fence_after();
+                    TT(1);
+                    ++st;
+                    uint32_t a[32], b[32], c2[32], d[16], e[8];
+                    if (valid > 0) {
+                        const uint32_t ta = tmem + buf * B4_ROWS + lane_base + (uint32_t)c_lo;
+                        if (valid < cnt) premask_padding(ta, valid, cnt);
+                        if (cnt >= 32) tc::tmem_ld32(ta, a);
+                        if (cnt >= 64) tc::tmem_ld32(ta + 32, b);
+                        if (cnt >= 96) tc::tmem_ld32(ta + 64, c2);
+                        if (cnt & 16) tc::tmem_ld16(ta + o16, d);
+                        if (cnt & 8) tc::tmem_ld8(ta + o8, e);
+                        tc::tmem_wait_ld();
+                    }
+                    TT(2);
+                    // the accumulators are in registers: hand the buffer back BEFORE the maxima, so that the next
+                    // MMA into it overlaps them (the ld -> release -> MMA -> ld chain bounds the tile period)
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                    TT(3);
+                    if (valid > 0) {
+                        if (cnt >= 32) max_piece<32>(a, M[m]);
+                        if (cnt >= 64) max_piece<32>(b, M[m]);
+                        if (cnt >= 96) max_piece<32>(c2, M[m]);
+                        if (cnt & 16) max_piece<16>(d, M[m]);
+                        if (cnt & 8) max_piece<8>(e, M[m]);
+                    }
+                    TT(4);
+                }
+                if (lt.last_of_kf) {
+                    // ---- keyframe finished: top-2 of this warp's 4 subset maxima, merged with the partner warp
+                    float f1[MA4], f2[MA4];
+#pragma unroll
+                    for (int m = 0; m < MA4; ++m) {
+                        const float h1 = fmaxf(M[m][0], M[m][1]), l1 = fminf(M[m][0], M[m][1]);
+                        const float h2 = fmaxf(M[m][2], M[m][3]), l2 = fminf(M[m][2], M[m][3]);
+                        f1[m] = fmaxf(h1, h2);
+                        f2[m] = fmaxf(fminf(h1, h2), h1 >= h2 ? l1 : l2);
+                        if (part == 1) xchg[(quad * MA4 + m) * 32 + lane] = make_float2(f1[m], f2[m]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) M[m][k] = -INFINITY;
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                    if (part == 0) {
+#pragma unroll
+                        for (int m = 0; m < MA4; ++m) {
+                            if (m >= ma) break;
+                            const float2 o = xchg[(quad * MA4 + m) * 32 + lane];
+                            const float g1 = fmaxf(f1[m], o.x);
+                            const float g2 = fmaxf(fminf(f1[m], o.x), fmaxf(f2[m], o.y));
+                            const long long row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                            uint32_t d1 = g1 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g1) * 0.5f);
+                            uint32_t d2 = g2 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g2) * 0.5f);
+                            p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);   // (exact d1, upper bound of d2)
+                        }
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                }
+            }
+        }
+#ifdef NCLT_TC_TIMING
+        // phase cycles of epilogue warps 0 and 4 of CTA 0: [other (loop, finalize), wait-full, loads, release, maxima]
+        if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.clk)
+            for (int i = 0; i < 5; ++i) p.clk[2 + part * 5 + i] = (unsigned long long)tt_acc[i];
+#endif
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0 && p.clk) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicMax(p.clk, (unsigned long long)(clock64() - clk0));
+        atomicMax(p.clk + 1, ns1 - ns0);
+    }
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -448,18 +752,24 @@ static void tc_cache_free(TcLibCache* cch) {
 }
 
 void nclt_tc_release(nclt_lib* L) {
-    if (L && L->tc_cache) {
-        tc_cache_free(static_cast<TcLibCache*>(L->tc_cache));
-        delete static_cast<TcLibCache*>(L->tc_cache);
-        L->tc_cache = nullptr;
+    if (!L) return;
+    for (void** slot : {&L->tc_cache, &L->tc4_cache}) {
+        if (*slot) {
+            tc_cache_free(static_cast<TcLibCache*>(*slot));
+            delete static_cast<TcLibCache*>(*slot);
+            *slot = nullptr;
+        }
     }
 }
 
-static int tc_build_library(nclt_ctx* c, nclt_lib* L) {
-    TcLibCache* cch = static_cast<TcLibCache*>(L->tc_cache);
+// fp4 = false: fp8 images (256 B per descriptor, tiles of <= 256 rows); fp4 = true: e2m1 images (128 B per
+// descriptor, tiles of <= 240 rows, a keyframe's rows spread evenly over its tiles)
+static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
+    void** slot = fp4 ? &L->tc4_cache : &L->tc_cache;
+    TcLibCache* cch = static_cast<TcLibCache*>(*slot);
     if (!cch) {
         cch = new TcLibCache();
-        L->tc_cache = cch;
+        *slot = cch;
     }
     if (cch->built_for_kf == L->n_kf && cch->built_for_desc == L->n_desc) return NCLT_OK;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -475,20 +785,26 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L) {
             LibTile t{(uint32_t)off256, 16, 0, k, 1};
             tiles.push_back(t);
             row0.push_back(start);
-            off256 += 16;
+            off256 += fp4 ? 8 : 16;
             continue;
         }
-        for (int r = 0; r < cnt; r += 256) {
-            int nv = std::min(256, cnt - r);
+        int per = 256;
+        if (fp4) {
+            const int nt = (cnt + B4_ROWS - 1) / B4_ROWS;
+            per = (((cnt + nt - 1) / nt) + 15) & ~15;          // <= 240
+        }
+        for (int r = 0; r < cnt; r += per) {
+            int nv = std::min(per, cnt - r);
             int n = (nv + 15) & ~15;
-            LibTile t{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, k, r + 256 >= cnt ? 1 : 0};
+            LibTile t{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, k, r + per >= cnt ? 1 : 0};
             tiles.push_back(t);
             row0.push_back(start + r);
-            off256 += (size_t)n;     // n * 256 bytes / 256
+            off256 += fp4 ? (size_t)n / 2 : (size_t)n;     // n * (128 | 256) bytes / 256
         }
     }
     cch->kf_first_tile[L->n_kf] = (int)tiles.size();
     cch->n_tiles = (int)tiles.size();
+    tiles.push_back(LibTile{0, 16, 0, -1, 0});     // sentinel: the epilogue prefetches entry t + 1
     if (cch->n_tiles == 0) { cch->built_for_kf = L->n_kf; cch->built_for_desc = L->n_desc; return NCLT_OK; }
     int* d_row0 = nullptr;
     CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
@@ -496,8 +812,12 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L) {
     CU_TRY(c, cudaMalloc(&d_row0, row0.size() * sizeof(int)));
     CU_TRY(c, cudaMemcpyAsync(cch->d_tiles, tiles.data(), tiles.size() * sizeof(LibTile), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(d_row0, row0.data(), row0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    k_expand_library<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
-                                                          cch->n_tiles, cch->d_img);
+    if (fp4)
+        k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
+                                                               cch->n_tiles, cch->d_img);
+    else
+        k_expand_library<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
+                                                              cch->n_tiles, cch->d_img);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -509,16 +829,18 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L) {
 
 // all keyframes, every frame: knn2 + Lowe ratio via tensor cores. Same outputs as the integer path.
 int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
-                       int32_t* out_pairs, int32_t* out_n) {
+                       int32_t* out_pairs, int32_t* out_n, bool fp4) {
     int rc;
-    if ((rc = tc_build_library(c, L))) return rc;
-    TcLibCache* cch = static_cast<TcLibCache*>(L->tc_cache);
+    if ((rc = tc_build_library(c, L, fp4))) return rc;
+    TcLibCache* cch = static_cast<TcLibCache*>(fp4 ? L->tc4_cache : L->tc_cache);
+    const int ma_tiles = fp4 ? MA4 : MA;
+    const size_t a_tile_bytes = fp4 ? A4_TILE_BYTES : A_TILE_BYTES;
     const int n_kf = L->n_kf;
     if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
     const long long rows = (long long)B * Nq;
     const int n_mtiles = (int)((rows + 127) / 128);
     const long long rows_pad = (long long)n_mtiles * 128;
-    const int n_groups = (n_mtiles + MA - 1) / MA;
+    const int n_groups = (n_mtiles + ma_tiles - 1) / ma_tiles;
     // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
     // >= ~24 items per SM so that the last (partial) wave of the static round-robin costs a few percent
     int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 24 + n_groups - 1) / n_groups));
@@ -539,24 +861,33 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     // candidate work list: every (query, keyframe) pair may be a candidate in the worst case
     const long long all_pairs = rows * (long long)n_kf;
     const int work_cap = (int)std::min<long long>(all_pairs, 1LL << 28);
-    size_t need = pad256((size_t)n_mtiles * A_TILE_BYTES) + pad256((size_t)n_kf * rows_pad * 4) +
+    size_t need = pad256((size_t)n_mtiles * a_tile_bytes) + pad256((size_t)n_kf * rows_pad * 4) +
                   pad256((size_t)work_cap * sizeof(WorkItem)) + 256;
     if ((rc = nclt_scratch_reserve(c, need))) return rc;
     Carver cv(c);
-    uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * A_TILE_BYTES);
+    uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * a_tile_bytes);
     uint32_t* d12 = cv.take<uint32_t>((size_t)n_kf * rows_pad);
     WorkItem* work = cv.take<WorkItem>((size_t)work_cap);
     int* work_count = cv.take<int>(1);
     {
         long long threads = rows_pad * 16;
-        k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
+        if (fp4)
+            k_expand_queries4<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
+        else
+            k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
         c->launches++;
     }
     TcParams p;
     p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = n_mtiles; p.n_groups = n_groups;
     p.n_splits = n_splits; p.split_tile = d_split; p.rows_total = rows; p.out = d12; p.rows_pad = rows_pad;
-    const size_t smem = (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
-    CU_TRY(c, cudaFuncSetAttribute(k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!c->d_tc_clk && c->prof) {      // diagnostics only in profile mode (allocation is not capturable)
+        CU_TRY(c, cudaMalloc(&c->d_tc_clk, 128));
+    }
+    p.clk = c->prof ? c->d_tc_clk : nullptr;
+    if (p.clk) CU_TRY(c, cudaMemsetAsync(p.clk, 0, 128, c->stream));
+    const size_t smem = fp4 ? (size_t)MA4 * A4_TILE_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 128 + (size_t)4 * MA4 * 32 * 8
+                            : (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
+    CU_TRY(c, cudaFuncSetAttribute(fp4 ? k_tc4_top2 : k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(c->sm_count, n_groups * n_splits);
     if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
         int g = atoi(env);
@@ -583,7 +914,7 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
         attr[0].val.priority = prio_hi;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CU_TRY(c, cudaLaunchKernelEx(&cfg, k_tc_top2, p));
+        CU_TRY(c, cudaLaunchKernelEx(&cfg, fp4 ? k_tc4_top2 : k_tc_top2, p));
     }
     nclt_prof_mark(c);
     c->launches++;
@@ -600,5 +931,19 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
         c->launches += 3;
     }
     CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}
+
+// SM clock the last profiled k_tc*_top2 launch actually ran at (cycles / wall time of its longest CTA)
+extern "C" int nclt_ctx_tc_clock(nclt_ctx* c, double* mhz, double* kernel_ms, unsigned long long* raw16) {
+    if (!c) return NCLT_ERR_ARG;
+    unsigned long long h[16] = {0};
+    if (c->d_tc_clk) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, cudaMemcpy(h, c->d_tc_clk, 128, cudaMemcpyDeviceToHost));
+    }
+    if (raw16) memcpy(raw16, h, 128);
+    if (mhz) *mhz = h[1] ? (double)h[0] / (double)h[1] * 1e3 : 0.0;
+    if (kernel_ms) *kernel_ms = (double)h[1] * 1e-6;
     return NCLT_OK;
 }

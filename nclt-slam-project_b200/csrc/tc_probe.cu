@@ -217,50 +217,14 @@ extern "C" double nclt_tc_bench(nclt_ctx* c, int N, int iters, int mode, double*
 }
 
 // =========================================================================================
-// kind::mxf4 (block-scaled fp4, K = 64 per instruction) probe: +-1.0 as e2m1 nibbles (0x2 / 0xA),
-// all scale factors = 1.0 (UE8M0 0x7F, a TMEM region filled with 0x7F7F7F7F so that the SF layout
-// does not matter), f32 accumulators.  Same check: accumulator == 256 - 2 * Hamming.
+// kind::mxf4 probe (helpers in tc_common.cuh): one 128 x N x 256 tile, optionally with the accumulators
+// pre-loaded with MX_MAGIC; the caller checks accumulator == 256 - 2 * Hamming (tools/mxf4_probe.py,
+// tests/test_tc_gpu.py).
 // =========================================================================================
 namespace {
 
-__device__ __forceinline__ uint2 expand16_fp4(uint32_t bits16) {
-    // 16 descriptor bits -> 16 e2m1 nibbles = 8 bytes; bit t -> nibble t (low nibble first)
-    uint32_t w[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        uint32_t b = (bits16 >> (8 * i)) & 0xFFu, s = 0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) s |= ((b >> t) & 1u) << (4 * t + 3);
-        w[i] = 0x22222222u | s;
-    }
-    return make_uint2(w[0], w[1]);
-}
-__device__ __forceinline__ uint32_t image_offset4(int rows, int r, int kb) {   // kb = byte index (2 elements per byte)
-    return (uint32_t)(kb >> 4) * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kb & 15);
-}
-__host__ __device__ constexpr uint32_t idesc_mxf4(int M, int N) {
-    return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc, uint32_t sfa,
-                                         uint32_t sfb) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32_const(uint32_t taddr, uint32_t v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
-        "r"(v)
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restrict__ a_bits, const uint32_t* __restrict__ b_bits,
-                                                       int N, uint32_t* out /*[128][N] f32 bits*/) {
+                                                       int N, int magic, uint32_t* out /*[128][N] f32 bits*/) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;              // 128 x 128 B
     uint8_t* sB = smem + 16384;      // N x 128 B
@@ -270,12 +234,12 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     for (int i = tid; i < 128 * 16; i += 128) {
         int r = i >> 4, c = i & 15;           // c = 16-bit group -> 8 bytes at byte offset c*8
         uint32_t w = a_bits[r * 8 + (c >> 1)];
-        *reinterpret_cast<uint2*>(sA + image_offset4(128, r, c * 8)) = expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+        *reinterpret_cast<uint2*>(sA + tc::image_offset4(128, r, c * 8)) = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
     }
     for (int i = tid; i < N * 16; i += 128) {
         int r = i >> 4, c = i & 15;
         uint32_t w = b_bits[r * 8 + (c >> 1)];
-        *reinterpret_cast<uint2*>(sB + image_offset4(N, r, c * 8)) = expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
+        *reinterpret_cast<uint2*>(sB + tc::image_offset4(N, r, c * 8)) = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
     }
     tc::fence_proxy_async();
     if (tid == 0) { tc::mbar_init(&s_bar, 1); tc::mbar_fence_init(); }
@@ -284,17 +248,21 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = s_tmem;
-    tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + 480u, 0x7F7F7F7Fu);    // scale factors = 1.0 everywhere
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    tc::tmem_st32_const(tmem + lane_base + 480u, 0x7F7F7F7Fu);    // scale factors = 1.0 everywhere
+    if (magic)
+        for (int c0 = 0; c0 < N; c0 += 16) tc::tmem_st16_const(tmem + lane_base + (uint32_t)c0, tc::MX_MAGIC);
+    tc::tmem_wait_st();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     if (tid == 0) {
-        const uint32_t idesc = idesc_mxf4(128, N);
+        const uint32_t idesc = tc::idesc_mxf4(128, N);
         const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
         for (int k = 0; k < 4; ++k) {
             uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
             uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
-            mma_mxf4(tmem, da, db, idesc, k > 0 ? 1u : 0u, tmem + 480u, tmem + 496u);
+            tc::mma_mxf4(tmem, da, db, idesc, (k > 0 || magic) ? 1u : 0u, tmem + 480u, tmem + 496u);
         }
         tc::mma_commit(&s_bar);
     }
@@ -303,7 +271,7 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     const uint32_t row = warp * 32 + lane;
     for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t r[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tc::tmem_ld32(tmem + lane_base + (uint32_t)c0, r);
         tc::tmem_wait_ld();
         for (int j = 0; j < 32; ++j)
             if (c0 + j < N) out[(size_t)row * N + c0 + j] = r[j];
@@ -313,8 +281,336 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-// MMA-only / MMA + f32 max epilogue rate of the mxf4 path (mode 0 / 1)
-__global__ void __launch_bounds__(320) k_tc_bench_mxf4(int N, int iters, int mode, float* sink, long long* cycles) {
+// Rates of the mxf4 path on resident tiles (N = 240):
+//   mode 0: MMAs only            mode 1: + f32 loads and fmaxf
+//   mode 2: + the real epilogue: pre-loaded accumulators, packed 16-bit loads, half2 max, re-arm stores
+// NWQ epilogue warps per TMEM lane quadrant (2: 120 columns each, 3: 80 columns each).
+template <int NWQ>
+__global__ void __launch_bounds__(32 * (4 * NWQ + 2)) k_tc_bench_mxf4(int N, int iters, int mode, float* sink, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 16384;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (16384 + N * 128) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x2A2A2A2Au, 0xA2A2A2A2u, 0x22AA22AAu, 0xAA22AA22u);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 4 * NWQ); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp < 4) {
+        const uint32_t lb = (uint32_t)(warp * 32) << 16;
+        tc::tmem_st32_const(tmem + lb + 480u, 0x7F7F7F7Fu);
+        if (mode == 2)
+            for (int c0 = 0; c0 < 480; c0 += 16) tc::tmem_st16_const(tmem + lb + (uint32_t)c0, tc::MX_MAGIC);
+        tc::tmem_wait_st();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    long long t0 = clock64();
+    if (warp == 4 * NWQ + 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_mxf4(128, N);
+            const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+            for (int it = 0; it < iters; ++it) {
+                int buf = it & 1;
+                if (mode > 0 && it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+                    uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+                    tc::mma_mxf4(tmem + buf * 240, da, db, idesc, (k > 0 || mode == 2) ? 1u : 0u, tmem + 480u, tmem + 496u);
+                }
+                tc::mma_commit(&s_full[buf]);
+            }
+        }
+    } else if (warp < 4 * NWQ) {
+        const int quad = warp & 3, part = warp >> 2;
+        const uint32_t lb = (uint32_t)(quad * 32) << 16;
+        float m0 = -1e30f, m1 = -1e30f;
+        __half2 h0 = __float2half2_rn(0.f), h1 = h0;
+        for (int it = 0; it < iters; ++it) {
+            int buf = it & 1;
+            tc::mbar_wait(&s_full[buf], (it >> 1) & 1);
+            tc::tc_fence_after();
+            if (mode == 1) {
+                const int c_lo = part * (N / NWQ);
+                for (int c0 = 0; c0 + 32 <= N / NWQ; c0 += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(tmem + buf * 240 + lb + c_lo + c0, r);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        m0 = fmaxf(m0, __uint_as_float(r[j]));
+                        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                    }
+                }
+            } else if (mode == 2) {
+                if (NWQ == 2) {          // 120 columns: 64 + 32 + 16 + 8
+                    const uint32_t ta = tmem + buf * 240 + lb + part * 120;
+                    uint32_t r0[32], r1[16], r2[8], r3[4];
+                    tc::tmem_ld32_pack16(ta, r0);
+                    tc::tmem_ld16_pack16(ta + 64, r1);
+                    tc::tmem_ld8_pack16(ta + 96, r2);
+                    tc::tmem_ld4_pack16(ta + 112, r3);
+                    tc::tmem_wait_ld();
+                    tc::tmem_st64_const(ta, tc::MX_MAGIC);
+                    tc::tmem_st32_const(ta + 64, tc::MX_MAGIC);
+                    tc::tmem_st16_const(ta + 96, tc::MX_MAGIC);
+                    tc::tmem_st8_const(ta + 112, tc::MX_MAGIC);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r0[j])); }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r1[j])); }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r2[j])); }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r3[j])); }
+                    tc::tmem_wait_st();
+                } else {                 // 80 columns: 64 + 16
+                    const uint32_t ta = tmem + buf * 240 + lb + part * 80;
+                    uint32_t r0[32], r2[8];
+                    tc::tmem_ld32_pack16(ta, r0);
+                    tc::tmem_ld8_pack16(ta + 64, r2);
+                    tc::tmem_wait_ld();
+                    tc::tmem_st64_const(ta, tc::MX_MAGIC);
+                    tc::tmem_st16_const(ta + 64, tc::MX_MAGIC);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r0[j])); }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r2[j])); }
+                    tc::tmem_wait_st();
+                }
+            }
+            else if (mode == 4) {    // packed loads + half2 max only (no re-arm stores)
+                const uint32_t ta = tmem + buf * 240 + lb + part * 120;
+                uint32_t r0[32], r1[16], r2[8], r3[4];
+                tc::tmem_ld32_pack16(ta, r0);
+                tc::tmem_ld16_pack16(ta + 64, r1);
+                tc::tmem_ld8_pack16(ta + 96, r2);
+                tc::tmem_ld4_pack16(ta + 112, r3);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r0[j])); }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r1[j])); }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r2[j])); }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { __half2& h = (j & 1) ? h1 : h0; h = __hmax2(h, *reinterpret_cast<__half2*>(&r3[j])); }
+            } else if (mode == 5) {  // f32 cells, three-input max, all 120 columns, two batches in flight
+                const uint32_t ta = tmem + buf * 240 + lb + part * 120;
+                uint32_t a[32], b[32], c2[32], d[16], e[8];
+                tc::tmem_ld32(ta, a);
+                tc::tmem_ld32(ta + 32, b);
+                tc::tmem_wait_ld();
+                tc::tmem_ld32(ta + 64, c2);
+                tc::tmem_ld16(ta + 96, d);
+                tc::tmem_ld8(ta + 112, e);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    m0 = tc::fmax3(m0, __uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+                    m1 = tc::fmax3(m1, __uint_as_float(b[j]), __uint_as_float(b[j + 1]));
+                }
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) m0 = tc::fmax3(m0, __uint_as_float(c2[j]), __uint_as_float(c2[j + 1]));
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) m1 = tc::fmax3(m1, __uint_as_float(d[j]), __uint_as_float(d[j + 1]));
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) m1 = tc::fmax3(m1, __uint_as_float(e[j]), __uint_as_float(e[j + 1]));
+            }
+            else if (mode == 6) {    // f32 cells, NWQ = 3 (80 columns) or 4 (60 columns)
+                const uint32_t ta = tmem + buf * 240 + lb + part * (240 / NWQ);
+                uint32_t a[32], b[32], d[16], e[8], f[4];
+                tc::tmem_ld32(ta, a);
+                if (NWQ == 3) {
+                    tc::tmem_ld32(ta + 32, b);
+                    tc::tmem_ld16(ta + 64, d);
+                } else {
+                    tc::tmem_ld16(ta + 32, d);
+                    tc::tmem_ld8(ta + 48, e);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]) : "r"(ta + 56) : "memory");
+                }
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) m0 = tc::fmax3(m0, __uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) m1 = tc::fmax3(m1, __uint_as_float(d[j]), __uint_as_float(d[j + 1]));
+                if (NWQ == 3) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) m1 = tc::fmax3(m1, __uint_as_float(b[j]), __uint_as_float(b[j + 1]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) m0 = tc::fmax3(m0, __uint_as_float(e[j]), __uint_as_float(e[j + 1]));
+                    m1 = tc::fmax3(m1, __uint_as_float(f[0]), __uint_as_float(f[1]));
+                    m1 = tc::fmax3(m1, __uint_as_float(f[2]), __uint_as_float(f[3]));
+                }
+            }
+            if (mode > 0) {
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s_empty[buf]);
+            }
+        }
+        float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        if (m0 + m1 + f0.x + f0.y + f1.x + f1.y == 12345.f) sink[tid] = 1.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int nclt_tc_probe_mxf4(nclt_ctx* c, const uint8_t* a_desc, const uint8_t* b_desc, int N, int magic, uint32_t* out) {
+    if (!c || !a_desc || !b_desc || !out || N < 16 || N > 240 || (N % 16)) return nclt_fail(c, NCLT_ERR_ARG, "tc_probe_mxf4 args");
+    cudaSetDevice(c->device);
+    ScratchScope scope(c);
+    int rc;
+    size_t out_elems = (size_t)128 * N;
+    if ((rc = nclt_scratch_reserve(c, pad256(128 * 32) + pad256((size_t)N * 32) + pad256(out_elems * 4)))) return rc;
+    Carver cv(c);
+    uint32_t* da = cv.take<uint32_t>(128 * 8);
+    uint32_t* db = cv.take<uint32_t>((size_t)N * 8);
+    uint32_t* dout = cv.take<uint32_t>(out_elems);
+    CU_TRY(c, cudaMemcpyAsync(da, a_desc, 128 * 32, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(db, b_desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
+    size_t smem = 16384 + (size_t)N * 128;
+    CU_TRY(c, cudaFuncSetAttribute(k_tc_probe_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_probe_mxf4<<<1, 128, smem, c->stream>>>(da, db, N, magic, dout);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return NCLT_OK;
+}
+
+// mode 0/1/2 as above; mode 3 = mode 2 with three epilogue warps per lane quadrant
+extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, double* cycles_per_tile) {
+    if (!c || N < 16 || N > 240 || (N % 16) || iters < 4 || (mode >= 2 && N != 240)) return -1.0;
+    cudaSetDevice(c->device);
+    float* sink = nullptr;
+    long long* cyc = nullptr;
+    int blocks = c->sm_count;
+    if (cudaMalloc(&sink, 512 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
+    size_t smem = 16384 + (size_t)N * 128;
+    cudaFuncSetAttribute(k_tc_bench_mxf4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tc_bench_mxf4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tc_bench_mxf4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto go = [&](int n_it) {
+        if (mode == 3) k_tc_bench_mxf4<3><<<blocks, 448, smem, c->stream>>>(N, n_it, 2, sink, cyc);
+        else if (mode == 6) k_tc_bench_mxf4<3><<<blocks, 448, smem, c->stream>>>(N, n_it, 6, sink, cyc);
+        else if (mode == 7) k_tc_bench_mxf4<4><<<blocks, 576, smem, c->stream>>>(N, n_it, 6, sink, cyc);
+        else k_tc_bench_mxf4<2><<<blocks, 320, smem, c->stream>>>(N, n_it, mode, sink, cyc);
+    };
+    go(8);
+    cudaEventRecord(e0, c->stream);
+    go(iters);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    if (cycles_per_tile) *cycles_per_tile = (double)h / iters;
+    c->launches += 2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mxf4", e); return -1.0; }
+    return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
+}
+
+// ---- TMEM read-port microbenchmark: NW warps loop tcgen05.ld (32 columns each, `batch` loads per wait) --------
+namespace {
+__global__ void k_tmem_bw(int iters, int batch, int with_max, float* sink, long long* cycles) {
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t lb = (uint32_t)((warp & 3) * 32) << 16;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        uint32_t a[32], b[32], c[32], d[32];
+        const uint32_t ta = tmem + lb + (uint32_t)((it * 32 * batch + (warp >> 2) * 128) & 255);
+        tc::tmem_ld32(ta, a);
+        if (batch >= 2) tc::tmem_ld32(ta + 32, b);
+        if (batch >= 3) tc::tmem_ld32(ta + 64, c);
+        if (batch >= 4) tc::tmem_ld32(ta + 96, d);
+        tc::tmem_wait_ld();
+        if (with_max) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                m0 = tc::fmax3(m0, __uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+                if (batch >= 2) m1 = tc::fmax3(m1, __uint_as_float(b[j]), __uint_as_float(b[j + 1]));
+                if (batch >= 3) m2 = tc::fmax3(m2, __uint_as_float(c[j]), __uint_as_float(c[j + 1]));
+                if (batch >= 4) m3 = tc::fmax3(m3, __uint_as_float(d[j]), __uint_as_float(d[j + 1]));
+            }
+        } else {
+            acc ^= a[0] ^ a[31];
+            if (batch >= 2) acc ^= b[0] ^ b[31];
+            if (batch >= 3) acc ^= c[0] ^ c[31];
+            if (batch >= 4) acc ^= d[0] ^ d[31];
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    if (m0 + m1 + m2 + m3 + (float)acc == 12345.f) sink[tid] = 1.f;
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+// bytes per clock per SM that `warps` warps pull out of TMEM with 32-column loads, `batch` loads per wait
+extern "C" double nclt_tmem_bw(nclt_ctx* c, int warps, int batch, int with_max) {
+    if (!c || warps < 1 || warps > 32 || batch < 1 || batch > 4) return -1.0;
+    cudaSetDevice(c->device);
+    float* sink = nullptr;
+    long long* cyc = nullptr;
+    if (cudaMalloc(&sink, 1024 * 4) != cudaSuccess || cudaMalloc(&cyc, c->sm_count * 8) != cudaSuccess) return -1.0;
+    const int iters = 4000;
+    k_tmem_bw<<<c->sm_count, warps * 32, 0, c->stream>>>(64, batch, with_max, sink, cyc);
+    k_tmem_bw<<<c->sm_count, warps * 32, 0, c->stream>>>(iters, batch, with_max, sink, cyc);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(sink);
+    cudaFree(cyc);
+    c->launches += 2;
+    if (e != cudaSuccess || h <= 0) return -1.0;
+    return (double)warps * iters * batch * 32.0 * 128.0 / (double)h;
+}
+
+// ---- mxf4 epilogue design probe: 16 epilogue warps in two sets that take alternate tiles (set s owns accumulator
+// buffer s), accumulators pre-armed with MX_MAGIC, packed 16-bit loads, re-arm stores, three-input u16x2 maxima ----
+namespace {
+template <int variant>
+__global__ void __launch_bounds__(576) k_tc_bench_mx16(int iters, float* sink, long long* cycles) {
+    constexpr int N = 240;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + 16384;
@@ -333,52 +629,73 @@ __global__ void __launch_bounds__(320) k_tc_bench_mxf4(int N, int iters, int mod
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = s_tmem;
-    if (warp < 4) tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + 480u, 0x7F7F7F7Fu);
+    if (warp < 4) {
+        const uint32_t lb = (uint32_t)(warp * 32) << 16;
+        tc::tmem_st32_const(tmem + lb + 480u, 0x7F7F7F7Fu);
+        for (int c0 = 0; c0 < 480; c0 += 16) tc::tmem_st16_const(tmem + lb + (uint32_t)c0, tc::MX_MAGIC);
+        tc::tmem_wait_st();
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     long long t0 = clock64();
-    if (warp == 9) {
+    if (warp == 17) {
         if (lane == 0) {
-            const uint32_t idesc = idesc_mxf4(128, N);
+            const uint32_t idesc = tc::idesc_mxf4(128, N);
             const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
             for (int it = 0; it < iters; ++it) {
                 int buf = it & 1;
-                if (mode > 0 && it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
+                if (it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
                 tc::tc_fence_after();
                 for (int k = 0; k < 4; ++k) {
                     uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
                     uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
-                    mma_mxf4(tmem + buf * 240, da, db, idesc, k > 0 ? 1u : 0u, tmem + 480u, tmem + 496u);
+                    tc::mma_mxf4(tmem + buf * 240, da, db, idesc, 1u, tmem + 480u, tmem + 496u);
                 }
                 tc::mma_commit(&s_full[buf]);
             }
         }
-    } else if (warp < 8) {
-        const int quad = warp & 3, half = warp >> 2;
-        float m0 = -1e30f, m1 = -1e30f;
-        for (int it = 0; it < iters; ++it) {
-            int buf = it & 1;
-            tc::mbar_wait(&s_full[buf], (it >> 1) & 1);
+    } else if (warp < 16) {
+        const int quad = warp & 3, part = (warp >> 2) & 1, set = warp >> 3;
+        const uint32_t ta = tmem + set * 240 + ((uint32_t)(quad * 32) << 16) + part * 120;
+        uint32_t h0 = 0, h1 = 0;
+        for (int it = set; it < iters; it += 2) {
+            tc::mbar_wait(&s_full[set], (it >> 1) & 1);
             tc::tc_fence_after();
-            if (mode > 0) {
-                const int c_lo = half * (N / 2);
-                for (int c0 = 0; c0 + 32 <= N / 2; c0 += 32) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(tmem + buf * 240 + ((uint32_t)(quad * 32) << 16) + c_lo + c0, r);
-                    tc::tmem_wait_ld();
+            uint32_t r0[32], r1[16], r2[8], r3[4];
+            tc::tmem_ld32_pack16(ta, r0);
+            tc::tmem_ld16_pack16(ta + 64, r1);
+            tc::tmem_ld8_pack16(ta + 96, r2);
+            tc::tmem_ld4_pack16(ta + 112, r3);
+            tc::tmem_wait_ld();
+            // STTM takes a block of N consecutive registers: small stores keep the constant block small
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        m0 = fmaxf(m0, __uint_as_float(r[j]));
-                        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
-                    }
-                }
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s_empty[buf]);
+            for (int c0 = 0; c0 < 120; c0 += 8) tc::tmem_st8_const(ta + c0, tc::MX_MAGIC);
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s_empty[set]);
+            if (variant == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) { uint32_t& h = (j & 2) ? h1 : h0; h = __vimax3_u16x2(h, r0[j], r0[j + 1]); }
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) { uint32_t& h = (j & 2) ? h1 : h0; h = __vimax3_u16x2(h, r1[j], r1[j + 1]); }
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) { uint32_t& h = (j & 2) ? h1 : h0; h = __vimax3_u16x2(h, r2[j], r2[j + 1]); }
+                h0 = __vimax3_u16x2(h0, r3[0], r3[1]);
+                h1 = __vimax3_u16x2(h1, r3[2], r3[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { uint32_t& h = (j & 1) ? h1 : h0; h = __vmaxu2(h, r0[j]); }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { uint32_t& h = (j & 1) ? h1 : h0; h = __vmaxu2(h, r1[j]); }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { uint32_t& h = (j & 1) ? h1 : h0; h = __vmaxu2(h, r2[j]); }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { uint32_t& h = (j & 1) ? h1 : h0; h = __vmaxu2(h, r3[j]); }
             }
         }
-        if (m0 + m1 == 12345.f) sink[tid] = 1.f;
+        if (h0 + h1 == 12345u) sink[tid] = 1.f;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -386,47 +703,26 @@ __global__ void __launch_bounds__(320) k_tc_bench_mxf4(int N, int iters, int mod
     if (tid == 0) cycles[blockIdx.x] = t1 - t0;
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
-
 }  // namespace
 
-extern "C" int nclt_tc_probe_mxf4(nclt_ctx* c, const uint8_t* a_desc, const uint8_t* b_desc, int N, uint32_t* out) {
-    if (!c || !a_desc || !b_desc || !out || N < 16 || N > 240 || (N % 16)) return nclt_fail(c, NCLT_ERR_ARG, "tc_probe_mxf4 args");
-    cudaSetDevice(c->device);
-    ScratchScope scope(c);
-    int rc;
-    size_t out_elems = (size_t)128 * N;
-    if ((rc = nclt_scratch_reserve(c, pad256(128 * 32) + pad256((size_t)N * 32) + pad256(out_elems * 4)))) return rc;
-    Carver cv(c);
-    uint32_t* da = cv.take<uint32_t>(128 * 8);
-    uint32_t* db = cv.take<uint32_t>((size_t)N * 8);
-    uint32_t* dout = cv.take<uint32_t>(out_elems);
-    CU_TRY(c, cudaMemcpyAsync(da, a_desc, 128 * 32, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(db, b_desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
-    size_t smem = 16384 + (size_t)N * 128;
-    CU_TRY(c, cudaFuncSetAttribute(k_tc_probe_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tc_probe_mxf4<<<1, 128, smem, c->stream>>>(da, db, N, dout);
-    c->launches++;
-    CU_TRY(c, cudaGetLastError());
-    CU_TRY(c, cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    return NCLT_OK;
-}
-
-extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, double* cycles_per_tile) {
-    if (!c || N < 16 || N > 240 || (N % 16) || iters < 4) return -1.0;
+extern "C" double nclt_tc_bench_mx16(nclt_ctx* c, int iters, int variant, double* cycles_per_tile) {
+    if (!c || iters < 4) return -1.0;
     cudaSetDevice(c->device);
     float* sink = nullptr;
     long long* cyc = nullptr;
     int blocks = c->sm_count;
-    if (cudaMalloc(&sink, 320 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
-    size_t smem = 16384 + (size_t)N * 128;
-    cudaFuncSetAttribute(k_tc_bench_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaMalloc(&sink, 1024 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
+    size_t smem = 16384 + (size_t)240 * 128;
+    cudaFuncSetAttribute(k_tc_bench_mx16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tc_bench_mx16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    k_tc_bench_mxf4<<<blocks, 320, smem, c->stream>>>(N, 8, mode, sink, cyc);
+    if (variant == 0) k_tc_bench_mx16<0><<<blocks, 576, smem, c->stream>>>(8, sink, cyc);
+    else k_tc_bench_mx16<1><<<blocks, 576, smem, c->stream>>>(8, sink, cyc);
     cudaEventRecord(e0, c->stream);
-    k_tc_bench_mxf4<<<blocks, 320, smem, c->stream>>>(N, iters, mode, sink, cyc);
+    if (variant == 0) k_tc_bench_mx16<0><<<blocks, 576, smem, c->stream>>>(iters, sink, cyc);
+    else k_tc_bench_mx16<1><<<blocks, 576, smem, c->stream>>>(iters, sink, cyc);
     cudaEventRecord(e1, c->stream);
     cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0;
@@ -439,6 +735,6 @@ extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, do
     cudaEventDestroy(e1);
     cudaFree(sink);
     cudaFree(cyc);
-    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mxf4", e); return -1.0; }
-    return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mx16", e); return -1.0; }
+    return (double)blocks * iters * 128.0 * 240.0 / (ms * 1e-3);
 }

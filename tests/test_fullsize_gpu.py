@@ -36,10 +36,11 @@ def _localize(data, desc, pts2d, engine, order=None, per_item=False):
 def test_engines_agree_and_find_planted_keyframe(full):
     data, desc, pts2d, kstar = full
     a = _localize(data, desc, pts2d, 'int', per_item=True)
-    b = _localize(data, desc, pts2d, 'tensor', per_item=True)
-    for k in ('best_cand', 'n_inliers', 'item_nmatch', 'item_ok', 'item_ninl'):
-        assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(a['rvec'], b['rvec']) and np.array_equal(a['tvec'], b['tvec'])
+    for eng in ('tensor', 'tensor4'):
+        b = _localize(data, desc, pts2d, eng, per_item=True)
+        for k in ('best_cand', 'n_inliers', 'item_nmatch', 'item_ok', 'item_ninl'):
+            assert np.array_equal(a[k], b[k]), (eng, k)
+        assert np.array_equal(a['rvec'], b['rvec']) and np.array_equal(a['tvec'], b['tvec'])
     assert np.array_equal(b['best_cand'], kstar)                  # exactly the planted keyframe wins
     nm = b['item_nmatch'].copy()
     nm[np.arange(len(kstar)), kstar] = 0
@@ -49,12 +50,12 @@ def test_engines_agree_and_find_planted_keyframe(full):
 
 def test_idempotent_and_permutation_invariant(full):
     data, desc, pts2d, kstar = full
-    a = _localize(data, desc, pts2d, 'tensor')
-    b = _localize(data, desc, pts2d, 'tensor')
+    a = _localize(data, desc, pts2d, 'tensor4')
+    b = _localize(data, desc, pts2d, 'tensor4')
     for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
         assert np.array_equal(a[k], b[k]), k                      # bitwise reproducible
     perm = np.random.default_rng(1).permutation(400)
-    c = _localize(data, desc, pts2d, 'tensor', order=perm)
+    c = _localize(data, desc, pts2d, 'tensor4', order=perm)
     assert np.array_equal(perm[c['best_cand']], a['best_cand'])
     assert np.array_equal(c['n_inliers'], a['n_inliers']) and np.array_equal(c['rvec'], a['rvec'])
 
@@ -63,7 +64,7 @@ def test_spot_check_pairs_against_oracle(full):
     data, desc, pts2d, kstar = full
     from nclt_slam_project_b200 import _lib
     from nclt_slam_project_b200.library import LandmarkLibrary
-    for engine in ('int', 'tensor'):
+    for engine in ('int', 'tensor', 'tensor4'):
         c = _lib.Context(0)
         c.set_engine(engine)
         lib = LandmarkLibrary.from_pkl_dict(data, ctx=c)

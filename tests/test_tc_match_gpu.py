@@ -5,10 +5,10 @@ import pytest
 
 from oracle import hamming as oh
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.parametrize('eng', ['tensor', 'tensor4'])]   # fp8 and block-scaled fp4 flavours
 
 
-def _run(n_kf, n_desc, B, nq, ragged, low, planted, seed=5, q_n=None):
+def _run(eng, n_kf, n_desc, B, nq, ragged, low, planted, seed=5, q_n=None):
     from nclt_slam_project_b200 import synth, _lib
     from nclt_slam_project_b200.library import LandmarkLibrary
     data = synth.make_library(seed, n_kf=n_kf, n_desc=n_desc, ragged=ragged)
@@ -20,7 +20,7 @@ def _run(n_kf, n_desc, B, nq, ragged, low, planted, seed=5, q_n=None):
     if low:
         desc &= 3
     ctx = _lib.Context(0)
-    ctx.set_engine('tensor')
+    ctx.set_engine(eng)
     lib = LandmarkLibrary.from_pkl_dict(data, ctx=ctx)
     pairs, n = lib.ratio(desc, q_n)
     for b in range(B):
@@ -39,30 +39,30 @@ def _run(n_kf, n_desc, B, nq, ragged, low, planted, seed=5, q_n=None):
     return int(n.sum())
 
 
-def test_tc_ratio_small(ctx):
-    assert _run(n_kf=5, n_desc=300, B=2, nq=200, ragged=True, low=False, planted=100) > 50
+def test_tc_ratio_small(ctx, eng):
+    assert _run(eng, n_kf=5, n_desc=300, B=2, nq=200, ragged=True, low=False, planted=100) > 50
 
 
-def test_tc_ratio_full_keyframes(ctx):
+def test_tc_ratio_full_keyframes(ctx, eng):
     # 1000-row keyframes = 3 full 256-row tiles + one 232-row tile; rows span 3 resident query tiles
-    assert _run(n_kf=7, n_desc=1000, B=3, nq=1000, ragged=False, low=False, planted=500) > 1000
+    assert _run(eng, n_kf=7, n_desc=1000, B=3, nq=1000, ragged=False, low=False, planted=500) > 1000
 
 
-def test_tc_ratio_heavy_ties_and_ragged(ctx):
-    _run(n_kf=9, n_desc=600, B=2, nq=333, ragged=True, low=True, planted=0)
+def test_tc_ratio_heavy_ties_and_ragged(ctx, eng):
+    _run(eng, n_kf=9, n_desc=600, B=2, nq=333, ragged=True, low=True, planted=0)
 
 
-def test_tc_ratio_short_frames_and_tiny_keyframes(ctx):
+def test_tc_ratio_short_frames_and_tiny_keyframes(ctx, eng):
     from nclt_slam_project_b200 import _lib
     from nclt_slam_project_b200.library import LandmarkLibrary
     rng = np.random.default_rng(8)
-    kfs = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in (0, 1, 2, 17, 256, 257, 513)]
+    kfs = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in (0, 1, 2, 17, 240, 241, 256, 257, 513)]
     q = rng.integers(0, 256, (3, 150, 32), dtype=np.uint8)
-    q[0, :10] = kfs[4][:10]
-    q[1, 5:9] = kfs[6][100:104]
+    q[0, :10] = kfs[6][:10]
+    q[1, 5:9] = kfs[8][100:104]
     q_n = np.array([150, 77, 1], dtype=np.int32)
     ctx2 = _lib.Context(0)
-    ctx2.set_engine('tensor')
+    ctx2.set_engine(eng)
     lib = LandmarkLibrary(kfs, ctx=ctx2)
     pairs, n = lib.ratio(q, q_n)
     for b in range(3):
@@ -73,19 +73,19 @@ def test_tc_ratio_short_frames_and_tiny_keyframes(ctx):
             qi, ti, _ = oh.knn2_ratio(q[b, :q_n[b]], t)
             assert n[b, k] == len(qi), (b, k)
             assert np.array_equal(pairs[b, k, :len(qi), 0], qi) and np.array_equal(pairs[b, k, :len(qi), 1], ti)
-    assert n[0, 4] >= 10 and n[1, 6] >= 4
+    assert n[0, 6] >= 10 and n[1, 8] >= 4
 
 
-def test_tc_pipeline_equals_integer_pipeline(ctx):
+def test_tc_pipeline_equals_integer_pipeline(ctx, eng):
     from nclt_slam_project_b200 import synth, _lib
     from nclt_slam_project_b200.library import LandmarkLibrary
     from nclt_slam_project_b200.pipeline import localize_batch
     data = synth.make_library(31, n_kf=20, n_desc=700, ragged=True)
     desc, pts2d, kstar, _ = synth.make_frame_batch(data, range(3100, 3108), n_desc=800, n_planted=300)
     outs = []
-    for eng in ('int', 'tensor'):
+    for e in ('int', eng):
         c = _lib.Context(0)
-        c.set_engine(eng)
+        c.set_engine(e)
         lib = LandmarkLibrary.from_pkl_dict(data, ctx=c)
         outs.append(localize_batch(lib, desc, pts2d, per_item=True))
         lib.close()
