@@ -370,11 +370,11 @@ __global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTi
     }
 }
 
-// W accumulator cells of one row -> running maxima of 4 disjoint column subsets
+// W accumulator cells of one row -> running maxima of 8 disjoint column subsets
 template <int W>
-__device__ __forceinline__ void max_piece(const uint32_t (&r)[W], float (&M)[4]) {
+__device__ __forceinline__ void max_piece(const uint32_t (&r)[W], float (&M)[8]) {
 #pragma unroll
-    for (int j = 0; j < W; j += 2) M[(j >> 1) & 3] = tc::fmax3(M[(j >> 1) & 3], __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+    for (int j = 0; j < W; j += 2) M[(j >> 1) & 7] = tc::fmax3(M[(j >> 1) & 7], __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
 }
 // Padding columns [valid, cnt) of a keyframe's last tile are overwritten with -inf IN TMEM before the loads, so
 // that the epilogue has a single (unmasked) code path: one copy of the hot loop instead of two per piece.
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
-            tc::mbar_init(&acc_empty[s], 8);
+            tc::mbar_init(&acc_empty[s], 4);
         }
         tc::mbar_fence_init();
     }
@@ -478,16 +478,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
                     const uint32_t idesc = tc::idesc_mxf4(128, n);
                     const uint32_t lboB = (uint32_t)n * 16u;
                     const uint32_t bbase = tc::smem_u32(sB + s * B4_STAGE_BYTES);
-                    for (int m = 0; m < ma; ++m, ++st) {
+                    // an odd number of query tiles gets one empty step per library tile: steps per tile stay even,
+                    // so epilogue set s always owns accumulator buffer s and sees every phase of its barriers
+                    const int ma_pad = (ma + 1) & ~1;
+                    for (int m = 0; m < ma_pad; ++m, ++st) {
                         const int buf = st & 1;
                         tc::mbar_wait(&acc_empty[buf], ((st >> 1) & 1) ^ 1);
                         tc::tc_fence_after();
-                        const uint32_t abase = tc::smem_u32(sA + m * A4_TILE_BYTES);
+                        if (m < ma) {
+                            const uint32_t abase = tc::smem_u32(sA + m * A4_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint64_t da = tc::smem_desc(abase + k * 4096u, 2048u, 128u);
-                            uint64_t db = tc::smem_desc(bbase + k * 2u * lboB, lboB, 128u);
-                            tc::mma_mxf4(tmem + buf * B4_ROWS, da, db, idesc, k > 0 ? 1u : 0u, tmem + SF_COL, tmem + SF_COL + 16u);
+                            for (int k = 0; k < 4; ++k) {
+                                uint64_t da = tc::smem_desc(abase + k * 4096u, 2048u, 128u);
+                                uint64_t db = tc::smem_desc(bbase + k * 2u * lboB, lboB, 128u);
+                                tc::mma_mxf4(tmem + buf * B4_ROWS, da, db, idesc, k > 0 ? 1u : 0u, tmem + SF_COL, tmem + SF_COL + 16u);
+                            }
                         }
                         tc::mma_commit(&acc_full[buf]);
                     }
@@ -499,10 +504,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
         }
     } else {
         // =========================== epilogue (warps 0-7) ===========================
-        // warp w: TMEM lane quadrant w % 4, column half w / 4 (<= 120 columns = up to 5 loads in flight, one wait)
-        const int quad = warp & 3, part = warp >> 2;
+        // Warps 0-3 take the even steps (query tiles) of every library tile, warps 4-7 the odd ones; warp w reads
+        // TMEM lane quadrant w % 4, ALL columns, in two batches of n/2 columns (<= 120 registers).  The two warps
+        // that share an SM sub-partition are therefore in different phases - one waits on tcgen05.ld while the
+        // other runs its FMNMX3 chain - and each warp has two step periods for its load -> max -> load -> max chain.
+        // A row's 8 subset maxima live in one thread: no cross-warp merge at the end of a keyframe.
+        const int quad = warp & 3, set = warp >> 2;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        uint32_t st = 0;
+        uint32_t st_base = 0;
 #ifdef NCLT_TC_TIMING
         long long tt_acc[5] = {0, 0, 0, 0, 0}, tt_last = clock64();
 #define TT(i) { long long now_ = clock64(); tt_acc[i] += now_ - tt_last; tt_last = now_; }
@@ -513,91 +522,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
             const int split = item / p.n_groups, group = item % p.n_groups;
             const int m0 = group * MA4;
             const int ma = min(MA4, p.n_mtiles - m0);
-            float M[MA4][4];
+            const int ma_pad = (ma + 1) & ~1;
+            float M[MA4 / 2][8];
 #pragma unroll
-            for (int m = 0; m < MA4; ++m)
+            for (int mm = 0; mm < MA4 / 2; ++mm)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) M[m][k] = -INFINITY;
+                for (int k = 0; k < 8; ++k) M[mm][k] = -INFINITY;
             const int t_end = p.split_tile[split + 1];
             LibTile nxt = p.tiles[p.split_tile[split]];
             for (int t = p.split_tile[split]; t < t_end; ++t) {
                 const LibTile lt = nxt;
                 nxt = p.tiles[t + 1];                         // prefetch (the table carries one sentinel entry)
-                const int cnt = lt.n >> 1;                    // columns of this warp: multiple of 8, <= 120
-                const int c_lo = part * cnt;
-                const int valid = min(max((int)lt.n_valid - c_lo, 0), cnt);
+                const int n = lt.n;
+                const int cnt = n >> 1;                       // columns per batch: multiple of 8, <= 120
                 const int o16 = cnt & ~31, o8 = cnt & ~15;
 #pragma unroll
-                for (int m = 0; m < MA4; ++m) {
-                    if (m >= ma) break;
-                    const int buf = st & 1;
+                for (int mm = 0; mm < MA4 / 2; ++mm) {
+                    const int m = set + 2 * mm;
+                    if (m >= ma_pad) break;
+                    const uint32_t st = st_base + (uint32_t)m;
+                    const int buf = st & 1;                   // == set
                     TT(0);
                     tc::mbar_wait(&acc_full[buf], (st >> 1) & 1);
                     tc::tc_fence_after();
                     TT(1);
-                    ++st;
-                    uint32_t a[32], b[32], c2[32], d[16], e[8];
-                    if (valid > 0) {
-                        const uint32_t ta = tmem + buf * B4_ROWS + lane_base + (uint32_t)c_lo;
-                        if (valid < cnt) premask_padding(ta, valid, cnt);
-                        if (cnt >= 32) tc::tmem_ld32(ta, a);
-                        if (cnt >= 64) tc::tmem_ld32(ta + 32, b);
-                        if (cnt >= 96) tc::tmem_ld32(ta + 64, c2);
-                        if (cnt & 16) tc::tmem_ld16(ta + o16, d);
-                        if (cnt & 8) tc::tmem_ld8(ta + o8, e);
-                        tc::tmem_wait_ld();
+                    if (m >= ma) {                            // the empty step of an odd group: just hand it back
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                        break;
                     }
-                    TT(2);
-                    // the accumulators are in registers: hand the buffer back BEFORE the maxima, so that the next
-                    // MMA into it overlaps them (the ld -> release -> MMA -> ld chain bounds the tile period)
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-                    TT(3);
-                    if (valid > 0) {
-                        if (cnt >= 32) max_piece<32>(a, M[m]);
-                        if (cnt >= 64) max_piece<32>(b, M[m]);
-                        if (cnt >= 96) max_piece<32>(c2, M[m]);
-                        if (cnt & 16) max_piece<16>(d, M[m]);
-                        if (cnt & 8) max_piece<8>(e, M[m]);
+                    const uint32_t ta = tmem + buf * B4_ROWS + lane_base;
+                    if ((int)lt.n_valid < n) premask_padding(ta, lt.n_valid, n);
+                    uint32_t a[32], b[32], c2[32], d[16], e[8];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t th = ta + (uint32_t)(half * cnt);
+                        if (cnt >= 32) tc::tmem_ld32(th, a);
+                        if (cnt >= 64) tc::tmem_ld32(th + 32, b);
+                        if (cnt >= 96) tc::tmem_ld32(th + 64, c2);
+                        if (cnt & 16) tc::tmem_ld16(th + o16, d);
+                        if (cnt & 8) tc::tmem_ld8(th + o8, e);
+                        tc::tmem_wait_ld();
+                        if (half == 1) {
+                            // every column is in registers: hand the buffer back before the last maxima
+                            TT(2);
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                            TT(3);
+                        }
+                        if (cnt >= 32) max_piece<32>(a, M[mm]);
+                        if (cnt >= 64) max_piece<32>(b, M[mm]);
+                        if (cnt >= 96) max_piece<32>(c2, M[mm]);
+                        if (cnt & 16) max_piece<16>(d, M[mm]);
+                        if (cnt & 8) max_piece<8>(e, M[mm]);
                     }
                     TT(4);
                 }
+                st_base += (uint32_t)ma_pad;
                 if (lt.last_of_kf) {
-                    // ---- keyframe finished: top-2 of this warp's 4 subset maxima, merged with the partner warp
-                    float f1[MA4], f2[MA4];
+                    // ---- keyframe finished: top-2 of the 8 subset maxima of each row
 #pragma unroll
-                    for (int m = 0; m < MA4; ++m) {
-                        const float h1 = fmaxf(M[m][0], M[m][1]), l1 = fminf(M[m][0], M[m][1]);
-                        const float h2 = fmaxf(M[m][2], M[m][3]), l2 = fminf(M[m][2], M[m][3]);
-                        f1[m] = fmaxf(h1, h2);
-                        f2[m] = fmaxf(fminf(h1, h2), h1 >= h2 ? l1 : l2);
-                        if (part == 1) xchg[(quad * MA4 + m) * 32 + lane] = make_float2(f1[m], f2[m]);
+                    for (int mm = 0; mm < MA4 / 2; ++mm) {
+                        const int m = set + 2 * mm;
+                        float h[4], l[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) M[m][k] = -INFINITY;
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                    if (part == 0) {
-#pragma unroll
-                        for (int m = 0; m < MA4; ++m) {
-                            if (m >= ma) break;
-                            const float2 o = xchg[(quad * MA4 + m) * 32 + lane];
-                            const float g1 = fmaxf(f1[m], o.x);
-                            const float g2 = fmaxf(fminf(f1[m], o.x), fmaxf(f2[m], o.y));
+                        for (int k = 0; k < 4; ++k) {
+                            h[k] = fmaxf(M[mm][2 * k], M[mm][2 * k + 1]);
+                            l[k] = fminf(M[mm][2 * k], M[mm][2 * k + 1]);
+                        }
+                        const float ha = fmaxf(h[0], h[1]), la = fmaxf(fminf(h[0], h[1]), h[0] >= h[1] ? l[0] : l[1]);
+                        const float hb = fmaxf(h[2], h[3]), lb = fmaxf(fminf(h[2], h[3]), h[2] >= h[3] ? l[2] : l[3]);
+                        const float g1 = fmaxf(ha, hb), g2 = fmaxf(fminf(ha, hb), ha >= hb ? la : lb);
+                        if (m < ma) {
                             const long long row = (long long)(m0 + m) * 128 + quad * 32 + lane;
                             uint32_t d1 = g1 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g1) * 0.5f);
                             uint32_t d2 = g2 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g2) * 0.5f);
                             p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);   // (exact d1, upper bound of d2)
                         }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) M[mm][k] = -INFINITY;
                     }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
                 }
             }
         }
 #ifdef NCLT_TC_TIMING
-        // phase cycles of epilogue warps 0 and 4 of CTA 0: [other (loop, finalize), wait-full, loads, release, maxima]
+        // phase cycles of epilogue warps 0 and 4 of CTA 0: [other (loop, finalize), wait-full, loads + first maxima, release, last maxima]
         if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.clk)
-            for (int i = 0; i < 5; ++i) p.clk[2 + part * 5 + i] = (unsigned long long)tt_acc[i];
+            for (int i = 0; i < 5; ++i) p.clk[2 + set * 5 + i] = (unsigned long long)tt_acc[i];
 #endif
     }
     tc::tc_fence_before();
@@ -790,8 +803,15 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
         }
         int per = 256;
         if (fp4) {
-            const int nt = (cnt + B4_ROWS - 1) / B4_ROWS;
-            per = (((cnt + nt - 1) / nt) + 15) & ~15;          // <= 240
+            // greedy full tiles: the accumulator hand-over (MMA -> tcgen05.ld -> release -> MMA) has a large fixed
+            // cost per step, so a few 240-column steps plus one short one beat evenly sized steps
+            per = B4_ROWS;
+            if (const char* env = getenv("NCLT_TC4_BALANCED")) {
+                if (atoi(env)) {
+                    const int nt = (cnt + B4_ROWS - 1) / B4_ROWS;
+                    per = (((cnt + nt - 1) / nt) + 15) & ~15;
+                }
+            }
         }
         for (int r = 0; r < cnt; r += per) {
             int nv = std::min(per, cnt - r);

@@ -12,6 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a B200 (run with -m gpu under gpurun)')
 
 
+def pytest_collection_modifyitems(config, items):
+    # a kernel that deadlocks must fail the test, not hang the GPU box (needs pytest-timeout; no-op without it)
+    if not config.pluginmanager.hasplugin('timeout'):
+        return
+    for item in items:
+        if item.get_closest_marker('gpu') and not item.get_closest_marker('timeout'):
+            item.add_marker(pytest.mark.timeout(300))
+
+
 def _have_gpu():
     try:
         import torch

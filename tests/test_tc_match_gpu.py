@@ -48,6 +48,14 @@ def test_tc_ratio_full_keyframes(ctx, eng):
     assert _run(eng, n_kf=7, n_desc=1000, B=3, nq=1000, ragged=False, low=False, planted=500) > 1000
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('nq', [100, 600, 850])
+def test_tc_ratio_odd_query_tile_groups(ctx, eng, nq):
+    # 1 / 5 / 7 query tiles of 128 rows: groups of 4 resident tiles with an odd remainder, keyframes of 3 library
+    # tiles each (the fp4 kernel's two epilogue warp sets alternate steps; odd groups get one empty step per tile)
+    _run(eng, n_kf=6, n_desc=500, B=1, nq=nq, ragged=False, low=False, planted=nq // 2)
+
+
 def test_tc_ratio_heavy_ties_and_ragged(ctx, eng):
     _run(eng, n_kf=9, n_desc=600, B=2, nq=333, ragged=True, low=True, planted=0)
 
