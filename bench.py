@@ -170,8 +170,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
-    ap.add_argument('--engine', default='tensor', choices=['int', 'tensor', 'tensor4'],
-                    help='matching engine: integer pipe (LOP3+POPC) or tcgen05 tensor cores (identical results)')
+    ap.add_argument('--engine', default='tensor4', choices=['int', 'tensor', 'tensor4'],
+                    help='matching engine: integer pipe (LOP3+POPC), tcgen05 fp8 (tensor) or block-scaled fp4 (tensor4); identical results')
     ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
     ap.add_argument('--ref-frames-per-step', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -341,7 +341,7 @@ def main():
     k_avg_s = (k_ms / max(k_n, 1)) * 1e-3
     cmp_per_s = cmp_per_launch / k_avg_s if k_avg_s > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'traffic_tc.json' if args.engine == 'tensor' else 'traffic_hamming.json')
+    tp = os.path.join(ROOT, 'profiles', {'tensor': 'traffic_tc.json', 'tensor4': 'traffic_tc4.json'}.get(args.engine, 'traffic_hamming.json'))
     if os.path.exists(tp):
         try:
             # ncu --set full capture (profiles/README.md), scaled from its batch to this one
@@ -382,13 +382,29 @@ def main():
         _L.nclt_tc_bench.restype = C.c_double
         _L.nclt_tc_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         cyc = C.c_double()
-        mma_pairs = _L.nclt_tc_bench(eng.ctx.h, 256, 4000, 0, C.byref(cyc))
-        peak = mma_pairs * 512.0 / 1e12
-        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s (fp8, 512 flop per 256-bit comparison)',
-                    'frac': achieved / peak if peak > 0 else None, 'kernel': 'k_tc_top2',
-                    'peak_source': 'MMA-only tcgen05 fp8 probe on this GPU in this run (32 comparisons/clk/SM)',
-                    'peak_measured_peaks_x2': 2.0 * bf16, 'frac_vs_measured_peaks_x2': achieved / (2.0 * bf16),
-                    'peak_measured_peaks_source': src}
+        if args.engine == 'tensor4':
+            # block-scaled fp4: MMA-only probe of tcgen05.mma kind::mxf4 M=128 N=240 (64 comparisons/clk/SM);
+            # nominal fp4 dense = 4 x bf16, kept beside it from MEASURED_PEAKS.json
+            _L.nclt_tc_bench_mxf4.restype = C.c_double
+            _L.nclt_tc_bench_mxf4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+            mma_pairs = _L.nclt_tc_bench_mxf4(eng.ctx.h, 240, 4000, 0, C.byref(cyc))
+            peak = mma_pairs * 512.0 / 1e12
+            roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak,
+                        'unit': 'TFLOP/s (fp4 block-scaled, 512 flop per 256-bit comparison)',
+                        'frac': achieved / peak if peak > 0 else None, 'kernel': 'k_tc4_top2',
+                        'peak_source': 'MMA-only tcgen05 kind::mxf4 probe on this GPU in this run (64 comparisons/clk/SM); '
+                                       'the kernel is bound by the accumulator hand-over (TMEM read-out of every f32 '
+                                       'cell between MMAs), see DESIGN.md',
+                        'peak_measured_peaks_x4': 4.0 * bf16, 'frac_vs_measured_peaks_x4': achieved / (4.0 * bf16),
+                        'peak_measured_peaks_source': src.replace('x 2 (fp8 runs at twice', 'x 4 (fp4 runs at four times')}
+        else:
+            mma_pairs = _L.nclt_tc_bench(eng.ctx.h, 256, 4000, 0, C.byref(cyc))
+            peak = mma_pairs * 512.0 / 1e12
+            roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s (fp8, 512 flop per 256-bit comparison)',
+                        'frac': achieved / peak if peak > 0 else None, 'kernel': 'k_tc_top2',
+                        'peak_source': 'MMA-only tcgen05 fp8 probe on this GPU in this run (32 comparisons/clk/SM)',
+                        'peak_measured_peaks_x2': 2.0 * bf16, 'frac_vs_measured_peaks_x2': achieved / (2.0 * bf16),
+                        'peak_measured_peaks_source': src}
     roofline.update(common)
 
     # ---- CPU baseline (rank 0, bounded sample) ----------------------------------------------

@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker('gpu') and not item.get_closest_marker('timeout'):
-            item.add_marker(pytest.mark.timeout(300))
+            item.add_marker(pytest.mark.timeout(300, method='thread'))   # 'thread': the process may be stuck inside a CUDA call
 
 
 def _have_gpu():
