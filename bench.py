@@ -169,7 +169,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='frames per step per GPU')
+    ap.add_argument('--batch', type=int, default=512, help='frames per step per GPU')
     ap.add_argument('--engine', default='tensor4', choices=['int', 'tensor', 'tensor4'],
                     help='matching engine: integer pipe (LOP3+POPC), tcgen05 fp8 (tensor) or block-scaled fp4 (tensor4); identical results')
     ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
