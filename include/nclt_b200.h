@@ -48,9 +48,10 @@ unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
  * (>= 0; synchronises the stream). A caller that sees > 0 re-runs those batches synchronously. */
 int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
 /* matching engine for the "every frame against every keyframe" ratio mode (cand == NULL):
- * 0 = integer pipe (LOP3+POPC, the default), 1 = tcgen05 tensor cores (fp8 +-1 operands, fp16
- * accumulators in TMEM, exact index recovery); both produce identical results. Candidate-list
- * and crossCheck matching always use the integer pipe. */
+ * 0 = integer pipe (LOP3+POPC, the default), 1 = tcgen05 tensor cores with fp8 +-1 operands and fp16
+ * accumulators in TMEM, 2 = tcgen05 block-scaled fp4 (kind::mxf4) +-1 operands with f32 accumulators
+ * (the fastest); all three produce identical results (exact index recovery on the integer pipe).
+ * Candidate-list and crossCheck matching always use the integer pipe. */
 int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
 /* enable/disable CUDA-event timing of the dominant kernel (the Hamming top-2 launches) on this
  * context; nclt_ctx_profile_read synchronises, returns the summed device time and launch count

@@ -129,7 +129,7 @@ class PipelinedLocalizer:
     the FP64 / integer pipes) co-resides with it, so the tail is hidden behind the next batch's matching.
     Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
 
-    def __init__(self, library_arrays, device=0, params=None, engine='tensor'):
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4'):
         self.engines = [DeviceLocalizer(library_arrays, device, params) for _ in range(2)]
         for e in self.engines:
             e.ctx.set_engine(engine)
