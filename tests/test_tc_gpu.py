@@ -37,3 +37,25 @@ def test_single_tile_matches_popcount(ctx, N):
         lo = (packed & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.int32)
         hi = (packed >> 16).astype(np.uint16).view(np.float16).astype(np.int32)
         assert np.array_equal(lo, want[:, 0::2]) and np.array_equal(hi, want[:, 1::2])
+
+
+@pytest.mark.parametrize('N', [16, 64, 208, 240])
+def test_single_tile_block_scaled_fp4(ctx, N):
+    """kind::mxf4 (+-1.0 as e2m1 nibbles, all scale factors 1.0, f32 accumulators), plain and with the
+    accumulators pre-loaded with 1.5 * 2^23 + 0x4000 (the exact integer then sits in the low mantissa bits)."""
+    from nclt_slam_project_b200._lib import lib
+    lib.nclt_tc_probe_mxf4.restype = C.c_int
+    lib.nclt_tc_probe_mxf4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(1000 + N)
+    a = rng.integers(0, 256, (128, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    b[:8] = a[:8]                                    # Hamming 0
+    b[8:16] = ~a[8:16]                               # Hamming 256
+    want = 256 - 2 * oh.hamming_matrix(a, b).astype(np.int64)
+    for magic in (0, 1):
+        out = np.zeros((128, N), dtype=np.uint32)
+        ctx.check(lib.nclt_tc_probe_mxf4(ctx.h, a.ctypes.data, b.ctypes.data, N, magic, out.ctypes.data))
+        if magic:
+            assert np.array_equal(out.astype(np.int64), 0x4B404000 + want)
+        else:
+            assert np.array_equal(out.view(np.float32).astype(np.int64), want)
