@@ -37,6 +37,25 @@ LIB_SEED = 20261018
 METRIC = 'query frames/s (match+PnP-RANSAC)'
 
 
+# stdout carries exactly one JSON line: everything libraries print to fd 1 (NCCL's version banner, ...) is sent to
+# stderr, the line itself goes to a private duplicate of the original stdout
+_JSON_OUT = None
+
+
+def claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -160,7 +179,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -185,11 +204,11 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
 
+    claim_stdout()
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
 
-    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line only)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -432,7 +451,7 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
