@@ -176,8 +176,11 @@ typedef struct nclt_localize_params {
  * q u8[B,Nq,32], q_pts2d f32[B,Nq,2] keypoint pixel coordinates, q_n/cand as for nclt_match_*.
  * Per frame: out_best_cand i32[B] winning candidate SLOT (-1 = none accepted), out_n_inliers i32[B],
  * out_reproj f32[B], out_rvec/out_tvec f64[B,3] (teach camera in the current camera frame, as
- * solvePnPRansac returns it).  out_n_problems: HOST int, PnP problems solved; passing NULL to the
- * _dev variant selects the fully asynchronous mode (no host synchronisation, see nclt_ctx_overflow).
+ * solvePnPRansac returns it).  out_n_problems: HOST int, PnP problems solved; passing NULL selects the
+ * fully asynchronous mode (no host synchronisation, see nclt_ctx_overflow): the _dev variant just enqueues
+ * its kernels; the host-pointer variant enqueues input copies + kernels + result copies and returns -
+ * its host buffers (page-locked for real overlap) must stay valid, and hold the results, only after
+ * nclt_ctx_sync().  Two contexts used alternately overlap one batch's copies with the other's kernels.
  * Optional per (frame, candidate) outputs (NULL ok): out_item_nmatch i32[B,C] matches after the
  * ratio / crossCheck filter, out_item_ok u8[B,C], out_item_ninl i32[B,C], out_item_err f32[B,C],
  * out_item_rvec/out_item_tvec f64[B,C,3] (valid where nmatch >= min_matches). */

@@ -285,9 +285,13 @@ extern "C" int nclt_localize_batch(nclt_ctx* c, const nclt_lib* L, const uint8_t
     if (d_ier) LOC_TRY(cudaMemcpyAsync(out_item_err, d_ier, items * 4, cudaMemcpyDeviceToHost, s));
     if (d_irv) LOC_TRY(cudaMemcpyAsync(out_item_rvec, d_irv, items * 24, cudaMemcpyDeviceToHost, s));
     if (d_itv) LOC_TRY(cudaMemcpyAsync(out_item_tvec, d_itv, items * 24, cudaMemcpyDeviceToHost, s));
-    LOC_TRY(cudaStreamSynchronize(s));
+    // out_n_problems == NULL: asynchronous - everything is enqueued on the context stream (input copies, the
+    // device pipeline with its problem count kept on the device, result copies); the caller keeps its (pinned)
+    // host buffers alive and calls nclt_ctx_sync() before reading them.  The staging scratch released below is
+    // only re-used by later calls on the same stream, i.e. after this batch.
+    if (out_n_problems) LOC_TRY(cudaStreamSynchronize(s));
 done:
-    cudaStreamSynchronize(s);
+    if (out_n_problems || rc) cudaStreamSynchronize(s);
     return rc;
 #undef LOC_TRY
 }

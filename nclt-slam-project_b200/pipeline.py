@@ -16,10 +16,12 @@ MODE_RATIO = 0       # checkpoint_a_selftest.py:68-71
 MODE_CROSSCHECK = 1  # visual_landmark_matcher.py:327
 
 
-def localize_batch(library, desc, pts2d, q_n=None, cand=None, params=None, per_item=False):
+def localize_batch(library, desc, pts2d, q_n=None, cand=None, params=None, per_item=False, out=None, wait=True):
     """desc u8[B,Nq,32], pts2d f32[B,Nq,2] -> dict(best_cand i32[B] (slot, -1 = none), n_inliers,
     reproj, rvec f64[B,3], tvec f64[B,3], n_problems; with per_item=True also item_nmatch,
-    item_ok, item_ninl, item_err, item_rvec, item_tvec over [B,C])."""
+    item_ok, item_ninl, item_err, item_rvec, item_tvec over [B,C]).
+    wait=False: asynchronous (see StreamingLocalizer) - `out` must then be caller-owned (pinned) result arrays, the
+    inputs must stay alive, and the results are valid after library.ctx.sync(); n_problems is not reported."""
     ctx = library.ctx
     prm = params or LocalizeParams()
     desc = as_c(desc, np.uint8)
@@ -35,9 +37,12 @@ def localize_batch(library, desc, pts2d, q_n=None, cand=None, params=None, per_i
     else:
         cand = as_c(cand, np.int32).reshape(B, -1)
         Cn = cand.shape[1]
-    out = {'best_cand': np.full(B, -1, dtype=np.int32), 'n_inliers': np.zeros(B, dtype=np.int32),
-           'reproj': np.zeros(B, dtype=np.float32), 'rvec': np.zeros((B, 3)), 'tvec': np.zeros((B, 3)),
-           'n_problems': 0}
+    if out is None:
+        if not wait:
+            raise ValueError('wait=False needs caller-owned result arrays (out=...)')
+        out = {'best_cand': np.full(B, -1, dtype=np.int32), 'n_inliers': np.zeros(B, dtype=np.int32),
+               'reproj': np.zeros(B, dtype=np.float32), 'rvec': np.zeros((B, 3)), 'tvec': np.zeros((B, 3))}
+    out['n_problems'] = 0
     item = {}
     if per_item:
         item = {'item_nmatch': np.zeros((B, Cn), dtype=np.int32), 'item_ok': np.zeros((B, Cn), dtype=np.uint8),
@@ -50,7 +55,7 @@ def localize_batch(library, desc, pts2d, q_n=None, cand=None, params=None, per_i
     ctx.check(_c.nclt_localize_batch(
         ctx.h, library.h, ptr(desc), ptr(pts2d), ptr(q_n), B, Nq, ptr(cand), Cn, C.byref(prm),
         ptr(out['best_cand']), ptr(out['n_inliers']), ptr(out['reproj']), ptr(out['rvec']), ptr(out['tvec']),
-        C.addressof(nprob), ptr(item.get('item_nmatch')), ptr(item.get('item_ok')), ptr(item.get('item_ninl')),
+        C.addressof(nprob) if wait else None, ptr(item.get('item_nmatch')), ptr(item.get('item_ok')), ptr(item.get('item_ninl')),
         ptr(item.get('item_err')), ptr(item.get('item_rvec')), ptr(item.get('item_tvec'))))
     out['n_problems'] = int(nprob.value)
     out.update(item)
@@ -147,3 +152,67 @@ class PipelinedLocalizer:
 
     def overflow(self):
         return sum(e.ctx.overflow() for e in self.engines)
+
+
+class StreamingLocalizer:
+    """Host-buffer replay API: batches of host (ideally page-locked) arrays in, per-frame results in page-locked
+    host arrays out, through the host-pointer C ABI in its asynchronous mode.  `depth` contexts (own CUDA stream,
+    scratch and library copy each) are used round-robin, so the input / result copies of one batch overlap the
+    kernels of the previous one.
+
+        sl = StreamingLocalizer((descs, pts3d))
+        tickets = [sl.submit(desc_b, pts_b) for ...]     # returns at once; at most `depth` batches are in flight
+        res = sl.result(ticket)                           # dict of NumPy arrays, valid until `depth` submits later
+    """
+
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', depth=2):
+        import torch
+        from .library import LandmarkLibrary
+        self.torch = torch
+        self.params = params or LocalizeParams()
+        self.slots = []
+        descs, pts3 = library_arrays
+        for _ in range(depth):
+            ctx = _lib.Context(device)
+            ctx.set_engine(engine)
+            self.slots.append({'ctx': ctx, 'lib': LandmarkLibrary(descs, pts3, ctx=ctx), 'out': None, 'keep': None,
+                               'ticket': -1})
+        self.k = 0
+
+    def _pinned(self, shape, dtype):
+        t = self.torch.empty(shape, dtype=dtype).pin_memory()
+        return t.numpy()
+
+    def submit(self, desc, pts2d, q_n=None):
+        t = self.torch
+        slot = self.slots[self.k % len(self.slots)]
+        slot['ctx'].sync()                                # the batch that used this slot `depth` submits ago
+        B = len(desc)
+        if slot['out'] is None or len(slot['out']['best_cand']) != B:
+            slot['out'] = {'best_cand': self._pinned((B,), t.int32), 'n_inliers': self._pinned((B,), t.int32),
+                           'reproj': self._pinned((B,), t.float32), 'rvec': self._pinned((B, 3), t.float64),
+                           'tvec': self._pinned((B, 3), t.float64)}
+        desc, pts2d = as_c(desc, np.uint8), as_c(pts2d, np.float32)
+        q_n = None if q_n is None else as_c(q_n, np.int32)
+        slot['keep'] = (desc, pts2d, q_n)                 # inputs must outlive the asynchronous copies
+        localize_batch(slot['lib'], desc, pts2d, q_n=q_n, params=self.params, out=slot['out'], wait=False)
+        slot['ticket'] = self.k
+        self.k += 1
+        return slot['ticket']
+
+    def result(self, ticket):
+        slot = self.slots[ticket % len(self.slots)]
+        if slot['ticket'] != ticket:
+            raise ValueError(f'ticket {ticket} has been overwritten (only the last {len(self.slots)} batches are kept)')
+        slot['ctx'].sync()
+        return slot['out']
+
+    def overflow(self):
+        return sum(s['ctx'].overflow() for s in self.slots)
+
+    def close(self):
+        for s in self.slots:
+            s['ctx'].sync()
+            s['lib'].close()
+            s['ctx'].close()
+        self.slots = []

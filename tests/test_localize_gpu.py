@@ -73,3 +73,35 @@ def test_two_identical_candidates_first_wins(ctx):
     cand = np.array([[3, 1, 0]], dtype=np.int32)
     n_pub, out = _check(data, lib, f['desc'][None], f['pts2d'][None], cand, 0)
     assert n_pub == 1 and out['best_cand'][0] == 0
+
+
+def test_streaming_localizer_matches_blocking_call(ctx):
+    """Asynchronous host-pointer mode (two contexts alternating) == the blocking call, batch by batch."""
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import localize_batch, StreamingLocalizer
+    data = synth.make_library(77, n_kf=12, n_desc=400, ragged=True)
+    lms = data['landmarks']
+    batches = [synth.make_frame_batch(data, range(7000 + 10 * i, 7000 + 10 * i + 6), n_desc=500, n_planted=200)
+               for i in range(5)]
+    sl = StreamingLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]), depth=2)
+    lib = LandmarkLibrary.from_pkl_dict(data, ctx=ctx)
+    tickets = []
+    got = []
+    for i, (desc, pts2d, kstar, _) in enumerate(batches):
+        tickets.append(sl.submit(desc, pts2d))
+        if i >= 1:
+            r = sl.result(tickets[i - 1])
+            got.append({k: np.array(v) for k, v in r.items() if k != 'n_problems'})
+    r = sl.result(tickets[-1])
+    got.append({k: np.array(v) for k, v in r.items() if k != 'n_problems'})
+    assert sl.overflow() == 0
+    for (desc, pts2d, kstar, _), g in zip(batches, got):
+        want = localize_batch(lib, desc, pts2d)
+        for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
+            assert np.array_equal(g[k], want[k]), k
+        assert np.array_equal(g['best_cand'], kstar)
+    with pytest.raises(ValueError):
+        sl.result(tickets[0])                      # overwritten two submits later
+    sl.close()
+    lib.close()
