@@ -54,6 +54,7 @@ struct FrameIn {
     const float* depth;       // [F][Hd][Wd] or null
     const uint16_t* depth16;  // [F][Hd][Wd] or null
     int Hd, Wd, step;
+    int compact;              // 1: the buffer holds only the sampled rows (v = 0, step, 2*step, ...): [F][ceil(Hd/step)][Wd]
     float fx, fy, cx, cy;
     // point mode
     const float* pts;         // [F][Nmax][3] or null
@@ -76,7 +77,8 @@ __device__ __forceinline__ bool sample_point(const FrameIn& in, int f, int s, in
         return isfinite(X) && isfinite(Y) && isfinite(Z);      // _parse_pc2 finite filter
     }
     int v = (s / cols) * in.step, u = (s % cols) * in.step;
-    size_t off = ((size_t)f * in.Hd + v) * in.Wd + u;
+    size_t off = in.compact ? ((size_t)f * ((in.Hd + in.step - 1) / in.step) + v / in.step) * in.Wd + u
+                            : ((size_t)f * in.Hd + v) * in.Wd + u;
     float z = in.depth ? in.depth[off] : (float)in.depth16[off] / 1000.0f;
     bool ok = (z > 0.3f) && (z < 10.0f) && isfinite(z);
     float px = ((float)u - in.cx) / in.fx * z;      // float32, this order, no FMA (-fmad=false)
@@ -455,9 +457,9 @@ static int check_occ(nclt_ctx* c, nclt_occ* o) {
     return NCLT_OK;
 }
 
-extern "C" int nclt_occ_integrate_depth_dev(nclt_ctx* c, nclt_occ* o, const void* depth, int is_u16, int F, int Hd,
-                                            int Wd, const double* T, double fx, double fy, double cx, double cy,
-                                            float* out_pts, int32_t* out_pts_n, int pts_cap) {
+static int occ_integrate_depth_impl(nclt_ctx* c, nclt_occ* o, const void* depth, int is_u16, int compact, int F, int Hd,
+                                    int Wd, const double* T, double fx, double fy, double cx, double cy,
+                                    float* out_pts, int32_t* out_pts_n, int pts_cap) {
     int rc = check_occ(c, o);
     if (rc) return rc;
     if (F < 0 || Hd <= 0 || Wd <= 0 || (F > 0 && (!depth || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_depth args");
@@ -465,9 +467,38 @@ extern "C" int nclt_occ_integrate_depth_dev(nclt_ctx* c, nclt_occ* o, const void
     if (is_u16) in.depth16 = static_cast<const uint16_t*>(depth);
     else in.depth = static_cast<const float*>(depth);
     in.Hd = Hd; in.Wd = Wd; in.step = 4;          // step = 4 (tf_wall_clock_relay.py:876)
+    in.compact = compact;
     in.fx = (float)fx; in.fy = (float)fy; in.cx = (float)cx; in.cy = (float)cy;
     in.T = T;
     return occ_integrate_dev(c, o, in, F, out_pts, out_pts_n, pts_cap);
+}
+
+extern "C" int nclt_occ_integrate_depth_dev(nclt_ctx* c, nclt_occ* o, const void* depth, int is_u16, int F, int Hd,
+                                            int Wd, const double* T, double fx, double fy, double cx, double cy,
+                                            float* out_pts, int32_t* out_pts_n, int pts_cap) {
+    return occ_integrate_depth_impl(c, o, depth, is_u16, 0, F, Hd, Wd, T, fx, fy, cx, cy, out_pts, out_pts_n, pts_cap);
+}
+
+// Host depth frames -> device staging.  The path only ever reads every 4th row (and every 4th pixel of it), so only
+// those rows cross PCIe: one strided 2-D copy (source pitch = 4 rows) moves a quarter of the bytes into a compact
+// [F][Hd/4][Wd] buffer.  Needs Hd % 4 == 0 (so that the sampled rows of consecutive frames are equally spaced);
+// otherwise the frames are copied whole.  Returns the staging pointer and whether it is compact.
+static int stage_depth(nclt_ctx* c, const void* depth, int is_u16, int F, int Hd, int Wd, char* stage, int* compact) {
+    const size_t esz = is_u16 ? 2 : 4;
+    cudaError_t e;
+    if (Hd % 4 == 0) {
+        *compact = 1;
+        e = cudaMemcpy2DAsync(stage, (size_t)Wd * esz, depth, (size_t)4 * Wd * esz, (size_t)Wd * esz, (size_t)F * (Hd / 4),
+                              cudaMemcpyHostToDevice, c->stream);
+    } else {
+        *compact = 0;
+        e = cudaMemcpyAsync(stage, depth, (size_t)F * Hd * Wd * esz, cudaMemcpyHostToDevice, c->stream);
+    }
+    return e == cudaSuccess ? NCLT_OK : nclt_fail(c, NCLT_ERR_CUDA, "depth H2D", e);
+}
+static size_t staged_depth_bytes(int is_u16, int F, int Hd, int Wd) {
+    const size_t esz = is_u16 ? 2 : 4;
+    return (Hd % 4 == 0) ? (size_t)F * (Hd / 4) * Wd * esz : (size_t)F * Hd * Wd * esz;
 }
 
 extern "C" int nclt_occ_integrate_points_dev(nclt_ctx* c, nclt_occ* o, const float* pts, const int32_t* n, int F,
@@ -487,17 +518,22 @@ extern "C" int nclt_occ_integrate_depth(nclt_ctx* c, nclt_occ* o, const void* de
     if (F < 0 || Hd <= 0 || Wd <= 0 || (F > 0 && (!depth || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_depth args");
     if (F == 0) return NCLT_OK;
     cudaSetDevice(c->device);
-    size_t px = (size_t)F * Hd * Wd, esz = is_u16 ? 2 : 4;
-    char* stage = nullptr;
-    cudaError_t e = cudaMalloc(&stage, pad256(px * esz) + pad256((size_t)F * 128));
-    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc depth staging", e);
-    double* dT = reinterpret_cast<double*>(stage + pad256(px * esz));
-    e = cudaMemcpyAsync(stage, depth, px * esz, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, (size_t)F * 128, cudaMemcpyHostToDevice, c->stream);
-    rc = e == cudaSuccess ? nclt_occ_integrate_depth_dev(c, o, stage, is_u16, F, Hd, Wd, dT, fx, fy, cx, cy, nullptr, nullptr, 0)
-                          : nclt_fail(c, NCLT_ERR_CUDA, "depth H2D", e);
+    // staging from the context scratch (no cudaMalloc / cudaFree per call: both synchronise the device)
+    const size_t db = staged_depth_bytes(is_u16, F, Hd, Wd);
+    ScratchScope scope(c);
+    if ((rc = nclt_scratch_reserve(c, pad256(db) + pad256((size_t)F * 128) + 512))) return rc;
+    Carver cv(c);
+    char* stage = cv.take<char>(db);
+    double* dT = cv.take<double>((size_t)F * 16);
+    int compact = 0;
+    rc = stage_depth(c, depth, is_u16, F, Hd, Wd, stage, &compact);
+    if (rc == NCLT_OK) {
+        cudaError_t e = cudaMemcpyAsync(dT, T, (size_t)F * 128, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) rc = nclt_fail(c, NCLT_ERR_CUDA, "T H2D", e);
+    }
+    if (rc == NCLT_OK)
+        rc = occ_integrate_depth_impl(c, o, stage, is_u16, compact, F, Hd, Wd, dT, fx, fy, cx, cy, nullptr, nullptr, 0);
     cudaStreamSynchronize(c->stream);
-    cudaFree(stage);
     return rc;
 }
 
@@ -508,19 +544,19 @@ extern "C" int nclt_occ_integrate_points(nclt_ctx* c, nclt_occ* o, const float* 
     if (F < 0 || Nmax <= 0 || (F > 0 && (!pts || !n || !T))) return nclt_fail(c, NCLT_ERR_ARG, "occ_integrate_points args");
     if (F == 0) return NCLT_OK;
     cudaSetDevice(c->device);
-    size_t pb = (size_t)F * Nmax * 12;
-    char* stage = nullptr;
-    cudaError_t e = cudaMalloc(&stage, pad256(pb) + pad256((size_t)F * 4) + pad256((size_t)F * 128));
-    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc points staging", e);
-    int* dn = reinterpret_cast<int*>(stage + pad256(pb));
-    double* dT = reinterpret_cast<double*>(stage + pad256(pb) + pad256((size_t)F * 4));
-    e = cudaMemcpyAsync(stage, pts, pb, cudaMemcpyHostToDevice, c->stream);
+    const size_t pb = (size_t)F * Nmax * 12;
+    ScratchScope scope(c);
+    if ((rc = nclt_scratch_reserve(c, pad256(pb) + pad256((size_t)F * 4) + pad256((size_t)F * 128) + 768))) return rc;
+    Carver cv(c);
+    float* dp = cv.take<float>((size_t)F * Nmax * 3);
+    int* dn = cv.take<int>((size_t)F);
+    double* dT = cv.take<double>((size_t)F * 16);
+    cudaError_t e = cudaMemcpyAsync(dp, pts, pb, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dT, T, (size_t)F * 128, cudaMemcpyHostToDevice, c->stream);
-    rc = e == cudaSuccess ? nclt_occ_integrate_points_dev(c, o, reinterpret_cast<float*>(stage), dn, F, Nmax, dT)
+    rc = e == cudaSuccess ? nclt_occ_integrate_points_dev(c, o, dp, dn, F, Nmax, dT)
                           : nclt_fail(c, NCLT_ERR_CUDA, "points H2D", e);
     cudaStreamSynchronize(c->stream);
-    cudaFree(stage);
     return rc;
 }
 
@@ -536,27 +572,31 @@ extern "C" int nclt_depth_to_points(nclt_ctx* c, const void* depth, int is_u16, 
     nclt_occ* o = nullptr;
     int rc = nclt_occ_create(c, 0.0, 0.0, 1.0, 1, 1, &o);
     if (rc) return rc;
-    size_t px = (size_t)F * Hd * Wd, esz = is_u16 ? 2 : 4;
-    char* stage = nullptr;
-    size_t ob = (size_t)F * pts_cap * 12;
-    cudaError_t e = cudaMalloc(&stage, pad256(px * esz) + pad256((size_t)F * 128) + pad256(ob) + pad256((size_t)F * 4));
-    if (e != cudaSuccess) { nclt_occ_destroy(c, o); return nclt_fail(c, NCLT_ERR_NOMEM, "cudaMalloc staging", e); }
-    double* dT = reinterpret_cast<double*>(stage + pad256(px * esz));
-    float* dp = reinterpret_cast<float*>(stage + pad256(px * esz) + pad256((size_t)F * 128));
-    int* dn = reinterpret_cast<int*>(reinterpret_cast<char*>(dp) + pad256(ob));
-    e = cudaMemcpyAsync(stage, depth, px * esz, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dT, 0, (size_t)F * 128, c->stream);
-    if (e == cudaSuccess)
-        rc = nclt_occ_integrate_depth_dev(c, o, stage, is_u16, F, Hd, Wd, dT, fx, fy, cx, cy, dp, dn, pts_cap);
-    else
-        rc = nclt_fail(c, NCLT_ERR_CUDA, "depth H2D", e);
-    if (rc == NCLT_OK) {
-        e = cudaMemcpyAsync(out_pts, dp, ob, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_n, dn, (size_t)F * 4, cudaMemcpyDeviceToHost, c->stream);
-        if (e != cudaSuccess) rc = nclt_fail(c, NCLT_ERR_CUDA, "points D2H", e);
+    const size_t db = staged_depth_bytes(is_u16, F, Hd, Wd);
+    const size_t ob = (size_t)F * pts_cap * 12;
+    {
+        ScratchScope scope(c);
+        rc = nclt_scratch_reserve(c, pad256(db) + pad256((size_t)F * 128) + pad256(ob) + pad256((size_t)F * 4) + 1024);
+        if (rc == NCLT_OK) {
+            Carver cv(c);
+            char* stage = cv.take<char>(db);
+            double* dT = cv.take<double>((size_t)F * 16);
+            float* dp = cv.take<float>((size_t)F * pts_cap * 3);
+            int* dn = cv.take<int>((size_t)F);
+            int compact = 0;
+            rc = stage_depth(c, depth, is_u16, F, Hd, Wd, stage, &compact);
+            if (rc == NCLT_OK && cudaMemsetAsync(dT, 0, (size_t)F * 128, c->stream) != cudaSuccess)
+                rc = nclt_fail(c, NCLT_ERR_CUDA, "memset T", cudaGetLastError());
+            if (rc == NCLT_OK)
+                rc = occ_integrate_depth_impl(c, o, stage, is_u16, compact, F, Hd, Wd, dT, fx, fy, cx, cy, dp, dn, pts_cap);
+            if (rc == NCLT_OK) {
+                cudaError_t e = cudaMemcpyAsync(out_pts, dp, ob, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(out_n, dn, (size_t)F * 4, cudaMemcpyDeviceToHost, c->stream);
+                if (e != cudaSuccess) rc = nclt_fail(c, NCLT_ERR_CUDA, "points D2H", e);
+            }
+            cudaStreamSynchronize(c->stream);
+        }
     }
-    cudaStreamSynchronize(c->stream);
-    cudaFree(stage);
     nclt_occ_destroy(c, o);
     return rc;
 }

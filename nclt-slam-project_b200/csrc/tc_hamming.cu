@@ -405,7 +405,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
     uint64_t* acc_full = bars + 8;    // [2]
     uint64_t* acc_empty = bars + 10;  // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
-    float2* xchg = reinterpret_cast<float2*>(bars + 14);   // [4 quadrants][MA4][32 lanes]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
