@@ -123,3 +123,33 @@ def test_fallback_path_large_cloud(ctx):
         ref.cb(pts, t)
     assert np.array_equal(m.units, ref.grid)
     assert m.total_points_integrated == ref.total_points_integrated
+
+
+@pytest.mark.parametrize('H,W', [(480, 640), (478, 640), (37, 50)])
+def test_host_path_equals_device_path_and_oracle(ctx, H, W):
+    """The host-pointer entry copies only the sampled rows (strided 2-D copy) when H % 4 == 0 and whole frames
+    otherwise; both must give the grid of the device-resident path and of the sequential oracle."""
+    import torch
+    from nclt_slam_project_b200.mapper import TeachDepthMapper, integrate_depth_device, tf_to_matrix
+    rng = np.random.default_rng(H * 1000 + W)
+    F = 5
+    depth = rng.uniform(0.2, 9.0, (F, H, W)).astype(np.float32)
+    depth[rng.random((F, H, W)) < 0.05] = np.nan
+    tfs = [oo.yaw_tf(1.0 + 0.3 * f, -0.5 * f, 0.4 * f) for f in range(F)]
+    T = np.stack([tf_to_matrix(*t) for t in tfs])
+    cfg = (-20.0, -20.0, 40.0, 40.0, 0.1)
+    kw = dict(fx=W / 2.0, fy=W / 2.0, cx=W / 2.0, cy=H / 2.0)
+    a = TeachDepthMapper('/tmp/nclt_t_host', *cfg, ctx=ctx)
+    a.integrate_depth(depth, T, **kw)
+    b = TeachDepthMapper('/tmp/nclt_t_dev', *cfg, ctx=ctx)
+    integrate_depth_device(b, torch.from_numpy(depth).cuda(), torch.from_numpy(T).cuda(), **kw)
+    ctx.sync()
+    ref = oo.OracleMapperInt(*cfg)
+    for f in range(F):
+        ref.cb(oo.depth_to_points(depth[f], **kw), tfs[f])
+    ua, ub = a.units, b.units
+    assert np.array_equal(ua, ub)
+    assert np.array_equal(ua, ref.grid)
+    assert a.total_points_integrated == ref.total_points_integrated
+    a.close()
+    b.close()
