@@ -738,3 +738,91 @@ extern "C" double nclt_tc_bench_mx16(nclt_ctx* c, int iters, int variant, double
     if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mx16", e); return -1.0; }
     return (double)blocks * iters * 128.0 * 240.0 / (ms * 1e-3);
 }
+
+// ---- do tcgen05.mma streams issued by TWO different warps pipeline like one stream? -------------------------
+// variant 0: one thread issues every tile (buffers alternate); variant 1: warp 0 issues the even tiles into buffer 0,
+// warp 1 the odd tiles into buffer 1; each issuer waits for its own previous tile (commit -> mbarrier) first.
+namespace {
+__global__ void __launch_bounds__(128) k_tc_bench_two_issuers(int iters, int variant, long long* cycles) {
+    constexpr int N = 240;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 16384;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_done[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (16384 + N * 128) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x2A2A2A2Au, 0xA2A2A2A2u, 0x22AA22AAu, 0xAA22AA22u);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        tc::mbar_init(&s_done[0], 1);
+        tc::mbar_init(&s_done[1], 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp < 4) {
+        tc::tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + 480u, 0x7F7F7F7Fu);
+        tc::tmem_wait_st();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    long long t0 = clock64();
+    const uint32_t idesc = tc::idesc_mxf4(128, N);
+    const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+    auto issue = [&](int buf) {
+        for (int k = 0; k < 4; ++k) {
+            uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+            uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+            tc::mma_mxf4(tmem + buf * 240, da, db, idesc, k > 0 ? 1u : 0u, tmem + 480u, tmem + 496u);
+        }
+        tc::mma_commit(&s_done[buf]);
+    };
+    if (variant == 0) {
+        if (tid == 0)
+            for (int it = 0; it < iters; ++it) {
+                const int buf = it & 1;
+                if (it >= 2) tc::mbar_wait(&s_done[buf], ((it >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                issue(buf);
+            }
+    } else if (warp < 2 && lane == 0) {
+        for (int it = warp; it < iters; it += 2) {
+            if (it >= 2) tc::mbar_wait(&s_done[warp], ((it >> 1) - 1) & 1);
+            tc::tc_fence_after();
+            issue(warp);
+        }
+    }
+    if (tid == 0) {                          // wait for the last two tiles
+        tc::mbar_wait(&s_done[(iters - 1) & 1], ((iters - 1) >> 1) & 1);
+        tc::mbar_wait(&s_done[(iters - 2) & 1], ((iters - 2) >> 1) & 1);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" double nclt_tc_bench_two_issuers(nclt_ctx* c, int iters, int variant) {
+    if (!c || iters < 4 || (iters & 1)) return -1.0;
+    cudaSetDevice(c->device);
+    long long* cyc = nullptr;
+    if (cudaMalloc(&cyc, c->sm_count * 8) != cudaSuccess) return -1.0;
+    size_t smem = 16384 + (size_t)240 * 128;
+    cudaFuncSetAttribute(k_tc_bench_two_issuers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_tc_bench_two_issuers<<<c->sm_count, 128, smem, c->stream>>>(8, variant, cyc);
+    k_tc_bench_two_issuers<<<c->sm_count, 128, smem, c->stream>>>(iters, variant, cyc);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(cyc);
+    c->launches += 2;
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_two_issuers", e); return -1.0; }
+    return (double)h / iters;
+}
