@@ -400,6 +400,10 @@ extern "C" int nclt_match_flat2_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if ((unsigned long long)idx_offset + (unsigned)L->n_desc > NCLT_KEY_IDX_MASK)
         return nclt_fail(c, NCLT_ERR_ARG, "global index exceeds 23 bits");
     if (B == 0) return NCLT_OK;
+    // tensor engines: per-keyframe (d1, d2 bound) on tcgen05, then an exact re-scan of the two keyframes that can
+    // hold the global top-2 (tc_hamming.cu); identical keys
+    if (c->engine >= 1 && L->n_kf > 0 && L->n_kf < 65536 && (long long)B * Nq < (1LL << 30))
+        return tc_match_flat2(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, idx_offset, out_keys, c->engine == 2);
     // the whole library is one segment; split its rows so that the grid fills the GPU
     int want = (c->sm_count * 8 + B - 1) / B;
     int max_split = std::max(1, (L->n_desc + 2047) / 2048);

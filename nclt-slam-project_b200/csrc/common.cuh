@@ -123,6 +123,8 @@ double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
 void nclt_tc_release(nclt_lib* L);
 int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
                        int32_t* out_pairs, int32_t* out_n, bool fp4);
+int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, uint32_t idx_offset,
+                   uint32_t* out_keys, bool fp4);
 
 // ---- pnp.cu ----
 struct PnpBuffers {

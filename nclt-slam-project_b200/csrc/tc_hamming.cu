@@ -846,59 +846,64 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     return NCLT_OK;
 }
 
-// all keyframes, every frame: knn2 + Lowe ratio via tensor cores. Same outputs as the integer path.
-int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
-                       int32_t* out_pairs, int32_t* out_n, bool fp4) {
+// ---- shared first stage: (exact d1, upper bound of d2) of every query row against every keyframe -------------
+struct TcPlan {
+    TcLibCache* cch;
+    bool fp4;
+    long long rows, rows_pad;
+    int n_mtiles, n_groups, n_splits;
+    size_t q_img_bytes, d12_bytes;
+};
+
+// library image + work split table for a batch of B x Nq query rows; no kernel launches, no scratch
+static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl) {
     int rc;
     if ((rc = tc_build_library(c, L, fp4))) return rc;
     TcLibCache* cch = static_cast<TcLibCache*>(fp4 ? L->tc4_cache : L->tc_cache);
     const int ma_tiles = fp4 ? MA4 : MA;
     const size_t a_tile_bytes = fp4 ? A4_TILE_BYTES : A_TILE_BYTES;
     const int n_kf = L->n_kf;
-    if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
-    const long long rows = (long long)B * Nq;
-    const int n_mtiles = (int)((rows + 127) / 128);
-    const long long rows_pad = (long long)n_mtiles * 128;
-    const int n_groups = (n_mtiles + ma_tiles - 1) / ma_tiles;
+    pl->cch = cch;
+    pl->fp4 = fp4;
+    pl->rows = (long long)B * Nq;
+    pl->n_mtiles = (int)((pl->rows + 127) / 128);
+    pl->rows_pad = (long long)pl->n_mtiles * 128;
+    pl->n_groups = (pl->n_mtiles + ma_tiles - 1) / ma_tiles;
     // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
     // >= ~24 items per SM so that the last (partial) wave of the static round-robin costs a few percent
-    int n_splits = std::max(1, std::min(n_kf, (c->sm_count * 24 + n_groups - 1) / n_groups));
-    if (cch->split_groups != n_groups || cch->split_n != n_splits) {
-        std::vector<int> split_tile(n_splits + 1);
-        for (int s = 0; s <= n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / n_splits];
+    pl->n_splits = std::max(1, std::min(std::max(n_kf, 1), (c->sm_count * 24 + pl->n_groups - 1) / pl->n_groups));
+    pl->q_img_bytes = (size_t)pl->n_mtiles * a_tile_bytes;
+    pl->d12_bytes = (size_t)n_kf * pl->rows_pad * 4;
+    if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
+    if (cch->split_groups != pl->n_groups || cch->split_n != pl->n_splits) {
+        std::vector<int> split_tile(pl->n_splits + 1);
+        for (int s = 0; s <= pl->n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / pl->n_splits];
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         if (cch->d_split) cudaFree(cch->d_split);
         cch->d_split = nullptr;
-        CU_TRY(c, cudaMalloc(&cch->d_split, (n_splits + 1) * sizeof(int)));
-        CU_TRY(c, cudaMemcpy(cch->d_split, split_tile.data(), (n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        cch->split_groups = n_groups;
-        cch->split_n = n_splits;
+        CU_TRY(c, cudaMalloc(&cch->d_split, (pl->n_splits + 1) * sizeof(int)));
+        CU_TRY(c, cudaMemcpy(cch->d_split, split_tile.data(), (pl->n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        cch->split_groups = pl->n_groups;
+        cch->split_n = pl->n_splits;
     }
-    int* d_split = cch->d_split;
+    return NCLT_OK;
+}
 
-    ScratchScope scope(c);
-    // candidate work list: every (query, keyframe) pair may be a candidate in the worst case
-    const long long all_pairs = rows * (long long)n_kf;
-    const int work_cap = (int)std::min<long long>(all_pairs, 1LL << 28);
-    size_t need = pad256((size_t)n_mtiles * a_tile_bytes) + pad256((size_t)n_kf * rows_pad * 4) +
-                  pad256((size_t)work_cap * sizeof(WorkItem)) + 256;
-    if ((rc = nclt_scratch_reserve(c, need))) return rc;
-    Carver cv(c);
-    uint8_t* q_img = cv.take<uint8_t>((size_t)n_mtiles * a_tile_bytes);
-    uint32_t* d12 = cv.take<uint32_t>((size_t)n_kf * rows_pad);
-    WorkItem* work = cv.take<WorkItem>((size_t)work_cap);
-    int* work_count = cv.take<int>(1);
+// expands the queries into q_img and runs k_tc*_top2: d12[kf * rows_pad + row] = d1 | d2bound << 16
+static int tc_run_top2(nclt_ctx* c, const TcPlan& pl, const uint8_t* q, uint8_t* q_img, uint32_t* d12) {
+    const bool fp4 = pl.fp4;
+    TcLibCache* cch = pl.cch;
     {
-        long long threads = rows_pad * 16;
+        long long threads = pl.rows_pad * 16;
         if (fp4)
-            k_expand_queries4<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
+            k_expand_queries4<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
         else
-            k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), rows, q_img);
+            k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
         c->launches++;
     }
     TcParams p;
-    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = n_mtiles; p.n_groups = n_groups;
-    p.n_splits = n_splits; p.split_tile = d_split; p.rows_total = rows; p.out = d12; p.rows_pad = rows_pad;
+    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
+    p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.rows_total = pl.rows; p.out = d12; p.rows_pad = pl.rows_pad;
     if (!c->d_tc_clk && c->prof) {      // diagnostics only in profile mode (allocation is not capturable)
         CU_TRY(c, cudaMalloc(&c->d_tc_clk, 128));
     }
@@ -907,7 +912,7 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     const size_t smem = fp4 ? (size_t)MA4 * A4_TILE_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 128 + (size_t)4 * MA4 * 32 * 8
                             : (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
     CU_TRY(c, cudaFuncSetAttribute(fp4 ? k_tc4_top2 : k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(c->sm_count, n_groups * n_splits);
+    int grid = std::min(c->sm_count, pl.n_groups * pl.n_splits);
     if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
         int g = atoi(env);
         if (g > 0) grid = std::min(grid, g);
@@ -916,7 +921,7 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     {
         // Highest launch priority: when two engines alternate (PipelinedLocalizer) this kernel's CTAs must be
         // placed before the small tail CTAs of the previous batch (each of which would otherwise pin some of
-        // the 224 KB of shared memory a k_tc_top2 CTA needs and delay it).
+        // the shared memory a k_tc*_top2 CTA needs and delay it).
         static int prio_hi = 1 << 30;
         if (prio_hi == (1 << 30)) {
             int least = 0, greatest = 0;
@@ -937,11 +942,34 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     }
     nclt_prof_mark(c);
     c->launches++;
+    return NCLT_OK;
+}
+
+// all keyframes, every frame: knn2 + Lowe ratio via tensor cores. Same outputs as the integer path.
+int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
+                       int32_t* out_pairs, int32_t* out_n, bool fp4) {
+    int rc;
+    TcPlan pl;
+    if ((rc = tc_plan(c, L, B, Nq, fp4, &pl))) return rc;
+    const int n_kf = L->n_kf;
+    if (n_kf == 0 || pl.cch->n_tiles == 0) return NCLT_OK;
+    ScratchScope scope(c);
+    // candidate work list: every (query, keyframe) pair may be a candidate in the worst case
+    const long long all_pairs = pl.rows * (long long)n_kf;
+    const int work_cap = (int)std::min<long long>(all_pairs, 1LL << 28);
+    size_t need = pad256(pl.q_img_bytes) + pad256(pl.d12_bytes) + pad256((size_t)work_cap * sizeof(WorkItem)) + 256;
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    uint8_t* q_img = cv.take<uint8_t>(pl.q_img_bytes);
+    uint32_t* d12 = cv.take<uint32_t>(pl.d12_bytes / 4);
+    WorkItem* work = cv.take<WorkItem>((size_t)work_cap);
+    int* work_count = cv.take<int>(1);
+    if ((rc = tc_run_top2(c, pl, q, q_img, d12))) return rc;
     {
         const int n_items = B * n_kf;
         const unsigned blocks = (unsigned)(((long long)n_items * 32 + 127) / 128);
         CU_TRY(c, cudaMemsetAsync(work_count, 0, 4, c->stream));
-        k_tc_candidates<<<blocks, 128, 0, c->stream>>>(d12, rows_pad, Nq, q_n, n_kf, n_items, num, den, L->d_count,
+        k_tc_candidates<<<blocks, 128, 0, c->stream>>>(d12, pl.rows_pad, Nq, q_n, n_kf, n_items, num, den, L->d_count,
                                                       reinterpret_cast<int2*>(out_pairs), out_n, work, work_count, work_cap);
         k_tc_verify<<<c->sm_count * 16, 128, 0, c->stream>>>(work, work_count, work_cap, Nq, n_kf, num, den,
                                                             reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start,
@@ -949,6 +977,92 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
         k_tc_compact<<<blocks, 128, 0, c->stream>>>(n_items, Nq, reinterpret_cast<int2*>(out_pairs), out_n);
         c->launches += 3;
     }
+    CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}
+
+// ---- flat global top-2 (BASELINE config 5) on the tensor cores -------------------------------------------------
+// The global best row of a query lies in the keyframe kf_a with the smallest (d1, keyframe index) - global row indices
+// grow with the keyframe index, so this is also the lowest global index among ties; the global second best is either
+// the second best row of kf_a or the best row of kf_b, the smallest (d1, keyframe) among the OTHER keyframes.  Both
+// keyframes are then re-scanned exactly on the integer pipe (2 x <= 1000 rows per query instead of millions).
+__global__ void __launch_bounds__(256) k_flat_select(const uint32_t* __restrict__ d12, long long rows_pad, long long rows,
+                                                     int n_kf, int2* __restrict__ sel /*[rows] (kf_a, kf_b), -1 = none*/) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;            // keys d1 << 16 | kf (n_kf < 65536)
+    for (int kf = 0; kf < n_kf; ++kf) {
+        const uint32_t d1 = d12[(size_t)kf * rows_pad + row] & 0xFFFFu;
+        if (d1 == 0xFFFFu) continue;                         // keyframe without rows
+        const uint32_t key = (d1 << 16) | (uint32_t)kf;
+        const uint32_t mx = max(k1, key);
+        k1 = min(k1, key);
+        k2 = min(k2, mx);
+    }
+    sel[row] = make_int2(k1 == 0xFFFFFFFFu ? -1 : (int)(k1 & 0xFFFFu), k2 == 0xFFFFFFFFu ? -1 : (int)(k2 & 0xFFFFu));
+}
+
+__global__ void __launch_bounds__(128) k_flat_rescan(const int2* __restrict__ sel, long long rows, int Nq,
+                                                     const int* __restrict__ q_n, const uint4* __restrict__ q_desc,
+                                                     const uint4* __restrict__ lib_desc, const int* __restrict__ kf_start,
+                                                     const int* __restrict__ kf_count, uint32_t idx_offset,
+                                                     uint2* __restrict__ out_keys) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int b = (int)(row / Nq), qi = (int)(row % Nq);
+    uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;            // keys dist << 23 | global row
+    if (!q_n || qi < q_n[b]) {
+        const int2 s = sel[row];
+        const uint4 a0 = __ldg(q_desc + row * 2), a1 = __ldg(q_desc + row * 2 + 1);
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int kf = which == 0 ? s.x : s.y;
+            if (kf < 0) continue;
+            const int start = kf_start[kf], nt = kf_count[kf];
+            const uint4* trows = lib_desc + (size_t)start * 2;
+            for (int j = lane; j < nt; j += 32) {
+                const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
+                const uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
+                                   __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
+                const uint32_t key = (d << NCLT_KEY_SHIFT) | (idx_offset + (uint32_t)(start + j));
+                const uint32_t mx = max(m1, key);
+                m1 = min(m1, key);
+                m2 = min(m2, mx);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+            const uint32_t lo = min(m1, o1), hi = max(m1, o1);
+            m2 = min(min(m2, o2), hi);
+            m1 = lo;
+        }
+    }
+    if (lane == 0) out_keys[row] = make_uint2(m1, m2);
+}
+
+int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, uint32_t idx_offset,
+                   uint32_t* out_keys, bool fp4) {
+    int rc;
+    TcPlan pl;
+    if ((rc = tc_plan(c, L, B, Nq, fp4, &pl))) return rc;
+    const int n_kf = L->n_kf;
+    ScratchScope scope(c);
+    size_t need = pad256(pl.q_img_bytes) + pad256(pl.d12_bytes) + pad256((size_t)pl.rows * sizeof(int2)) + 256;
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    uint8_t* q_img = cv.take<uint8_t>(pl.q_img_bytes);
+    uint32_t* d12 = cv.take<uint32_t>(pl.d12_bytes / 4);
+    int2* sel = cv.take<int2>((size_t)pl.rows);
+    if (n_kf > 0 && pl.cch->n_tiles > 0) {
+        if ((rc = tc_run_top2(c, pl, q, q_img, d12))) return rc;
+    }
+    k_flat_select<<<(unsigned)((pl.rows + 255) / 256), 256, 0, c->stream>>>(d12, pl.rows_pad, pl.rows, n_kf, sel);
+    k_flat_rescan<<<(unsigned)((pl.rows * 32 + 127) / 128), 128, 0, c->stream>>>(
+        sel, pl.rows, Nq, q_n, reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start, L->d_count, idx_offset,
+        reinterpret_cast<uint2*>(out_keys));
+    c->launches += 2;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
 }

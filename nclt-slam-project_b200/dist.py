@@ -69,7 +69,7 @@ def merge_keys_numpy(parts):
 class ShardedLibrary:
     """Rank-local shard of a union library + the all-gather merge (config 5)."""
 
-    def __init__(self, descriptors, points3d=None, device=None):
+    def __init__(self, descriptors, points3d=None, device=None, engine='tensor4'):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -85,6 +85,7 @@ class ShardedLibrary:
         # one torch stream shared by the C-ABI kernels and the NCCL collective (stream-ordered)
         self.stream = torch.cuda.Stream(self.device)
         self.ctx = _lib.Context(self.device.index, self.stream.cuda_stream)
+        self.ctx.set_engine(engine)      # tensor engines: per-keyframe top-2 on tcgen05 + exact re-scan of two keyframes
         self.local = LandmarkLibrary(descriptors[lo:hi], None if points3d is None else points3d[lo:hi], ctx=self.ctx)
         self.kf_cum = np.concatenate([[0], np.cumsum(counts)])
 

@@ -16,6 +16,7 @@ def main():
     ap.add_argument('--desc', type=int, default=1000)
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--engine', default='tensor4', choices=['int', 'tensor', 'tensor4'])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -36,7 +37,7 @@ def main():
     class _Lazy(list):
         pass
     descs = [kfs[k] if kfs[k] is not None else np.zeros((args.desc, 32), np.uint8) for k in range(n_kf)]
-    sl = ShardedLibrary(descs, device=local)
+    sl = ShardedLibrary(descs, device=local, engine=args.engine)
     dev = torch.device('cuda', local)
     q = torch.from_numpy(np.random.default_rng(7).integers(0, 256, (args.batch, 1000, 32), dtype=np.uint8)).to(dev)
     for _ in range(2):
@@ -61,7 +62,8 @@ def main():
         print(json.dumps({'metric': 'cross-route relocalisation frames/s (flat top-2 over the union library)',
                           'n_gpus': world, 'library_rows': n_kf * args.desc, 'frames_per_s': frames / (ms * 1e-3),
                           'hamming_cmp_per_s': cmp / (ms * 1e-3), 'ms_per_step': ms / args.steps, 'batch': args.batch,
-                          'engine': 'integer pipe (LOP3+POPC), library sharded by keyframe range, all_gather of u32[B,1000,2]',
+                          'engine': args.engine + ' (int = LOP3+POPC; tensor* = per-keyframe top-2 on tcgen05 + exact re-scan of two keyframes), '
+                                    'library sharded by keyframe range, all_gather of u32[B,1000,2]',
                           'dist_checksum': int(dd.sum().item()), 'idx_checksum': int(idx.sum().item())}))
     if world > 1:
         dist.destroy_process_group()
