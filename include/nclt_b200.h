@@ -51,7 +51,8 @@ int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
  * 0 = integer pipe (LOP3+POPC, the default), 1 = tcgen05 tensor cores with fp8 +-1 operands and fp16
  * accumulators in TMEM, 2 = tcgen05 block-scaled fp4 (kind::mxf4) +-1 operands with f32 accumulators
  * (the fastest); all three produce identical results (exact index recovery on the integer pipe).
- * Candidate-list and crossCheck matching always use the integer pipe. */
+ * Used by nclt_match_ratio[_dev] / nclt_localize_batch[_dev] with cand == NULL and by
+ * nclt_match_flat2_dev; candidate-list and crossCheck matching always use the integer pipe. */
 int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
 /* enable/disable CUDA-event timing of the dominant kernel (the Hamming top-2 launches) on this
  * context; nclt_ctx_profile_read synchronises, returns the summed device time and launch count
@@ -112,7 +113,9 @@ int nclt_match_cross_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, c
 /* BASELINE config 5 (no reference analogue; closest: experiments/63_global_reloc/scripts/
  * visual_landmark_matcher.py:314-345): flat global top-2 of every query row over ALL library
  * rows of this rank.  out_keys u32[B,Nq,2]: key = dist<<23 | (idx_offset + library row),
- * 0xFFFFFFFF = missing; keys from several ranks merge with nclt_merge_top2_dev. */
+ * 0xFFFFFFFF = missing; keys from several ranks merge with nclt_merge_top2_dev.  With a tensor engine
+ * selected (nclt_ctx_set_engine) the keyframe structure of the library is used: per-keyframe top-2 on
+ * tcgen05, then an exact re-scan of the two keyframes that can hold the global top-2; same keys. */
 int nclt_match_flat2_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
                          int Nq, uint32_t idx_offset, uint32_t* out_keys);
 /* parts u32[nparts,B*Nq,2] -> out_keys u32[B*Nq,2], out_idx i32[B*Nq,2], out_dist u16[B*Nq,2]
