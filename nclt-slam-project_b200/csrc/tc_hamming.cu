@@ -805,12 +805,6 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
             // greedy full tiles: the accumulator hand-over (MMA -> tcgen05.ld -> release -> MMA) has a large fixed
             // cost per step, so a few 240-column steps plus one short one beat evenly sized steps
             per = B4_ROWS;
-            if (const char* env = getenv("NCLT_TC4_BALANCED")) {
-                if (atoi(env)) {
-                    const int nt = (cnt + B4_ROWS - 1) / B4_ROWS;
-                    per = (((cnt + nt - 1) / nt) + 15) & ~15;
-                }
-            }
         }
         for (int r = 0; r < cnt; r += per) {
             int nv = std::min(per, cnt - r);

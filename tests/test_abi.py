@@ -7,9 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, 'include', 'nclt_b200.h')).read()
-    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(nclt_[a-z0-9_]+)\s*\(', src)))
+    names = set()
+    for h in ('nclt_b200.h', 'nclt_b200_diag.h'):      # the drop-in boundary + the diagnostic entry points
+        src = open(os.path.join(ROOT, 'include', h)).read()
+        src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+        names |= set(re.findall(r'\b(nclt_[a-z0-9_]+)\s*\(', src))
+    return sorted(names)
 
 
 def test_header_symbols_exported():
