@@ -33,8 +33,10 @@ double nclt_tmem_bw(nclt_ctx* ctx, int warps, int batch, int with_max);
 /* SM clocks per 128 x 240 x 256 mxf4 tile when one thread issues every tile (variant 0) or two warps alternate. */
 double nclt_tc_bench_two_issuers(nclt_ctx* ctx, int iters, int variant);
 /* With nclt_ctx_profile(ctx, 1): effective SM clock (clock64 / globaltimer of the longest CTA) and duration of the
- * last k_tc*_top2 launch; raw16 (optional, 16 x u64): [cycles, ns, phase counters of a -DNCLT_TC_TIMING build]. */
-int nclt_ctx_tc_clock(nclt_ctx* ctx, double* mhz, double* kernel_ms, unsigned long long* raw16);
+ * last k_tc*_top2 launch; raw64 (optional, 64 x u64): [0] cycles, [1] ns, [2..15] phase counters of a
+ * -DNCLT_TC_TIMING build, [16 + 2i] / [17 + 2i] globaltimer ns of the earliest CTA start / latest CTA end of the
+ * i-th most recent launches (ring of 24, slot = launch number mod 24). */
+int nclt_ctx_tc_clock(nclt_ctx* ctx, double* mhz, double* kernel_ms, unsigned long long* raw64);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,8 @@ struct nclt_ctx {
     size_t prof_used = 0;
     // async pipeline: PnP problems dropped because a batch produced more than its problem capacity
     int* d_overflow = nullptr;
-    unsigned long long* d_tc_clk = nullptr;   // tensor-kernel clock diagnostics (profile mode)
+    unsigned long long* d_tc_clk = nullptr;   // tensor-kernel clock diagnostics (profile mode), 64 x u64
+    int tc_clk_launch = 0;
 };
 
 struct nclt_lib {

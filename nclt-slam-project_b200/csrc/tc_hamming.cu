@@ -99,6 +99,7 @@ struct TcParams {
     uint32_t* out;             // [n_kf][rows_pad] : d1 | d2 << 16
     long long rows_pad;        // n_mtiles * 128
     unsigned long long* clk;   // diagnostics: [0] max SM cycles, [1] max globaltimer ns of a CTA (nclt_ctx_tc_clock)
+    int clk_slot;              // [16 + 2 * slot] / [17 + 2 * slot]: earliest CTA start / latest CTA end of this launch (globaltimer ns)
 };
 
 // Epilogue primitive. Exact running top-2 costs 3 half2 min/max per register and made the
@@ -314,6 +315,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         atomicMax(p.clk, (unsigned long long)(clock64() - clk0));
         atomicMax(p.clk + 1, ns1 - ns0);
+        atomicMin(p.clk + 16 + 2 * p.clk_slot, ns0);
+        atomicMax(p.clk + 17 + 2 * p.clk_slot, ns1);
     }
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
@@ -619,6 +622,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         atomicMax(p.clk, (unsigned long long)(clock64() - clk0));
         atomicMax(p.clk + 1, ns1 - ns0);
+        atomicMin(p.clk + 16 + 2 * p.clk_slot, ns0);
+        atomicMax(p.clk + 17 + 2 * p.clk_slot, ns1);
     }
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
@@ -899,10 +904,18 @@ static int tc_run_top2(nclt_ctx* c, const TcPlan& pl, const uint8_t* q, uint8_t*
     p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
     p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.rows_total = pl.rows; p.out = d12; p.rows_pad = pl.rows_pad;
     if (!c->d_tc_clk && c->prof) {      // diagnostics only in profile mode (allocation is not capturable)
-        CU_TRY(c, cudaMalloc(&c->d_tc_clk, 128));
+        CU_TRY(c, cudaMalloc(&c->d_tc_clk, 512));
+        CU_TRY(c, cudaMemsetAsync(c->d_tc_clk, 0, 512, c->stream));
+        c->tc_clk_launch = 0;
     }
     p.clk = c->prof ? c->d_tc_clk : nullptr;
-    if (p.clk) CU_TRY(c, cudaMemsetAsync(p.clk, 0, 128, c->stream));
+    p.clk_slot = 0;
+    if (p.clk) {
+        p.clk_slot = c->tc_clk_launch++ % 24;
+        CU_TRY(c, cudaMemsetAsync(p.clk, 0, 128, c->stream));
+        CU_TRY(c, cudaMemsetAsync(p.clk + 16 + 2 * p.clk_slot, 0xFF, 8, c->stream));     // start: atomicMin
+        CU_TRY(c, cudaMemsetAsync(p.clk + 17 + 2 * p.clk_slot, 0, 8, c->stream));        // end: atomicMax
+    }
     const size_t smem = fp4 ? (size_t)MA4 * A4_TILE_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 128 + (size_t)4 * MA4 * 32 * 8
                             : (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
     CU_TRY(c, cudaFuncSetAttribute(fp4 ? k_tc4_top2 : k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1062,14 +1075,14 @@ int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_
 }
 
 // SM clock the last profiled k_tc*_top2 launch actually ran at (cycles / wall time of its longest CTA)
-extern "C" int nclt_ctx_tc_clock(nclt_ctx* c, double* mhz, double* kernel_ms, unsigned long long* raw16) {
+extern "C" int nclt_ctx_tc_clock(nclt_ctx* c, double* mhz, double* kernel_ms, unsigned long long* raw64) {
     if (!c) return NCLT_ERR_ARG;
-    unsigned long long h[16] = {0};
+    unsigned long long h[64] = {0};
     if (c->d_tc_clk) {
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        CU_TRY(c, cudaMemcpy(h, c->d_tc_clk, 128, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(h, c->d_tc_clk, 512, cudaMemcpyDeviceToHost));
     }
-    if (raw16) memcpy(raw16, h, 128);
+    if (raw64) memcpy(raw64, h, 512);
     if (mhz) *mhz = h[1] ? (double)h[0] / (double)h[1] * 1e3 : 0.0;
     if (kernel_ms) *kernel_ms = (double)h[1] * 1e-6;
     return NCLT_OK;

@@ -22,7 +22,7 @@ for engine in sys.argv[1:] or ('tensor', 'tensor4'):
     for _ in range(3):
         eng.run(d, p, sync_count=False)
         mhz, ms = C.c_double(), C.c_double()
-        raw = np.zeros(16, dtype=np.uint64)
+        raw = np.zeros(64, dtype=np.uint64)
         L.nclt_ctx_tc_clock(eng.ctx.h, C.byref(mhz), C.byref(ms), raw.ctypes.data)
         print(f'{engine}: kernel {ms.value:.3f} ms at {mhz.value:.0f} MHz effective SM clock', flush=True)
         if raw[2:12].any():      # built with -DNCLT_TC_TIMING
