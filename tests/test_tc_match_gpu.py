@@ -103,3 +103,41 @@ def test_tc_pipeline_equals_integer_pipeline(ctx, eng):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(a['rvec'], b['rvec']) and np.array_equal(a['tvec'], b['tvec'])
     assert np.array_equal(a['best_cand'], kstar)
+
+
+@pytest.mark.timeout(600)
+def test_tc_ratio_random_shapes_equal_integer_engine(ctx, eng):
+    """Randomised shapes (keyframe sizes around the tile limits 240 / 256 / 480 / 512, ragged frames, duplicated
+    rows -> ties, low-entropy descriptors): the tensor engines must reproduce the integer engine pair for pair."""
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    rng = np.random.default_rng(20261018)
+    specials = [0, 1, 2, 15, 16, 17, 239, 240, 241, 255, 256, 257, 479, 480, 481, 511, 512, 513, 720, 1000]
+    for case in range(12):
+        n_kf = int(rng.integers(1, 9))
+        counts = [int(rng.choice(specials)) if rng.random() < 0.7 else int(rng.integers(0, 700)) for _ in range(n_kf)]
+        hi = 256 if case % 3 else 4                      # every third case: heavy ties
+        kfs = [rng.integers(0, hi, (n, 32), dtype=np.uint8) for n in counts]
+        B = int(rng.integers(1, 4))
+        nq = int(rng.choice([1, 31, 128, 129, 300, 640]))
+        q = rng.integers(0, hi, (B, nq, 32), dtype=np.uint8)
+        for k, t in enumerate(kfs):                      # plant exact and near matches, duplicated inside the keyframe
+            if len(t) >= 4 and nq >= 4:
+                m = min(len(t) // 2, nq // 2, 40)
+                q[k % B, :m] = t[:m]
+                t[len(t) - m:] = t[:m]
+        q_n = rng.integers(1, nq + 1, B).astype(np.int32) if case % 2 else None
+        res = []
+        for e in ('int', eng):
+            c = _lib.Context(0)
+            c.set_engine(e)
+            lib = LandmarkLibrary(kfs, ctx=c)
+            pairs, n = lib.ratio(q, q_n)
+            res.append((pairs.copy(), n.copy()))
+            lib.close()
+            c.close()
+        (pa, na), (pb, nb) = res
+        assert np.array_equal(na, nb), (case, counts, B, nq)
+        for b in range(B):
+            for k in range(n_kf):
+                assert np.array_equal(pa[b, k, :na[b, k]], pb[b, k, :nb[b, k]]), (case, b, k, counts)
