@@ -652,15 +652,43 @@ __global__ void __launch_bounds__(128) k_tc_candidates(const uint32_t* __restric
     const uint32_t* src = d12 + (size_t)kf * rows_pad + (size_t)b * Nq;
     int2* dst = out_pairs + (size_t)item * Nq;
     int cnt = 0;
-    if (nt >= 2) {
+    auto is_cand = [&](uint32_t v) {
+        const uint32_t d1 = v & 0xFFFFu, d2b = v >> 16;
+        return d1 != 0xFFFFu && (d2b == 0xFFFFu || (uint32_t)den * d1 < (uint32_t)num * d2b);
+    };
+    if (nt >= 2 && (Nq & 3) == 0) {
+        // 128 queries per iteration, one 16-byte load per lane (HBM-bound pass over 4 B per (query, keyframe));
+        // candidates are rare (the planted keyframe's matches), so the ordered emission is the slow path
+        const uint4* src4 = reinterpret_cast<const uint4*>(src);
+        for (int q0 = 0; q0 < nq; q0 += 128) {
+            const int q = q0 + 4 * lane;
+            uint4 v = make_uint4(0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu);
+            if (q < nq) v = __ldg(src4 + (q >> 2));
+            const bool f0 = q < nq && is_cand(v.x), f1 = q + 1 < nq && is_cand(v.y);
+            const bool f2 = q + 2 < nq && is_cand(v.z), f3 = q + 3 < nq && is_cand(v.w);
+            if (!__any_sync(0xFFFFFFFFu, f0 | f1 | f2 | f3)) continue;
+            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, f0), b1 = __ballot_sync(0xFFFFFFFFu, f1);
+            const unsigned b2 = __ballot_sync(0xFFFFFFFFu, f2), b3 = __ballot_sync(0xFFFFFFFFu, f3);
+            const unsigned lt = (1u << lane) - 1u;
+            const int n = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(work_count, n);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            int r = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);   // query order: lane-major
+            const bool f[4] = {f0, f1, f2, f3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (f[i]) {
+                    dst[cnt + r] = make_int2(q + i, -1);
+                    if (base + r < work_cap) work[base + r] = WorkItem{item, cnt + r};
+                    ++r;
+                }
+            cnt += n;
+        }
+    } else if (nt >= 2) {
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
-            bool cand = false;
-            if (q < nq) {
-                uint32_t v = src[q];
-                uint32_t d1 = v & 0xFFFFu, d2b = v >> 16;
-                cand = d1 != 0xFFFFu && (d2b == 0xFFFFu || (uint32_t)den * d1 < (uint32_t)num * d2b);
-            }
+            const bool cand = q < nq && is_cand(src[q]);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
             if (m) {
                 const int n = __popc(m);
