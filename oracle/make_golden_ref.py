@@ -220,3 +220,100 @@ def golden_tick(out_dir):
         desc=np.stack([np.pad(t[1], ((0, 500 - len(t[1])), (0, 0))) for t in ticks]),
         pts2d=np.stack([np.pad(t[2], ((0, 500 - len(t[2])), (0, 0))) for t in ticks]))
     print('tick_golden.npz', [t[0]['csv'][-1] for t in ticks])
+
+
+def _lift_depth(rng, kind):
+    """Synthetic aligned depth in millimetres: a ground ramp below the horizon, boxes at other ranges
+    (depth discontinuities), holes (0), far background beyond the 15 m gate."""
+    v = np.arange(480, dtype=np.float64)[:, None]
+    u = np.arange(640, dtype=np.float64)[None, :]
+    z = np.where(v > 245, 0.48 * 320.0 / np.maximum(v - 240.0, 1.0), 40.0) + 0.0 * u        # ground plane seen from 0.48 m
+    for _ in range(12):
+        u0, v0 = int(rng.integers(0, 600)), int(rng.integers(150, 440))
+        w, h = int(rng.integers(20, 120)), int(rng.integers(20, 120))
+        z[v0:v0 + h, u0:u0 + w] = rng.uniform(0.3, 18.0)
+    z = z + rng.normal(0, 0.004, z.shape)
+    mm = np.clip(z * 1000.0, 0, 65535).astype(np.uint16)
+    mm[rng.random(mm.shape) < (0.25 if kind == 'holes' else 0.03)] = 0
+    if kind == 'far':
+        mm[:] = 30000
+    return mm
+
+
+def golden_lift(out_dir):
+    """The teach-time recorder: VisualLandmarkRecorder._tick (visual_landmark_recorder.py:211-306) run unmodified
+    under ROS stubs with a stand-in ORB; every tick's inputs and the `landmarks` record it appended (or not)."""
+    import importlib
+    import pickle
+    ros_stubs.import_reference()                      # installs the stubs and the scripts/common path
+    import sys
+    saved = sys.argv
+    sys.argv = ['x']
+    try:
+        rec_mod = importlib.import_module('visual_landmark_recorder')
+    finally:
+        sys.argv = saved
+    tmp = tempfile.mkdtemp()
+    pkl = os.path.join(tmp, 'out', 'landmarks.pkl')
+    node = rec_mod.VisualLandmarkRecorder(pkl, min_disp_m=2.0)
+
+    class _Kp:
+        def __init__(self, pt):
+            self.pt = (float(pt[0]), float(pt[1]))
+
+    class _Orb:
+        def detectAndCompute(self, gray, mask):
+            d, p = self.next
+            return [_Kp(q) for q in p], d
+
+    node.orb = _Orb()
+    node.last_rgb = np.zeros((480, 640, 3), dtype=np.uint8)
+    rng = np.random.default_rng(2026)
+    kinds = ['ok', 'near', 'ok', 'holes', 'far', 'ok', 'few', 'ok']
+    x = 0.0
+    ticks = []
+    for i, kind in enumerate(kinds):
+        x += 0.5 if kind == 'near' else 3.0          # 'near': displacement < min_disp -> tick returns early
+        n = 40 if kind == 'few' else 500
+        pts = np.stack([rng.uniform(-3, 643, n), rng.uniform(100, 483, n)], axis=1).astype(np.float32)
+        pts[:25, 0] = np.round(pts[:25, 0]) + 0.5     # exact halves: np.round is half-to-even
+        pts[25:50, 1] = np.round(pts[25:50, 1]) + 0.5
+        desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        depth = _lift_depth(rng, kind)
+        node.orb.next = (desc, pts)
+        node.last_depth = depth
+        node.last_rgb_ts = 100.0 + i
+        base = (x, 0.1 * i, 0.0, 0.0, 0.0, float(np.sin(0.05 * i)), float(np.cos(0.05 * i)))
+        node._read_pose = (lambda bp=base: bp)
+        before = len(node.landmarks)
+        node._tick()
+        rec = node.landmarks[-1] if len(node.landmarks) > before else None
+        ticks.append((kind, pts, desc, depth, base, rec))
+    node._save()
+    saved_pkl = pickle.load(open(pkl, 'rb'))
+    assert len(saved_pkl['landmarks']) == len(node.landmarks)
+    NMAX = 500
+    def pad(a, shape, dtype):
+        out = np.zeros(shape, dtype=dtype)
+        out[:len(a)] = a
+        return out
+    np.savez_compressed(
+        os.path.join(out_dir, 'lift_golden.npz'),
+        kinds=np.array([t[0] for t in ticks]),
+        n_kpts=np.array([len(t[1]) for t in ticks], dtype=np.int32),
+        kpts=np.stack([pad(t[1], (NMAX, 2), np.float32) for t in ticks]),
+        desc=np.stack([pad(t[2], (NMAX, 32), np.uint8) for t in ticks]),
+        depth=np.stack([t[3] for t in ticks]),
+        base_pose=np.array([t[4] for t in ticks], dtype=np.float64),
+        recorded=np.array([t[5] is not None for t in ticks]),
+        n_feat=np.array([t[5]['n_features'] if t[5] else 0 for t in ticks], dtype=np.int32),
+        cam_pose=np.array([t[5]['pose'] if t[5] else [0] * 7 for t in ticks], dtype=np.float64),
+        ts=np.array([t[5]['ts'] if t[5] else 0.0 for t in ticks], dtype=np.float64),
+        rec_desc=np.stack([pad(t[5]['descriptors'], (NMAX, 32), np.uint8) if t[5] else np.zeros((NMAX, 32), np.uint8) for t in ticks]),
+        rec_kp2d=np.stack([pad(t[5]['keypoints_2d'], (NMAX, 2), np.float32) if t[5] else np.zeros((NMAX, 2), np.float32) for t in ticks]),
+        rec_kp3d=np.stack([pad(t[5]['keypoints_3d_cam'], (NMAX, 3), np.float32) if t[5] else np.zeros((NMAX, 3), np.float32) for t in ticks]),
+        pkl_keys=np.array(sorted(saved_pkl.keys())),
+        pkl_intrinsics=np.array([saved_pkl['intrinsics'][k] for k in ('fx', 'fy', 'cx', 'cy', 'width', 'height')], dtype=np.float64),
+        pkl_b2c_t=np.array(saved_pkl['base_to_cam_translation'], dtype=np.float64),
+        pkl_b2c_R=np.array(saved_pkl['base_to_cam_rot'], dtype=np.float64))
+    print('lift_golden.npz', [(t[0], t[5]['n_features'] if t[5] else None) for t in ticks])
