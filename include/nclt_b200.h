@@ -240,6 +240,31 @@ int nclt_depth_to_points(nclt_ctx* ctx, const void* depth, int is_u16, int F, in
 int nclt_occ_read(nclt_ctx* ctx, nclt_occ* occ, float* out_logodds, uint8_t* out_pgm, int32_t* out_units,
                   int64_t* out_counters);
 
+/* ---- teach-time keypoint lifting --------------------------------------
+ * Replaces the per-keypoint Python loop of scripts/common/visual_landmark_recorder.py:247-291:
+ * ORB keypoints (kp.pt, float32) + the aligned depth image (u16 millimetres, recorder:36-50) ->
+ * the keypoints the recorder keeps and their optical-frame 3-D points.  Gates, in the reference's
+ * arithmetic: np.round to the pixel, 1 <= u < W-1, 1 <= v < H-1, v > ground_y (recorder:250-253);
+ * depth_min < d < depth_max with d = float32(mm)/1000 (:260,:268); float32 std of the > 0.01 m
+ * values of the 3x3 neighbourhood < depth_std_max, 999 when fewer than 3 (:261-267,:269);
+ * X = (u - cx) * d / fx in float64, rounded to float32 (:283-286).  F frames per call.
+ * kpts_xy f32[F,Nmax,2], n_kpts i32[F] -> out_keep i32[F,Nmax] (indices into the frame's
+ * keypoints, ascending = ORB order), out_pts3d f32[F,Nmax,3], out_n i32[F].  The frame-level
+ * gate "fewer than 30 points -> no landmark" (:271-279) is the caller's (recorder.py). */
+typedef struct nclt_lift_params {
+    double fx, fy, cx, cy;        /* recorder:53-54 */
+    int32_t ground_y;             /* GROUND_Y_THRESHOLD = 180 (recorder:72) */
+    float depth_min_m;            /* DEPTH_MIN_M = 0.5 */
+    float depth_max_m;            /* DEPTH_MAX_M = 15.0 */
+    float depth_std_max_m;        /* DEPTH_VAR_MAX_M = 0.30 */
+} nclt_lift_params;
+int nclt_lift_keypoints(nclt_ctx* ctx, const uint16_t* depth_mm, int F, int H, int W, const float* kpts_xy,
+                        const int32_t* n_kpts, int Nmax, const nclt_lift_params* prm, int32_t* out_keep,
+                        float* out_pts3d, int32_t* out_n);
+int nclt_lift_keypoints_dev(nclt_ctx* ctx, const uint16_t* depth_mm, int F, int H, int W, const float* kpts_xy,
+                            const int32_t* n_kpts, int Nmax, const nclt_lift_params* prm, int32_t* out_keep,
+                            float* out_pts3d, int32_t* out_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,20 @@ class PnpParams(C.Structure):
 
 
 _pp = C.POINTER(PnpParams)
+
+
+class LiftParams(C.Structure):
+    """nclt_lift_params; defaults = the constants at visual_landmark_recorder.py:53-72."""
+    _fields_ = [('fx', _dbl), ('fy', _dbl), ('cx', _dbl), ('cy', _dbl), ('ground_y', C.c_int32),
+                ('depth_min_m', C.c_float), ('depth_max_m', C.c_float), ('depth_std_max_m', C.c_float)]
+
+    def __init__(self, fx=320.0, fy=320.0, cx=320.0, cy=240.0, ground_y=180, depth_min_m=0.5, depth_max_m=15.0,
+                 depth_std_max_m=0.30):
+        super().__init__(fx, fy, cx, cy, ground_y, depth_min_m, depth_max_m, depth_std_max_m)
+
+
+for _n in ('nclt_lift_keypoints', 'nclt_lift_keypoints_dev'):
+    _sig(_n, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(LiftParams), _vp, _vp, _vp)
 _sig('nclt_pnp_ransac', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 11))
 _sig('nclt_pnp_ransac_dev', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, *([_vp] * 6))
 _sig('nclt_pnp_score', _i, _vp, _vp, _vp, _vp, _i, _i, _pp, _vp, _vp)

@@ -51,6 +51,26 @@ class LandmarkLibrary:
         with open(path, 'rb') as f:
             return cls.from_pkl_dict(pickle.load(f), ctx=ctx)
 
+    @classmethod
+    def from_packed(cls, path, ctx=None):
+        """Load the flat binary written by recorder.write_packed: offsets / descriptors / 3-D points are already in the
+        layout nclt_lib_create takes, so the memory-mapped arrays go to the device without per-keyframe copies."""
+        from .recorder import read_packed
+        d = read_packed(path)
+        self = cls.__new__(cls)
+        self.ctx = ctx or _lib.default_context()
+        offs = np.ascontiguousarray(d['offsets'], dtype=np.int32)
+        n_kf = len(offs) - 1
+        desc = np.ascontiguousarray(d['descriptors']) if len(d['descriptors']) else np.zeros((1, 32), dtype=np.uint8)
+        pts = np.ascontiguousarray(d['points3d'], dtype=np.float32) if len(d['points3d']) else np.zeros((1, 3), dtype=np.float32)
+        self.offsets = offs
+        self.counts = np.diff(offs).astype(np.int32)
+        self.poses = np.array(d['poses'])
+        h = C.c_void_p()
+        self.ctx.check(_c.nclt_lib_create(self.ctx.h, n_kf, ptr(offs), ptr(desc), ptr(pts), C.byref(h)))
+        self.h = h
+        return self
+
     def append(self, descriptors, points3d=None):
         """Add one keyframe at runtime (visual_landmark_matcher.py:492-496)."""
         d = as_c(descriptors, np.uint8).reshape(-1, 32)
