@@ -33,6 +33,12 @@ RANSAC_ITERATIONS = 200
 MIN_INLIERS = 10
 CONSISTENCY_M = 5.0
 TICK_HZ = 2.0
+# exp 63 global relocalisation (experiments/63_global_reloc/scripts/visual_landmark_matcher.py:82-86)
+RELOC_AGE_S = 20.0
+RELOC_DRIFT_M = 3.0
+RELOC_MAX_CANDIDATES = 25
+RELOC_MIN_INLIERS = 18
+RELOC_REPROJ_MAX_PX = 1.5
 
 CSV_HEADER = ('ts,vio_x,vio_y,candidates_tried,best_n_inliers,'
               'best_reproj_err,anchor_x,anchor_y,outcome\n')
@@ -179,23 +185,49 @@ class LandmarkMatcher:
         with open(self.log_csv, 'a') as f:
             f.write(f'{ts:.3f},{vio_xy[0]:.3f},{vio_xy[1]:.3f},{n_tried},{n_in},{err},{ax},{ay},{outcome}\n')
 
-    def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0):
+    def reloc_candidates(self, base_pose, desc_curr):
+        """exp 63 global relocalisation pool (63_global_reloc/.../visual_landmark_matcher.py:328-345): every
+        heading-compatible landmark, scored by its crossCheck match count against the current frame (one batched GPU
+        call instead of a cv2 call per landmark), >= MIN_MATCHES, sorted by (count, index) descending, top 25."""
+        cur = self._heading_of(base_pose)
+        dh = self.heading - cur
+        hdg_err = np.abs(np.arctan2(np.sin(dh), np.cos(dh)))
+        pool = [int(i) for i in np.where(hdg_err < math.radians(HEADING_TOL_DEG))[0]
+                if self.library.counts[i] >= MIN_MATCHES]
+        if not pool:
+            return []
+        _, _, n = self.library.cross(np.asarray(desc_curr)[None], None, np.asarray(pool, dtype=np.int32)[None])
+        scored = [(int(c), li) for c, li in zip(n[0], pool) if c >= MIN_MATCHES]
+        scored.sort(reverse=True)
+        return [li for _, li in scored[:RELOC_MAX_CANDIDATES]]
+
+    def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0, drift_est=0.0):
         """One matcher tick from the ORB output onwards. Returns a dict with 'outcome' (the CSV
         outcome string), and on publish 'anchor_pose', 'std', 'covariance', 'n_inliers',
-        'reproj_err', 'lm_idx'."""
+        'reproj_err', 'lm_idx'.  drift_est: tf_relay's SLAM-vs-encoder disagreement (/tmp/drift_est.txt in exp 63);
+        with the default 0 the tick is the production node's, otherwise exp 63's kidnapped-robot fallback can fire."""
         self.n_attempts += 1
         vio_xy = (base_pose[0], base_pose[1])
         cand_idx = self.select_candidates(base_pose)
         if desc_curr is None or len(desc_curr) < MIN_MATCHES:
             self._log(ts, vio_xy, len(cand_idx), 0, '', None, 'curr_no_features')
             return {'outcome': 'curr_no_features', 'candidates': cand_idx}
+        relocating = False
+        if (not cand_idx and self.mode != 'ratio' and (ts - self.last_anchor_ts) > RELOC_AGE_S
+                and drift_est > RELOC_DRIFT_M):
+            cand_idx = self.reloc_candidates(base_pose, desc_curr)
+            relocating = True
         if not cand_idx:
             self._log(ts, vio_xy, 0, 0, '', None, 'no_candidates')
             return {'outcome': 'no_candidates', 'candidates': cand_idx}
-        cand = np.full((1, MAX_CANDIDATES), -1, dtype=np.int32)
+        cand = np.full((1, max(MAX_CANDIDATES, len(cand_idx))), -1, dtype=np.int32)
         cand[0, :len(cand_idx)] = cand_idx
+        params = self.params
+        if relocating:
+            params = LocalizeParams(mode=self.params.mode, min_matches=MIN_MATCHES, min_inliers=RELOC_MIN_INLIERS,
+                                    reproj_max_px=RELOC_REPROJ_MAX_PX, pnp=self.params.pnp)
         out = localize_batch(self.library, np.asarray(desc_curr)[None], np.asarray(pts_curr_2d, dtype=np.float32)[None],
-                             None, cand, self.params)
+                             None, cand, params)
         slot = int(out['best_cand'][0])
         if slot < 0:
             self._log(ts, vio_xy, len(cand_idx), 0, '', None, 'no_pnp_accept')
@@ -207,8 +239,8 @@ class LandmarkMatcher:
                                      self.base_to_cam_t, self.base_to_cam_R)
         consistency_d = math.hypot(anchor_pose[0] - vio_xy[0], anchor_pose[1] - vio_xy[1])
         res = {'candidates': cand_idx, 'anchor_pose': anchor_pose, 'n_inliers': n_inliers, 'reproj_err': reproj_err,
-               'lm_idx': lm_idx, 'shift': consistency_d}
-        if consistency_d > CONSISTENCY_M:
+               'lm_idx': lm_idx, 'shift': consistency_d, 'relocating': relocating}
+        if not relocating and consistency_d > CONSISTENCY_M:     # the jump is the point of a relocalisation (exp 63)
             res['outcome'] = f'consistency_fail_{consistency_d:.1f}m'
             self._log(ts, vio_xy, len(cand_idx), n_inliers, f'{reproj_err:.2f}', anchor_pose[:2], res['outcome'])
             return res

@@ -317,3 +317,94 @@ def golden_lift(out_dir):
         pkl_b2c_t=np.array(saved_pkl['base_to_cam_translation'], dtype=np.float64),
         pkl_b2c_R=np.array(saved_pkl['base_to_cam_rot'], dtype=np.float64))
     print('lift_golden.npz', [(t[0], t[5]['n_features'] if t[5] else None) for t in ticks])
+
+
+def golden_reloc(out_dir):
+    """exp 63 global relocalisation: experiments/63_global_reloc/scripts/visual_landmark_matcher.py::_tick run
+    unmodified under ROS stubs (stand-in ORB; '/tmp/drift_est.txt' served from memory).  Ticks far from every
+    landmark with a large drift estimate trigger the whole-library search."""
+    import builtins
+    import importlib.util
+    import pickle
+    ros_stubs.import_reference()
+    import sys
+    path = os.path.join(ros_stubs.REFERENCE_COMMON, '..', '..', 'experiments', '63_global_reloc', 'scripts',
+                        'visual_landmark_matcher.py')
+    saved = sys.argv
+    sys.argv = ['x']
+    try:
+        spec = importlib.util.spec_from_file_location('visual_landmark_matcher_exp63', os.path.normpath(path))
+        vm = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(vm)
+    finally:
+        sys.argv = saved
+    vm.ACCUM_ENABLE = False
+    drift = {'value': 0.0}
+
+    def fake_open(name, *a, **k):
+        if name == '/tmp/drift_est.txt':
+            return io.StringIO(f"{drift['value']}\n")
+        return builtins.open(name, *a, **k)
+
+    vm.open = fake_open
+    import types
+    clock = {'ts': 0.0}
+    vm.time = types.SimpleNamespace(time=lambda: clock['ts'])
+    data = synth.make_library(63, n_kf=60, n_desc=300, ragged=True, route_len_m=120.0)
+    tmp = tempfile.mkdtemp()
+    pkl = os.path.join(tmp, 'south_landmarks.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump(data, f)
+    csv = os.path.join(tmp, 'log', 'anchor_matches.csv')
+    node = vm.VisualLandmarkMatcher(pkl, csv)
+    node.last_rgb = np.zeros((480, 640, 3), dtype=np.uint8)
+    node.last_depth = np.full((480, 640), 2000, dtype=np.uint16)
+
+    class _Kp:
+        def __init__(self, pt):
+            self.pt = (float(pt[0]), float(pt[1]))
+
+    class _Orb:
+        def detectAndCompute(self, gray, mask):
+            d, p = self.next
+            return [_Kp(q) for q in p], d
+
+    node.orb = _Orb()
+    rng = np.random.default_rng(63)
+    # (kind, drift estimate, ts): 'lost' = robot reported 60 m off the route, frame really taken at landmark k
+    plan = [('local', 0.0, 30.0), ('lost_nodrift', 0.5, 60.0), ('lost', 8.0, 90.0), ('lost_recent', 8.0, 95.0),
+            ('lost', 6.0, 130.0), ('lost_random', 9.0, 170.0), ('lost', 12.0, 210.0), ('lost_weak', 7.0, 250.0)]
+    ticks = []
+    for i, (kind, dr, ts) in enumerate(plan):
+        k = int(rng.integers(5, 55))
+        planted = 0 if kind == 'lost_random' else (60 if kind == 'lost_weak' else 200)
+        fr = synth.make_frame(data, 6300 + i, k_star=k, n_desc=500, n_planted=planted)
+        lm = data['landmarks'][k]
+        bx, by = lm['pose'][0] - 0.35 + rng.normal(0, 0.3), lm['pose'][1] + rng.normal(0, 0.3)
+        if kind != 'local':
+            by += 60.0
+        yaw = rng.normal(0, 0.1)
+        base_pose = (float(bx), float(by), 0.0, 0.0, 0.0, float(np.sin(yaw / 2)), float(np.cos(yaw / 2)))
+        node.orb.next = (fr['desc'], fr['pts2d'])
+        node._read_pose = (lambda bp=base_pose: bp)
+        drift['value'] = dr
+        clock['ts'] = ts                              # the node stamps ticks with time.time() (line 291)
+        n_before = len(node.anchor_pub.sent)
+        node._tick()
+        line = open(csv).read().strip().split('\n')[-1].split(',')
+        rec = {'kind': kind, 'base_pose': base_pose, 'csv': line, 'published': len(node.anchor_pub.sent) > n_before,
+               'drift': dr, 'k': k}
+        if rec['published']:
+            m = node.anchor_pub.sent[-1]
+            p, o = m.pose.pose.position, m.pose.pose.orientation
+            rec['anchor'] = [p.x, p.y, p.z, o.x, o.y, o.z, o.w]
+        ticks.append((rec, fr['desc'], fr['pts2d']))
+    np.savez_compressed(
+        os.path.join(out_dir, 'reloc_golden.npz'), lib_seed=np.int64(63),
+        kinds=np.array([t[0]['kind'] for t in ticks]), base_pose=np.array([t[0]['base_pose'] for t in ticks]),
+        drift=np.array([t[0]['drift'] for t in ticks]), k_true=np.array([t[0]['k'] for t in ticks], dtype=np.int32),
+        ts=np.array([float(t[0]['csv'][0]) for t in ticks]),
+        csv=np.array([','.join(t[0]['csv'][1:]) for t in ticks]), published=np.array([t[0]['published'] for t in ticks]),
+        anchor=np.array([t[0].get('anchor', [0] * 7) for t in ticks], dtype=np.float64),
+        desc=np.stack([t[1] for t in ticks]), pts2d=np.stack([t[2] for t in ticks]))
+    print('reloc_golden.npz', [(t[0]['kind'], t[0]['csv'][0], t[0]['csv'][-1]) for t in ticks])

@@ -79,3 +79,31 @@ def test_match_golden_from_cv2(ctx):
                 for i in range(n[b, k]):
                     rows.append([b, k, pairs[b, k, i, 0], pairs[b, k, i, 1], int(d[b, k, i])])
         assert np.array_equal(np.array(rows, dtype=np.int32), g[f'{tag}_cross'])
+
+
+def test_global_relocalisation_against_exp63_node(ctx, tmp_path):
+    """exp 63's kidnapped-robot fallback (whole-library crossCheck ranking -> top 25 -> PnP with
+    18 inliers / 1.5 px, no consistency gate) against the exp 63 node itself (tests/golden/reloc_golden.npz)."""
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.matcher import LandmarkMatcher
+    g = np.load(os.path.join(GD, 'reloc_golden.npz'))
+    data = synth.make_library(int(g['lib_seed']), n_kf=60, n_desc=300, ragged=True, route_len_m=120.0)
+    csv = str(tmp_path / 'log' / 'anchor_matches.csv')
+    m = LandmarkMatcher(data, csv, mode='crosscheck')
+    kinds = [str(k) for k in g['kinds']]
+    n_reloc = 0
+    for i, kind in enumerate(kinds):
+        r = m.tick(g['desc'][i], g['pts2d'][i], tuple(g['base_pose'][i]), ts=float(g['ts'][i]), drift_est=float(g['drift'][i]))
+        ref = str(g['csv'][i]).split(',')
+        got = open(csv).read().strip().split('\n')[-1].split(',')[1:]
+        assert got[-1] == ref[-1], (i, kind, got, ref)
+        assert got[:4] == ref[:4] and got[4] == ref[4], (i, kind, got, ref)
+        assert bool(g['published'][i]) == r['outcome'].startswith('published')
+        if g['published'][i]:
+            a = np.array(r['anchor_pose'])
+            assert np.abs(a[:3] - g['anchor'][i, :3]).max() < 1e-3 and np.abs(a[3:] - g['anchor'][i, 3:]).max() < 1e-4
+            if r['relocating']:
+                n_reloc += 1
+                assert r['lm_idx'] == int(g['k_true'][i]) and r['shift'] > 50.0      # jumped back onto the route
+    assert n_reloc >= 2
+    assert kinds.count('lost_nodrift') == 1 and kinds.count('lost_recent') == 1
