@@ -265,6 +265,19 @@ int nclt_lift_keypoints_dev(nclt_ctx* ctx, const uint16_t* depth_mm, int F, int 
                             const int32_t* n_kpts, int Nmax, const nclt_lift_params* prm, int32_t* out_keep,
                             float* out_pts3d, int32_t* out_n);
 
+/* ---- hit-count occupancy ----------------------------------------------
+ * datasets/rover/scripts/occupancy_astar.py:142-187 `build_occupancy`: points f64[N,3] (world, HOST),
+ * labels i8[N] (0 floor, 1 obstacle, -1 ignore) -> per X-Z cell floor / obstacle hit counts
+ * (np.add.at) and occupancy i8 (-1 unknown, 0 free, 1 occupied; known = total >= min_total,
+ * occupied = obstacle >= min_obstacle).  Grid: origin = min of the classified points - 0.5 m,
+ * n = int((max + 0.5 - origin) / grid_res) + 1 (lines 155-161), cell = clip(int((p - origin) /
+ * grid_res), 0, n - 1), row-major [nz][nx].  out_origin f64[2] = (x_min, z_min), out_dims i32[2] =
+ * (nx, nz); out_occ i8[cell_cap], out_floor / out_obs i32[cell_cap] (NULL ok).  Fails with
+ * NCLT_ERR_ARG (out_dims filled in) when nx * nz > cell_cap, or when no label is >= 0. */
+int nclt_hitcount_occupancy(nclt_ctx* ctx, const double* points, const int8_t* labels, long long N, double grid_res,
+                            int min_total, int min_obstacle, long long cell_cap, double* out_origin,
+                            int32_t* out_dims, int8_t* out_occ, int32_t* out_floor, int32_t* out_obs);
+
 #ifdef __cplusplus
 }
 #endif

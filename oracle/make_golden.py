@@ -93,12 +93,12 @@ def golden_pnp(count=48, nmax=300):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['match', 'pnp', 'selftest', 'map', 'tick', 'lift', 'reloc']
+    which = sys.argv[1:] or ['match', 'pnp', 'selftest', 'map', 'tick', 'lift', 'reloc', 'hitcount']
     if 'match' in which:
         golden_match()
     if 'pnp' in which:
         golden_pnp()
-    if 'selftest' in which or 'map' in which or 'tick' in which or 'lift' in which or 'reloc' in which:
+    if 'selftest' in which or 'map' in which or 'tick' in which or 'lift' in which or 'reloc' in which or 'hitcount' in which:
         from oracle import make_golden_ref      # needs /root/reference
         if 'selftest' in which:
             make_golden_ref.golden_selftest(OUT)
@@ -110,3 +110,5 @@ if __name__ == '__main__':
             make_golden_ref.golden_lift(OUT)
         if 'reloc' in which:
             make_golden_ref.golden_reloc(OUT)
+        if 'hitcount' in which:
+            make_golden_ref.golden_hitcount(OUT)

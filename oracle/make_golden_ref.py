@@ -408,3 +408,58 @@ def golden_reloc(out_dir):
         anchor=np.array([t[0].get('anchor', [0] * 7) for t in ticks], dtype=np.float64),
         desc=np.stack([t[1] for t in ticks]), pts2d=np.stack([t[2] for t in ticks]))
     print('reloc_golden.npz', [(t[0]['kind'], t[0]['csv'][0], t[0]['csv'][-1]) for t in ticks])
+
+
+def golden_hitcount(out_dir):
+    """datasets/rover/scripts/occupancy_astar.py::build_occupancy (and backproject_depth for realistic inputs), imported
+    unmodified with matplotlib stubbed out (it is only used for the figures)."""
+    import importlib.util
+    import sys
+    import types
+    for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.patches'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.use = lambda *a, **k: None
+            sys.modules[name] = m
+    path = os.path.normpath(os.path.join(ros_stubs.REFERENCE_COMMON, '..', '..', '..', '..', 'datasets', 'rover', 'scripts',
+                                         'occupancy_astar.py'))
+    # The script as shipped does not import: line 46 (`y_rel = y_point - y_camera`) is a comment that lost its '#'.
+    # Its top-level statements are therefore executed one by one and the ones that raise NameError are skipped
+    # (exactly that line); every function and constant is the reference's own, untouched.
+    import ast
+    src = open(path).read()
+    ns = {'__name__': 'occupancy_astar_ref', '__file__': path}
+    skipped = []
+    for node in ast.parse(src, path).body:
+        try:
+            exec(compile(ast.Module([node], []), path, 'exec'), ns)
+        except NameError as e:
+            skipped.append((node.lineno, str(e)))
+    assert [ln for ln, _ in skipped] == [46], skipped
+    oa = types.SimpleNamespace(**ns)
+    ns['log'] = lambda *a, **k: None            # the functions look `log` up in their globals
+    rng = np.random.default_rng(44)
+    pts_all, lab_all = [], []
+    for f in range(12):                                  # a short walk through a synthetic garden, RealSense intrinsics
+        v = np.arange(480, dtype=np.float64)[:, None]
+        z = np.where(v > 260, 0.6 * 593.14 / np.maximum(v - 245.16, 1.0), 9.0) + np.zeros((480, 640))
+        for _ in range(6):
+            u0, v0 = int(rng.integers(0, 600)), int(rng.integers(60, 400))
+            z[v0:v0 + int(rng.integers(30, 150)), u0:u0 + int(rng.integers(20, 90))] = rng.uniform(0.4, 5.5)
+        depth = np.clip((z + rng.normal(0, 0.01, z.shape)) * 1000.0, 0, 65535).astype(np.uint16)
+        depth[rng.random(depth.shape) < 0.05] = 0
+        T = np.eye(4)
+        yaw = 0.15 * f
+        T[:3, :3] = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        T[:3, 3] = [0.4 * f, -0.6, 0.3 * f]
+        p, l = oa.backproject_depth(depth, T, oa.PIXEL_STEP)
+        pts_all.append(p)
+        lab_all.append(l)
+    points = np.concatenate(pts_all)
+    labels = np.concatenate(lab_all)
+    occ, x_min, z_min, nx, nz = oa.build_occupancy(points, labels, oa.GRID_RES)
+    np.savez_compressed(os.path.join(out_dir, 'hitcount_golden.npz'), points=points, labels=labels,
+                        occupancy=occ, x_min=np.float64(x_min), z_min=np.float64(z_min), nx=np.int64(nx), nz=np.int64(nz),
+                        grid_res=np.float64(oa.GRID_RES), min_total=np.int64(oa.MIN_HITS_TOTAL),
+                        min_obstacle=np.int64(oa.MIN_HITS_OBSTACLE))
+    print('hitcount_golden.npz', points.shape, (nz, nx), {int(k): int((occ == k).sum()) for k in (-1, 0, 1)})
