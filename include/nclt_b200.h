@@ -278,6 +278,29 @@ int nclt_hitcount_occupancy(nclt_ctx* ctx, const double* points, const int8_t* l
                             int min_total, int min_obstacle, long long cell_cap, double* out_origin,
                             int32_t* out_dims, int8_t* out_occ, int32_t* out_floor, int32_t* out_obs);
 
+/* ---- ORB feature extraction --------------------------------------------
+ * Replaces `cv2.ORB_create(nfeatures=500)` + `cv2.cvtColor(BGR2GRAY)` + `orb.detectAndCompute(gray, None)`
+ * at scripts/common/visual_landmark_matcher.py:207,305-306 and visual_landmark_recorder.py:159,240-241
+ * (cv2 defaults: scaleFactor 1.2, 8 levels, edgeThreshold 31, WTA_K 2, HARRIS_SCORE, patch 31, FAST
+ * threshold 20), for F frames of W x H per call.  Keypoints, their ORDER and descriptors are bit-identical
+ * to cv2 4.13.0.  img: u8[F,H,W] (channels = 1) or u8[F,H,W,3] BGR (channels = 3).
+ * out_kp f32[F,out_cap,6] = (pt.x, pt.y, size, angle, response, octave) per keypoint, out_desc
+ * u8[F,out_cap,32], out_n i32[F].  out_cap >= 500: a level keeps every keypoint that ties with its last
+ * retained Harris response, so a frame can exceed nfeatures; NCLT_ERR_STATE if it exceeds out_cap.
+ * The handle owns its device planes (pyramid, score map, blurred pyramid: ~4 MB per frame slot at
+ * 640 x 480) - one handle, one caller at a time, like nclt_ctx.  The selection step (retainBest) runs
+ * on the host between two device phases, so the call synchronises the context's stream. */
+typedef struct nclt_orb nclt_orb;
+int nclt_orb_create(nclt_ctx* ctx, int W, int H, int max_frames, int out_cap, nclt_orb** out);
+int nclt_orb_destroy(nclt_ctx* ctx, nclt_orb* orb);
+/* per-level geometry of the handle: width, height, features retained, scale (8 entries each; NULL ok) */
+int nclt_orb_levels(const nclt_orb* orb, int32_t* out_w, int32_t* out_h, int32_t* out_n, float* out_scale);
+int nclt_orb_detect_and_compute(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
+                                float* out_kp, uint8_t* out_desc, int32_t* out_n);
+/* img, out_kp, out_desc, out_n are DEVICE pointers */
+int nclt_orb_detect_and_compute_dev(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
+                                    float* out_kp, uint8_t* out_desc, int32_t* out_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,11 @@ double nclt_tc_bench_two_issuers(nclt_ctx* ctx, int iters, int variant);
  * i-th most recent launches (ring of 24, slot = launch number mod 24). */
 int nclt_ctx_tc_clock(nclt_ctx* ctx, double* mhz, double* kernel_ms, unsigned long long* raw64);
 
+/* Intermediate planes of the last nclt_orb_detect_and_compute call (stage-by-stage parity tests): what 0 = pyramid
+ * level, 1 = FAST score map (score, 0 = no corner; only defined >= 30 px from the border), 2 = blurred level.
+ * out: HOST u8[h,w] of that level (nclt_orb_levels gives w, h). */
+int nclt_orb_debug_plane(nclt_ctx* ctx, nclt_orb* orb, int what, int frame, int level, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,12 @@ for _n in ('nclt_localize_batch', 'nclt_localize_batch_dev'):
 
 
 _sig('nclt_hitcount_occupancy', _i, _vp, _vp, _vp, C.c_longlong, _dbl, _i, _i, C.c_longlong, _vp, _vp, _vp, _vp, _vp)
+_sig('nclt_orb_create', _i, _vp, _i, _i, _i, _i, C.POINTER(_vp))
+_sig('nclt_orb_destroy', _i, _vp, _vp)
+_sig('nclt_orb_levels', _i, _vp, _vp, _vp, _vp, _vp)
+for _n in ('nclt_orb_detect_and_compute', 'nclt_orb_detect_and_compute_dev'):
+    _sig(_n, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp)
+_sig('nclt_orb_debug_plane', _i, _vp, _vp, _i, _i, _i, _vp)
 _sig('nclt_occ_create', _i, _vp, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_vp))
 _sig('nclt_occ_destroy', _i, _vp, _vp)
 _sig('nclt_occ_reset', _i, _vp, _vp)

@@ -1,0 +1,539 @@
+// ORB feature extraction: `cv2.ORB_create(nfeatures=500).detectAndCompute(gray, None)` of
+// scripts/common/visual_landmark_matcher.py:207,305-306 and visual_landmark_recorder.py:159,240-241, for batches of
+// frames.  OpenCV is a third-party dependency of the reference (opencv-python, not vendored); the stages below follow
+// its published ORB (features2d) and are pinned against cv2 4.13.0 bit for bit (keypoint order included):
+//   gray      BGR -> gray, 15-bit fixed point (b*3735 + g*19235 + r*9798 + 2^14) >> 15
+//   pyramid   8 levels, scale 1.2^l (float), each level resized from the previous one with the bit-exact bilinear
+//             resize (INTER_LINEAR_EXACT: 8.8 fixed-point weights, horizontal then vertical, (v + 2^15) >> 16)
+//   FAST      9-of-16 segment test, threshold 20, score = largest threshold keeping the pixel a corner, 3x3 strict NMS
+//   Harris    7x7 block of 3x3 Sobel products at every NMS survivor at least 31 px from the border
+//   select    per level: retainBest(2n) by FAST score, then retainBest(n) by Harris - HOST side, with the very
+//             std::nth_element / std::partition calls OpenCV makes (their permutation defines the output order)
+//   angle     intensity centroid over the radius-15 disc, cv::fastAtan2 polynomial
+//   blur      7x7 sigma-2 Gaussian as OpenCV's separable float filter runs it on a pyramid sub-matrix: row pass
+//             sequential FMAs, column pass symmetric pairs with FMAs, round half to even
+//   rBRIEF    256 rotated pair tests (orb_pattern.h) on the blurred level
+// Byte work bound by HBM / L2: every stage reads and writes u8 planes once; nothing is GEMM shaped.
+#include "common.cuh"
+#include "scratch.cuh"
+#include "orb_pattern.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+constexpr int kLevels = 8;
+constexpr int kEdge = 31;        // edgeThreshold
+constexpr int kHalfPatch = 15;   // patchSize / 2
+constexpr int kFastThr = 20;
+
+struct OrbGeom {
+    int w[kLevels], h[kLevels], pitch[kLevels];
+    long long off[kLevels];     // byte offset of the level inside one frame's pyramid
+    long long frame_bytes;
+    float scale[kLevels];
+    int umax[kHalfPatch + 2];
+    float atan_p1, atan_p3, atan_p5, atan_p7;
+    float gk[4];                // Gaussian taps: gk[0] centre .. gk[3] outermost
+    float deg2rad;
+};
+
+__constant__ signed char c_pattern[256 * 4];
+
+struct Cand { uint32_t tag, key; float score, harris; };          // tag = frame * 8 + level, key = y << 16 | x
+struct Sel { int frame, level, x, y; float harris; int slot; };   // slot = row inside the frame's output
+
+// ---- level 0 ----
+__global__ void __launch_bounds__(256) k_orb_level0(const uint8_t* __restrict__ src, int channels, int W, int H, int pitch,
+                                                    long long frame_bytes, uint8_t* __restrict__ pyr) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* s = src + ((size_t)f * H + y) * (size_t)W * channels + (size_t)x * channels;
+    int g;
+    if (channels == 1) g = s[0];
+    else g = (s[0] * 3735 + s[1] * 19235 + s[2] * 9798 + 16384) >> 15;
+    pyr[(size_t)f * frame_bytes + (size_t)y * pitch + x] = (uint8_t)g;
+}
+
+// ---- bit-exact bilinear resize of one level from the previous one ----
+// tab: [sx(dw) | ax(dw) | sy(dh) | ay(dh)] int32, from the host in double arithmetic
+__global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                    uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+                                                    long long frame_bytes, const int* __restrict__ tab) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= dw) return;
+    const int sx = tab[x], ax = tab[dw + x], sy = tab[2 * dw + y], ay = tab[2 * dw + dh + y];
+    const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+    const uint8_t* s = src + (size_t)f * frame_bytes;
+    const uint8_t* r0 = s + (size_t)sy * spitch;
+    const uint8_t* r1 = s + (size_t)sy1 * spitch;
+    const unsigned h0 = r0[sx] * (256 - ax) + r0[sx1] * ax;
+    const unsigned h1 = r1[sx] * (256 - ax) + r1[sx1] * ax;
+    const unsigned v = h0 * (256 - ay) + h1 * ay;
+    dst[(size_t)f * frame_bytes + (size_t)y * dpitch + x] = (uint8_t)((v + 32768u) >> 16);
+}
+
+// ---- FAST 9-16 score map ----
+__device__ __forceinline__ bool has9(unsigned m) {     // 9 contiguous set bits in a circular 16-bit mask
+    unsigned r = m | (m << 16);
+    unsigned a = r & (r >> 1);
+    a &= a >> 2;
+    a &= a >> 4;          // 8 contiguous
+    a &= r >> 8;          // 9
+    return (a & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, uint8_t* __restrict__ score) {
+    const int f = blockIdx.z / kLevels, l = blockIdx.z % kLevels;
+    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31) + kEdge - 1, y = blockIdx.y * 8 + (threadIdx.x >> 5) + kEdge - 1;
+    if (x > w - kEdge || y > h - kEdge) return;
+    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
+    const uint8_t* c = pyr + base + (size_t)y * p + x;
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * p];          d[1] = v - c[3 * p + 1];   d[2] = v - c[2 * p + 2];    d[3] = v - c[p + 3];
+    d[4] = v - c[3];              d[5] = v - c[-p + 3];      d[6] = v - c[-2 * p + 2];   d[7] = v - c[-3 * p + 1];
+    d[8] = v - c[-3 * p];         d[9] = v - c[-3 * p - 1];  d[10] = v - c[-2 * p - 2];  d[11] = v - c[-p - 3];
+    d[12] = v - c[-3];            d[13] = v - c[p - 3];      d[14] = v - c[2 * p - 2];   d[15] = v - c[3 * p - 1];
+    unsigned dark = 0, bright = 0;            // ring darker / brighter than the centre by more than the threshold
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        dark |= (d[k] > kFastThr ? 1u : 0u) << k;
+        bright |= (d[k] < -kFastThr ? 1u : 0u) << k;
+    }
+    int s = 0;
+    if (has9(dark) || has9(bright)) {
+        // score = (max over the 16 arcs of 9 of the smallest |difference| of one sign) - 1
+        int best = kFastThr;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            int mn = d[k], mx = d[k];
+#pragma unroll
+            for (int j = 1; j < 9; ++j) {
+                const int e = d[(k + j) & 15];
+                mn = min(mn, e);
+                mx = max(mx, e);
+            }
+            best = max(best, max(mn, -mx));
+        }
+        s = best - 1;
+    }
+    score[base + (size_t)y * p + x] = (uint8_t)s;
+}
+
+// ---- NMS + border filter + Harris response, candidates appended to one list ----
+__global__ void __launch_bounds__(256) k_orb_nms(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbGeom g,
+                                                 Cand* __restrict__ cand, unsigned* __restrict__ n_cand, unsigned cap,
+                                                 float harris_scale4) {
+    const int f = blockIdx.z / kLevels, l = blockIdx.z % kLevels;
+    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31) + kEdge, y = blockIdx.y * 8 + (threadIdx.x >> 5) + kEdge;
+    if (x >= w - kEdge || y >= h - kEdge) return;
+    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
+    const uint8_t* sc = score + base + (size_t)y * p + x;
+    const int s = sc[0];
+    if (s == 0) return;
+    if (!(s > sc[-1] && s > sc[1] && s > sc[-p - 1] && s > sc[-p] && s > sc[-p + 1] && s > sc[p - 1] && s > sc[p] &&
+          s > sc[p + 1]))
+        return;
+    const uint8_t* c = pyr + base + (size_t)y * p + x;
+    int a = 0, b = 0, cc = 0;
+    for (int dy = -3; dy <= 3; ++dy)
+        for (int dx = -3; dx <= 3; ++dx) {
+            const uint8_t* q = c + dy * p + dx;
+            const int Ix = (q[1] - q[-1]) * 2 + (q[-p + 1] - q[-p - 1]) + (q[p + 1] - q[p - 1]);
+            const int Iy = (q[p] - q[-p]) * 2 + (q[p - 1] - q[-p - 1]) + (q[p + 1] - q[-p + 1]);
+            a += Ix * Ix;
+            b += Iy * Iy;
+            cc += Ix * Iy;
+        }
+    const float fa = (float)a, fb = (float)b, fc = (float)cc;
+    const float t = __fadd_rn(fa, fb);
+    const float r = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t), t)),
+                              harris_scale4);
+    const unsigned slot = atomicAdd(n_cand, 1u);
+    if (slot < cap) cand[slot] = Cand{(uint32_t)(f * kLevels + l), (uint32_t)(y << 16 | x), (float)s, r};
+}
+
+// ---- Gaussian blur, 32x32 output tile per CTA ----
+__global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, OrbGeom g, uint8_t* __restrict__ blur) {
+    const int f = blockIdx.z / kLevels, l = blockIdx.z % kLevels;
+    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (x0 >= w || y0 >= h) return;
+    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
+    __shared__ float tile[38][39];
+    __shared__ float rowp[38][33];
+    for (int i = threadIdx.x; i < 38 * 38; i += 256) {
+        const int ty = i / 38, tx = i % 38;
+        const int yy = min(max(y0 + ty - 3, 0), h - 1), xx = min(max(x0 + tx - 3, 0), w - 1);   // clamped: only pixels
+        tile[ty][tx] = (float)pyr[base + (size_t)yy * p + xx];                                 // >= 9 px inside are used
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 38 * 32; i += 256) {
+        const int ty = i / 32, tx = i % 32;
+        float s = __fmul_rn(tile[ty][tx], g.gk[3]);
+        s = fmaf(tile[ty][tx + 1], g.gk[2], s);
+        s = fmaf(tile[ty][tx + 2], g.gk[1], s);
+        s = fmaf(tile[ty][tx + 3], g.gk[0], s);
+        s = fmaf(tile[ty][tx + 4], g.gk[1], s);
+        s = fmaf(tile[ty][tx + 5], g.gk[2], s);
+        s = fmaf(tile[ty][tx + 6], g.gk[3], s);
+        rowp[ty][tx] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        const int ty = i / 32, tx = i % 32;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= w || y >= h) continue;
+        float s = __fmul_rn(g.gk[0], rowp[ty + 3][tx]);
+        s = fmaf(g.gk[1], __fadd_rn(rowp[ty + 4][tx], rowp[ty + 2][tx]), s);
+        s = fmaf(g.gk[2], __fadd_rn(rowp[ty + 5][tx], rowp[ty + 1][tx]), s);
+        s = fmaf(g.gk[3], __fadd_rn(rowp[ty + 6][tx], rowp[ty][tx]), s);
+        int v = __float2int_rn(s);
+        blur[base + (size_t)y * p + x] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// ---- orientation + rBRIEF, one warp per keypoint ----
+__device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbGeom& g) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = 2.220446049250313e-16f;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(g.atan_p7, c2), g.atan_p5), c2), g.atan_p3), c2), g.atan_p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(g.atan_p7, c2), g.atan_p5), c2), g.atan_p3), c2), g.atan_p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, OrbGeom g,
+                                                      const Sel* __restrict__ sel, int n_sel, int cap,
+                                                      float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n_sel) return;
+    const Sel s = sel[k];
+    const int p = g.pitch[s.level];
+    const size_t base = (size_t)s.frame * g.frame_bytes + g.off[s.level];
+    const uint8_t* c = pyr + base + (size_t)s.y * p + s.x;
+    // intensity centroid: lane = row v + 15
+    int m01 = 0, m10 = 0;
+    if (lane <= 2 * kHalfPatch) {
+        const int v = lane - kHalfPatch, d = g.umax[v < 0 ? -v : v];
+        const uint8_t* r = c + v * p;
+        int rs = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int val = r[u];
+            m10 += u * val;
+            rs += val;
+        }
+        m01 = v * rs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+        m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10, g);
+    const float sc = g.scale[s.level];
+    const float px = s.level ? __fmul_rn((float)s.x, sc) : (float)s.x;
+    const float py = s.level ? __fmul_rn((float)s.y, sc) : (float)s.y;
+    // descriptor centre exactly as computeOrbDescriptors derives it from the scaled keypoint
+    const float inv = __fdiv_rn(1.f, sc);
+    const int cx = __float2int_rn(__fmul_rn(px, inv)), cy = __float2int_rn(__fmul_rn(py, inv));
+    const float ar = __fmul_rn(angle, g.deg2rad);
+    const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+    const uint8_t* bc = blur + base + (size_t)cy * p + cx;
+    unsigned byte = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const signed char* q = c_pattern + (lane * 8 + i) * 4;
+        const float x0 = (float)q[0], y0 = (float)q[1], x1 = (float)q[2], y1 = (float)q[3];
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+        const int t0 = bc[iy0 * p + ix0], t1 = bc[iy1 * p + ix1];
+        byte |= (t0 < t1 ? 1u : 0u) << i;
+    }
+    const size_t row = (size_t)s.frame * cap + s.slot;
+    out_desc[row * 32 + lane] = (uint8_t)byte;
+    if (lane == 0) {
+        float* o = out_kp + row * 6;
+        o[0] = px;
+        o[1] = py;
+        o[2] = __fmul_rn(31.f, sc);
+        o[3] = angle;
+        o[4] = s.harris;
+        o[5] = (float)s.level;
+    }
+}
+
+// KeyPointsFilter::retainBest on (response, index) pairs: same std::nth_element / std::partition calls, same
+// comparators, hence the same permutation as OpenCV's vector<KeyPoint>.
+struct RespIdx { float r; int i; };
+void retain_best(std::vector<RespIdx>& v, int n_points) {
+    if (n_points >= 0 && v.size() > (size_t)n_points) {
+        if (n_points == 0) { v.clear(); return; }
+        std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(),
+                         [](const RespIdx& a, const RespIdx& b) { return a.r > b.r; });
+        const float ambiguous = v[n_points - 1].r;
+        auto e = std::partition(v.begin() + n_points, v.end(), [ambiguous](const RespIdx& a) { return a.r >= ambiguous; });
+        v.resize(e - v.begin());
+    }
+}
+
+}  // namespace
+
+struct nclt_orb {
+    int W = 0, H = 0, max_frames = 0, nfeatures = 500;
+    OrbGeom g;
+    int n_level[kLevels];
+    unsigned cand_cap_per_frame = 0;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_score = nullptr, *d_in = nullptr;
+    Cand* d_cand = nullptr;
+    unsigned* d_ncand = nullptr;
+    int* d_tab[kLevels] = {};
+    Sel* d_sel = nullptr;
+    float* d_kp = nullptr;
+    uint8_t* d_desc = nullptr;
+    int out_cap = 0;
+    float harris_scale4 = 0.f;
+    std::vector<Cand> h_cand;
+    std::vector<Sel> h_sel;
+};
+
+extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
+    if (!o) return NCLT_OK;
+    if (c) cudaSetDevice(c->device);
+    cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
+    cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
+    for (int l = 0; l < kLevels; ++l) cudaFree(o->d_tab[l]);
+    delete o;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int out_cap, nclt_orb** out) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!out || W < 200 || H < 200 || W > 8192 || H > 8192 || max_frames <= 0 || out_cap < 500)
+        return nclt_fail(c, NCLT_ERR_ARG, "orb_create: bad arguments (W, H in [200, 8192], out_cap >= 500)");
+    cudaSetDevice(c->device);
+    nclt_orb* o = new nclt_orb();
+    o->W = W; o->H = H; o->max_frames = max_frames; o->out_cap = out_cap;
+    OrbGeom& g = o->g;
+    // ORB_Impl: scaleFactor is stored as a double holding the float 1.2f; getScale() = (float)pow(scaleFactor, level)
+    const double scale_factor = (double)1.2f;
+    long long off = 0;
+    unsigned cand_cap = 0;
+    for (int l = 0; l < kLevels; ++l) {
+        g.scale[l] = (float)std::pow(scale_factor, (double)l);
+        g.w[l] = (int)lrintf((float)W / g.scale[l]);
+        g.h[l] = (int)lrintf((float)H / g.scale[l]);
+        g.pitch[l] = (g.w[l] + 15) & ~15;
+        g.off[l] = off;
+        off += (long long)g.pitch[l] * g.h[l];
+        const int iw = std::max(g.w[l] - 2 * kEdge, 0), ih = std::max(g.h[l] - 2 * kEdge, 0);
+        cand_cap += (unsigned)(((iw + 1) / 2) * ((ih + 1) / 2));        // strict 3x3 maxima: at most one per 2x2 cell
+    }
+    g.frame_bytes = (off + 255) & ~255LL;
+    o->cand_cap_per_frame = cand_cap;
+    // features per level (ORB_Impl::detectAndCompute)
+    {
+        const float factor = (float)(1.0 / scale_factor);
+        float nd = o->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)kLevels));
+        int sum = 0;
+        for (int l = 0; l < kLevels - 1; ++l) {
+            o->n_level[l] = (int)lrintf(nd);
+            sum += o->n_level[l];
+            nd *= factor;
+        }
+        o->n_level[kLevels - 1] = std::max(o->nfeatures - sum, 0);
+    }
+    // disc of the intensity centroid
+    {
+        const int hp = kHalfPatch;
+        int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+        for (int v = 0; v <= vmax; ++v) g.umax[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
+        for (int v = hp, v0 = 0; v >= vmin; --v) {
+            while (g.umax[v0] == g.umax[v0 + 1]) ++v0;
+            g.umax[v] = v0;
+            ++v0;
+        }
+    }
+    const float rad2deg = (float)(180 / 3.1415926535897932384626433832795);
+    g.atan_p1 = 0.9997878412794807f * rad2deg;
+    g.atan_p3 = -0.3258083974640975f * rad2deg;
+    g.atan_p5 = 0.1555786518463281f * rad2deg;
+    g.atan_p7 = -0.04432655554792128f * rad2deg;
+    g.deg2rad = (float)(3.1415926535897932384626433832795 / 180.f);
+    // getGaussianKernel(7, 2, CV_32F): bit patterns of the four distinct taps (centre first)
+    const uint32_t gk_bits[4] = {0x3e5d4ae0u, 0x3e434a39u, 0x3e06387eu, 0x3d8fafb1u};
+    for (int i = 0; i < 4; ++i) memcpy(&g.gk[i], &gk_bits[i], 4);
+    {
+        const float sc = 1.f / ((1 << 2) * 7 * 255.f);
+        o->harris_scale4 = sc * sc * sc * sc;
+    }
+    const size_t fb = (size_t)g.frame_bytes * max_frames;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&o->d_pyr, fb); A((void**)&o->d_blur, fb); A((void**)&o->d_score, fb);
+    A((void**)&o->d_in, (size_t)W * H * 3 * max_frames);
+    A((void**)&o->d_cand, (size_t)cand_cap * max_frames * sizeof(Cand));
+    A((void**)&o->d_ncand, 256);
+    A((void**)&o->d_sel, (size_t)out_cap * max_frames * sizeof(Sel));
+    A((void**)&o->d_kp, (size_t)out_cap * max_frames * 6 * sizeof(float));
+    A((void**)&o->d_desc, (size_t)out_cap * max_frames * 32);
+    // resize tables (resize.cpp, bit-exact linear): src = (d + 0.5) * (src / dst) - 0.5 in double, weight round(frac * 256)
+    for (int l = 1; l < kLevels && e == cudaSuccess; ++l) {
+        const int sw = g.w[l - 1], sh = g.h[l - 1], dw = g.w[l], dh = g.h[l];
+        std::vector<int> tab(2 * dw + 2 * dh);
+        auto fill = [](int src, int dst, int* s, int* a) {
+            const double scale = (double)src / dst;
+            for (int d = 0; d < dst; ++d) {
+                double f = (d + 0.5) * scale - 0.5;
+                int i = (int)std::floor(f);
+                double fr = f - i;
+                if (i < 0) { fr = 0; i = 0; }
+                if (i >= src - 1) { fr = 0; i = src - 1; }
+                s[d] = i;
+                a[d] = (int)lrint(fr * 256);
+            }
+        };
+        fill(sw, dw, tab.data(), tab.data() + dw);
+        fill(sh, dh, tab.data() + 2 * dw, tab.data() + 2 * dw + dh);
+        A((void**)&o->d_tab[l], tab.size() * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(o->d_tab[l], tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_pattern, kOrbPattern, sizeof(kOrbPattern));
+    if (e == cudaSuccess) e = cudaMemset(o->d_score, 0, fb);
+    if (e != cudaSuccess) {
+        nclt_orb_destroy(c, o);
+        return nclt_fail(c, e == cudaErrorMemoryAllocation ? NCLT_ERR_NOMEM : NCLT_ERR_CUDA, "orb_create", e);
+    }
+    *out = o;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_orb_levels(const nclt_orb* o, int32_t* out_w, int32_t* out_h, int32_t* out_n, float* out_scale) {
+    if (!o) return NCLT_ERR_ARG;
+    for (int l = 0; l < kLevels; ++l) {
+        if (out_w) out_w[l] = o->g.w[l];
+        if (out_h) out_h[l] = o->g.h[l];
+        if (out_n) out_n[l] = o->n_level[l];
+        if (out_scale) out_scale[l] = o->g.scale[l];
+    }
+    return NCLT_OK;
+}
+
+static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_device, int channels, int F, float* out_kp,
+                   uint8_t* out_desc, int32_t* out_n, bool out_on_device) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!o || !img || (channels != 1 && channels != 3) || F <= 0 || F > o->max_frames || !out_kp || !out_desc || !out_n)
+        return nclt_fail(c, NCLT_ERR_ARG, "orb_detect_and_compute: bad arguments");
+    cudaSetDevice(c->device);
+    const OrbGeom& g = o->g;
+    cudaStream_t st = c->stream;
+    const uint8_t* d_img = img;
+    if (!img_on_device) {
+        CU_TRY(c, cudaMemcpyAsync(o->d_in, img, (size_t)o->W * o->H * channels * F, cudaMemcpyHostToDevice, st));
+        d_img = o->d_in;
+    }
+    CU_TRY(c, cudaMemsetAsync(o->d_ncand, 0, 4, st));
+    k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
+    for (int l = 1; l < kLevels; ++l)
+        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
+                                                                             g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
+                                                                             g.pitch[l], g.frame_bytes, o->d_tab[l]);
+    const dim3 gf((g.w[0] - 2 * kEdge + 2 + 31) / 32, (g.h[0] - 2 * kEdge + 2 + 7) / 8, F * kLevels);
+    k_orb_fast<<<gf, 256, 0, st>>>(o->d_pyr, g, o->d_score);
+    const unsigned cap = o->cand_cap_per_frame * (unsigned)F;
+    k_orb_nms<<<gf, 256, 0, st>>>(o->d_pyr, o->d_score, g, o->d_cand, o->d_ncand, cap, o->harris_scale4);
+    c->launches += 10;
+    unsigned n_cand = 0;
+    CU_TRY(c, cudaMemcpyAsync(&n_cand, o->d_ncand, 4, cudaMemcpyDeviceToHost, st));
+    // the blur does not depend on the selection: queue it before the host waits
+    k_orb_blur<<<dim3((g.w[0] + 31) / 32, (g.h[0] + 31) / 32, F * kLevels), 256, 0, st>>>(o->d_pyr, g, o->d_blur);
+    c->launches += 1;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(st));
+    if (n_cand > cap) return nclt_fail(c, NCLT_ERR_STATE, "orb: candidate list overflow (cannot happen for strict 3x3 maxima)");
+    o->h_cand.resize(n_cand);
+    if (n_cand) {
+        CU_TRY(c, cudaMemcpyAsync(o->h_cand.data(), o->d_cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+    }
+    // host: FAST's row-major order, then the two retainBest passes per (frame, level)
+    std::sort(o->h_cand.begin(), o->h_cand.end(),
+              [](const Cand& a, const Cand& b) { return a.tag != b.tag ? a.tag < b.tag : a.key < b.key; });
+    o->h_sel.clear();
+    std::vector<int32_t> n_out(F, 0);
+    std::vector<RespIdx> v;
+    size_t i = 0;
+    int rc_overflow = 0;
+    while (i < o->h_cand.size()) {
+        size_t j = i;
+        const uint32_t tag = o->h_cand[i].tag;
+        while (j < o->h_cand.size() && o->h_cand[j].tag == tag) ++j;
+        const int f = (int)(tag / kLevels), l = (int)(tag % kLevels);
+        v.resize(j - i);
+        for (size_t k = i; k < j; ++k) v[k - i] = RespIdx{o->h_cand[k].score, (int)k};
+        retain_best(v, 2 * o->n_level[l]);
+        for (RespIdx& r : v) r.r = o->h_cand[r.i].harris;
+        retain_best(v, o->n_level[l]);
+        for (const RespIdx& r : v) {
+            const Cand& cd = o->h_cand[r.i];
+            if (n_out[f] >= o->out_cap) { rc_overflow = 1; break; }
+            o->h_sel.push_back(Sel{f, l, (int)(cd.key & 0xFFFF), (int)(cd.key >> 16), cd.harris, n_out[f]++});
+        }
+        i = j;
+    }
+    if (rc_overflow) return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
+    const int n_sel = (int)o->h_sel.size();
+    float* d_kp = out_on_device ? out_kp : o->d_kp;
+    uint8_t* d_desc = out_on_device ? out_desc : o->d_desc;
+    if (n_sel) {
+        CU_TRY(c, cudaMemcpyAsync(o->d_sel, o->h_sel.data(), (size_t)n_sel * sizeof(Sel), cudaMemcpyHostToDevice, st));
+        k_orb_describe<<<(n_sel + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, n_sel, o->out_cap, d_kp, d_desc);
+        c->launches += 1;
+        CU_TRY(c, cudaGetLastError());
+    }
+    if (out_on_device) {
+        CU_TRY(c, cudaMemcpyAsync(out_n, n_out.data(), (size_t)F * 4, cudaMemcpyHostToDevice, st));
+    } else {
+        memcpy(out_n, n_out.data(), (size_t)F * 4);
+        CU_TRY(c, cudaMemcpyAsync(out_kp, d_kp, (size_t)F * o->out_cap * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaMemcpyAsync(out_desc, d_desc, (size_t)F * o->out_cap * 32, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(c, cudaStreamSynchronize(st));
+    return NCLT_OK;
+}
+
+extern "C" int nclt_orb_detect_and_compute(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int channels, int F, float* out_kp,
+                                           uint8_t* out_desc, int32_t* out_n) {
+    return orb_run(c, o, img, false, channels, F, out_kp, out_desc, out_n, false);
+}
+extern "C" int nclt_orb_detect_and_compute_dev(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int channels, int F,
+                                               float* out_kp, uint8_t* out_desc, int32_t* out_n) {
+    return orb_run(c, o, img, true, channels, F, out_kp, out_desc, out_n, true);
+}
+
+extern "C" int nclt_orb_debug_plane(nclt_ctx* c, nclt_orb* o, int what, int frame, int level, uint8_t* out) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!o || !out || what < 0 || what > 2 || frame < 0 || frame >= o->max_frames || level < 0 || level >= kLevels)
+        return nclt_fail(c, NCLT_ERR_ARG, "orb_debug_plane: bad arguments");
+    cudaSetDevice(c->device);
+    const uint8_t* base = (what == 0 ? o->d_pyr : what == 1 ? o->d_score : o->d_blur) + (size_t)frame * o->g.frame_bytes + o->g.off[level];
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaMemcpy2D(out, o->g.w[level], base, o->g.pitch[level], o->g.w[level], o->g.h[level], cudaMemcpyDeviceToHost));
+    return NCLT_OK;
+}

@@ -190,3 +190,18 @@ def make_depth_frame(seed, pose, cyl_density=0.02, h=IMG_H, w=IMG_W, bad_frac=0.
     depth[bad & (kinds == 1)] = np.inf
     depth[bad & (kinds == 2)] = np.nan
     return depth
+
+
+def make_camera_frame(seed, h=IMG_H, w=IMG_W, bgr=False, n_rect=300, noise=4.0):
+    """A synthetic textured camera image for ORB: overlapping constant rectangles (corners and
+    edges at every scale) plus sensor noise, uint8 [h,w] or BGR [h,w,3]."""
+    rng = np.random.default_rng(seed)
+    ch = 3 if bgr else 1
+    img = np.zeros((h, w, ch), np.float32)
+    for _ in range(n_rect):
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        rw, rh = (int(v) for v in rng.integers(5, 80, 2))
+        img[y:y + rh, x:x + rw] += rng.uniform(-60, 60, ch).astype(np.float32)
+    img += 128 + rng.normal(0, noise, (h, w, ch)).astype(np.float32)
+    out = np.clip(img, 0, 255).astype(np.uint8)
+    return out if bgr else out[..., 0]

@@ -1,0 +1,107 @@
+"""GPU: ORB extraction (csrc/orb.cu behind nclt_orb_*) against the CPU oracle (oracle/orb.py,
+itself pinned bit for bit against cv2 4.13), against cv2 directly where it is importable, and against the committed
+cv2 outputs of tests/golden/orb_golden.npz.  Bar: keypoints (pt, size, angle, response, octave), their ORDER and the
+256-bit descriptors bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import nclt_slam_project_b200  # noqa: F401
+from nclt_slam_project_b200 import synth
+from oracle import orb as oo
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'orb_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def orb(ctx):
+    from nclt_slam_project_b200.orb import ORB
+    return ORB(nfeatures=500, width=640, height=480, max_frames=4, ctx=ctx)
+
+
+def _check(kp, desc, n, f, ref_k, ref_d, what):
+    m = int(n[f])
+    assert m == len(ref_k), (what, m, len(ref_k))
+    k = kp[f, :m]
+    for col, name in enumerate(('pt.x', 'pt.y', 'size', 'angle', 'response', 'octave')):
+        bad = np.nonzero(k[:, col].view(np.uint32) != ref_k[:, col].view(np.uint32))[0]
+        assert len(bad) == 0, (what, name, len(bad), bad[:5], k[bad[:5], col], ref_k[bad[:5], col])
+    bad = np.nonzero((desc[f, :m] != ref_d).any(1))[0]
+    assert len(bad) == 0, (what, 'descriptors', len(bad), bad[:5])
+
+
+def test_stage_planes_equal_the_oracle(orb):
+    gray = synth.make_camera_frame(21)
+    orb.detect_and_compute_batch(gray[None])
+    pyr = oo.pyramid(gray)
+    w, h, nper, scale = orb.levels()
+    _, sizes, ref_n = oo.level_params(640, 480)
+    assert [(int(a), int(b)) for a, b in zip(w, h)] == sizes and list(nper) == ref_n
+    for l in range(8):
+        assert np.array_equal(orb.debug_plane('pyramid', 0, l), pyr[l]), ('pyramid', l)
+    for l in range(8):
+        ref = oo.fast_score_map(pyr[l])
+        got = orb.debug_plane('score', 0, l)
+        assert np.array_equal(got[30:-30, 30:-30], ref[30:-30, 30:-30].astype(np.uint8)), ('score', l)
+        assert (ref[30:-30, 30:-30] > 0).sum() > 20
+    for l in range(8):
+        assert np.array_equal(orb.debug_plane('blur', 0, l)[3:-3, 3:-3], oo.blur7(pyr[l])[3:-3, 3:-3]), ('blur', l)
+
+
+def test_batch_equals_oracle_and_cv2(orb):
+    frames = np.stack([synth.make_camera_frame(s) for s in (0, 1, 2, 3)])
+    kp, desc, n = orb.detect_and_compute_batch(frames)
+    try:
+        import cv2
+        cv = cv2.ORB_create(nfeatures=500)
+    except ImportError:
+        cv = None
+    for f in range(4):
+        rk, rd = oo.detect_and_compute(frames[f])
+        assert len(rk) >= 490
+        _check(kp, desc, n, f, rk, rd, f'frame {f} vs oracle')
+        if cv is not None:
+            ck, cd = cv.detectAndCompute(frames[f], None)
+            ck = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in ck], np.float32)
+            _check(kp, desc, n, f, ck, cd, f'frame {f} vs cv2')
+
+
+def test_response_ties_and_noise(orb):
+    """Tiled image: hundreds of identical corners, so both retainBest passes hit their tie rule (a level keeps more
+    than its quota, 514 keypoints in all); white noise: tens of thousands of FAST corners per frame."""
+    tile = synth.make_camera_frame(9, 96, 128, n_rect=20, noise=0.0)
+    frames = np.stack([np.tile(tile, (5, 5)), np.random.default_rng(0).integers(0, 256, (480, 640), dtype=np.uint8)])
+    kp, desc, n = orb.detect_and_compute_batch(frames)
+    for f in range(2):
+        rk, rd = oo.detect_and_compute(frames[f])
+        _check(kp, desc, n, f, rk, rd, f'frame {f}')
+    assert int(n[0]) > 500
+
+
+def test_call_surface_bgr_flat_and_resize(ctx):
+    from nclt_slam_project_b200.orb import ORB_create
+    orb = ORB_create(nfeatures=500, ctx=ctx)
+    bgr = synth.make_camera_frame(31, bgr=True)
+    kps, desc = orb.detectAndCompute(bgr, None)                       # BGR in: gray conversion on the device
+    rk, rd = oo.detect_and_compute(oo.bgr2gray(bgr))
+    assert len(kps) == len(rk) and np.array_equal(desc, rd)
+    assert np.array_equal(np.array([k.pt for k in kps], np.float32), rk[:, :2])
+    assert [k.octave for k in kps] == rk[:, 5].astype(int).tolist()
+    kps, desc = orb.detectAndCompute(np.full((480, 640), 90, np.uint8), None)     # matcher:307 'curr_no_features'
+    assert len(kps) == 0 and desc is None
+    g = np.load(G)                                                    # other image sizes: the handle is rebuilt
+    for i in range(3):
+        kps, desc = orb.detectAndCompute(g[f'img{i}'], None)
+        k = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kps], np.float32)
+        assert np.array_equal(k.view(np.uint32), g[f'kp{i}'].view(np.uint32)) and np.array_equal(desc, g[f'desc{i}'])
+
+
+def test_bad_arguments(ctx):
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.orb import ORB
+    with pytest.raises(_lib.NcltError):
+        ORB(width=100, height=100, ctx=ctx)
+    with pytest.raises(ValueError):
+        ORB(nfeatures=1000, ctx=ctx)

@@ -1,0 +1,85 @@
+#!/usr/bin/env python3
+"""ORB extraction throughput: batches of 640x480 gray frames through nclt_orb_detect_and_compute.
+One JSON object: frames/s with the frames resident in HBM (device-pointer entry point; the call still contains the
+host selection step and its two small transfers), frames/s from pinned host buffers (end to end), the share of the
+device phases, and cv2.ORB_create(500).detectAndCompute on the host cores for a bounded sample, with parity checked."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--cpu-frames', type=int, default=32)
+    args = ap.parse_args()
+    import torch
+    import nclt_slam_project_b200  # noqa
+    from nclt_slam_project_b200 import _lib, synth
+    from nclt_slam_project_b200._lib import lib as L, ptr
+    from nclt_slam_project_b200.orb import ORB
+    F = args.batch
+    uniq = np.stack([synth.make_camera_frame(100 + s) for s in range(min(F, 16))])
+    frames = uniq[np.arange(F) % len(uniq)].copy()
+    dev = torch.device('cuda', 0)
+    stream = torch.cuda.Stream(dev)
+    ctx = _lib.Context(0, stream.cuda_stream)
+    orb = ORB(max_frames=F, ctx=ctx)
+    kp, desc, n = orb.detect_and_compute_batch(frames)
+    out = {'frames_per_batch': F, 'keypoints_per_frame': float(n.mean())}
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+        cv = cv2.ORB_create(nfeatures=500)
+        m = min(args.cpu_frames, F)
+        t0 = time.perf_counter()
+        ref = [cv.detectAndCompute(frames[f], None) for f in range(m)]
+        cpu_s = time.perf_counter() - t0
+        for f in range(m):
+            ck = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in ref[f][0]], np.float32)
+            assert int(n[f]) == len(ck) and np.array_equal(kp[f, :len(ck)].view(np.uint32), ck.view(np.uint32))
+            assert np.array_equal(desc[f, :len(ck)], ref[f][1])
+        out['cv2_frames_per_s'] = m / cpu_s
+        out['cv2_threads'] = os.cpu_count()
+        out['parity_frames_checked'] = m
+    except ImportError:
+        pass
+    with torch.cuda.stream(stream):
+        d_img = torch.from_numpy(frames).to(dev)
+        d_kp = torch.empty((F, orb.out_cap, 6), dtype=torch.float32, device=dev)
+        d_desc = torch.empty((F, orb.out_cap, 32), dtype=torch.uint8, device=dev)
+        d_n = torch.empty(F, dtype=torch.int32, device=dev)
+    stream.synchronize()
+
+    def dev_call():
+        ctx.check(L.nclt_orb_detect_and_compute_dev(ctx.h, orb._h, ptr(d_img), 1, F, ptr(d_kp), ptr(d_desc), ptr(d_n)))
+
+    h_img = torch.from_numpy(frames).pin_memory()
+    h_kp = torch.empty((F, orb.out_cap, 6), dtype=torch.float32).pin_memory()
+    h_desc = torch.empty((F, orb.out_cap, 32), dtype=torch.uint8).pin_memory()
+    h_n = torch.empty(F, dtype=torch.int32).pin_memory()
+
+    def host_call():
+        ctx.check(L.nclt_orb_detect_and_compute(ctx.h, orb._h, ptr(h_img), 1, F, ptr(h_kp), ptr(h_desc), ptr(h_n)))
+
+    for name, fn in (('device_resident', dev_call), ('end_to_end', host_call)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        out[name + '_frames_per_s'] = F / dt
+        out[name + '_ms_per_batch'] = dt * 1e3
+    assert np.array_equal(h_n.numpy(), n) and np.array_equal(d_desc.cpu().numpy(), desc)
+    if 'cv2_frames_per_s' in out:
+        out['speedup_vs_cv2_end_to_end'] = out['end_to_end_frames_per_s'] / out['cv2_frames_per_s']
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
