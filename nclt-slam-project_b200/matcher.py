@@ -201,6 +201,18 @@ class LandmarkMatcher:
         scored.sort(reverse=True)
         return [li for _, li in scored[:RELOC_MAX_CANDIDATES]]
 
+    def tick_image(self, bgr, base_pose, ts=0.0, drift_est=0.0):
+        """The tick from the camera image onwards (matcher:305-310): BGR -> gray -> ORB(500) on the GPU
+        (orb.py, bit-identical to cv2's detectAndCompute), `pts_curr_2d = [k.pt ...]`, then `tick`."""
+        if getattr(self, 'orb', None) is None:
+            from .orb import ORB
+            self.orb = ORB(nfeatures=500, ctx=self.library.ctx)                      # matcher:207
+        kp, desc, n = self.orb.detect_and_compute_batch(np.asarray(bgr)[None])
+        m = int(n[0])
+        if m == 0:
+            return self.tick(None, None, base_pose, ts, drift_est)
+        return self.tick(desc[0, :m], kp[0, :m, :2], base_pose, ts, drift_est)
+
     def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0, drift_est=0.0):
         """One matcher tick from the ORB output onwards. Returns a dict with 'outcome' (the CSV
         outcome string), and on publish 'anchor_pose', 'std', 'covariance', 'n_inliers',

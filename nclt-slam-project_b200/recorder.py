@@ -99,6 +99,16 @@ class LandmarkRecorder:
         self.last_landmark_pose_world = cam_pose
         return record
 
+    def tick_image(self, bgr, depth_mm, base_pose, ts):
+        """recorder._tick from the camera image onwards (lines 240-246): BGR -> gray -> ORB(500) on the GPU (orb.py,
+        bit-identical to cv2's detectAndCompute), then `tick`."""
+        if getattr(self, 'orb', None) is None:
+            from .orb import ORB
+            self.orb = ORB(nfeatures=500, ctx=self.ctx)                              # recorder:159
+        kp, desc, n = self.orb.detect_and_compute_batch(np.asarray(bgr)[None])
+        m = int(n[0])
+        return self.tick(kp[0, :m, :2], desc[0, :m] if m else None, depth_mm, base_pose, ts)
+
     def as_pkl_dict(self):
         return {'intrinsics': {'fx': FX, 'fy': FY, 'cx': CX, 'cy': CY, 'width': W, 'height': H},
                 'base_to_cam_translation': BASE_TO_CAM_TRANSLATION.tolist(),
