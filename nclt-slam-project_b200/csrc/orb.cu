@@ -106,20 +106,34 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     }
     int s = 0;
     if (has9(dark) || has9(bright)) {
-        // score = (max over the 16 arcs of 9 of the smallest |difference| of one sign) - 1
-        int best = kFastThr;
+        // score = (max over the 16 arcs of 9 of the smallest difference of one sign) - 1.  Differences are biased
+        // to non-negative values (a = 255 + d for "darker", b = 255 - d for "brighter") and the 9-wide circular
+        // minima are built by doubling: windows of 2, 4, 8, then one more element.
+        int a[16], b[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            int mn = d[k], mx = d[k];
-#pragma unroll
-            for (int j = 1; j < 9; ++j) {
-                const int e = d[(k + j) & 15];
-                mn = min(mn, e);
-                mx = max(mx, e);
-            }
-            best = max(best, max(mn, -mx));
+            a[k] = 255 + d[k];
+            b[k] = 255 - d[k];
         }
-        s = best - 1;
+        int a2[16], b2[16], a4[16], b4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a2[k] = min(a[k], a[(k + 1) & 15]);
+            b2[k] = min(b[k], b[(k + 1) & 15]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a4[k] = min(a2[k], a2[(k + 2) & 15]);
+            b4[k] = min(b2[k], b2[(k + 2) & 15]);
+        }
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int a9 = min(min(a4[k], a4[(k + 4) & 15]), a[(k + 8) & 15]);
+            const int b9 = min(min(b4[k], b4[(k + 4) & 15]), b[(k + 8) & 15]);
+            best = max(best, max(a9, b9));
+        }
+        s = best - 255 - 1;
     }
     score[base + (size_t)y * p + x] = (uint8_t)s;
 }
