@@ -288,8 +288,8 @@ int nclt_hitcount_occupancy(nclt_ctx* ctx, const double* points, const int8_t* l
  * u8[F,out_cap,32], out_n i32[F].  out_cap >= 500: a level keeps every keypoint that ties with its last
  * retained Harris response, so a frame can exceed nfeatures; NCLT_ERR_STATE if it exceeds out_cap.
  * The handle owns its device planes (pyramid, score map, blurred pyramid: ~4 MB per frame slot at
- * 640 x 480) - one handle, one caller at a time, like nclt_ctx.  The selection step (retainBest) runs
- * on the host between two device phases, so the call synchronises the context's stream. */
+ * 640 x 480 plus ~6 MB of candidate lists) - one handle, one caller at a time, like nclt_ctx.  The call
+ * returns after its results have been read back (it synchronises the context's stream once). */
 typedef struct nclt_orb nclt_orb;
 int nclt_orb_create(nclt_ctx* ctx, int W, int H, int max_frames, int out_cap, nclt_orb** out);
 int nclt_orb_destroy(nclt_ctx* ctx, nclt_orb* orb);
@@ -297,6 +297,14 @@ int nclt_orb_destroy(nclt_ctx* ctx, nclt_orb* orb);
 int nclt_orb_levels(const nclt_orb* orb, int32_t* out_w, int32_t* out_h, int32_t* out_n, float* out_scale);
 int nclt_orb_detect_and_compute(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
                                 float* out_kp, uint8_t* out_desc, int32_t* out_n);
+/* Where the per-level selection (OpenCV's KeyPointsFilter::retainBest, twice) runs: 0 = on the device (default; the
+ * libstdc++ nth_element / partition steps restated for one GPU thread per level, csrc/orb_select.cuh - the whole call
+ * is then one stream of kernels and one read-back), 1 = on the host with the std:: algorithms themselves (one extra
+ * round trip).  Mode 0 falls back to mode 1 by itself in the one case it does not restate (introselect's heap-select
+ * branch); nclt_orb_host_fallbacks counts those calls.  Results are identical in both modes.  Mode 2 is a
+ * diagnostic: device selection followed by a forced hand-over (tests the fall-back path). */
+int nclt_orb_set_select(nclt_ctx* ctx, nclt_orb* orb, int mode);
+long long nclt_orb_host_fallbacks(const nclt_orb* orb);
 /* img, out_kp, out_desc, out_n are DEVICE pointers */
 int nclt_orb_detect_and_compute_dev(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
                                     float* out_kp, uint8_t* out_desc, int32_t* out_n);

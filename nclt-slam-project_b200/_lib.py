@@ -111,6 +111,8 @@ _sig('nclt_orb_destroy', _i, _vp, _vp)
 _sig('nclt_orb_levels', _i, _vp, _vp, _vp, _vp, _vp)
 for _n in ('nclt_orb_detect_and_compute', 'nclt_orb_detect_and_compute_dev'):
     _sig(_n, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp)
+_sig('nclt_orb_set_select', _i, _vp, _vp, _i)
+_sig('nclt_orb_host_fallbacks', C.c_longlong, _vp)
 _sig('nclt_orb_debug_plane', _i, _vp, _vp, _i, _i, _i, _vp)
 _sig('nclt_occ_create', _i, _vp, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_vp))
 _sig('nclt_occ_destroy', _i, _vp, _vp)

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "scratch.cuh"
 #include "orb_pattern.h"
+#include "orb_select.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -233,9 +234,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x, const OrbGeom&
 
 __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, OrbGeom g,
                                                       const Sel* __restrict__ sel, int n_sel, int cap,
+                                                      const int* __restrict__ n_out,
                                                       float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
+    // n_out == nullptr: sel is a dense list of n_sel entries; else sel is [frame][cap] with n_out[frame] valid rows
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= n_sel) return;
+    if (n_out && (k % cap) >= n_out[k / cap]) return;
     const Sel s = sel[k];
     const int p = g.pitch[s.level];
     const size_t base = (size_t)s.frame * g.frame_bytes + g.off[s.level];
@@ -293,9 +297,8 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
     }
 }
 
-// KeyPointsFilter::retainBest on (response, index) pairs: same std::nth_element / std::partition calls, same
-// comparators, hence the same permutation as OpenCV's vector<KeyPoint>.
-struct RespIdx { float r; int i; };
+// KeyPointsFilter::retainBest on the host with the real std:: algorithms (select mode 1 and the fall-back of the
+// device selection): same calls, same comparators, hence the same permutation as OpenCV's vector<KeyPoint>.
 void retain_best(std::vector<RespIdx>& v, int n_points) {
     if (n_points >= 0 && v.size() > (size_t)n_points) {
         if (n_points == 0) { v.clear(); return; }
@@ -304,6 +307,147 @@ void retain_best(std::vector<RespIdx>& v, int n_points) {
         const float ambiguous = v[n_points - 1].r;
         auto e = std::partition(v.begin() + n_points, v.end(), [ambiguous](const RespIdx& a) { return a.r >= ambiguous; });
         v.resize(e - v.begin());
+    }
+}
+
+// ---- device-side selection path ----
+struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_frame; };
+
+__device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
+    const int s = sc[0];
+    return s != 0 && s > sc[-1] && s > sc[1] && s > sc[-p - 1] && s > sc[-p] && s > sc[-p + 1] && s > sc[p - 1] && s > sc[p] &&
+           s > sc[p + 1];
+}
+
+__device__ __forceinline__ float harris_at(const uint8_t* c, int p, float harris_scale4) {
+    int a = 0, b = 0, cc = 0;
+    for (int dy = -3; dy <= 3; ++dy)
+        for (int dx = -3; dx <= 3; ++dx) {
+            const uint8_t* q = c + dy * p + dx;
+            const int Ix = (q[1] - q[-1]) * 2 + (q[-p + 1] - q[-p - 1]) + (q[p + 1] - q[p - 1]);
+            const int Iy = (q[p] - q[-p]) * 2 + (q[p - 1] - q[-p - 1]) + (q[p + 1] - q[-p + 1]);
+            a += Ix * Ix;
+            b += Iy * Iy;
+            cc += Ix * Iy;
+        }
+    const float fa = (float)a, fb = (float)b, fc = (float)cc;
+    const float t = __fadd_rn(fa, fb);
+    return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t), t)), harris_scale4);
+}
+
+// NMS survivors of one (frame, level) in FAST's row-major order: one CTA counts per row, scans, then writes.
+// grid (kLevels, F), 1024 threads, dynamic smem = (rows + 1) ints.
+__global__ void __launch_bounds__(1024) k_orb_nms_ordered(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbGeom g,
+                                                          LevelTab lt, float harris_scale4, uint32_t* __restrict__ key,
+                                                          float* __restrict__ fscore, float* __restrict__ harris, int* __restrict__ cnt) {
+    extern __shared__ int rowoff[];
+    const int l = blockIdx.x, f = blockIdx.y;
+    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (rows <= 0 || cols <= 0) {
+        if (threadIdx.x == 0) cnt[f * kLevels + l] = 0;
+        return;
+    }
+    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
+    for (int r = warp; r < rows; r += nwarp) {
+        const uint8_t* sc = score + base + (size_t)(r + kEdge) * p + kEdge;
+        int n = 0;
+        for (int x0 = 0; x0 < cols; x0 += 32) {
+            const int x = x0 + lane;
+            n += __popc(__ballot_sync(0xFFFFFFFFu, x < cols && nms_max(sc + x, p)));
+        }
+        if (lane == 0) rowoff[r + 1] = n;
+    }
+    __syncthreads();
+    if (warp == 0) {            // inclusive scan of rowoff[1..rows] in place, rowoff[0] = 0
+        int carry = 0;
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int r = r0 + lane;
+            int v = r < rows ? rowoff[r + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= o) v += u;
+            }
+            if (r < rows) rowoff[r + 1] = v + carry;
+            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        if (lane == 0) {
+            rowoff[0] = 0;
+            cnt[f * kLevels + l] = carry;
+        }
+    }
+    __syncthreads();
+    const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
+    for (int r = warp; r < rows; r += nwarp) {
+        const int y = r + kEdge;
+        const uint8_t* sc = score + base + (size_t)y * p + kEdge;
+        int pos = rowoff[r];
+        for (int x0 = 0; x0 < cols; x0 += 32) {
+            const int x = x0 + lane;
+            const bool hit = x < cols && nms_max(sc + x, p);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hit) {
+                const int o = pos + __popc(m & ((1u << lane) - 1u));
+                key[ob + o] = (uint32_t)(y << 16 | (x + kEdge));
+                fscore[ob + o] = (float)sc[x];
+                harris[ob + o] = harris_at(pyr + base + (size_t)y * p + x + kEdge, p, harris_scale4);
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
+// The two retainBest passes per level, one warp per level (lane 0 runs the sequential algorithms of orb_select.cuh,
+// all lanes do the copies), one CTA of 8 warps per frame; then the frame's keypoint list in level order.
+// flags[0] |= 1: introselect ran out of its recursion budget (host fall-back), |= 2: more keypoints than out_cap.
+__global__ void __launch_bounds__(256) k_orb_select(LevelTab lt, const uint32_t* __restrict__ key, const float* __restrict__ fscore,
+                                                    const float* __restrict__ harris, const int* __restrict__ cnt,
+                                                    RespIdx* __restrict__ work, Sel* __restrict__ sel, int out_cap,
+                                                    int* __restrict__ n_out, int* __restrict__ flags) {
+    __shared__ int kept[kLevels];
+    const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
+    RespIdx* v = work + ob;
+    const int n = cnt[f * kLevels + l];
+    for (int i = lane; i < n; i += 32) v[i] = RespIdx{fscore[ob + i], i};
+    __syncwarp();
+    int m = 0;
+    if (lane == 0) m = orbsel::retain_best(v, n, 2 * lt.n_level[l]);
+    m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    if (m >= 0) {
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) v[i].r = harris[ob + v[i].i];
+        __syncwarp();
+        if (lane == 0) m = orbsel::retain_best(v, m, lt.n_level[l]);
+        m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    }
+    if (m < 0) {
+        if (lane == 0) atomicOr(flags, 1);
+        m = 0;
+    }
+    if (lane == 0) kept[l] = m;
+    __syncthreads();
+    int first = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kLevels; ++k) {
+        if (k < l) first += kept[k];
+        total += kept[k];
+    }
+    if (total > out_cap) {
+        if (threadIdx.x == 0) {
+            atomicOr(flags, 2);
+            n_out[f] = 0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) n_out[f] = total;
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        const RespIdx r = v[i];
+        const uint32_t k = key[ob + r.i];
+        sel[(size_t)f * out_cap + first + i] = Sel{f, l, (int)(k & 0xFFFF), (int)(k >> 16), r.r, first + i};
     }
 }
 
@@ -325,6 +469,15 @@ struct nclt_orb {
     float harris_scale4 = 0.f;
     std::vector<Cand> h_cand;
     std::vector<Sel> h_sel;
+    // device-side selection (select_mode 0)
+    int select_mode = 0;
+    LevelTab lt;
+    uint32_t* d_key = nullptr;
+    float *d_fscore = nullptr, *d_harris = nullptr;
+    RespIdx* d_work = nullptr;
+    int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr;
+    int* h_pinned = nullptr;      // [0] flags, [1..] n_out
+    unsigned long long host_fallbacks = 0;
 };
 
 extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
@@ -332,6 +485,9 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (c) cudaSetDevice(c->device);
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
+    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_harris); cudaFree(o->d_work); cudaFree(o->d_cnt);
+    cudaFree(o->d_nout); cudaFree(o->d_flags);
+    if (o->h_pinned) cudaFreeHost(o->h_pinned);
     for (int l = 0; l < kLevels; ++l) cudaFree(o->d_tab[l]);
     delete o;
     return NCLT_OK;
@@ -357,8 +513,10 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
         g.off[l] = off;
         off += (long long)g.pitch[l] * g.h[l];
         const int iw = std::max(g.w[l] - 2 * kEdge, 0), ih = std::max(g.h[l] - 2 * kEdge, 0);
+        o->lt.cand_off[l] = (int)cand_cap;
         cand_cap += (unsigned)(((iw + 1) / 2) * ((ih + 1) / 2));        // strict 3x3 maxima: at most one per 2x2 cell
     }
+    o->lt.cand_per_frame = (int)cand_cap;
     g.frame_bytes = (off + 255) & ~255LL;
     o->cand_cap_per_frame = cand_cap;
     // features per level (ORB_Impl::detectAndCompute)
@@ -372,6 +530,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
             nd *= factor;
         }
         o->n_level[kLevels - 1] = std::max(o->nfeatures - sum, 0);
+        for (int l = 0; l < kLevels; ++l) o->lt.n_level[l] = o->n_level[l];
     }
     // disc of the intensity centroid
     {
@@ -404,6 +563,15 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_in, (size_t)W * H * 3 * max_frames);
     A((void**)&o->d_cand, (size_t)cand_cap * max_frames * sizeof(Cand));
     A((void**)&o->d_ncand, 256);
+    A((void**)&o->d_key, (size_t)cand_cap * max_frames * 4);
+    A((void**)&o->d_fscore, (size_t)cand_cap * max_frames * 4);
+    A((void**)&o->d_harris, (size_t)cand_cap * max_frames * 4);
+    A((void**)&o->d_work, (size_t)cand_cap * max_frames * sizeof(RespIdx));
+    A((void**)&o->d_cnt, (size_t)max_frames * kLevels * 4);
+    A((void**)&o->d_nout, (size_t)max_frames * 4);
+    A((void**)&o->d_flags, 256);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&o->h_pinned, (size_t)(max_frames + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemset(o->d_flags, 0, 256);
     A((void**)&o->d_sel, (size_t)out_cap * max_frames * sizeof(Sel));
     A((void**)&o->d_kp, (size_t)out_cap * max_frames * 6 * sizeof(float));
     A((void**)&o->d_desc, (size_t)out_cap * max_frames * 32);
@@ -449,6 +617,72 @@ extern "C" int nclt_orb_levels(const nclt_orb* o, int32_t* out_w, int32_t* out_h
     return NCLT_OK;
 }
 
+// phase 1, common to both selection modes: pyramid, FAST score map, blurred pyramid
+static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channels, int F) {
+    const OrbGeom& g = o->g;
+    cudaStream_t st = c->stream;
+    k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
+    for (int l = 1; l < kLevels; ++l)
+        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
+                                                                             g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
+                                                                             g.pitch[l], g.frame_bytes, o->d_tab[l]);
+    const dim3 gf((g.w[0] - 2 * kEdge + 2 + 31) / 32, (g.h[0] - 2 * kEdge + 2 + 7) / 8, F * kLevels);
+    k_orb_fast<<<gf, 256, 0, st>>>(o->d_pyr, g, o->d_score);
+    k_orb_blur<<<dim3((g.w[0] + 31) / 32, (g.h[0] + 31) / 32, F * kLevels), 256, 0, st>>>(o->d_pyr, g, o->d_blur);
+    c->launches += 10;
+    CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}
+
+// select mode 1 (and the fall-back of mode 0): candidates to the host, std::sort into FAST's row-major order, the two
+// retainBest passes per (frame, level) with the real std:: algorithms.  Fills d_sel (dense) and n_out.
+static int orb_select_host(nclt_ctx* c, nclt_orb* o, int F, std::vector<int32_t>& n_out, int* n_sel_out) {
+    const OrbGeom& g = o->g;
+    cudaStream_t st = c->stream;
+    CU_TRY(c, cudaMemsetAsync(o->d_ncand, 0, 4, st));
+    const dim3 gf((g.w[0] - 2 * kEdge + 2 + 31) / 32, (g.h[0] - 2 * kEdge + 2 + 7) / 8, F * kLevels);
+    const unsigned cap = o->cand_cap_per_frame * (unsigned)F;
+    k_orb_nms<<<gf, 256, 0, st>>>(o->d_pyr, o->d_score, g, o->d_cand, o->d_ncand, cap, o->harris_scale4);
+    c->launches += 1;
+    unsigned n_cand = 0;
+    CU_TRY(c, cudaMemcpyAsync(&n_cand, o->d_ncand, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaStreamSynchronize(st));
+    if (n_cand > cap) return nclt_fail(c, NCLT_ERR_STATE, "orb: candidate list overflow (cannot happen for strict 3x3 maxima)");
+    o->h_cand.resize(n_cand);
+    if (n_cand) {
+        CU_TRY(c, cudaMemcpyAsync(o->h_cand.data(), o->d_cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+    }
+    std::sort(o->h_cand.begin(), o->h_cand.end(),
+              [](const Cand& a, const Cand& b) { return a.tag != b.tag ? a.tag < b.tag : a.key < b.key; });
+    o->h_sel.clear();
+    n_out.assign(F, 0);
+    std::vector<RespIdx> v;
+    size_t i = 0;
+    while (i < o->h_cand.size()) {
+        size_t j = i;
+        const uint32_t tag = o->h_cand[i].tag;
+        while (j < o->h_cand.size() && o->h_cand[j].tag == tag) ++j;
+        const int f = (int)(tag / kLevels), l = (int)(tag % kLevels);
+        v.resize(j - i);
+        for (size_t k = i; k < j; ++k) v[k - i] = RespIdx{o->h_cand[k].score, (int)k};
+        retain_best(v, 2 * o->n_level[l]);
+        for (RespIdx& r : v) r.r = o->h_cand[r.i].harris;
+        retain_best(v, o->n_level[l]);
+        for (const RespIdx& r : v) {
+            const Cand& cd = o->h_cand[r.i];
+            if (n_out[f] >= o->out_cap)
+                return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
+            o->h_sel.push_back(Sel{f, l, (int)(cd.key & 0xFFFF), (int)(cd.key >> 16), cd.harris, n_out[f]++});
+        }
+        i = j;
+    }
+    *n_sel_out = (int)o->h_sel.size();
+    if (*n_sel_out)
+        CU_TRY(c, cudaMemcpyAsync(o->d_sel, o->h_sel.data(), (size_t)*n_sel_out * sizeof(Sel), cudaMemcpyHostToDevice, st));
+    return NCLT_OK;
+}
+
 static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_device, int channels, int F, float* out_kp,
                    uint8_t* out_desc, int32_t* out_n, bool out_on_device) {
     if (!c) return NCLT_ERR_ARG;
@@ -462,62 +696,48 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         CU_TRY(c, cudaMemcpyAsync(o->d_in, img, (size_t)o->W * o->H * channels * F, cudaMemcpyHostToDevice, st));
         d_img = o->d_in;
     }
-    CU_TRY(c, cudaMemsetAsync(o->d_ncand, 0, 4, st));
-    k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
-    for (int l = 1; l < kLevels; ++l)
-        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
-                                                                             g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
-                                                                             g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    const dim3 gf((g.w[0] - 2 * kEdge + 2 + 31) / 32, (g.h[0] - 2 * kEdge + 2 + 7) / 8, F * kLevels);
-    k_orb_fast<<<gf, 256, 0, st>>>(o->d_pyr, g, o->d_score);
-    const unsigned cap = o->cand_cap_per_frame * (unsigned)F;
-    k_orb_nms<<<gf, 256, 0, st>>>(o->d_pyr, o->d_score, g, o->d_cand, o->d_ncand, cap, o->harris_scale4);
-    c->launches += 10;
-    unsigned n_cand = 0;
-    CU_TRY(c, cudaMemcpyAsync(&n_cand, o->d_ncand, 4, cudaMemcpyDeviceToHost, st));
-    // the blur does not depend on the selection: queue it before the host waits
-    k_orb_blur<<<dim3((g.w[0] + 31) / 32, (g.h[0] + 31) / 32, F * kLevels), 256, 0, st>>>(o->d_pyr, g, o->d_blur);
-    c->launches += 1;
-    CU_TRY(c, cudaGetLastError());
-    CU_TRY(c, cudaStreamSynchronize(st));
-    if (n_cand > cap) return nclt_fail(c, NCLT_ERR_STATE, "orb: candidate list overflow (cannot happen for strict 3x3 maxima)");
-    o->h_cand.resize(n_cand);
-    if (n_cand) {
-        CU_TRY(c, cudaMemcpyAsync(o->h_cand.data(), o->d_cand, (size_t)n_cand * sizeof(Cand), cudaMemcpyDeviceToHost, st));
-        CU_TRY(c, cudaStreamSynchronize(st));
-    }
-    // host: FAST's row-major order, then the two retainBest passes per (frame, level)
-    std::sort(o->h_cand.begin(), o->h_cand.end(),
-              [](const Cand& a, const Cand& b) { return a.tag != b.tag ? a.tag < b.tag : a.key < b.key; });
-    o->h_sel.clear();
-    std::vector<int32_t> n_out(F, 0);
-    std::vector<RespIdx> v;
-    size_t i = 0;
-    int rc_overflow = 0;
-    while (i < o->h_cand.size()) {
-        size_t j = i;
-        const uint32_t tag = o->h_cand[i].tag;
-        while (j < o->h_cand.size() && o->h_cand[j].tag == tag) ++j;
-        const int f = (int)(tag / kLevels), l = (int)(tag % kLevels);
-        v.resize(j - i);
-        for (size_t k = i; k < j; ++k) v[k - i] = RespIdx{o->h_cand[k].score, (int)k};
-        retain_best(v, 2 * o->n_level[l]);
-        for (RespIdx& r : v) r.r = o->h_cand[r.i].harris;
-        retain_best(v, o->n_level[l]);
-        for (const RespIdx& r : v) {
-            const Cand& cd = o->h_cand[r.i];
-            if (n_out[f] >= o->out_cap) { rc_overflow = 1; break; }
-            o->h_sel.push_back(Sel{f, l, (int)(cd.key & 0xFFFF), (int)(cd.key >> 16), cd.harris, n_out[f]++});
-        }
-        i = j;
-    }
-    if (rc_overflow) return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
-    const int n_sel = (int)o->h_sel.size();
+    int rc = orb_front(c, o, d_img, channels, F);
+    if (rc) return rc;
     float* d_kp = out_on_device ? out_kp : o->d_kp;
     uint8_t* d_desc = out_on_device ? out_desc : o->d_desc;
+    bool host_select = o->select_mode == 1;
+    if (!host_select) {
+        // everything stays on the device; one read of (flags, n_out) at the end
+        const int rows0 = std::max(g.h[0] - 2 * kEdge, 1);
+        k_orb_nms_ordered<<<dim3(kLevels, F), 1024, (size_t)(rows0 + 1) * sizeof(int), st>>>(
+            o->d_pyr, o->d_score, g, o->lt, o->harris_scale4, o->d_key, o->d_fscore, o->d_harris, o->d_cnt);
+        k_orb_select<<<F, 256, 0, st>>>(o->lt, o->d_key, o->d_fscore, o->d_harris, o->d_cnt, o->d_work, o->d_sel, o->out_cap,
+                                        o->d_nout, o->d_flags);
+        k_orb_describe<<<(F * o->out_cap + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, F * o->out_cap, o->out_cap,
+                                                                 o->d_nout, d_kp, d_desc);
+        c->launches += 3;
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(o->h_pinned, o->d_flags, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaMemcpyAsync(o->h_pinned + 1, o->d_nout, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+        if (!out_on_device) {
+            CU_TRY(c, cudaMemcpyAsync(out_kp, d_kp, (size_t)F * o->out_cap * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaMemcpyAsync(out_desc, d_desc, (size_t)F * o->out_cap * 32, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU_TRY(c, cudaMemcpyAsync(out_n, o->d_nout, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        CU_TRY(c, cudaStreamSynchronize(st));
+        int flags = o->h_pinned[0];
+        if (flags) CU_TRY(c, cudaMemsetAsync(o->d_flags, 0, 4, st));
+        if (o->select_mode == 2) flags |= 1;      // diagnostic: exercise the hand-over to the host
+        if (flags & 2) return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
+        if (flags & 1) {
+            host_select = true;      // introselect left its quick-select phase somewhere: redo the selection on the host
+            o->host_fallbacks++;
+        } else {
+            if (!out_on_device) memcpy(out_n, o->h_pinned + 1, (size_t)F * 4);
+            return NCLT_OK;
+        }
+    }
+    std::vector<int32_t> n_out;
+    int n_sel = 0;
+    if ((rc = orb_select_host(c, o, F, n_out, &n_sel))) return rc;
     if (n_sel) {
-        CU_TRY(c, cudaMemcpyAsync(o->d_sel, o->h_sel.data(), (size_t)n_sel * sizeof(Sel), cudaMemcpyHostToDevice, st));
-        k_orb_describe<<<(n_sel + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, n_sel, o->out_cap, d_kp, d_desc);
+        k_orb_describe<<<(n_sel + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, n_sel, o->out_cap, nullptr, d_kp, d_desc);
         c->launches += 1;
         CU_TRY(c, cudaGetLastError());
     }
@@ -531,6 +751,16 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     CU_TRY(c, cudaStreamSynchronize(st));
     return NCLT_OK;
 }
+
+/* select mode: 0 = selection on the device (default), 1 = on the host with the std:: algorithms,
+ * 2 = diagnostic: device selection, then behave as if it had asked for the host fall-back */
+extern "C" int nclt_orb_set_select(nclt_ctx* c, nclt_orb* o, int mode) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!o || mode < 0 || mode > 2) return nclt_fail(c, NCLT_ERR_ARG, "orb_set_select: mode 0 (device), 1 (host) or 2 (diagnostic)");
+    o->select_mode = mode;
+    return NCLT_OK;
+}
+extern "C" long long nclt_orb_host_fallbacks(const nclt_orb* o) { return o ? (long long)o->host_fallbacks : -1; }
 
 extern "C" int nclt_orb_detect_and_compute(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int channels, int F, float* out_kp,
                                            uint8_t* out_desc, int32_t* out_n) {

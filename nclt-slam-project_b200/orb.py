@@ -38,12 +38,13 @@ class KeyPoint:
 
 
 class ORB:
-    def __init__(self, nfeatures=500, width=640, height=480, max_frames=1, out_cap=None, ctx=None):
+    def __init__(self, nfeatures=500, width=640, height=480, max_frames=1, out_cap=None, ctx=None, select='device'):
         if nfeatures != 500:
             raise ValueError('only cv2.ORB_create(nfeatures=500) (the reference configuration) is built')
         self.ctx = ctx or _lib.default_context()
         self.width, self.height, self.max_frames = int(width), int(height), int(max_frames)
         self.out_cap = int(out_cap or 640)
+        self.select = select
         self._h = None
         self._make()
 
@@ -52,6 +53,12 @@ class ORB:
         h = C.c_void_p()
         self.ctx.check(_c.nclt_orb_create(self.ctx.h, self.width, self.height, self.max_frames, self.out_cap, C.byref(h)))
         self._h = h
+        self.ctx.check(_c.nclt_orb_set_select(self.ctx.h, self._h, {'device': 0, 'host': 1, 'force_fallback': 2}[self.select]))
+
+    @property
+    def host_fallbacks(self):
+        """calls whose device-side selection handed over to the host (introselect's heap-select branch)."""
+        return int(_c.nclt_orb_host_fallbacks(self._h))
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:

@@ -15,10 +15,13 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'orb_golden.npz')
 
 
-@pytest.fixture(scope='module')
-def orb(ctx):
+@pytest.fixture(scope='module', params=['device', 'host'])
+def orb(ctx, request):
+    """select='device': retainBest restated for the GPU (csrc/orb_select.cuh); 'host': the std:: algorithms."""
     from nclt_slam_project_b200.orb import ORB
-    return ORB(nfeatures=500, width=640, height=480, max_frames=4, ctx=ctx)
+    o = ORB(nfeatures=500, width=640, height=480, max_frames=4, ctx=ctx, select=request.param)
+    yield o
+    assert o.host_fallbacks == 0
 
 
 def _check(kp, desc, n, f, ref_k, ref_d, what):
@@ -96,6 +99,17 @@ def test_call_surface_bgr_flat_and_resize(ctx):
         kps, desc = orb.detectAndCompute(g[f'img{i}'], None)
         k = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave) for p in kps], np.float32)
         assert np.array_equal(k.view(np.uint32), g[f'kp{i}'].view(np.uint32)) and np.array_equal(desc, g[f'desc{i}'])
+
+
+def test_forced_hand_over_to_the_host(ctx):
+    from nclt_slam_project_b200.orb import ORB
+    o = ORB(max_frames=2, ctx=ctx, select='force_fallback')
+    frames = np.stack([synth.make_camera_frame(s) for s in (40, 41)])
+    kp, desc, n = o.detect_and_compute_batch(frames)
+    assert o.host_fallbacks == 1
+    for f in range(2):
+        rk, rd = oo.detect_and_compute(frames[f])
+        _check(kp, desc, n, f, rk, rd, f'frame {f}')
 
 
 def test_bad_arguments(ctx):

@@ -14,6 +14,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--cpu-frames', type=int, default=32)
+    ap.add_argument('--select', default='device')
     args = ap.parse_args()
     import torch
     import nclt_slam_project_b200  # noqa
@@ -26,9 +27,9 @@ def main():
     dev = torch.device('cuda', 0)
     stream = torch.cuda.Stream(dev)
     ctx = _lib.Context(0, stream.cuda_stream)
-    orb = ORB(max_frames=F, ctx=ctx)
+    orb = ORB(max_frames=F, ctx=ctx, select=args.select)
     kp, desc, n = orb.detect_and_compute_batch(frames)
-    out = {'frames_per_batch': F, 'keypoints_per_frame': float(n.mean())}
+    out = {'select': args.select, 'frames_per_batch': F, 'keypoints_per_frame': float(n.mean())}
     try:
         import cv2
         cv2.setNumThreads(os.cpu_count())
@@ -78,6 +79,7 @@ def main():
     assert np.array_equal(h_n.numpy(), n) and np.array_equal(d_desc.cpu().numpy(), desc)
     if 'cv2_frames_per_s' in out:
         out['speedup_vs_cv2_end_to_end'] = out['end_to_end_frames_per_s'] / out['cv2_frames_per_s']
+    out['host_fallbacks'] = orb.host_fallbacks
     print(json.dumps(out))
 
 
