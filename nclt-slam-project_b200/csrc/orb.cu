@@ -43,6 +43,17 @@ struct OrbGeom {
 
 __constant__ signed char c_pattern[256 * 4];
 
+// One launch covers all levels without empty CTAs: blockIdx.x runs over the tiles of level 0, then level 1, ...
+struct BlockMap { int first[kLevels + 1]; int bx[kLevels]; };
+__device__ __forceinline__ void block_of(const BlockMap& m, int b, int& l, int& bx, int& by) {
+    l = 0;
+#pragma unroll
+    for (int k = 1; k < kLevels; ++k) l += (b >= m.first[k]) ? 1 : 0;
+    const int t = b - m.first[l];
+    by = t / m.bx[l];
+    bx = t - by * m.bx[l];
+}
+
 struct Cand { uint32_t tag, key; float score, harris; };          // tag = frame * 8 + level, key = y << 16 | x
 struct Sel { int frame, level, x, y; float harris; int slot; };   // slot = row inside the frame's output
 
@@ -86,14 +97,25 @@ __device__ __forceinline__ bool has9(unsigned m) {     // 9 contiguous set bits 
     return (a & 0xFFFFu) != 0;
 }
 
-__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, uint8_t* __restrict__ score) {
-    const int f = blockIdx.z / kLevels, l = blockIdx.z % kLevels;
+__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, uint8_t* __restrict__ score) {
+    const int f = blockIdx.y;
+    int l, bx, by;
+    block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31) + kEdge - 1, y = blockIdx.y * 8 + (threadIdx.x >> 5) + kEdge - 1;
+    const int x = bx * 32 + (threadIdx.x & 31) + kEdge - 1, y = by * 8 + (threadIdx.x >> 5) + kEdge - 1;
     if (x > w - kEdge || y > h - kEdge) return;
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     const uint8_t* c = pyr + base + (size_t)y * p + x;
     const int v = c[0];
+    {   // an arc of 9 contains one pixel of every opposite pair: two pairs inside the threshold band -> no corner
+        const int e0 = v - c[3 * p], e8 = v - c[-3 * p], e4 = v - c[3], e12 = v - c[-3];
+        const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
+        const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
+        if (in0 || in4) {
+            score[base + (size_t)y * p + x] = 0;
+            return;
+        }
+    }
     int d[16];
     d[0] = v - c[3 * p];          d[1] = v - c[3 * p + 1];   d[2] = v - c[2 * p + 2];    d[3] = v - c[p + 3];
     d[4] = v - c[3];              d[5] = v - c[-p + 3];      d[6] = v - c[-2 * p + 2];   d[7] = v - c[-3 * p + 1];
@@ -174,11 +196,12 @@ __global__ void __launch_bounds__(256) k_orb_nms(const uint8_t* __restrict__ pyr
 }
 
 // ---- Gaussian blur, 32x32 output tile per CTA ----
-__global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, OrbGeom g, uint8_t* __restrict__ blur) {
-    const int f = blockIdx.z / kLevels, l = blockIdx.z % kLevels;
+__global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, uint8_t* __restrict__ blur) {
+    const int f = blockIdx.y;
+    int l, bx, by;
+    block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    if (x0 >= w || y0 >= h) return;
+    const int x0 = bx * 32, y0 = by * 32;
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     __shared__ float tile[38][39];
     __shared__ float rowp[38][33];
@@ -244,18 +267,17 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
     const int p = g.pitch[s.level];
     const size_t base = (size_t)s.frame * g.frame_bytes + g.off[s.level];
     const uint8_t* c = pyr + base + (size_t)s.y * p + s.x;
-    // intensity centroid: lane = row v + 15
+    // intensity centroid over the disc: lane = column u + 15, the warp walks the 31 rows (one coalesced read each)
     int m01 = 0, m10 = 0;
-    if (lane <= 2 * kHalfPatch) {
-        const int v = lane - kHalfPatch, d = g.umax[v < 0 ? -v : v];
-        const uint8_t* r = c + v * p;
-        int rs = 0;
-        for (int u = -d; u <= d; ++u) {
-            const int val = r[u];
-            m10 += u * val;
-            rs += val;
+    {
+        const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            if (lane <= 2 * kHalfPatch && au <= g.umax[v < 0 ? -v : v]) {
+                const int val = c[v * p + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
         }
-        m01 = v * rs;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -311,7 +333,7 @@ void retain_best(std::vector<RespIdx>& v, int n_points) {
 }
 
 // ---- device-side selection path ----
-struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_frame; };
+struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_frame; int row_off[kLevels]; int rows_total; };
 
 __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
     const int s = sc[0];
@@ -319,110 +341,187 @@ __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
            s > sc[p + 1];
 }
 
-__device__ __forceinline__ float harris_at(const uint8_t* c, int p, float harris_scale4) {
-    int a = 0, b = 0, cc = 0;
-    for (int dy = -3; dy <= 3; ++dy)
-        for (int dx = -3; dx <= 3; ++dx) {
-            const uint8_t* q = c + dy * p + dx;
-            const int Ix = (q[1] - q[-1]) * 2 + (q[-p + 1] - q[-p - 1]) + (q[p + 1] - q[p - 1]);
-            const int Iy = (q[p] - q[-p]) * 2 + (q[p - 1] - q[-p - 1]) + (q[p + 1] - q[-p + 1]);
-            a += Ix * Ix;
-            b += Iy * Iy;
-            cc += Ix * Iy;
-        }
-    const float fa = (float)a, fb = (float)b, fc = (float)cc;
-    const float t = __fadd_rn(fa, fb);
-    return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t), t)), harris_scale4);
-}
-
-// NMS survivors of one (frame, level) in FAST's row-major order: one CTA counts per row, scans, then writes.
-// grid (kLevels, F), 1024 threads, dynamic smem = (rows + 1) ints.
-__global__ void __launch_bounds__(1024) k_orb_nms_ordered(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbGeom g,
-                                                          LevelTab lt, float harris_scale4, uint32_t* __restrict__ key,
-                                                          float* __restrict__ fscore, float* __restrict__ harris, int* __restrict__ cnt) {
-    extern __shared__ int rowoff[];
-    const int l = blockIdx.x, f = blockIdx.y;
+// NMS survivors of every (frame, level) in FAST's row-major order, two launches over 8-row chunks (one warp per row):
+// k_orb_nms_count leaves the survivors per row, k_orb_nms_emit sums the rows above its chunk and writes
+// (position, FAST score) at the final offsets.  rowcnt: [F][rows_total], rows of level l start at
+// lt.row_off[l].
+__global__ void __launch_bounds__(256) k_orb_nms_count(const uint8_t* __restrict__ score, OrbGeom g, LevelTab lt, BlockMap bm,
+                                                       int* __restrict__ rowcnt) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int l, bx, by;
+    block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
     const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int r = by * 8 + warp;
+    if (r >= rows || cols <= 0) return;
+    const uint8_t* sc = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p + kEdge;
+    int n = 0;
+    for (int x0 = 0; x0 < cols; x0 += 32) {
+        const int x = x0 + lane;
+        n += __popc(__ballot_sync(0xFFFFFFFFu, x < cols && nms_max(sc + x, p)));
+    }
+    if (lane == 0) rowcnt[(size_t)f * lt.rows_total + lt.row_off[l] + r] = n;
+}
+
+__global__ void __launch_bounds__(256) k_orb_nms_emit(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbGeom g,
+                                                      LevelTab lt, BlockMap bm, float harris_scale4, const int* __restrict__ rowcnt,
+                                                      uint32_t* __restrict__ key, float* __restrict__ fscore,
+                                                      int* __restrict__ cnt) {
+    __shared__ int part[8];
+    __shared__ int rowbase[9];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int l, bx, by;
+    block_of(bm, blockIdx.x, l, bx, by);
+    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
     if (rows <= 0 || cols <= 0) {
-        if (threadIdx.x == 0) cnt[f * kLevels + l] = 0;
+        if (threadIdx.x == 0 && by == 0) cnt[f * kLevels + l] = 0;
         return;
     }
-    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
-    for (int r = warp; r < rows; r += nwarp) {
-        const uint8_t* sc = score + base + (size_t)(r + kEdge) * p + kEdge;
-        int n = 0;
-        for (int x0 = 0; x0 < cols; x0 += 32) {
-            const int x = x0 + lane;
-            n += __popc(__ballot_sync(0xFFFFFFFFu, x < cols && nms_max(sc + x, p)));
-        }
-        if (lane == 0) rowoff[r + 1] = n;
-    }
-    __syncthreads();
-    if (warp == 0) {            // inclusive scan of rowoff[1..rows] in place, rowoff[0] = 0
-        int carry = 0;
-        for (int r0 = 0; r0 < rows; r0 += 32) {
-            const int r = r0 + lane;
-            int v = r < rows ? rowoff[r + 1] : 0;
+    const int* rc = rowcnt + (size_t)f * lt.rows_total + lt.row_off[l];
+    const int r0 = by * 8;
+    int sum = 0;
+    for (int r = threadIdx.x; r < r0; r += 256) sum += rc[r];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
-                if (lane >= o) v += u;
-            }
-            if (r < rows) rowoff[r + 1] = v + carry;
-            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) part[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int k = 0; k < 8; ++k) b += part[k];
+        for (int k = 0; k < 8; ++k) {
+            rowbase[k] = b;
+            if (r0 + k < rows) b += rc[r0 + k];
         }
-        if (lane == 0) {
-            rowoff[0] = 0;
-            cnt[f * kLevels + l] = carry;
-        }
+        rowbase[8] = b;
+        if (r0 + 8 >= rows) cnt[f * kLevels + l] = b;       // the chunk holding the last row knows the total
     }
     __syncthreads();
+    const int r = r0 + warp;
+    if (r >= rows) return;
+    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
-    for (int r = warp; r < rows; r += nwarp) {
-        const int y = r + kEdge;
-        const uint8_t* sc = score + base + (size_t)y * p + kEdge;
-        int pos = rowoff[r];
-        for (int x0 = 0; x0 < cols; x0 += 32) {
-            const int x = x0 + lane;
-            const bool hit = x < cols && nms_max(sc + x, p);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-            if (hit) {
-                const int o = pos + __popc(m & ((1u << lane) - 1u));
-                key[ob + o] = (uint32_t)(y << 16 | (x + kEdge));
-                fscore[ob + o] = (float)sc[x];
-                harris[ob + o] = harris_at(pyr + base + (size_t)y * p + x + kEdge, p, harris_scale4);
-            }
-            pos += __popc(m);
+    const int y = r + kEdge;
+    const uint8_t* sc = score + base + (size_t)y * p + kEdge;
+    int pos = rowbase[warp];
+    if (rowbase[warp + 1] == pos) return;
+    for (int x0 = 0; x0 < cols; x0 += 32) {
+        const int x = x0 + lane;
+        const bool hit = x < cols && nms_max(sc + x, p);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) {
+            const int o = pos + __popc(m & ((1u << lane) - 1u));
+            key[ob + o] = (uint32_t)(y << 16 | (x + kEdge));
+            fscore[ob + o] = (float)sc[x];
         }
+        pos += __popc(m);
     }
 }
 
-// The two retainBest passes per level, one warp per level (lane 0 runs the sequential algorithms of orb_select.cuh,
-// all lanes do the copies), one CTA of 8 warps per frame; then the frame's keypoint list in level order.
+// The two retainBest passes, one warp per level (lane 0 runs the sequential algorithms of orb_select.cuh, all lanes
+// do the copies), one CTA of 8 warps per frame, the working arrays in shared memory when the frame's candidates fit
+// (kSelSmemEntries; white-noise frames do not and work in global memory):
+//   k_orb_select1   retainBest(2 n_level) on the FAST scores                       -> work[], kept1[]
+//   k_orb_harris    Harris response of the survivors only, one warp per keypoint   -> work[].r
+//   k_orb_select2   retainBest(n_level) on the Harris responses, the frame's keypoint list in level order
 // flags[0] |= 1: introselect ran out of its recursion budget (host fall-back), |= 2: more keypoints than out_cap.
-__global__ void __launch_bounds__(256) k_orb_select(LevelTab lt, const uint32_t* __restrict__ key, const float* __restrict__ fscore,
-                                                    const float* __restrict__ harris, const int* __restrict__ cnt,
-                                                    RespIdx* __restrict__ work, Sel* __restrict__ sel, int out_cap,
-                                                    int* __restrict__ n_out, int* __restrict__ flags) {
-    __shared__ int kept[kLevels];
+constexpr int kSelSmemEntries = 20480;       // 160 KB
+
+__device__ __forceinline__ RespIdx* sel_buffer(RespIdx* smem, int* soff, const int* counts, int l, RespIdx* global_buf, bool& in_smem) {
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < kLevels; ++k) {
+            soff[k] = t;
+            t += counts[k];
+        }
+        soff[kLevels] = t;
+    }
+    __syncthreads();
+    in_smem = soff[kLevels] <= kSelSmemEntries;
+    return in_smem ? smem + soff[l] : global_buf;
+}
+
+__global__ void __launch_bounds__(256) k_orb_select1(LevelTab lt, const float* __restrict__ fscore, const int* __restrict__ cnt,
+                                                     RespIdx* __restrict__ work, int* __restrict__ kept1, int* __restrict__ flags) {
+    extern __shared__ RespIdx sel_smem[];
+    __shared__ int soff[kLevels + 1];
     const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
-    RespIdx* v = work + ob;
+    bool in_smem;
+    RespIdx* v = sel_buffer(sel_smem, soff, cnt + f * kLevels, l, work + ob, in_smem);
     const int n = cnt[f * kLevels + l];
     for (int i = lane; i < n; i += 32) v[i] = RespIdx{fscore[ob + i], i};
     __syncwarp();
     int m = 0;
     if (lane == 0) m = orbsel::retain_best(v, n, 2 * lt.n_level[l]);
     m = __shfl_sync(0xFFFFFFFFu, m, 0);
-    if (m >= 0) {
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) v[i].r = harris[ob + v[i].i];
-        __syncwarp();
-        if (lane == 0) m = orbsel::retain_best(v, m, lt.n_level[l]);
-        m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    __syncwarp();
+    if (m < 0) {
+        if (lane == 0) atomicOr(flags, 1);
+        m = 0;
     }
+    if (in_smem)
+        for (int i = lane; i < m; i += 32) work[ob + i] = v[i];
+    if (lane == 0) kept1[f * kLevels + l] = m;
+}
+
+// grid (kLevels * 8, F): 64 warps per (frame, level) stride over its survivors; lanes = the 49 cells of the 7x7 block
+__global__ void __launch_bounds__(256) k_orb_harris(const uint8_t* __restrict__ pyr, OrbGeom g, LevelTab lt, float harris_scale4,
+                                                    const uint32_t* __restrict__ key, const int* __restrict__ kept1,
+                                                    RespIdx* __restrict__ work) {
+    const int f = blockIdx.y, l = blockIdx.x >> 3, lane = threadIdx.x & 31;
+    const int w0 = (blockIdx.x & 7) * 8 + (threadIdx.x >> 5);
+    const int m = kept1[f * kLevels + l], p = g.pitch[l];
+    const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
+    const uint8_t* img = pyr + (size_t)f * g.frame_bytes + g.off[l];
+    for (int i = w0; i < m; i += 64) {
+        const uint32_t k = key[ob + work[ob + i].i];
+        const uint8_t* c = img + (size_t)(k >> 16) * p + (k & 0xFFFF);
+        int a = 0, b = 0, cc = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int cell = lane + 32 * t;
+            if (cell < 49) {
+                const uint8_t* q = c + (cell / 7 - 3) * p + (cell % 7 - 3);
+                const int Ix = (q[1] - q[-1]) * 2 + (q[-p + 1] - q[-p - 1]) + (q[p + 1] - q[p - 1]);
+                const int Iy = (q[p] - q[-p]) * 2 + (q[p - 1] - q[-p - 1]) + (q[p + 1] - q[-p + 1]);
+                a += Ix * Ix;
+                b += Iy * Iy;
+                cc += Ix * Iy;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+            cc += __shfl_xor_sync(0xFFFFFFFFu, cc, o);
+        }
+        if (lane == 0) {
+            const float fa = (float)a, fb = (float)b, fc = (float)cc;
+            const float t = __fadd_rn(fa, fb);
+            work[ob + i].r = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t), t)),
+                                       harris_scale4);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_orb_select2(LevelTab lt, const uint32_t* __restrict__ key, const int* __restrict__ kept1,
+                                                     RespIdx* __restrict__ work, Sel* __restrict__ sel, int out_cap,
+                                                     int* __restrict__ n_out, int* __restrict__ flags) {
+    extern __shared__ RespIdx sel_smem[];
+    __shared__ int soff[kLevels + 1];
+    __shared__ int kept[kLevels];
+    const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
+    bool in_smem;
+    RespIdx* v = sel_buffer(sel_smem, soff, kept1 + f * kLevels, l, work + ob, in_smem);
+    const int n = kept1[f * kLevels + l];
+    if (in_smem)
+        for (int i = lane; i < n; i += 32) v[i] = work[ob + i];
+    __syncwarp();
+    int m = 0;
+    if (lane == 0) m = orbsel::retain_best(v, n, lt.n_level[l]);
+    m = __shfl_sync(0xFFFFFFFFu, m, 0);
     if (m < 0) {
         if (lane == 0) atomicOr(flags, 1);
         m = 0;
@@ -443,7 +542,6 @@ __global__ void __launch_bounds__(256) k_orb_select(LevelTab lt, const uint32_t*
         return;
     }
     if (threadIdx.x == 0) n_out[f] = total;
-    __syncwarp();
     for (int i = lane; i < m; i += 32) {
         const RespIdx r = v[i];
         const uint32_t k = key[ob + r.i];
@@ -473,9 +571,13 @@ struct nclt_orb {
     int select_mode = 0;
     LevelTab lt;
     uint32_t* d_key = nullptr;
-    float *d_fscore = nullptr, *d_harris = nullptr;
+    float* d_fscore = nullptr;
+    int* d_kept1 = nullptr;
     RespIdx* d_work = nullptr;
-    int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr;
+    int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
+    BlockMap bm_fast, bm_blur, bm_rows;
+    cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     int* h_pinned = nullptr;      // [0] flags, [1..] n_out
     unsigned long long host_fallbacks = 0;
 };
@@ -485,8 +587,11 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (c) cudaSetDevice(c->device);
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
-    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_harris); cudaFree(o->d_work); cudaFree(o->d_cnt);
-    cudaFree(o->d_nout); cudaFree(o->d_flags);
+    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_cnt);
+    cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt);
+    if (o->side) cudaStreamDestroy(o->side);
+    if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
+    if (o->ev_blur) cudaEventDestroy(o->ev_blur);
     if (o->h_pinned) cudaFreeHost(o->h_pinned);
     for (int l = 0; l < kLevels; ++l) cudaFree(o->d_tab[l]);
     delete o;
@@ -517,6 +622,22 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
         cand_cap += (unsigned)(((iw + 1) / 2) * ((ih + 1) / 2));        // strict 3x3 maxima: at most one per 2x2 cell
     }
     o->lt.cand_per_frame = (int)cand_cap;
+    {
+        int rows_total = 0, nf = 0, nb = 0, nr = 0;
+        for (int l = 0; l < kLevels; ++l) {
+            const int rows = std::max(g.h[l] - 2 * kEdge, 0), cols = std::max(g.w[l] - 2 * kEdge, 0);
+            o->lt.row_off[l] = rows_total;
+            rows_total += rows;
+            o->bm_fast.first[l] = nf; o->bm_fast.bx[l] = std::max((cols + 2 + 31) / 32, 1);
+            nf += (rows > 0 && cols > 0) ? o->bm_fast.bx[l] * ((rows + 2 + 7) / 8) : 0;
+            o->bm_blur.first[l] = nb; o->bm_blur.bx[l] = (g.w[l] + 31) / 32;
+            nb += o->bm_blur.bx[l] * ((g.h[l] + 31) / 32);
+            o->bm_rows.first[l] = nr; o->bm_rows.bx[l] = 1;
+            nr += std::max((rows + 7) / 8, 1);
+        }
+        o->lt.rows_total = std::max(rows_total, 1);
+        o->bm_fast.first[kLevels] = nf; o->bm_blur.first[kLevels] = nb; o->bm_rows.first[kLevels] = nr;
+    }
     g.frame_bytes = (off + 255) & ~255LL;
     o->cand_cap_per_frame = cand_cap;
     // features per level (ORB_Impl::detectAndCompute)
@@ -565,13 +686,19 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_ncand, 256);
     A((void**)&o->d_key, (size_t)cand_cap * max_frames * 4);
     A((void**)&o->d_fscore, (size_t)cand_cap * max_frames * 4);
-    A((void**)&o->d_harris, (size_t)cand_cap * max_frames * 4);
+    A((void**)&o->d_kept1, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_work, (size_t)cand_cap * max_frames * sizeof(RespIdx));
     A((void**)&o->d_cnt, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_nout, (size_t)max_frames * 4);
     A((void**)&o->d_flags, 256);
+    A((void**)&o->d_rowcnt, (size_t)o->lt.rows_total * max_frames * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_pyr, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_blur, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&o->h_pinned, (size_t)(max_frames + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(o->d_flags, 0, 256);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemEntries * (int)sizeof(RespIdx));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemEntries * (int)sizeof(RespIdx));
     A((void**)&o->d_sel, (size_t)out_cap * max_frames * sizeof(Sel));
     A((void**)&o->d_kp, (size_t)out_cap * max_frames * 6 * sizeof(float));
     A((void**)&o->d_desc, (size_t)out_cap * max_frames * 32);
@@ -626,9 +753,11 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
         k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
                                                                              g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
                                                                              g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    const dim3 gf((g.w[0] - 2 * kEdge + 2 + 31) / 32, (g.h[0] - 2 * kEdge + 2 + 7) / 8, F * kLevels);
-    k_orb_fast<<<gf, 256, 0, st>>>(o->d_pyr, g, o->d_score);
-    k_orb_blur<<<dim3((g.w[0] + 31) / 32, (g.h[0] + 31) / 32, F * kLevels), 256, 0, st>>>(o->d_pyr, g, o->d_blur);
+    CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
+    CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
+    k_orb_blur<<<dim3(o->bm_blur.first[kLevels], F), 256, 0, o->side>>>(o->d_pyr, g, o->bm_blur, o->d_blur);
+    CU_TRY(c, cudaEventRecord(o->ev_blur, o->side));
+    if (o->bm_fast.first[kLevels] > 0) k_orb_fast<<<dim3(o->bm_fast.first[kLevels], F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, o->d_score);
     c->launches += 10;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
@@ -703,14 +832,17 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     bool host_select = o->select_mode == 1;
     if (!host_select) {
         // everything stays on the device; one read of (flags, n_out) at the end
-        const int rows0 = std::max(g.h[0] - 2 * kEdge, 1);
-        k_orb_nms_ordered<<<dim3(kLevels, F), 1024, (size_t)(rows0 + 1) * sizeof(int), st>>>(
-            o->d_pyr, o->d_score, g, o->lt, o->harris_scale4, o->d_key, o->d_fscore, o->d_harris, o->d_cnt);
-        k_orb_select<<<F, 256, 0, st>>>(o->lt, o->d_key, o->d_fscore, o->d_harris, o->d_cnt, o->d_work, o->d_sel, o->out_cap,
-                                        o->d_nout, o->d_flags);
+        k_orb_nms_count<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt);
+        k_orb_nms_emit<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_pyr, o->d_score, g, o->lt, o->bm_rows, o->harris_scale4,
+                                                                            o->d_rowcnt, o->d_key, o->d_fscore, o->d_cnt);
+        const size_t sel_smem = (size_t)kSelSmemEntries * sizeof(RespIdx);
+        k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_kept1, o->d_flags);
+        k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
+        k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_sel, o->out_cap, o->d_nout, o->d_flags);
+        CU_TRY(c, cudaStreamWaitEvent(st, o->ev_blur, 0));
         k_orb_describe<<<(F * o->out_cap + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, F * o->out_cap, o->out_cap,
                                                                  o->d_nout, d_kp, d_desc);
-        c->launches += 3;
+        c->launches += 6;
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(o->h_pinned, o->d_flags, 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(c, cudaMemcpyAsync(o->h_pinned + 1, o->d_nout, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
@@ -736,6 +868,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     std::vector<int32_t> n_out;
     int n_sel = 0;
     if ((rc = orb_select_host(c, o, F, n_out, &n_sel))) return rc;
+    CU_TRY(c, cudaStreamWaitEvent(st, o->ev_blur, 0));
     if (n_sel) {
         k_orb_describe<<<(n_sel + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, n_sel, o->out_cap, nullptr, d_kp, d_desc);
         c->launches += 1;

@@ -35,6 +35,8 @@ def main():
         cv2.setNumThreads(os.cpu_count())
         cv = cv2.ORB_create(nfeatures=500)
         m = min(args.cpu_frames, F)
+        if m <= 0:
+            raise ImportError('cpu leg skipped')
         t0 = time.perf_counter()
         ref = [cv.detectAndCompute(frames[f], None) for f in range(m)]
         cpu_s = time.perf_counter() - t0
