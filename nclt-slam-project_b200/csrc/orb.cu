@@ -107,11 +107,14 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     const uint8_t* c = pyr + base + (size_t)y * p + x;
     const int v = c[0];
-    {   // an arc of 9 contains one pixel of every opposite pair: two pairs inside the threshold band -> no corner
-        const int e0 = v - c[3 * p], e8 = v - c[-3 * p], e4 = v - c[3], e12 = v - c[-3];
-        const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
-        const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
-        if (in0 || in4) {
+    {   // an arc of 9 contains two ADJACENT compass pixels (they are 4 apart): no adjacent pair darker, none brighter
+        // than the centre by more than the threshold -> no corner.  Rejects most pixels after 5 loads.
+        const int e0 = v - c[3 * p], e4 = v - c[3], e8 = v - c[-3 * p], e12 = v - c[-3];
+        const bool k0 = e0 > kFastThr, k4 = e4 > kFastThr, k8 = e8 > kFastThr, k12 = e12 > kFastThr;
+        const bool b0 = e0 < -kFastThr, b4 = e4 < -kFastThr, b8 = e8 < -kFastThr, b12 = e12 < -kFastThr;
+        const bool maybe = (k0 && k4) || (k4 && k8) || (k8 && k12) || (k12 && k0) || (b0 && b4) || (b4 && b8) || (b8 && b12) ||
+                           (b12 && b0);
+        if (!maybe) {
             score[base + (size_t)y * p + x] = 0;
             return;
         }
