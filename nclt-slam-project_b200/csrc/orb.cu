@@ -41,7 +41,7 @@ struct OrbGeom {
     float deg2rad;
 };
 
-__constant__ signed char c_pattern[256 * 4];
+__constant__ __align__(16) signed char c_pattern[256 * 4];
 
 // One launch covers all levels without empty CTAs: blockIdx.x runs over the tiles of level 0, then level 1, ...
 struct BlockMap { int first[kLevels + 1]; int bx[kLevels]; };
@@ -107,14 +107,12 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     const uint8_t* c = pyr + base + (size_t)y * p + x;
     const int v = c[0];
-    {   // an arc of 9 contains two ADJACENT compass pixels (they are 4 apart): no adjacent pair darker, none brighter
-        // than the centre by more than the threshold -> no corner.  Rejects most pixels after 5 loads.
-        const int e0 = v - c[3 * p], e4 = v - c[3], e8 = v - c[-3 * p], e12 = v - c[-3];
-        const bool k0 = e0 > kFastThr, k4 = e4 > kFastThr, k8 = e8 > kFastThr, k12 = e12 > kFastThr;
-        const bool b0 = e0 < -kFastThr, b4 = e4 < -kFastThr, b8 = e8 < -kFastThr, b12 = e12 < -kFastThr;
-        const bool maybe = (k0 && k4) || (k4 && k8) || (k8 && k12) || (k12 && k0) || (b0 && b4) || (b4 && b8) || (b8 && b12) ||
-                           (b12 && b0);
-        if (!maybe) {
+    {   // an arc of 9 contains one pixel of every opposite pair: two pairs inside the threshold band -> no corner
+        // (the stronger "two adjacent compass pixels" test costs more instructions than it saves: 621 vs 559 us)
+        const int e0 = v - c[3 * p], e8 = v - c[-3 * p], e4 = v - c[3], e12 = v - c[-3];
+        const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
+        const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
+        if (in0 || in4) {
             score[base + (size_t)y * p + x] = 0;
             return;
         }
@@ -263,6 +261,13 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
                                                       const int* __restrict__ n_out,
                                                       float* __restrict__ out_kp, uint8_t* __restrict__ out_desc) {
     // n_out == nullptr: sel is a dense list of n_sel entries; else sel is [frame][cap] with n_out[frame] valid rows
+    // the 256 test pairs, one 4-byte word each, transposed so that lane L's i-th test sits in bank L
+    __shared__ uint32_t pat[8][32];
+    {
+        const int t = threadIdx.x, L = t >> 3, i = t & 7;        // test t = 8 * L + i  (byte L, bit i)
+        pat[i][L] = reinterpret_cast<const uint32_t*>(c_pattern)[t];
+    }
+    __syncthreads();
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= n_sel) return;
     if (n_out && (k % cap) >= n_out[k / cap]) return;
@@ -300,8 +305,9 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
     unsigned byte = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const signed char* q = c_pattern + (lane * 8 + i) * 4;
-        const float x0 = (float)q[0], y0 = (float)q[1], x1 = (float)q[2], y1 = (float)q[3];
+        const uint32_t q = pat[i][lane];
+        const float x0 = (float)(signed char)(q & 0xFF), y0 = (float)(signed char)((q >> 8) & 0xFF);
+        const float x1 = (float)(signed char)((q >> 16) & 0xFF), y1 = (float)(signed char)(q >> 24);
         const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
         const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
         const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
@@ -748,6 +754,16 @@ extern "C" int nclt_orb_levels(const nclt_orb* o, int32_t* out_w, int32_t* out_h
 }
 
 // phase 1, common to both selection modes: pyramid, FAST score map, blurred pyramid
+// The blur needs only the pyramid.  It is queued on the side stream behind `after` (an event on the main stream) so
+// that it runs beside the selection kernels, which occupy one lane per level and leave the SMs idle.
+static int orb_blur_beside(nclt_ctx* c, nclt_orb* o, int F) {
+    CU_TRY(c, cudaEventRecord(o->ev_pyr, c->stream));
+    CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
+    k_orb_blur<<<dim3(o->bm_blur.first[kLevels], F), 256, 0, o->side>>>(o->d_pyr, o->g, o->bm_blur, o->d_blur);
+    CU_TRY(c, cudaEventRecord(o->ev_blur, o->side));
+    return NCLT_OK;
+}
+
 static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channels, int F) {
     const OrbGeom& g = o->g;
     cudaStream_t st = c->stream;
@@ -756,10 +772,6 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
         k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
                                                                              g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
                                                                              g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
-    CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
-    k_orb_blur<<<dim3(o->bm_blur.first[kLevels], F), 256, 0, o->side>>>(o->d_pyr, g, o->bm_blur, o->d_blur);
-    CU_TRY(c, cudaEventRecord(o->ev_blur, o->side));
     if (o->bm_fast.first[kLevels] > 0) k_orb_fast<<<dim3(o->bm_fast.first[kLevels], F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, o->d_score);
     c->launches += 10;
     CU_TRY(c, cudaGetLastError());
@@ -838,6 +850,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         k_orb_nms_count<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt);
         k_orb_nms_emit<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_pyr, o->d_score, g, o->lt, o->bm_rows, o->harris_scale4,
                                                                             o->d_rowcnt, o->d_key, o->d_fscore, o->d_cnt);
+        if ((rc = orb_blur_beside(c, o, F))) return rc;
         const size_t sel_smem = (size_t)kSelSmemEntries * sizeof(RespIdx);
         k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_kept1, o->d_flags);
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
@@ -868,6 +881,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
             return NCLT_OK;
         }
     }
+    if (o->select_mode == 1 && (rc = orb_blur_beside(c, o, F))) return rc;     // (the fall-back has queued it already)
     std::vector<int32_t> n_out;
     int n_sel = 0;
     if ((rc = orb_select_host(c, o, F, n_out, &n_sel))) return rc;
