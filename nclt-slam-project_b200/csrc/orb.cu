@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(256) k_orb_nms_emit(const uint8_t* __restrict_
 //   k_orb_harris    Harris response of the survivors only, one warp per keypoint   -> work[].r
 //   k_orb_select2   retainBest(n_level) on the Harris responses, the frame's keypoint list in level order
 // flags[0] |= 1: introselect ran out of its recursion budget (host fall-back), |= 2: more keypoints than out_cap.
-constexpr int kSelSmemEntries = 20480;       // 160 KB
+constexpr int kSelSmemEntries = 13312;       // x (8 B element + 2 x 2 B stopper-list slots) = 156 KB
+constexpr int kSelSmemBytes = kSelSmemEntries * 12;
 
 __device__ __forceinline__ RespIdx* sel_buffer(RespIdx* smem, int* soff, const int* counts, int l, RespIdx* global_buf, bool& in_smem) {
     if (threadIdx.x == 0) {
@@ -450,8 +451,19 @@ __device__ __forceinline__ RespIdx* sel_buffer(RespIdx* smem, int* soff, const i
     return in_smem ? smem + soff[l] : global_buf;
 }
 
+// retainBest by the whole warp (stopper lists, orb_select.cuh) when positions fit 16 bits, else by lane 0
+__device__ __forceinline__ int retain_any(RespIdx* v, int n, int n_points, unsigned short* Ls, unsigned short* Rs) {
+    if (n <= 65535) return orbsel::warp_retain_best(v, n, n_points, Ls, Rs);
+    int m = 0;
+    if ((threadIdx.x & 31) == 0) m = orbsel::retain_best(v, n, n_points);
+    m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    __syncwarp();
+    return m;
+}
+
 __global__ void __launch_bounds__(256) k_orb_select1(LevelTab lt, const float* __restrict__ fscore, const int* __restrict__ cnt,
-                                                     RespIdx* __restrict__ work, int* __restrict__ kept1, int* __restrict__ flags) {
+                                                     RespIdx* __restrict__ work, unsigned short* __restrict__ lists,
+                                                     int* __restrict__ kept1, int* __restrict__ flags) {
     extern __shared__ RespIdx sel_smem[];
     __shared__ int soff[kLevels + 1];
     const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -459,12 +471,11 @@ __global__ void __launch_bounds__(256) k_orb_select1(LevelTab lt, const float* _
     bool in_smem;
     RespIdx* v = sel_buffer(sel_smem, soff, cnt + f * kLevels, l, work + ob, in_smem);
     const int n = cnt[f * kLevels + l];
+    unsigned short* Ls = in_smem ? reinterpret_cast<unsigned short*>(sel_smem + kSelSmemEntries) + 2 * soff[l] : lists + 2 * ob;
+    unsigned short* Rs = Ls + n;
     for (int i = lane; i < n; i += 32) v[i] = RespIdx{fscore[ob + i], i};
     __syncwarp();
-    int m = 0;
-    if (lane == 0) m = orbsel::retain_best(v, n, 2 * lt.n_level[l]);
-    m = __shfl_sync(0xFFFFFFFFu, m, 0);
-    __syncwarp();
+    int m = retain_any(v, n, 2 * lt.n_level[l], Ls, Rs);
     if (m < 0) {
         if (lane == 0) atomicOr(flags, 1);
         m = 0;
@@ -515,8 +526,9 @@ __global__ void __launch_bounds__(256) k_orb_harris(const uint8_t* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) k_orb_select2(LevelTab lt, const uint32_t* __restrict__ key, const int* __restrict__ kept1,
-                                                     RespIdx* __restrict__ work, Sel* __restrict__ sel, int out_cap,
-                                                     int* __restrict__ n_out, int* __restrict__ flags) {
+                                                     RespIdx* __restrict__ work, unsigned short* __restrict__ lists,
+                                                     Sel* __restrict__ sel, int out_cap, int* __restrict__ n_out,
+                                                     int* __restrict__ flags) {
     extern __shared__ RespIdx sel_smem[];
     __shared__ int soff[kLevels + 1];
     __shared__ int kept[kLevels];
@@ -525,12 +537,12 @@ __global__ void __launch_bounds__(256) k_orb_select2(LevelTab lt, const uint32_t
     bool in_smem;
     RespIdx* v = sel_buffer(sel_smem, soff, kept1 + f * kLevels, l, work + ob, in_smem);
     const int n = kept1[f * kLevels + l];
+    unsigned short* Ls = in_smem ? reinterpret_cast<unsigned short*>(sel_smem + kSelSmemEntries) + 2 * soff[l] : lists + 2 * ob;
+    unsigned short* Rs = Ls + n;
     if (in_smem)
         for (int i = lane; i < n; i += 32) v[i] = work[ob + i];
     __syncwarp();
-    int m = 0;
-    if (lane == 0) m = orbsel::retain_best(v, n, lt.n_level[l]);
-    m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    int m = retain_any(v, n, lt.n_level[l], Ls, Rs);
     if (m < 0) {
         if (lane == 0) atomicOr(flags, 1);
         m = 0;
@@ -583,6 +595,7 @@ struct nclt_orb {
     float* d_fscore = nullptr;
     int* d_kept1 = nullptr;
     RespIdx* d_work = nullptr;
+    unsigned short* d_lists = nullptr;     // stopper lists of the warp partitions when a frame does not fit shared memory
     int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
     BlockMap bm_fast, bm_blur, bm_rows;
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
@@ -596,7 +609,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (c) cudaSetDevice(c->device);
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
-    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_cnt);
+    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists); cudaFree(o->d_cnt);
     cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt);
     if (o->side) cudaStreamDestroy(o->side);
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
@@ -697,6 +710,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_fscore, (size_t)cand_cap * max_frames * 4);
     A((void**)&o->d_kept1, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_work, (size_t)cand_cap * max_frames * sizeof(RespIdx));
+    A((void**)&o->d_lists, (size_t)cand_cap * max_frames * 2 * sizeof(unsigned short));
     A((void**)&o->d_cnt, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_nout, (size_t)max_frames * 4);
     A((void**)&o->d_flags, 256);
@@ -706,8 +720,8 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_blur, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&o->h_pinned, (size_t)(max_frames + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(o->d_flags, 0, 256);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemEntries * (int)sizeof(RespIdx));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemEntries * (int)sizeof(RespIdx));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes);
     A((void**)&o->d_sel, (size_t)out_cap * max_frames * sizeof(Sel));
     A((void**)&o->d_kp, (size_t)out_cap * max_frames * 6 * sizeof(float));
     A((void**)&o->d_desc, (size_t)out_cap * max_frames * 32);
@@ -851,10 +865,11 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         k_orb_nms_emit<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_pyr, o->d_score, g, o->lt, o->bm_rows, o->harris_scale4,
                                                                             o->d_rowcnt, o->d_key, o->d_fscore, o->d_cnt);
         if ((rc = orb_blur_beside(c, o, F))) return rc;
-        const size_t sel_smem = (size_t)kSelSmemEntries * sizeof(RespIdx);
-        k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_kept1, o->d_flags);
+        const size_t sel_smem = (size_t)kSelSmemBytes;
+        k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_lists, o->d_kept1, o->d_flags);
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
-        k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_sel, o->out_cap, o->d_nout, o->d_flags);
+        k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_lists, o->d_sel, o->out_cap, o->d_nout,
+                                                o->d_flags);
         CU_TRY(c, cudaStreamWaitEvent(st, o->ev_blur, 0));
         k_orb_describe<<<(F * o->out_cap + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, F * o->out_cap, o->out_cap,
                                                                  o->d_nout, d_kp, d_desc);

@@ -29,13 +29,16 @@ int main() {
             a[i] = RespIdx{r, i};
         }
         int np = rng() % (n + 3);
-        std::vector<RespIdx> b = a;
+        std::vector<RespIdx> b = a, c = a;
         int m_ref = ref_retain(a, np);
         int m = orbsel::retain_best(b.data(), n, np);
+        std::vector<unsigned short> Ls(n + 1), Rs(n + 1);
+        int m2 = orbsel::retain_best_lists(c.data(), n, np, Ls.data(), Rs.data());     // the form the GPU warps run
         ++cases;
+        if ((m < 0) != (m2 < 0)) { ++bad; continue; }
         if (m < 0) { ++fallbacks; continue; }
-        if (m != m_ref) { ++bad; continue; }
-        for (int i = 0; i < m; ++i) if (a[i].i != b[i].i) { ++bad; break; }
+        if (m != m_ref || m2 != m_ref) { ++bad; continue; }
+        for (int i = 0; i < m; ++i) if (a[i].i != b[i].i || a[i].i != c[i].i) { ++bad; break; }
     }
     printf("cases %ld bad %ld fallbacks %ld\n", cases, bad, fallbacks);
     return bad != 0;
