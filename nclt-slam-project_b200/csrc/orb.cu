@@ -97,69 +97,96 @@ __device__ __forceinline__ bool has9(unsigned m) {     // 9 contiguous set bits 
     return (a & 0xFFFFu) != 0;
 }
 
-__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, uint8_t* __restrict__ score) {
+// 32 x 32 pixel tile per CTA (256 threads), staged in shared memory with its 3-pixel ring.
+// Phase 1, four pixels per thread: the compass test - an arc of 9 contains one pixel of every opposite pair, so a
+// pair inside the threshold band on both sides rules the corner out; survivors (a few per cent, but scattered over
+// 40 % of the warps) go to a list in shared memory.  Phase 2: the threads walk that list densely - full segment test
+// on 16-bit arc masks, score by doubling minima - so the expensive path runs in full warps.
+constexpr int kFastTile = 32;
+__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, int block0,
+                                                  uint8_t* __restrict__ score) {
+    __shared__ uint8_t tile[kFastTile + 6][kFastTile + 8];
+    __shared__ unsigned short list[kFastTile * kFastTile];
+    __shared__ int n_list;
     const int f = blockIdx.y;
     int l, bx, by;
-    block_of(bm, blockIdx.x, l, bx, by);
+    block_of(bm, blockIdx.x + block0, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
-    const int x = bx * 32 + (threadIdx.x & 31) + kEdge - 1, y = by * 8 + (threadIdx.x >> 5) + kEdge - 1;
-    if (x > w - kEdge || y > h - kEdge) return;
+    const int x0 = bx * kFastTile + kEdge - 1, y0 = by * kFastTile + kEdge - 1;      // first pixel of the tile
+    const int xe = w - kEdge, ye = h - kEdge;                                        // last pixel scored (inclusive)
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
-    const uint8_t* c = pyr + base + (size_t)y * p + x;
-    const int v = c[0];
-    {   // an arc of 9 contains one pixel of every opposite pair: two pairs inside the threshold band -> no corner
-        // (the stronger "two adjacent compass pixels" test costs more instructions than it saves: 621 vs 559 us)
-        const int e0 = v - c[3 * p], e8 = v - c[-3 * p], e4 = v - c[3], e12 = v - c[-3];
+    if (threadIdx.x == 0) n_list = 0;
+    for (int i = threadIdx.x; i < (kFastTile + 6) * (kFastTile + 6); i += 256) {
+        const int ty = i / (kFastTile + 6), tx = i - ty * (kFastTile + 6);
+        const int yy = min(y0 + ty - 3, h - 1), xx = min(x0 + tx - 3, w - 1);         // x0 - 3 >= 27: no lower clamp needed
+        tile[ty][tx] = pyr[base + (size_t)yy * p + xx];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ty = (threadIdx.x >> 5) + 8 * r;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x > xe || y > ye) continue;
+        const uint8_t* c = &tile[ty + 3][tx + 3];
+        const int v = c[0];
+        const int e0 = v - c[3 * (kFastTile + 8)], e8 = v - c[-3 * (kFastTile + 8)], e4 = v - c[3], e12 = v - c[-3];
         const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
         const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
-        if (in0 || in4) {
-            score[base + (size_t)y * p + x] = 0;
-            return;
-        }
+        if (in0 || in4) score[base + (size_t)y * p + x] = 0;
+        else list[atomicAdd(&n_list, 1)] = (unsigned short)(ty * kFastTile + tx);
     }
-    int d[16];
-    d[0] = v - c[3 * p];          d[1] = v - c[3 * p + 1];   d[2] = v - c[2 * p + 2];    d[3] = v - c[p + 3];
-    d[4] = v - c[3];              d[5] = v - c[-p + 3];      d[6] = v - c[-2 * p + 2];   d[7] = v - c[-3 * p + 1];
-    d[8] = v - c[-3 * p];         d[9] = v - c[-3 * p - 1];  d[10] = v - c[-2 * p - 2];  d[11] = v - c[-p - 3];
-    d[12] = v - c[-3];            d[13] = v - c[p - 3];      d[14] = v - c[2 * p - 2];   d[15] = v - c[3 * p - 1];
-    unsigned dark = 0, bright = 0;            // ring darker / brighter than the centre by more than the threshold
+    __syncthreads();
+    const int n = n_list;
+    constexpr int P = kFastTile + 8;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int ty = list[i] / kFastTile, tx2 = list[i] % kFastTile;
+        const uint8_t* c = &tile[ty + 3][tx2 + 3];
+        const int v = c[0];
+        int d[16];
+        d[0] = v - c[3 * P];          d[1] = v - c[3 * P + 1];   d[2] = v - c[2 * P + 2];    d[3] = v - c[P + 3];
+        d[4] = v - c[3];              d[5] = v - c[-P + 3];      d[6] = v - c[-2 * P + 2];   d[7] = v - c[-3 * P + 1];
+        d[8] = v - c[-3 * P];         d[9] = v - c[-3 * P - 1];  d[10] = v - c[-2 * P - 2];  d[11] = v - c[-P - 3];
+        d[12] = v - c[-3];            d[13] = v - c[P - 3];      d[14] = v - c[2 * P - 2];   d[15] = v - c[3 * P - 1];
+        unsigned dark = 0, bright = 0;            // ring darker / brighter than the centre by more than the threshold
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        dark |= (d[k] > kFastThr ? 1u : 0u) << k;
-        bright |= (d[k] < -kFastThr ? 1u : 0u) << k;
+        for (int k = 0; k < 16; ++k) {
+            dark |= (d[k] > kFastThr ? 1u : 0u) << k;
+            bright |= (d[k] < -kFastThr ? 1u : 0u) << k;
+        }
+        int s = 0;
+        if (has9(dark) || has9(bright)) {
+            // score = (max over the 16 arcs of 9 of the smallest difference of one sign) - 1.  Differences are biased
+            // to non-negative values (a = 255 + d for "darker", b = 255 - d for "brighter") and the 9-wide circular
+            // minima are built by doubling: windows of 2, 4, 8, then one more element.
+            int a[16], b[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                a[k] = 255 + d[k];
+                b[k] = 255 - d[k];
+            }
+            int a2[16], b2[16], a4[16], b4[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                a2[k] = min(a[k], a[(k + 1) & 15]);
+                b2[k] = min(b[k], b[(k + 1) & 15]);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                a4[k] = min(a2[k], a2[(k + 2) & 15]);
+                b4[k] = min(b2[k], b2[(k + 2) & 15]);
+            }
+            int best = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int a9 = min(min(a4[k], a4[(k + 4) & 15]), a[(k + 8) & 15]);
+                const int b9 = min(min(b4[k], b4[(k + 4) & 15]), b[(k + 8) & 15]);
+                best = max(best, max(a9, b9));
+            }
+            s = best - 255 - 1;
+        }
+        score[base + (size_t)(y0 + ty) * p + x0 + tx2] = (uint8_t)s;
     }
-    int s = 0;
-    if (has9(dark) || has9(bright)) {
-        // score = (max over the 16 arcs of 9 of the smallest difference of one sign) - 1.  Differences are biased
-        // to non-negative values (a = 255 + d for "darker", b = 255 - d for "brighter") and the 9-wide circular
-        // minima are built by doubling: windows of 2, 4, 8, then one more element.
-        int a[16], b[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            a[k] = 255 + d[k];
-            b[k] = 255 - d[k];
-        }
-        int a2[16], b2[16], a4[16], b4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            a2[k] = min(a[k], a[(k + 1) & 15]);
-            b2[k] = min(b[k], b[(k + 1) & 15]);
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            a4[k] = min(a2[k], a2[(k + 2) & 15]);
-            b4[k] = min(b2[k], b2[(k + 2) & 15]);
-        }
-        int best = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int a9 = min(min(a4[k], a4[(k + 4) & 15]), a[(k + 8) & 15]);
-            const int b9 = min(min(b4[k], b4[(k + 4) & 15]), b[(k + 8) & 15]);
-            best = max(best, max(a9, b9));
-        }
-        s = best - 255 - 1;
-    }
-    score[base + (size_t)y * p + x] = (uint8_t)s;
 }
 
 // ---- NMS + border filter + Harris response, candidates appended to one list ----
@@ -650,8 +677,8 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
             const int rows = std::max(g.h[l] - 2 * kEdge, 0), cols = std::max(g.w[l] - 2 * kEdge, 0);
             o->lt.row_off[l] = rows_total;
             rows_total += rows;
-            o->bm_fast.first[l] = nf; o->bm_fast.bx[l] = std::max((cols + 2 + 31) / 32, 1);
-            nf += (rows > 0 && cols > 0) ? o->bm_fast.bx[l] * ((rows + 2 + 7) / 8) : 0;
+            o->bm_fast.first[l] = nf; o->bm_fast.bx[l] = std::max((cols + 2 + kFastTile - 1) / kFastTile, 1);
+            nf += (rows > 0 && cols > 0) ? o->bm_fast.bx[l] * ((rows + 2 + kFastTile - 1) / kFastTile) : 0;
             o->bm_blur.first[l] = nb; o->bm_blur.bx[l] = (g.w[l] + 31) / 32;
             nb += o->bm_blur.bx[l] * ((g.h[l] + 31) / 32);
             o->bm_rows.first[l] = nr; o->bm_rows.bx[l] = 1;
@@ -780,13 +807,16 @@ static int orb_blur_beside(nclt_ctx* c, nclt_orb* o, int F) {
 
 static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channels, int F) {
     const OrbGeom& g = o->g;
+    int rc_blur = 0;
     cudaStream_t st = c->stream;
-    k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
+    if (d_img)      // nullptr: level 0 is already in place
+        k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
     for (int l = 1; l < kLevels; ++l)
         k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
                                                                              g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
                                                                              g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    if (o->bm_fast.first[kLevels] > 0) k_orb_fast<<<dim3(o->bm_fast.first[kLevels], F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, o->d_score);
+    if (o->bm_fast.first[kLevels] > 0) k_orb_fast<<<dim3(o->bm_fast.first[kLevels], F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, 0, o->d_score);
+    if ((rc_blur = orb_blur_beside(c, o, F))) return rc_blur;       // beside the light kernels that follow (NMS, selection)
     c->launches += 10;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
@@ -851,8 +881,15 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     cudaStream_t st = c->stream;
     const uint8_t* d_img = img;
     if (!img_on_device) {
-        CU_TRY(c, cudaMemcpyAsync(o->d_in, img, (size_t)o->W * o->H * channels * F, cudaMemcpyHostToDevice, st));
-        d_img = o->d_in;
+        if (channels == 1 && g.pitch[0] == o->W) {
+            // gray host frames land directly in level 0 of the pyramid (one strided copy, no staging, no copy kernel)
+            CU_TRY(c, cudaMemcpy2DAsync(o->d_pyr, (size_t)g.frame_bytes, img, (size_t)o->W * o->H, (size_t)o->W * o->H, F,
+                                        cudaMemcpyHostToDevice, st));
+            d_img = nullptr;
+        } else {
+            CU_TRY(c, cudaMemcpyAsync(o->d_in, img, (size_t)o->W * o->H * channels * F, cudaMemcpyHostToDevice, st));
+            d_img = o->d_in;
+        }
     }
     int rc = orb_front(c, o, d_img, channels, F);
     if (rc) return rc;
@@ -864,7 +901,6 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         k_orb_nms_count<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt);
         k_orb_nms_emit<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_pyr, o->d_score, g, o->lt, o->bm_rows, o->harris_scale4,
                                                                             o->d_rowcnt, o->d_key, o->d_fscore, o->d_cnt);
-        if ((rc = orb_blur_beside(c, o, F))) return rc;
         const size_t sel_smem = (size_t)kSelSmemBytes;
         k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_lists, o->d_kept1, o->d_flags);
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
@@ -896,7 +932,6 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
             return NCLT_OK;
         }
     }
-    if (o->select_mode == 1 && (rc = orb_blur_beside(c, o, F))) return rc;     // (the fall-back has queued it already)
     std::vector<int32_t> n_out;
     int n_sel = 0;
     if ((rc = orb_select_host(c, o, F, n_out, &n_sel))) return rc;
