@@ -377,6 +377,20 @@ __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
            s > sc[p + 1];
 }
 
+// NMS over four pixels at once: one 32-bit read of the score row (almost always zero), neighbours only for corners.
+// row = first byte of the score row (16-byte aligned), wi = word index; bit k of the result = pixel 4 wi + k survives.
+__device__ __forceinline__ unsigned nms_word_hits(const uint8_t* row, int p, int wi, int xlo, int xhi) {
+    const uint32_t wv = *reinterpret_cast<const uint32_t*>(row + 4 * wi);
+    if (wv == 0) return 0;
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = 4 * wi + k;
+        if (((wv >> (8 * k)) & 0xFFu) && x >= xlo && x < xhi && nms_max(row + x, p)) hits |= 1u << k;
+    }
+    return hits;
+}
+
 // NMS survivors of every (frame, level) in FAST's row-major order, two launches over 8-row chunks (one warp per row):
 // k_orb_nms_count leaves the survivors per row, k_orb_nms_emit sums the rows above its chunk and writes
 // (position, FAST score) at the final offsets.  rowcnt: [F][rows_total], rows of level l start at
@@ -390,12 +404,12 @@ __global__ void __launch_bounds__(256) k_orb_nms_count(const uint8_t* __restrict
     const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
     const int r = by * 8 + warp;
     if (r >= rows || cols <= 0) return;
-    const uint8_t* sc = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p + kEdge;
+    const uint8_t* row = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p;
+    const int wi_max = (w - kEdge - 1) / 4;
     int n = 0;
-    for (int x0 = 0; x0 < cols; x0 += 32) {
-        const int x = x0 + lane;
-        n += __popc(__ballot_sync(0xFFFFFFFFu, x < cols && nms_max(sc + x, p)));
-    }
+    for (int wi = kEdge / 4 + lane; wi <= wi_max; wi += 32) n += __popc(nms_word_hits(row, p, wi, kEdge, w - kEdge));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
     if (lane == 0) rowcnt[(size_t)f * lt.rows_total + lt.row_off[l] + r] = n;
 }
 
@@ -438,19 +452,31 @@ __global__ void __launch_bounds__(256) k_orb_nms_emit(const uint8_t* __restrict_
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
     const int y = r + kEdge;
-    const uint8_t* sc = score + base + (size_t)y * p + kEdge;
+    const uint8_t* row = score + base + (size_t)y * p;
     int pos = rowbase[warp];
     if (rowbase[warp + 1] == pos) return;
-    for (int x0 = 0; x0 < cols; x0 += 32) {
-        const int x = x0 + lane;
-        const bool hit = x < cols && nms_max(sc + x, p);
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) {
-            const int o = pos + __popc(m & ((1u << lane) - 1u));
-            key[ob + o] = (uint32_t)(y << 16 | (x + kEdge));
-            fscore[ob + o] = (float)sc[x];
+    const int wi_max = (w - kEdge - 1) / 4;
+    for (int wi0 = kEdge / 4; wi0 <= wi_max; wi0 += 32) {
+        const int wi = wi0 + lane;
+        const unsigned hits = wi <= wi_max ? nms_word_hits(row, p, wi, kEdge, w - kEdge) : 0u;
+        const int c = __popc(hits);
+        if (__ballot_sync(0xFFFFFFFFu, c > 0) == 0) continue;
+        int incl = c;                                   // lanes hold ascending x: exclusive scan of the per-lane counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += u;
         }
-        pos += __popc(m);
+        int o = pos + incl - c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (hits & (1u << k)) {
+                const int x = 4 * wi + k;
+                key[ob + o] = (uint32_t)(y << 16 | x);
+                fscore[ob + o] = (float)row[x];
+                ++o;
+            }
+        pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
 }
 
@@ -626,7 +652,7 @@ struct nclt_orb {
     int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
     BlockMap bm_fast, bm_blur, bm_rows;
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
     int* h_pinned = nullptr;      // [0] flags, [1..] n_out
     unsigned long long host_fallbacks = 0;
 };
@@ -641,6 +667,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (o->side) cudaStreamDestroy(o->side);
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
     if (o->ev_blur) cudaEventDestroy(o->ev_blur);
+    if (o->ev_rs) cudaEventDestroy(o->ev_rs);
     if (o->h_pinned) cudaFreeHost(o->h_pinned);
     for (int l = 0; l < kLevels; ++l) cudaFree(o->d_tab[l]);
     delete o;
@@ -745,6 +772,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_pyr, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_blur, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_rs, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&o->h_pinned, (size_t)(max_frames + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(o->d_flags, 0, 256);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes);
@@ -811,13 +839,21 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
     cudaStream_t st = c->stream;
     if (d_img)      // nullptr: level 0 is already in place
         k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
+    // the seven dependent resizes are small, latency-bound launches: they run on the side stream while FAST already
+    // works on level 0 (45 % of all pixels); FAST of levels 1-7 follows when the chain is done
+    CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
+    CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
     for (int l = 1; l < kLevels; ++l)
-        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, st>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
-                                                                             g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
-                                                                             g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    if (o->bm_fast.first[kLevels] > 0) k_orb_fast<<<dim3(o->bm_fast.first[kLevels], F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, 0, o->d_score);
+        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, o->side>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
+                                                                                  g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
+                                                                                  g.pitch[l], g.frame_bytes, o->d_tab[l]);
+    CU_TRY(c, cudaEventRecord(o->ev_rs, o->side));
+    const int nb0 = o->bm_fast.first[1], nb = o->bm_fast.first[kLevels];
+    if (nb0 > 0) k_orb_fast<<<dim3(nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, 0, o->d_score);
+    CU_TRY(c, cudaStreamWaitEvent(st, o->ev_rs, 0));
+    if (nb > nb0) k_orb_fast<<<dim3(nb - nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, nb0, o->d_score);
     if ((rc_blur = orb_blur_beside(c, o, F))) return rc_blur;       // beside the light kernels that follow (NMS, selection)
-    c->launches += 10;
+    c->launches += 11;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
 }
