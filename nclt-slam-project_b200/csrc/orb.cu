@@ -6,9 +6,10 @@
 //   pyramid   8 levels, scale 1.2^l (float), each level resized from the previous one with the bit-exact bilinear
 //             resize (INTER_LINEAR_EXACT: 8.8 fixed-point weights, horizontal then vertical, (v + 2^15) >> 16)
 //   FAST      9-of-16 segment test, threshold 20, score = largest threshold keeping the pixel a corner, 3x3 strict NMS
-//   Harris    7x7 block of 3x3 Sobel products at every NMS survivor at least 31 px from the border
-//   select    per level: retainBest(2n) by FAST score, then retainBest(n) by Harris - HOST side, with the very
-//             std::nth_element / std::partition calls OpenCV makes (their permutation defines the output order)
+//   Harris    7x7 block of 3x3 Sobel products, for the survivors of the first cut (>= 31 px from the border)
+//   select    per level: retainBest(2n) by FAST score, then retainBest(n) by Harris.  The permutation OpenCV's
+//             std::nth_element / std::partition calls leave behind defines the output order; orb_select.cuh
+//             reproduces it on the device (one warp per level), the host std:: calls remain as fall-back
 //   angle     intensity centroid over the radius-15 disc, cv::fastAtan2 polynomial
 //   blur      7x7 sigma-2 Gaussian as OpenCV's separable float filter runs it on a pyramid sub-matrix: row pass
 //             sequential FMAs, column pass symmetric pairs with FMAs, round half to even
