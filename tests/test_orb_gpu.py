@@ -112,6 +112,35 @@ def test_forced_hand_over_to_the_host(ctx):
         _check(kp, desc, n, f, rk, rd, f'frame {f}')
 
 
+def test_large_frames_and_more_than_65535_candidates(ctx):
+    """1280 x 720: a textured frame, and white noise whose level 0 holds more NMS survivors than the 16-bit stopper
+    lists of the warp partition can index - that level takes the single-lane walk, in global memory."""
+    from nclt_slam_project_b200.orb import ORB
+    o = ORB(width=1280, height=720, max_frames=2, ctx=ctx)
+    frames = np.stack([synth.make_camera_frame(50, 720, 1280, n_rect=900),
+                       np.random.default_rng(3).integers(0, 256, (720, 1280), dtype=np.uint8)])
+    kp, desc, n = o.detect_and_compute_batch(frames)
+    assert (oo.fast_nms(frames[1])[0].size) > 65535
+    for f in range(2):
+        rk, rd = oo.detect_and_compute(frames[f])
+        _check(kp, desc, n, f, rk, rd, f'frame {f}')
+    assert o.host_fallbacks == 0
+
+
+@pytest.mark.parametrize('select', ['device', 'host'])
+def test_out_cap_overflow_is_an_error(ctx, select):
+    """The tiled frame yields 514 keypoints (ties at the Harris cut): out_cap = 500 must fail loudly, not truncate."""
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.orb import ORB
+    o = ORB(out_cap=500, ctx=ctx, select=select)
+    tile = synth.make_camera_frame(9, 96, 128, n_rect=20, noise=0.0)
+    with pytest.raises(_lib.NcltError, match='out_cap'):
+        o.detect_and_compute_batch(np.tile(tile, (5, 5))[None])
+    kp, desc, n = o.detect_and_compute_batch(synth.make_camera_frame(2)[None])      # the handle stays usable
+    rk, rd = oo.detect_and_compute(synth.make_camera_frame(2))
+    _check(kp, desc, n, 0, rk, rd, 'after the error')
+
+
 def test_bad_arguments(ctx):
     from nclt_slam_project_b200 import _lib
     from nclt_slam_project_b200.orb import ORB
