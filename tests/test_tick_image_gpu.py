@@ -1,0 +1,42 @@
+"""GPU: the teach -> repeat chain from camera frames: recorder.tick_image (ORB + keypoint lifting -> landmark record)
+and matcher.tick_image (ORB + crossCheck match + PnP-RANSAC + gates -> anchor), each against the same chain driven
+with the CPU oracle's ORB output (oracle/orb.py == cv2 bit for bit).  The robot revisits the taught poses, so the
+matcher must publish an anchor on the teach pose."""
+import numpy as np
+import pytest
+
+import nclt_slam_project_b200  # noqa: F401
+from nclt_slam_project_b200 import synth
+from oracle import orb as oo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_teach_then_repeat_from_images(ctx, tmp_path):
+    from nclt_slam_project_b200.matcher import LandmarkMatcher
+    from nclt_slam_project_b200.recorder import LandmarkRecorder
+    rec = LandmarkRecorder(str(tmp_path / 'teach' / 'landmarks.pkl'), ctx=ctx)
+    ref = LandmarkRecorder(str(tmp_path / 'ref' / 'landmarks.pkl'), ctx=ctx)
+    frames = [synth.make_camera_frame(60 + i, bgr=True) for i in range(3)]
+    poses = [(3.0 * i, 0.5 * i, 0.0, 0.0, 0.0, float(np.sin(0.05 * i)), float(np.cos(0.05 * i))) for i in range(3)]
+    rng = np.random.default_rng(1)
+    depth = (4000 + 600 * np.sin(np.arange(640) / 90.0)[None, :] + 3 * rng.standard_normal((480, 640))).astype(np.uint16)
+    for i, (bgr, pose) in enumerate(zip(frames, poses)):
+        r = rec.tick_image(bgr, depth, pose, float(i))
+        k, d = oo.detect_and_compute(oo.bgr2gray(bgr))
+        q = ref.tick(k[:, :2], d, depth, pose, float(i))
+        assert r is not None and q is not None and r['n_features'] == q['n_features'] >= 30
+        for key in ('descriptors', 'keypoints_2d', 'keypoints_3d_cam'):
+            assert np.array_equal(r[key], q[key]), key
+    m = LandmarkMatcher(rec.as_pkl_dict(), str(tmp_path / 'log' / 'm.csv'), ctx=ctx)
+    m2 = LandmarkMatcher(ref.as_pkl_dict(), str(tmp_path / 'log' / 'm2.csv'), ctx=ctx)
+    for i, (bgr, pose) in enumerate(zip(frames, poses)):
+        out = m.tick_image(bgr, pose, ts=10.0 + i)
+        k, d = oo.detect_and_compute(oo.bgr2gray(bgr))
+        exp = m2.tick(d, k[:, :2], pose, ts=10.0 + i)
+        assert out['outcome'] == exp['outcome'] and out['outcome'].startswith('published'), (out['outcome'], exp['outcome'])
+        assert out['lm_idx'] == exp['lm_idx'] == i and out['n_inliers'] == exp['n_inliers'] >= 100
+        assert np.allclose(out['anchor_pose'], exp['anchor_pose'], atol=1e-9)
+        assert abs(out['anchor_pose'][0] - pose[0]) < 0.02 and abs(out['anchor_pose'][1] - pose[1]) < 0.02
+    kps, desc = m.orb.detectAndCompute(np.zeros((480, 640, 3), np.uint8), None)        # matcher:307
+    assert m.tick_image(np.zeros((480, 640, 3), np.uint8), poses[0])['outcome'] == 'curr_no_features'
