@@ -5,6 +5,7 @@ A maintainer swaps, in visual_landmark_matcher.py / checkpoint_a_selftest.py,
     self.matcher = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)     (matcher:211)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)              (selftest:46)
     cv2.solvePnPRansac(...), cv2.projectPoints(...)                     (matcher:342-353)
+    self.orb = cv2.ORB_create(nfeatures=500)                            (matcher:207, recorder:159)
 
 for the objects below; argument meaning, return shapes and error behaviour follow cv2
 (INTEGRATION.md shows the three-line patch).  Everything executes on the GPU through the C ABI;
@@ -14,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from .library import LandmarkLibrary
+from .orb import KeyPoint, ORB_create  # noqa: F401  (cv2.ORB_create(nfeatures=500) / cv2.KeyPoint, orb.py)
 
 NORM_HAMMING = 6          # cv2.NORM_HAMMING
 SOLVEPNP_ITERATIVE = 0    # cv2.SOLVEPNP_ITERATIVE

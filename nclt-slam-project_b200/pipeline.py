@@ -81,6 +81,8 @@ class DeviceLocalizer:
         self.library = LandmarkLibrary(descs, pts3, ctx=self.ctx)
         self.params = params or LocalizeParams()
         self._out = {}
+        self._orb = None
+        self._orb_out = None
 
     def _buffers(self, B):
         t = self.torch
@@ -94,8 +96,35 @@ class DeviceLocalizer:
             self._out[B] = o
         return o
 
-    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True):
-        """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors -> dict of CUDA tensors + n_problems.
+    def run_frames(self, frames_dev, cand_dev=None, n_cand=None, sync_count=True):
+        """Camera frames in, poses out, nothing leaves the device in between: frames_dev u8[B,H,W] (gray) or
+        u8[B,H,W,3] (BGR) CUDA tensor -> ORB(500) (orb.py / nclt_orb_detect_and_compute_dev, bit-identical to the cv2
+        call at matcher:305-306) -> `run` on its descriptors and keypoint positions (matcher:310-380).
+        Returns run()'s dict plus 'n_keypoints' i32[B], 'keypoints' f32[B,cap,6], 'descriptors' u8[B,cap,32]."""
+        t = self.torch
+        from .orb import ORB
+        B, H, W = frames_dev.shape[0], frames_dev.shape[1], frames_dev.shape[2]
+        ch = 3 if frames_dev.dim() == 4 else 1
+        orb = getattr(self, '_orb', None)
+        if orb is None or (orb.width, orb.height) != (W, H) or orb.max_frames < B:
+            orb = self._orb = ORB(width=W, height=H, max_frames=B, ctx=self.ctx)
+            self._orb_out = None
+        if self._orb_out is None or self._orb_out[0].shape[0] != B:
+            self._orb_out = (t.empty((B, orb.out_cap, 6), dtype=t.float32, device=self.device),
+                             t.empty((B, orb.out_cap, 32), dtype=t.uint8, device=self.device),
+                             t.empty(B, dtype=t.int32, device=self.device))
+        kp, desc, n = self._orb_out
+        with t.cuda.stream(self.stream):
+            self.ctx.check(_c.nclt_orb_detect_and_compute_dev(self.ctx.h, orb._h, frames_dev.data_ptr(), ch, B,
+                                                              kp.data_ptr(), desc.data_ptr(), n.data_ptr()))
+            pts2d = kp[:, :, :2].contiguous()
+            r = self.run(desc, pts2d, cand_dev, n_cand, sync_count, qn_dev=n)
+        r.update(n_keypoints=n, keypoints=kp, descriptors=desc)
+        return r
+
+    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True, qn_dev=None):
+        """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors (qn_dev i32[B]: valid rows per frame, default all)
+        -> dict of CUDA tensors + n_problems.
         sync_count=False: fully asynchronous (no host sync; n_problems = -1; check ctx.overflow())."""
         B, Nq = desc_dev.shape[0], desc_dev.shape[1]
         Cn = n_cand if cand_dev is None else cand_dev.shape[1]
@@ -104,7 +133,8 @@ class DeviceLocalizer:
         o = self._buffers(B)
         nprob = C.c_int32(0)
         self.ctx.check(_c.nclt_localize_batch_dev(
-            self.ctx.h, self.library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(), None, B, Nq,
+            self.ctx.h, self.library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(),
+            None if qn_dev is None else qn_dev.data_ptr(), B, Nq,
             None if cand_dev is None else cand_dev.data_ptr(), Cn, C.byref(self.params),
             o['best_cand'].data_ptr(), o['n_inliers'].data_ptr(), o['reproj'].data_ptr(), o['rvec'].data_ptr(),
             o['tvec'].data_ptr(), C.addressof(nprob) if sync_count else None, None, None, None, None, None, None))

@@ -40,3 +40,35 @@ def test_teach_then_repeat_from_images(ctx, tmp_path):
         assert abs(out['anchor_pose'][0] - pose[0]) < 0.02 and abs(out['anchor_pose'][1] - pose[1]) < 0.02
     kps, desc = m.orb.detectAndCompute(np.zeros((480, 640, 3), np.uint8), None)        # matcher:307
     assert m.tick_image(np.zeros((480, 640, 3), np.uint8), poses[0])['outcome'] == 'curr_no_features'
+
+
+def test_device_resident_frames_to_poses(ctx, tmp_path):
+    """DeviceLocalizer.run_frames: frames (CUDA tensor) -> ORB -> all-keyframe matching -> PnP, without leaving the
+    device, equals the host-side chain (ORB arrays -> localize_batch) frame for frame."""
+    import torch
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import DeviceLocalizer, LocalizeParams, localize_batch
+    from nclt_slam_project_b200.recorder import LandmarkRecorder
+    rec = LandmarkRecorder(str(tmp_path / 'teach' / 'landmarks.pkl'), ctx=ctx)
+    frames = np.stack([synth.make_camera_frame(70 + i) for i in range(4)])
+    rng = np.random.default_rng(2)
+    depth = (5000 + 3 * rng.standard_normal((480, 640))).astype(np.uint16)
+    for i in range(4):
+        assert rec.tick_image(frames[i], depth, (3.0 * i, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0), float(i)) is not None
+    lms = rec.landmarks
+    prm = LocalizeParams(mode=1)                                              # crossCheck, the production mode
+    dl = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]), params=prm)
+    order = [2, 0, 3, 1]
+    q = torch.from_numpy(frames[order]).to(dl.device)
+    out = dl.run_frames(q)
+    torch.cuda.synchronize()
+    assert out['best_cand'].cpu().tolist() == order and int(out['n_inliers'].min()) >= 100
+    lib = LandmarkLibrary([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms], ctx=ctx)
+    for b, f in enumerate(order):
+        k, d = oo.detect_and_compute(frames[f])
+        n = int(out['n_keypoints'][b])
+        assert n == len(k) and np.array_equal(out['descriptors'][b, :n].cpu().numpy(), d)
+        ref = localize_batch(lib, d[None], k[None, :, :2].copy(), None, None, prm)
+        assert int(ref['best_cand'][0]) == f and int(ref['n_inliers'][0]) == int(out['n_inliers'][b])
+        assert np.allclose(ref['rvec'][0], out['rvec'][b].cpu().numpy(), atol=1e-12)
+        assert np.allclose(ref['tvec'][0], out['tvec'][b].cpu().numpy(), atol=1e-12)
