@@ -117,13 +117,16 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     const int xe = w - kEdge, ye = h - kEdge;                                        // last pixel scored (inclusive)
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     if (threadIdx.x == 0) n_list = 0;
-    for (int i = threadIdx.x; i < (kFastTile + 6) * (kFastTile + 6); i += 256) {
-        const int ty = i / (kFastTile + 6), tx = i - ty * (kFastTile + 6);
-        const int yy = min(y0 + ty - 3, h - 1), xx = min(x0 + tx - 3, w - 1);         // x0 - 3 >= 27: no lower clamp needed
-        tile[ty][tx] = pyr[base + (size_t)yy * p + xx];
+    const int tx = threadIdx.x & 31;
+    {   // x0 - 3 >= 27: no lower clamp needed; the upper clamp only touches pixels that are never scored
+        const int xa = min(x0 + tx - 3, w - 1), xb = min(x0 + tx + 29, w - 1);
+        for (int r = threadIdx.x >> 5; r < kFastTile + 6; r += 8) {
+            const uint8_t* row = pyr + base + (size_t)min(y0 + r - 3, h - 1) * p;
+            tile[r][tx] = row[xa];
+            if (tx < 6) tile[r][tx + 32] = row[xb];
+        }
     }
     __syncthreads();
-    const int tx = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int ty = (threadIdx.x >> 5) + 8 * r;
@@ -224,44 +227,50 @@ __global__ void __launch_bounds__(256) k_orb_nms(const uint8_t* __restrict__ pyr
     if (slot < cap) cand[slot] = Cand{(uint32_t)(f * kLevels + l), (uint32_t)(y << 16 | x), (float)s, r};
 }
 
-// ---- Gaussian blur, 32x32 output tile per CTA ----
+// ---- Gaussian blur, 32 x 64 output tile per CTA (threads = 32 columns x 8 row lanes, no index divisions) ----
+constexpr int kBlurH = 64;
 __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, uint8_t* __restrict__ blur) {
     const int f = blockIdx.y;
     int l, bx, by;
     block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
-    const int x0 = bx * 32, y0 = by * 32;
-    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
-    __shared__ float tile[38][39];
-    __shared__ float rowp[38][33];
-    for (int i = threadIdx.x; i < 38 * 38; i += 256) {
-        const int ty = i / 38, tx = i % 38;
-        const int yy = min(max(y0 + ty - 3, 0), h - 1), xx = min(max(x0 + tx - 3, 0), w - 1);   // clamped: only pixels
-        tile[ty][tx] = (float)pyr[base + (size_t)yy * p + xx];                                 // >= 9 px inside are used
+    const int x0 = bx * 32, y0 = by * kBlurH;
+    const uint8_t* src = pyr + (size_t)f * g.frame_bytes + g.off[l];
+    uint8_t* dst = blur + (size_t)f * g.frame_bytes + g.off[l];
+    __shared__ float tile[kBlurH + 6][39];
+    __shared__ float rowp[kBlurH + 6][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // clamped reads: only pixels >= 9 px inside the level are ever sampled, the clamp just keeps the reads in bounds
+    const int xa = min(max(x0 + tx - 3, 0), w - 1), xb = min(x0 + tx + 29, w - 1);
+    for (int r = ty; r < kBlurH + 6; r += 8) {
+        const uint8_t* row = src + (size_t)min(max(y0 + r - 3, 0), h - 1) * p;
+        tile[r][tx] = (float)row[xa];
+        if (tx < 6) tile[r][tx + 32] = (float)row[xb];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 38 * 32; i += 256) {
-        const int ty = i / 32, tx = i % 32;
-        float s = __fmul_rn(tile[ty][tx], g.gk[3]);
-        s = fmaf(tile[ty][tx + 1], g.gk[2], s);
-        s = fmaf(tile[ty][tx + 2], g.gk[1], s);
-        s = fmaf(tile[ty][tx + 3], g.gk[0], s);
-        s = fmaf(tile[ty][tx + 4], g.gk[1], s);
-        s = fmaf(tile[ty][tx + 5], g.gk[2], s);
-        s = fmaf(tile[ty][tx + 6], g.gk[3], s);
-        rowp[ty][tx] = s;
+    for (int r = ty; r < kBlurH + 6; r += 8) {
+        const float* t = &tile[r][tx];
+        float s = __fmul_rn(t[0], g.gk[3]);
+        s = fmaf(t[1], g.gk[2], s);
+        s = fmaf(t[2], g.gk[1], s);
+        s = fmaf(t[3], g.gk[0], s);
+        s = fmaf(t[4], g.gk[1], s);
+        s = fmaf(t[5], g.gk[2], s);
+        s = fmaf(t[6], g.gk[3], s);
+        rowp[r][tx] = s;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-        const int ty = i / 32, tx = i % 32;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= w || y >= h) continue;
-        float s = __fmul_rn(g.gk[0], rowp[ty + 3][tx]);
-        s = fmaf(g.gk[1], __fadd_rn(rowp[ty + 4][tx], rowp[ty + 2][tx]), s);
-        s = fmaf(g.gk[2], __fadd_rn(rowp[ty + 5][tx], rowp[ty + 1][tx]), s);
-        s = fmaf(g.gk[3], __fadd_rn(rowp[ty + 6][tx], rowp[ty][tx]), s);
-        int v = __float2int_rn(s);
-        blur[base + (size_t)y * p + x] = (uint8_t)min(max(v, 0), 255);
+    const int x = x0 + tx;
+    if (x >= w) return;
+    for (int r = ty; r < kBlurH; r += 8) {
+        const int y = y0 + r;
+        if (y >= h) break;
+        float s = __fmul_rn(g.gk[0], rowp[r + 3][tx]);
+        s = fmaf(g.gk[1], __fadd_rn(rowp[r + 4][tx], rowp[r + 2][tx]), s);
+        s = fmaf(g.gk[2], __fadd_rn(rowp[r + 5][tx], rowp[r + 1][tx]), s);
+        s = fmaf(g.gk[3], __fadd_rn(rowp[r + 6][tx], rowp[r][tx]), s);
+        const int v = __float2int_rn(s);
+        dst[(size_t)y * p + x] = (uint8_t)min(max(v, 0), 255);
     }
 }
 
@@ -708,7 +717,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
             o->bm_fast.first[l] = nf; o->bm_fast.bx[l] = std::max((cols + 2 + kFastTile - 1) / kFastTile, 1);
             nf += (rows > 0 && cols > 0) ? o->bm_fast.bx[l] * ((rows + 2 + kFastTile - 1) / kFastTile) : 0;
             o->bm_blur.first[l] = nb; o->bm_blur.bx[l] = (g.w[l] + 31) / 32;
-            nb += o->bm_blur.bx[l] * ((g.h[l] + 31) / 32);
+            nb += o->bm_blur.bx[l] * ((g.h[l] + kBlurH - 1) / kBlurH);
             o->bm_rows.first[l] = nr; o->bm_rows.bx[l] = 1;
             nr += std::max((rows + 7) / 8, 1);
         }
