@@ -25,9 +25,15 @@ def main():
     F = args.batch
     uniq = np.stack([synth.make_camera_frame(100 + s) for s in range(min(F, 16))])
     frames = uniq[np.arange(F) % len(uniq)].copy()
-    dev = torch.device('cuda', 0)
+    # under torchrun: one rank per GPU, frames sharded by rank (independent units, no collective on the data path)
+    world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
     stream = torch.cuda.Stream(dev)
-    ctx = _lib.Context(0, stream.cuda_stream)
+    ctx = _lib.Context(local, stream.cuda_stream)
     orb = ORB(max_frames=F, ctx=ctx, select=args.select)
     kp, desc, n = orb.detect_and_compute_batch(frames)
     out = {'select': args.select, 'frames_per_batch': F, 'keypoints_per_frame': float(n.mean())}
@@ -68,17 +74,27 @@ def main():
     def host_call():
         ctx.check(L.nclt_orb_detect_and_compute(ctx.h, orb._h, ptr(h_img), 1, F, ptr(h_kp), ptr(h_desc), ptr(h_n)))
 
+    def max_over_ranks(dt):
+        if world == 1:
+            return dt
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for name, fn in (('device_resident', dev_call), ('end_to_end', host_call)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             fn()
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.steps
-        out[name + '_frames_per_s'] = F / dt
+        dt = max_over_ranks((time.perf_counter() - t0) / args.steps)
+        out[name + '_frames_per_s'] = world * F / dt          # whole job: every rank processed F frames per step
         out[name + '_ms_per_batch'] = dt * 1e3
+    out['n_gpus'] = world
     assert np.array_equal(h_n.numpy(), n) and np.array_equal(d_desc.cpu().numpy(), desc)
     if args.pipelines > 1:
         # end to end with P independent (context, handle) pairs driven by P host threads (ctypes releases the GIL):
@@ -87,7 +103,7 @@ def main():
         workers = []
         for _ in range(args.pipelines):
             st = torch.cuda.Stream(dev)
-            cx = _lib.Context(0, st.cuda_stream)
+            cx = _lib.Context(local, st.cuda_stream)
             ob = ORB(max_frames=F, ctx=cx, select=args.select)
             bufs = (torch.from_numpy(frames).pin_memory(), torch.empty((F, ob.out_cap, 6), dtype=torch.float32).pin_memory(),
                     torch.empty((F, ob.out_cap, 32), dtype=torch.uint8).pin_memory(), torch.empty(F, dtype=torch.int32).pin_memory())
@@ -108,15 +124,18 @@ def main():
         for t in th:
             t.join()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        out['end_to_end_pipelined_frames_per_s'] = args.pipelines * args.steps * F / dt
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out['end_to_end_pipelined_frames_per_s'] = world * args.pipelines * args.steps * F / dt
         out['pipelines'] = args.pipelines
         for w in workers:
             assert np.array_equal(w[2][3].numpy(), n) and np.array_equal(w[2][2].numpy(), desc)
     if 'cv2_frames_per_s' in out:
         out['speedup_vs_cv2_end_to_end'] = out.get('end_to_end_pipelined_frames_per_s', out['end_to_end_frames_per_s']) / out['cv2_frames_per_s']
     out['host_fallbacks'] = orb.host_fallbacks
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
