@@ -379,7 +379,7 @@ void retain_best(std::vector<RespIdx>& v, int n_points) {
 }
 
 // ---- device-side selection path ----
-struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_frame; int row_off[kLevels]; int rows_total; };
+struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_frame; int row_off[kLevels]; int rows_total; int hit_stride; };
 
 __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
     const int s = sc[0];
@@ -401,12 +401,13 @@ __device__ __forceinline__ unsigned nms_word_hits(const uint8_t* row, int p, int
     return hits;
 }
 
-// NMS survivors of every (frame, level) in FAST's row-major order, two launches over 8-row chunks (one warp per row):
-// k_orb_nms_count leaves the survivors per row, k_orb_nms_emit sums the rows above its chunk and writes
-// (position, FAST score) at the final offsets.  rowcnt: [F][rows_total], rows of level l start at
-// lt.row_off[l].
-__global__ void __launch_bounds__(256) k_orb_nms_count(const uint8_t* __restrict__ score, OrbGeom g, LevelTab lt, BlockMap bm,
-                                                       int* __restrict__ rowcnt) {
+// NMS survivors of every (frame, level), one warp per row: the row's survivors in ascending x (position, FAST score)
+// go to the row's slot of `hx` / `hs` (hit_stride entries per row: a row holds at most one strict maximum per two
+// pixels), their number to rowcnt.  FAST's row-major order is then "rows in order, hits in order" - k_orb_select1
+// turns the per-row counts into offsets and gathers.  rowcnt: [F][rows_total], rows of level l start at lt.row_off[l].
+__global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict__ score, OrbGeom g, LevelTab lt, BlockMap bm,
+                                                      int* __restrict__ rowcnt, unsigned short* __restrict__ hx,
+                                                      uint8_t* __restrict__ hs) {
     const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l, bx, by;
     block_of(bm, blockIdx.x, l, bx, by);
@@ -415,57 +416,11 @@ __global__ void __launch_bounds__(256) k_orb_nms_count(const uint8_t* __restrict
     const int r = by * 8 + warp;
     if (r >= rows || cols <= 0) return;
     const uint8_t* row = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p;
+    const size_t slot = (size_t)f * lt.rows_total + lt.row_off[l] + r;
+    unsigned short* ox = hx + slot * lt.hit_stride;
+    uint8_t* os = hs + slot * lt.hit_stride;
     const int wi_max = (w - kEdge - 1) / 4;
-    int n = 0;
-    for (int wi = kEdge / 4 + lane; wi <= wi_max; wi += 32) n += __popc(nms_word_hits(row, p, wi, kEdge, w - kEdge));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
-    if (lane == 0) rowcnt[(size_t)f * lt.rows_total + lt.row_off[l] + r] = n;
-}
-
-__global__ void __launch_bounds__(256) k_orb_nms_emit(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ score, OrbGeom g,
-                                                      LevelTab lt, BlockMap bm, float harris_scale4, const int* __restrict__ rowcnt,
-                                                      uint32_t* __restrict__ key, float* __restrict__ fscore,
-                                                      int* __restrict__ cnt) {
-    __shared__ int part[8];
-    __shared__ int rowbase[9];
-    const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int l, bx, by;
-    block_of(bm, blockIdx.x, l, bx, by);
-    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
-    const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
-    if (rows <= 0 || cols <= 0) {
-        if (threadIdx.x == 0 && by == 0) cnt[f * kLevels + l] = 0;
-        return;
-    }
-    const int* rc = rowcnt + (size_t)f * lt.rows_total + lt.row_off[l];
-    const int r0 = by * 8;
-    int sum = 0;
-    for (int r = threadIdx.x; r < r0; r += 256) sum += rc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-    if (lane == 0) part[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int b = 0;
-        for (int k = 0; k < 8; ++k) b += part[k];
-        for (int k = 0; k < 8; ++k) {
-            rowbase[k] = b;
-            if (r0 + k < rows) b += rc[r0 + k];
-        }
-        rowbase[8] = b;
-        if (r0 + 8 >= rows) cnt[f * kLevels + l] = b;       // the chunk holding the last row knows the total
-    }
-    __syncthreads();
-    const int r = r0 + warp;
-    if (r >= rows) return;
-    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
-    const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
-    const int y = r + kEdge;
-    const uint8_t* row = score + base + (size_t)y * p;
-    int pos = rowbase[warp];
-    if (rowbase[warp + 1] == pos) return;
-    const int wi_max = (w - kEdge - 1) / 4;
+    int pos = 0;
     for (int wi0 = kEdge / 4; wi0 <= wi_max; wi0 += 32) {
         const int wi = wi0 + lane;
         const unsigned hits = wi <= wi_max ? nms_word_hits(row, p, wi, kEdge, w - kEdge) : 0u;
@@ -481,13 +436,13 @@ __global__ void __launch_bounds__(256) k_orb_nms_emit(const uint8_t* __restrict_
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (hits & (1u << k)) {
-                const int x = 4 * wi + k;
-                key[ob + o] = (uint32_t)(y << 16 | x);
-                fscore[ob + o] = (float)row[x];
+                ox[o] = (unsigned short)(4 * wi + k);
+                os[o] = row[4 * wi + k];
                 ++o;
             }
         pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
+    if (lane == 0) rowcnt[slot] = pos;
 }
 
 // The two retainBest passes, one warp per level (lane 0 runs the sequential algorithms of orb_select.cuh, all lanes
@@ -524,19 +479,46 @@ __device__ __forceinline__ int retain_any(RespIdx* v, int n, int n_points, unsig
     return m;
 }
 
-__global__ void __launch_bounds__(256) k_orb_select1(LevelTab lt, const float* __restrict__ fscore, const int* __restrict__ cnt,
+__global__ void __launch_bounds__(256) k_orb_select1(OrbGeom g, LevelTab lt, int* __restrict__ rowcnt, const unsigned short* __restrict__ hx,
+                                                     const uint8_t* __restrict__ hs, uint32_t* __restrict__ key,
                                                      RespIdx* __restrict__ work, unsigned short* __restrict__ lists,
                                                      int* __restrict__ kept1, int* __restrict__ flags) {
     extern __shared__ RespIdx sel_smem[];
     __shared__ int soff[kLevels + 1];
+    __shared__ int counts[kLevels];
     const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
+    const int rows = max(g.h[l] - 2 * kEdge, 0);
+    int* rc = rowcnt + (size_t)f * lt.rows_total + lt.row_off[l];
+    // per-row counts -> exclusive offsets, in place; n = survivors of the level
+    int n = 0;
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+        const int r = r0 + lane;
+        const int c = r < rows ? rc[r] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (r < rows) rc[r] = n + incl - c;
+        n += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) counts[l] = n;
+    __syncthreads();
     bool in_smem;
-    RespIdx* v = sel_buffer(sel_smem, soff, cnt + f * kLevels, l, work + ob, in_smem);
-    const int n = cnt[f * kLevels + l];
+    RespIdx* v = sel_buffer(sel_smem, soff, counts, l, work + ob, in_smem);
     unsigned short* Ls = in_smem ? reinterpret_cast<unsigned short*>(sel_smem + kSelSmemEntries) + 2 * soff[l] : lists + 2 * ob;
     unsigned short* Rs = Ls + n;
-    for (int i = lane; i < n; i += 32) v[i] = RespIdx{fscore[ob + i], i};
+    // gather in row-major order: one lane per row
+    for (int r = lane; r < rows; r += 32) {
+        const int o = rc[r], e = (r + 1 < rows) ? rc[r + 1] : n;
+        const size_t hb = ((size_t)f * lt.rows_total + lt.row_off[l] + r) * lt.hit_stride;
+        for (int k = 0; k < e - o; ++k) {
+            v[o + k] = RespIdx{(float)hs[hb + k], o + k};
+            key[ob + o + k] = (uint32_t)((r + kEdge) << 16 | hx[hb + k]);
+        }
+    }
     __syncwarp();
     int m = retain_any(v, n, 2 * lt.n_level[l], Ls, Rs);
     if (m < 0) {
@@ -655,11 +637,12 @@ struct nclt_orb {
     int select_mode = 0;
     LevelTab lt;
     uint32_t* d_key = nullptr;
-    float* d_fscore = nullptr;
+    unsigned short* d_hx = nullptr;      // per-row NMS survivors: x, FAST score
+    uint8_t* d_hs = nullptr;
     int* d_kept1 = nullptr;
     RespIdx* d_work = nullptr;
     unsigned short* d_lists = nullptr;     // stopper lists of the warp partitions when a frame does not fit shared memory
-    int *d_cnt = nullptr, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
+    int *d_cnt = nullptr /* unused since the selection kernel counts by itself */, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
     BlockMap bm_fast, bm_blur, bm_rows;
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
@@ -672,7 +655,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (c) cudaSetDevice(c->device);
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
-    cudaFree(o->d_key); cudaFree(o->d_fscore); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists); cudaFree(o->d_cnt);
+    cudaFree(o->d_key); cudaFree(o->d_hx); cudaFree(o->d_hs); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists); cudaFree(o->d_cnt);
     cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt);
     if (o->side) cudaStreamDestroy(o->side);
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
@@ -722,6 +705,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
             nr += std::max((rows + 7) / 8, 1);
         }
         o->lt.rows_total = std::max(rows_total, 1);
+        o->lt.hit_stride = (std::max(g.w[0] - 2 * kEdge, 0) + 1) / 2 + 1;
         o->bm_fast.first[kLevels] = nf; o->bm_blur.first[kLevels] = nb; o->bm_rows.first[kLevels] = nr;
     }
     g.frame_bytes = (off + 255) & ~255LL;
@@ -771,7 +755,6 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_cand, (size_t)cand_cap * max_frames * sizeof(Cand));
     A((void**)&o->d_ncand, 256);
     A((void**)&o->d_key, (size_t)cand_cap * max_frames * 4);
-    A((void**)&o->d_fscore, (size_t)cand_cap * max_frames * 4);
     A((void**)&o->d_kept1, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_work, (size_t)cand_cap * max_frames * sizeof(RespIdx));
     A((void**)&o->d_lists, (size_t)cand_cap * max_frames * 2 * sizeof(unsigned short));
@@ -779,6 +762,8 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_nout, (size_t)max_frames * 4);
     A((void**)&o->d_flags, 256);
     A((void**)&o->d_rowcnt, (size_t)o->lt.rows_total * max_frames * 4);
+    A((void**)&o->d_hx, (size_t)o->lt.rows_total * max_frames * o->lt.hit_stride * sizeof(unsigned short));
+    A((void**)&o->d_hs, (size_t)o->lt.rows_total * max_frames * o->lt.hit_stride);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_pyr, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_blur, cudaEventDisableTiming);
@@ -944,18 +929,17 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     bool host_select = o->select_mode == 1;
     if (!host_select) {
         // everything stays on the device; one read of (flags, n_out) at the end
-        k_orb_nms_count<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt);
-        k_orb_nms_emit<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_pyr, o->d_score, g, o->lt, o->bm_rows, o->harris_scale4,
-                                                                            o->d_rowcnt, o->d_key, o->d_fscore, o->d_cnt);
+        k_orb_nms_rows<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt, o->d_hx, o->d_hs);
         const size_t sel_smem = (size_t)kSelSmemBytes;
-        k_orb_select1<<<F, 256, sel_smem, st>>>(o->lt, o->d_fscore, o->d_cnt, o->d_work, o->d_lists, o->d_kept1, o->d_flags);
+        k_orb_select1<<<F, 256, sel_smem, st>>>(g, o->lt, o->d_rowcnt, o->d_hx, o->d_hs, o->d_key, o->d_work, o->d_lists, o->d_kept1,
+                                                o->d_flags);
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
         k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_lists, o->d_sel, o->out_cap, o->d_nout,
                                                 o->d_flags);
         CU_TRY(c, cudaStreamWaitEvent(st, o->ev_blur, 0));
         k_orb_describe<<<(F * o->out_cap + 7) / 8, 256, 0, st>>>(o->d_pyr, o->d_blur, g, o->d_sel, F * o->out_cap, o->out_cap,
                                                                  o->d_nout, d_kp, d_desc);
-        c->launches += 6;
+        c->launches += 5;
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(o->h_pinned, o->d_flags, 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(c, cudaMemcpyAsync(o->h_pinned + 1, o->d_nout, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
