@@ -248,27 +248,39 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
         if (tx < 6) tile[r][tx + 32] = (float)row[xb];
     }
     __syncthreads();
-    for (int r = ty; r < kBlurH + 6; r += 8) {
-        const float* t = &tile[r][tx];
-        float s = __fmul_rn(t[0], g.gk[3]);
-        s = fmaf(t[1], g.gk[2], s);
-        s = fmaf(t[2], g.gk[1], s);
-        s = fmaf(t[3], g.gk[0], s);
-        s = fmaf(t[4], g.gk[1], s);
-        s = fmaf(t[5], g.gk[2], s);
-        s = fmaf(t[6], g.gk[3], s);
-        rowp[r][tx] = s;
+    // row pass: four adjacent outputs per task from ten loaded values (each output keeps its own sequential FMA chain)
+    for (int t = threadIdx.x; t < (kBlurH + 6) * 8; t += 256) {
+        const int r = t >> 3, gx = (t & 7) * 4;
+        float v[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) v[j] = tile[r][gx + j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = __fmul_rn(v[j], g.gk[3]);
+            s = fmaf(v[j + 1], g.gk[2], s);
+            s = fmaf(v[j + 2], g.gk[1], s);
+            s = fmaf(v[j + 3], g.gk[0], s);
+            s = fmaf(v[j + 4], g.gk[1], s);
+            s = fmaf(v[j + 5], g.gk[2], s);
+            s = fmaf(v[j + 6], g.gk[3], s);
+            rowp[r][gx + j] = s;
+        }
     }
     __syncthreads();
+    // column pass: eight consecutive rows per thread from a 14-row window held in registers
     const int x = x0 + tx;
     if (x >= w) return;
-    for (int r = ty; r < kBlurH; r += 8) {
-        const int y = y0 + r;
+    float c[14];
+#pragma unroll
+    for (int j = 0; j < 14; ++j) c[j] = rowp[ty * 8 + j][tx];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int y = y0 + ty * 8 + j;
         if (y >= h) break;
-        float s = __fmul_rn(g.gk[0], rowp[r + 3][tx]);
-        s = fmaf(g.gk[1], __fadd_rn(rowp[r + 4][tx], rowp[r + 2][tx]), s);
-        s = fmaf(g.gk[2], __fadd_rn(rowp[r + 5][tx], rowp[r + 1][tx]), s);
-        s = fmaf(g.gk[3], __fadd_rn(rowp[r + 6][tx], rowp[r][tx]), s);
+        float s = __fmul_rn(g.gk[0], c[j + 3]);
+        s = fmaf(g.gk[1], __fadd_rn(c[j + 4], c[j + 2]), s);
+        s = fmaf(g.gk[2], __fadd_rn(c[j + 5], c[j + 1]), s);
+        s = fmaf(g.gk[3], __fadd_rn(c[j + 6], c[j]), s);
         const int v = __float2int_rn(s);
         dst[(size_t)y * p + x] = (uint8_t)min(max(v, 0), 255);
     }
@@ -911,6 +923,12 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     const OrbGeom& g = o->g;
     cudaStream_t st = c->stream;
     const uint8_t* d_img = img;
+    if (img_on_device && channels == 1 && g.pitch[0] == o->W) {
+        // gray device frames: one strided device copy into level 0 instead of the byte-per-thread kernel
+        CU_TRY(c, cudaMemcpy2DAsync(o->d_pyr, (size_t)g.frame_bytes, img, (size_t)o->W * o->H, (size_t)o->W * o->H, F,
+                                    cudaMemcpyDeviceToDevice, st));
+        d_img = nullptr;
+    }
     if (!img_on_device) {
         if (channels == 1 && g.pitch[0] == o->W) {
             // gray host frames land directly in level 0 of the pyramid (one strided copy, no staging, no copy kernel)
