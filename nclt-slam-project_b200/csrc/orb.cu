@@ -104,9 +104,10 @@ __device__ __forceinline__ bool has9(unsigned m) {     // 9 contiguous set bits 
 // 40 % of the warps) go to a list in shared memory.  Phase 2: the threads walk that list densely - full segment test
 // on 16-bit arc masks, score by doubling minima - so the expensive path runs in full warps.
 constexpr int kFastTile = 32;
+constexpr int kFastPitch = 48;      // 11 words per tile row: pixels x0 - 6 .. x0 + 37 (x0 - 6 is a multiple of 8)
 __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, int block0,
                                                   uint8_t* __restrict__ score) {
-    __shared__ uint8_t tile[kFastTile + 6][kFastTile + 8];
+    __shared__ __align__(16) uint8_t tile[kFastTile + 6][kFastPitch];     // column c holds pixel x0 - 6 + c
     __shared__ unsigned short list[kFastTile * kFastTile];
     __shared__ int n_list;
     const int f = blockIdx.y;
@@ -118,13 +119,13 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     const size_t base = (size_t)f * g.frame_bytes + g.off[l];
     if (threadIdx.x == 0) n_list = 0;
     const int tx = threadIdx.x & 31;
-    {   // x0 - 3 >= 27: no lower clamp needed; the upper clamp only touches pixels that are never scored
-        const int xa = min(x0 + tx - 3, w - 1), xb = min(x0 + tx + 29, w - 1);
-        for (int r = threadIdx.x >> 5; r < kFastTile + 6; r += 8) {
-            const uint8_t* row = pyr + base + (size_t)min(y0 + r - 3, h - 1) * p;
-            tile[r][tx] = row[xa];
-            if (tx < 6) tile[r][tx + 32] = row[xb];
-        }
+    // staging with 32-bit loads (rows are 16-byte aligned, x0 - 6 = 32 bx + 24); the clamps only touch pixels that are
+    // never scored
+    for (int i = threadIdx.x; i < (kFastTile + 6) * 11; i += 256) {
+        const int r = i / 11, k = i - r * 11;
+        const uint8_t* row = pyr + base + (size_t)min(y0 + r - 3, h - 1) * p;
+        const int xw = min(x0 - 6 + 4 * k, p - 4);
+        *reinterpret_cast<uint32_t*>(&tile[r][4 * k]) = *reinterpret_cast<const uint32_t*>(row + xw);
     }
     __syncthreads();
 #pragma unroll
@@ -132,9 +133,9 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
         const int ty = (threadIdx.x >> 5) + 8 * r;
         const int x = x0 + tx, y = y0 + ty;
         if (x > xe || y > ye) continue;
-        const uint8_t* c = &tile[ty + 3][tx + 3];
+        const uint8_t* c = &tile[ty + 3][tx + 6];
         const int v = c[0];
-        const int e0 = v - c[3 * (kFastTile + 8)], e8 = v - c[-3 * (kFastTile + 8)], e4 = v - c[3], e12 = v - c[-3];
+        const int e0 = v - c[3 * kFastPitch], e8 = v - c[-3 * kFastPitch], e4 = v - c[3], e12 = v - c[-3];
         const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
         const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
         if (in0 || in4) score[base + (size_t)y * p + x] = 0;
@@ -142,10 +143,10 @@ __global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ py
     }
     __syncthreads();
     const int n = n_list;
-    constexpr int P = kFastTile + 8;
+    constexpr int P = kFastPitch;
     for (int i = threadIdx.x; i < n; i += 256) {
         const int ty = list[i] / kFastTile, tx2 = list[i] % kFastTile;
-        const uint8_t* c = &tile[ty + 3][tx2 + 3];
+        const uint8_t* c = &tile[ty + 3][tx2 + 6];
         const int v = c[0];
         int d[16];
         d[0] = v - c[3 * P];          d[1] = v - c[3 * P + 1];   d[2] = v - c[2 * P + 2];    d[3] = v - c[P + 3];
@@ -237,15 +238,21 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
     const int x0 = bx * 32, y0 = by * kBlurH;
     const uint8_t* src = pyr + (size_t)f * g.frame_bytes + g.off[l];
     uint8_t* dst = blur + (size_t)f * g.frame_bytes + g.off[l];
-    __shared__ float tile[kBlurH + 6][39];
+    __shared__ float tile[kBlurH + 6][45];          // column c holds pixel x0 - 4 + c (44 staged, 11 words per row)
     __shared__ float rowp[kBlurH + 6][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    // clamped reads: only pixels >= 9 px inside the level are ever sampled, the clamp just keeps the reads in bounds
-    const int xa = min(max(x0 + tx - 3, 0), w - 1), xb = min(x0 + tx + 29, w - 1);
-    for (int r = ty; r < kBlurH + 6; r += 8) {
+    // staging with 32-bit loads; clamped reads: only pixels >= 9 px inside the level are ever sampled, the clamps just
+    // keep the reads inside the row
+    for (int i = threadIdx.x; i < (kBlurH + 6) * 11; i += 256) {
+        const int r = i / 11, k = i - r * 11;
         const uint8_t* row = src + (size_t)min(max(y0 + r - 3, 0), h - 1) * p;
-        tile[r][tx] = (float)row[xa];
-        if (tx < 6) tile[r][tx + 32] = (float)row[xb];
+        const int xw = min(max(x0 - 4 + 4 * k, 0), p - 4);
+        const uint32_t q = *reinterpret_cast<const uint32_t*>(row + xw);
+        float* t = &tile[r][4 * k];
+        t[0] = (float)(q & 0xFFu);
+        t[1] = (float)((q >> 8) & 0xFFu);
+        t[2] = (float)((q >> 16) & 0xFFu);
+        t[3] = (float)(q >> 24);
     }
     __syncthreads();
     // row pass: four adjacent outputs per task from ten loaded values (each output keeps its own sequential FMA chain)
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
         const int r = t >> 3, gx = (t & 7) * 4;
         float v[10];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) v[j] = tile[r][gx + j];
+        for (int j = 0; j < 10; ++j) v[j] = tile[r][gx + 1 + j];        // output x0 + gx + j taps x0 + gx + j - 3 ...
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float s = __fmul_rn(v[j], g.gk[3]);
