@@ -287,9 +287,11 @@ int nclt_hitcount_occupancy(nclt_ctx* ctx, const double* points, const int8_t* l
  * out_kp f32[F,out_cap,6] = (pt.x, pt.y, size, angle, response, octave) per keypoint, out_desc
  * u8[F,out_cap,32], out_n i32[F].  out_cap >= 500: a level keeps every keypoint that ties with its last
  * retained Harris response, so a frame can exceed nfeatures; NCLT_ERR_STATE if it exceeds out_cap.
- * The handle owns its device planes (pyramid, score map, blurred pyramid: ~4 MB per frame slot at
- * 640 x 480 plus ~6 MB of candidate lists) - one handle, one caller at a time, like nclt_ctx.  The call
- * returns after its results have been read back (it synchronises the context's stream once). */
+ * The handle owns its device memory: pyramid, score map, blurred pyramid, an input staging plane and
+ * worst-case candidate lists, ~11 MB per frame slot at 640 x 480 (max_frames slots) - one handle, one
+ * caller at a time, like nclt_ctx.  The call returns after its results have been read back (it
+ * synchronises the context's stream once; a second, internal stream runs the resize chain and the blur
+ * beside the other kernels). */
 typedef struct nclt_orb nclt_orb;
 int nclt_orb_create(nclt_ctx* ctx, int W, int H, int max_frames, int out_cap, nclt_orb** out);
 int nclt_orb_destroy(nclt_ctx* ctx, nclt_orb* orb);
