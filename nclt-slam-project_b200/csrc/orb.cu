@@ -105,7 +105,7 @@ __device__ __forceinline__ bool has9(unsigned m) {     // 9 contiguous set bits 
 // on 16-bit arc masks, score by doubling minima - so the expensive path runs in full warps.
 constexpr int kFastTile = 32;
 constexpr int kFastPitch = 48;      // 11 words per tile row: pixels x0 - 6 .. x0 + 37 (x0 - 6 is a multiple of 8)
-__global__ void __launch_bounds__(256) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, int block0,
+__global__ void __launch_bounds__(256, 6) k_orb_fast(const uint8_t* __restrict__ pyr, OrbGeom g, BlockMap bm, int block0,
                                                   uint8_t* __restrict__ score) {
     __shared__ __align__(16) uint8_t tile[kFastTile + 6][kFastPitch];     // column c holds pixel x0 - 6 + c
     __shared__ unsigned short list[kFastTile * kFastTile];
