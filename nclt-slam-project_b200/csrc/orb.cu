@@ -72,20 +72,25 @@ __global__ void __launch_bounds__(256) k_orb_level0(const uint8_t* __restrict__ 
 
 // ---- bit-exact bilinear resize of one level from the previous one ----
 // tab: [sx(dw) | ax(dw) | sy(dh) | ay(dh)] int32, from the host in double arithmetic
+constexpr int kResizeRows = 8;
 __global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                     uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
                                                     long long frame_bytes, const int* __restrict__ tab) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z;
     if (x >= dw) return;
-    const int sx = tab[x], ax = tab[dw + x], sy = tab[2 * dw + y], ay = tab[2 * dw + dh + y];
-    const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+    const int sx = tab[x], ax = tab[dw + x];
+    const int sx1 = min(sx + 1, sw - 1);
     const uint8_t* s = src + (size_t)f * frame_bytes;
-    const uint8_t* r0 = s + (size_t)sy * spitch;
-    const uint8_t* r1 = s + (size_t)sy1 * spitch;
-    const unsigned h0 = r0[sx] * (256 - ax) + r0[sx1] * ax;
-    const unsigned h1 = r1[sx] * (256 - ax) + r1[sx1] * ax;
-    const unsigned v = h0 * (256 - ay) + h1 * ay;
-    dst[(size_t)f * frame_bytes + (size_t)y * dpitch + x] = (uint8_t)((v + 32768u) >> 16);
+    for (int y = blockIdx.y * kResizeRows; y < min((blockIdx.y + 1) * kResizeRows, dh); ++y) {     // short rows: several per CTA
+        const int sy = tab[2 * dw + y], ay = tab[2 * dw + dh + y];
+        const int sy1 = min(sy + 1, sh - 1);
+        const uint8_t* r0 = s + (size_t)sy * spitch;
+        const uint8_t* r1 = s + (size_t)sy1 * spitch;
+        const unsigned h0 = r0[sx] * (256 - ax) + r0[sx1] * ax;
+        const unsigned h1 = r1[sx] * (256 - ax) + r1[sx1] * ax;
+        const unsigned v = h0 * (256 - ay) + h1 * ay;
+        dst[(size_t)f * frame_bytes + (size_t)y * dpitch + x] = (uint8_t)((v + 32768u) >> 16);
+    }
 }
 
 // ---- FAST 9-16 score map ----
@@ -402,8 +407,10 @@ struct LevelTab { int cand_off[kLevels]; int n_level[kLevels]; int cand_per_fram
 
 __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
     const int s = sc[0];
-    return s != 0 && s > sc[-1] && s > sc[1] && s > sc[-p - 1] && s > sc[-p] && s > sc[-p + 1] && s > sc[p - 1] && s > sc[p] &&
-           s > sc[p + 1];
+    if (s == 0) return false;
+    // eight independent loads, one compare: max of the neighbours (a short-circuit chain would serialise the loads)
+    const int n0 = sc[-1], n1 = sc[1], n2 = sc[-p - 1], n3 = sc[-p], n4 = sc[-p + 1], n5 = sc[p - 1], n6 = sc[p], n7 = sc[p + 1];
+    return s > max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
 }
 
 // NMS over four pixels at once: one 32-bit read of the score row (almost always zero), neighbours only for corners.
@@ -412,10 +419,12 @@ __device__ __forceinline__ unsigned nms_word_hits(const uint8_t* row, int p, int
     const uint32_t wv = *reinterpret_cast<const uint32_t*>(row + 4 * wi);
     if (wv == 0) return 0;
     unsigned hits = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    uint32_t m = wv;
+    while (m) {                                  // only the non-zero bytes (corners) are looked at
+        const int k = (__ffs(m) - 1) >> 3;
+        m &= ~(0xFFu << (8 * k));
         const int x = 4 * wi + k;
-        if (((wv >> (8 * k)) & 0xFFu) && x >= xlo && x < xhi && nms_max(row + x, p)) hits |= 1u << k;
+        if (x >= xlo && x < xhi && nms_max(row + x, p)) hits |= 1u << k;
     }
     return hits;
 }
@@ -424,6 +433,7 @@ __device__ __forceinline__ unsigned nms_word_hits(const uint8_t* row, int p, int
 // go to the row's slot of `hx` / `hs` (hit_stride entries per row: a row holds at most one strict maximum per two
 // pixels), their number to rowcnt.  FAST's row-major order is then "rows in order, hits in order" - k_orb_select1
 // turns the per-row counts into offsets and gathers.  rowcnt: [F][rows_total], rows of level l start at lt.row_off[l].
+constexpr int kNmsRowsPerCta = 32;
 __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict__ score, OrbGeom g, LevelTab lt, BlockMap bm,
                                                       int* __restrict__ rowcnt, unsigned short* __restrict__ hx,
                                                       uint8_t* __restrict__ hs) {
@@ -432,17 +442,26 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
     block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
     const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
-    const int r = by * 8 + warp;
-    if (r >= rows || cols <= 0) return;
+    if (cols <= 0) return;
+    for (int r = by * kNmsRowsPerCta + warp; r < min((by + 1) * kNmsRowsPerCta, rows); r += 8) {     // short rows: several per warp
     const uint8_t* row = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p;
     const size_t slot = (size_t)f * lt.rows_total + lt.row_off[l] + r;
     unsigned short* ox = hx + slot * lt.hit_stride;
     uint8_t* os = hs + slot * lt.hit_stride;
-    const int wi_max = (w - kEdge - 1) / 4;
+    const int vi_max = (w - kEdge - 1) / 16;                 // 16 scores (one uint4) per lane and step
+    const uint4* rowv = reinterpret_cast<const uint4*>(row);
     int pos = 0;
-    for (int wi0 = kEdge / 4; wi0 <= wi_max; wi0 += 32) {
-        const int wi = wi0 + lane;
-        const unsigned hits = wi <= wi_max ? nms_word_hits(row, p, wi, kEdge, w - kEdge) : 0u;
+    for (int vi0 = kEdge / 16; vi0 <= vi_max; vi0 += 32) {
+        const int vi = vi0 + lane;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (vi <= vi_max) q = rowv[vi];
+        unsigned hits = 0;                                   // bit k: pixel 16 vi + k survives
+        if (q.x | q.y | q.z | q.w) {
+            if (q.x) hits |= nms_word_hits(row, p, 4 * vi, kEdge, w - kEdge);
+            if (q.y) hits |= nms_word_hits(row, p, 4 * vi + 1, kEdge, w - kEdge) << 4;
+            if (q.z) hits |= nms_word_hits(row, p, 4 * vi + 2, kEdge, w - kEdge) << 8;
+            if (q.w) hits |= nms_word_hits(row, p, 4 * vi + 3, kEdge, w - kEdge) << 12;
+        }
         const int c = __popc(hits);
         if (__ballot_sync(0xFFFFFFFFu, c > 0) == 0) continue;
         int incl = c;                                   // lanes hold ascending x: exclusive scan of the per-lane counts
@@ -452,16 +471,17 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
             if (lane >= o) incl += u;
         }
         int o = pos + incl - c;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (hits & (1u << k)) {
-                ox[o] = (unsigned short)(4 * wi + k);
-                os[o] = row[4 * wi + k];
-                ++o;
-            }
+        while (hits) {
+            const int k = __ffs(hits) - 1;
+            hits &= hits - 1;
+            ox[o] = (unsigned short)(16 * vi + k);
+            os[o] = row[16 * vi + k];
+            ++o;
+        }
         pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     if (lane == 0) rowcnt[slot] = pos;
+    }
 }
 
 // The two retainBest passes, one warp per level (lane 0 runs the sequential algorithms of orb_select.cuh, all lanes
@@ -721,7 +741,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
             o->bm_blur.first[l] = nb; o->bm_blur.bx[l] = (g.w[l] + 31) / 32;
             nb += o->bm_blur.bx[l] * ((g.h[l] + kBlurH - 1) / kBlurH);
             o->bm_rows.first[l] = nr; o->bm_rows.bx[l] = 1;
-            nr += std::max((rows + 7) / 8, 1);
+            nr += std::max((rows + kNmsRowsPerCta - 1) / kNmsRowsPerCta, 1);
         }
         o->lt.rows_total = std::max(rows_total, 1);
         o->lt.hit_stride = (std::max(g.w[0] - 2 * kEdge, 0) + 1) / 2 + 1;
@@ -858,7 +878,7 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
     CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
     CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
     for (int l = 1; l < kLevels; ++l)
-        k_orb_resize<<<dim3((g.w[l] + 255) / 256, g.h[l], F), 256, 0, o->side>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
+        k_orb_resize<<<dim3((g.w[l] + 255) / 256, (g.h[l] + kResizeRows - 1) / kResizeRows, F), 256, 0, o->side>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
                                                                                   g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
                                                                                   g.pitch[l], g.frame_bytes, o->d_tab[l]);
     CU_TRY(c, cudaEventRecord(o->ev_rs, o->side));
