@@ -58,21 +58,24 @@ __device__ __forceinline__ void block_of(const BlockMap& m, int b, int& l, int& 
 struct Cand { uint32_t tag, key; float score, harris; };          // tag = frame * 8 + level, key = y << 16 | x
 struct Sel { int frame, level, x, y; float harris; int slot; };   // slot = row inside the frame's output
 
+constexpr int kResizeRows = 8;      // rows per CTA of the copy / resize kernels (tiny CTAs are bound by the CTA launch rate)
+
 // ---- level 0 ----
 __global__ void __launch_bounds__(256) k_orb_level0(const uint8_t* __restrict__ src, int channels, int W, int H, int pitch,
                                                     long long frame_bytes, uint8_t* __restrict__ pyr) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z;
     if (x >= W) return;
-    const uint8_t* s = src + ((size_t)f * H + y) * (size_t)W * channels + (size_t)x * channels;
-    int g;
-    if (channels == 1) g = s[0];
-    else g = (s[0] * 3735 + s[1] * 19235 + s[2] * 9798 + 16384) >> 15;
-    pyr[(size_t)f * frame_bytes + (size_t)y * pitch + x] = (uint8_t)g;
+    for (int y = blockIdx.y * kResizeRows; y < min((blockIdx.y + 1) * kResizeRows, H); ++y) {
+        const uint8_t* s = src + ((size_t)f * H + y) * (size_t)W * channels + (size_t)x * channels;
+        int g;
+        if (channels == 1) g = s[0];
+        else g = (s[0] * 3735 + s[1] * 19235 + s[2] * 9798 + 16384) >> 15;
+        pyr[(size_t)f * frame_bytes + (size_t)y * pitch + x] = (uint8_t)g;
+    }
 }
 
 // ---- bit-exact bilinear resize of one level from the previous one ----
 // tab: [sx(dw) | ax(dw) | sy(dh) | ay(dh)] int32, from the host in double arithmetic
-constexpr int kResizeRows = 8;
 __global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                     uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
                                                     long long frame_bytes, const int* __restrict__ tab) {
@@ -872,7 +875,7 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
     int rc_blur = 0;
     cudaStream_t st = c->stream;
     if (d_img)      // nullptr: level 0 is already in place
-        k_orb_level0<<<dim3((o->W + 255) / 256, o->H, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
+        k_orb_level0<<<dim3((o->W + 255) / 256, (o->H + kResizeRows - 1) / kResizeRows, F), 256, 0, st>>>(d_img, channels, o->W, o->H, g.pitch[0], g.frame_bytes, o->d_pyr);
     // the seven dependent resizes are small, latency-bound launches: they run on the side stream while FAST already
     // works on level 0 (45 % of all pixels); FAST of levels 1-7 follows when the chain is done
     CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
