@@ -684,7 +684,7 @@ struct nclt_orb {
     int* d_kept1 = nullptr;
     RespIdx* d_work = nullptr;
     unsigned short* d_lists = nullptr;     // stopper lists of the warp partitions when a frame does not fit shared memory
-    int *d_cnt = nullptr /* unused since the selection kernel counts by itself */, *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
+    int *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
     BlockMap bm_fast, bm_blur, bm_rows;
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
@@ -697,7 +697,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (c) cudaSetDevice(c->device);
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
-    cudaFree(o->d_key); cudaFree(o->d_hx); cudaFree(o->d_hs); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists); cudaFree(o->d_cnt);
+    cudaFree(o->d_key); cudaFree(o->d_hx); cudaFree(o->d_hs); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists);
     cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt);
     if (o->side) cudaStreamDestroy(o->side);
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
@@ -800,7 +800,6 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     A((void**)&o->d_kept1, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_work, (size_t)cand_cap * max_frames * sizeof(RespIdx));
     A((void**)&o->d_lists, (size_t)cand_cap * max_frames * 2 * sizeof(unsigned short));
-    A((void**)&o->d_cnt, (size_t)max_frames * kLevels * 4);
     A((void**)&o->d_nout, (size_t)max_frames * 4);
     A((void**)&o->d_flags, 256);
     A((void**)&o->d_rowcnt, (size_t)o->lt.rows_total * max_frames * 4);
