@@ -307,6 +307,15 @@ int nclt_orb_detect_and_compute(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img
  * diagnostic: device selection followed by a forced hand-over (tests the fall-back path). */
 int nclt_orb_set_select(nclt_ctx* ctx, nclt_orb* orb, int mode);
 long long nclt_orb_host_fallbacks(const nclt_orb* orb);
+/* The same call in two halves, so that one host thread can keep two handles busy (the PCIe copy of one batch under
+ * the kernels of the other; one context + handle per pipeline): nclt_orb_submit enqueues the input copy, every
+ * kernel and the result copies on the context's stream and returns; nclt_orb_wait synchronises, checks the
+ * selection flags (falls back to the host selection if asked to) and fills out_n.  The host buffers (page-locked for
+ * real overlap) must stay valid, and hold the results only after nclt_orb_wait returned 0.  A handle takes one
+ * submitted call at a time (NCLT_ERR_STATE otherwise); with host selection (mode 1) submit is the whole call. */
+int nclt_orb_submit(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F, float* out_kp,
+                    uint8_t* out_desc, int32_t* out_n);
+int nclt_orb_wait(nclt_ctx* ctx, nclt_orb* orb);
 /* img, out_kp, out_desc, out_n are DEVICE pointers */
 int nclt_orb_detect_and_compute_dev(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
                                     float* out_kp, uint8_t* out_desc, int32_t* out_n);

@@ -690,6 +690,12 @@ struct nclt_orb {
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
     int* h_pinned = nullptr;      // [0] flags, [1..] n_out
     unsigned long long host_fallbacks = 0;
+    // a submitted, not yet awaited call (nclt_orb_submit / nclt_orb_wait)
+    bool pending = false, p_out_on_device = false;
+    int p_F = 0;
+    float* p_kp = nullptr;
+    uint8_t* p_desc = nullptr;
+    int32_t* p_n = nullptr;
 };
 
 extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
@@ -943,11 +949,16 @@ static int orb_select_host(nclt_ctx* c, nclt_orb* o, int F, std::vector<int32_t>
     return NCLT_OK;
 }
 
+static int orb_finish(nclt_ctx* c, nclt_orb* o);
+static int orb_host_tail(nclt_ctx* c, nclt_orb* o, int F, float* out_kp, uint8_t* out_desc, int32_t* out_n, bool out_on_device);
+
+// enqueue = true: return with everything queued (device selection only); orb_finish() completes the call
 static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_device, int channels, int F, float* out_kp,
-                   uint8_t* out_desc, int32_t* out_n, bool out_on_device) {
+                   uint8_t* out_desc, int32_t* out_n, bool out_on_device, bool enqueue_only = false) {
     if (!c) return NCLT_ERR_ARG;
     if (!o || !img || (channels != 1 && channels != 3) || F <= 0 || F > o->max_frames || !out_kp || !out_desc || !out_n)
         return nclt_fail(c, NCLT_ERR_ARG, "orb_detect_and_compute: bad arguments");
+    if (o->pending) return nclt_fail(c, NCLT_ERR_STATE, "orb: a submitted call is pending on this handle (nclt_orb_wait first)");
     cudaSetDevice(c->device);
     const OrbGeom& g = o->g;
     cudaStream_t st = c->stream;
@@ -973,8 +984,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     if (rc) return rc;
     float* d_kp = out_on_device ? out_kp : o->d_kp;
     uint8_t* d_desc = out_on_device ? out_desc : o->d_desc;
-    bool host_select = o->select_mode == 1;
-    if (!host_select) {
+    if (o->select_mode != 1) {
         // everything stays on the device; one read of (flags, n_out) at the end
         k_orb_nms_rows<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt, o->d_hx, o->d_hs);
         const size_t sel_smem = (size_t)kSelSmemBytes;
@@ -996,19 +1006,40 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         } else {
             CU_TRY(c, cudaMemcpyAsync(out_n, o->d_nout, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
         }
-        CU_TRY(c, cudaStreamSynchronize(st));
-        int flags = o->h_pinned[0];
-        if (flags) CU_TRY(c, cudaMemsetAsync(o->d_flags, 0, 4, st));
-        if (o->select_mode == 2) flags |= 1;      // diagnostic: exercise the hand-over to the host
-        if (flags & 2) return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
-        if (flags & 1) {
-            host_select = true;      // introselect left its quick-select phase somewhere: redo the selection on the host
-            o->host_fallbacks++;
-        } else {
-            if (!out_on_device) memcpy(out_n, o->h_pinned + 1, (size_t)F * 4);
-            return NCLT_OK;
-        }
+        o->pending = true;
+        o->p_F = F; o->p_kp = out_kp; o->p_desc = out_desc; o->p_n = out_n; o->p_out_on_device = out_on_device;
+        return enqueue_only ? NCLT_OK : orb_finish(c, o);
     }
+    return orb_host_tail(c, o, F, out_kp, out_desc, out_n, out_on_device);
+}
+
+// second half of a device-selection call: wait, look at the flags, hand over to the host selection if asked to
+static int orb_finish(nclt_ctx* c, nclt_orb* o) {
+    if (!o->pending) return NCLT_OK;
+    o->pending = false;
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    const int F = o->p_F;
+    CU_TRY(c, cudaStreamSynchronize(st));
+    int flags = o->h_pinned[0];
+    if (flags) CU_TRY(c, cudaMemsetAsync(o->d_flags, 0, 4, st));
+    if (o->select_mode == 2) flags |= 1;      // diagnostic: exercise the hand-over to the host
+    if (flags & 2) return nclt_fail(c, NCLT_ERR_STATE, "orb: more keypoints than out_cap (response ties); raise out_cap");
+    if (flags & 1) {
+        o->host_fallbacks++;         // introselect left its quick-select phase somewhere: redo the selection on the host
+        return orb_host_tail(c, o, F, o->p_kp, o->p_desc, o->p_n, o->p_out_on_device);
+    }
+    if (!o->p_out_on_device) memcpy(o->p_n, o->h_pinned + 1, (size_t)F * 4);
+    return NCLT_OK;
+}
+
+// host selection (mode 1, or the fall-back of the device selection) + description + read-back; synchronous
+static int orb_host_tail(nclt_ctx* c, nclt_orb* o, int F, float* out_kp, uint8_t* out_desc, int32_t* out_n, bool out_on_device) {
+    const OrbGeom& g = o->g;
+    cudaStream_t st = c->stream;
+    float* d_kp = out_on_device ? out_kp : o->d_kp;
+    uint8_t* d_desc = out_on_device ? out_desc : o->d_desc;
+    int rc;
     std::vector<int32_t> n_out;
     int n_sel = 0;
     if ((rc = orb_select_host(c, o, F, n_out, &n_sel))) return rc;
@@ -1027,6 +1058,16 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
     }
     CU_TRY(c, cudaStreamSynchronize(st));
     return NCLT_OK;
+}
+
+extern "C" int nclt_orb_submit(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int channels, int F, float* out_kp, uint8_t* out_desc,
+                               int32_t* out_n) {
+    return orb_run(c, o, img, false, channels, F, out_kp, out_desc, out_n, false, true);
+}
+extern "C" int nclt_orb_wait(nclt_ctx* c, nclt_orb* o) {
+    if (!c) return NCLT_ERR_ARG;
+    if (!o) return nclt_fail(c, NCLT_ERR_ARG, "orb_wait: null handle");
+    return orb_finish(c, o);
 }
 
 /* select mode: 0 = selection on the device (default), 1 = on the host with the std:: algorithms,

@@ -95,6 +95,19 @@ class ORB:
         self.ctx.check(_c.nclt_orb_detect_and_compute(self.ctx.h, self._h, ptr(img), ch, F, ptr(kp), ptr(desc), ptr(n)))
         return kp, desc, n
 
+    def submit(self, frames, kp, desc, n):
+        """Asynchronous half of detect_and_compute_batch: frames u8[F,H,W(,3)] and the result arrays kp f32[F,cap,6],
+        desc u8[F,cap,32], n i32[F] are caller-owned (page-locked for real overlap: torch `.pin_memory()` arrays or
+        cudaHostRegister'ed NumPy) and must stay alive until `wait()`; results are valid after `wait()`."""
+        F = frames.shape[0]
+        ch = 3 if len(frames.shape) == 4 else 1
+        if (frames.shape[2], frames.shape[1]) != (self.width, self.height) or F > self.max_frames:
+            raise ValueError('submit: frames do not fit the handle (create ORB(width, height, max_frames) to match)')
+        self.ctx.check(_c.nclt_orb_submit(self.ctx.h, self._h, ptr(frames), ch, F, ptr(kp), ptr(desc), ptr(n)))
+
+    def wait(self):
+        self.ctx.check(_c.nclt_orb_wait(self.ctx.h, self._h))
+
     def detectAndCompute(self, image, mask=None):
         """cv2.ORB.detectAndCompute(image, None) -> (tuple of KeyPoint, desc u8[n,32] or None)."""
         if mask is not None:

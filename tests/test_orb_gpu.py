@@ -141,6 +141,37 @@ def test_out_cap_overflow_is_an_error(ctx, select):
     _check(kp, desc, n, 0, rk, rd, 'after the error')
 
 
+def test_submit_wait_two_handles_alternate():
+    """nclt_orb_submit / nclt_orb_wait: one host thread, two (context, handle) pipelines in flight; results equal the
+    synchronous call; a second submit on a busy handle is refused."""
+    import torch
+    from nclt_slam_project_b200 import _lib
+    from nclt_slam_project_b200.orb import ORB
+    pipes = []
+    for i in range(2):
+        cx = _lib.Context(0)
+        o = ORB(max_frames=3, ctx=cx)
+        frames = torch.from_numpy(np.stack([synth.make_camera_frame(80 + 3 * i + j) for j in range(3)])).pin_memory()
+        bufs = (torch.zeros((3, o.out_cap, 6), dtype=torch.float32).pin_memory(),
+                torch.zeros((3, o.out_cap, 32), dtype=torch.uint8).pin_memory(), torch.zeros(3, dtype=torch.int32).pin_memory())
+        pipes.append((o, frames, bufs))
+    for rep in range(3):
+        for o, frames, bufs in pipes:
+            o.submit(frames, *bufs)
+        with pytest.raises(_lib.NcltError, match='pending'):
+            pipes[0][0].submit(pipes[0][1], *pipes[0][2])
+        for o, frames, bufs in pipes:
+            o.wait()
+    for o, frames, (kp, desc, n) in pipes:
+        rk, rd, rn = o.detect_and_compute_batch(frames.numpy())
+        assert np.array_equal(n.numpy(), rn) and np.array_equal(desc.numpy(), rd)
+        for f in range(3):
+            m = int(rn[f])
+            assert np.array_equal(kp.numpy()[f, :m].view(np.uint32), rk[f, :m].view(np.uint32))
+            ok, od = oo.detect_and_compute(frames.numpy()[f])
+            assert m == len(ok) and np.array_equal(desc.numpy()[f, :m], od)
+
+
 def test_bad_arguments(ctx):
     from nclt_slam_project_b200 import _lib
     from nclt_slam_project_b200.orb import ORB

@@ -126,6 +126,22 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         out['end_to_end_pipelined_frames_per_s'] = world * args.pipelines * args.steps * F / dt
+        # the same with ONE host thread: submit on every handle, then wait on every handle
+        def alternate(steps):        # rolling: every handle always has a batch in flight except while it is re-armed
+            for cx, ob, (bi, bk, bd, bn) in workers:
+                cx.check(L.nclt_orb_submit(cx.h, ob._h, ptr(bi), 1, F, ptr(bk), ptr(bd), ptr(bn)))
+            for s_ in range(steps):
+                for cx, ob, (bi, bk, bd, bn) in workers:
+                    cx.check(L.nclt_orb_wait(cx.h, ob._h))
+                    if s_ + 1 < steps:
+                        cx.check(L.nclt_orb_submit(cx.h, ob._h, ptr(bi), 1, F, ptr(bk), ptr(bd), ptr(bn)))
+        alternate(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        alternate(args.steps)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        out['end_to_end_submit_wait_frames_per_s'] = world * args.pipelines * args.steps * F / dt
         out['pipelines'] = args.pipelines
         for w in workers:
             assert np.array_equal(w[2][3].numpy(), n) and np.array_equal(w[2][2].numpy(), desc)
