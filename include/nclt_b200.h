@@ -173,7 +173,9 @@ typedef struct nclt_localize_params {
 } nclt_localize_params;
 
 /* replaces the per-candidate loop body of visual_landmark_matcher.py:318-380 and
- * checkpoint_a_selftest.py:62-103 for B frames x C candidates: match, MIN_MATCHES gate, gather
+ * checkpoint_a_selftest.py:62-103 for B frames x C candidates: the `len(desc_t) < MIN_MATCHES -> continue` skip
+ * (matcher:321-322, selftest:64-65: a candidate keyframe with fewer than min_matches rows is never matched and
+ * reports 0 matches), match, MIN_MATCHES gate on the match count (matcher:330, selftest:72), gather
  * obj/img points, solvePnPRansac, MIN_INLIERS and mean-reprojection gates, and the "most inliers,
  * earliest candidate on ties" selection (matcher:379-380).
  * q u8[B,Nq,32], q_pts2d f32[B,Nq,2] keypoint pixel coordinates, q_n/cand as for nclt_match_*.

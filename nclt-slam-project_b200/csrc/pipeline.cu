@@ -14,12 +14,19 @@ namespace {
 // items with enough matches become PnP problems (order irrelevant: problems are independent)
 // `cap`: problem capacity of the buffers (asynchronous mode); what does not fit is counted in
 // `overflow` (the caller re-runs such a batch synchronously - parity is never silently lost).
-__global__ void k_select_problems(const int* __restrict__ n_pairs, int n_items, int min_matches, int* prob_item,
-                                  int* item_prob, int* count, int cap, int* overflow) {
+// A candidate keyframe with fewer than MIN_MATCHES descriptors is skipped BEFORE matching by the reference
+// (`len(desc_t) < MIN_MATCHES: continue`, checkpoint_a_selftest.py:64-65, visual_landmark_matcher.py:321-322):
+// in ratio mode a 2..9-row keyframe can collect >= MIN_MATCHES many-to-one matches, so the gate on the match
+// count alone is not enough.  Such items (and empty slots) report 0 matches.
+__global__ void k_select_problems(int* __restrict__ n_pairs, int n_items, int min_matches, const int* __restrict__ cand,
+                                  int C, const int* __restrict__ kf_count, int* prob_item, int* item_prob, int* count,
+                                  int cap, int* overflow) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     int slot = -1;
-    if (n_pairs[i] >= min_matches) {
+    const int kf = cand ? cand[i] : i % C;
+    if (kf < 0 || kf_count[kf] < min_matches) n_pairs[i] = 0;
+    if (kf >= 0 && n_pairs[i] >= min_matches) {
         slot = atomicAdd(count, 1);
         if (slot < cap) prob_item[slot] = i;
         else { slot = -1; if (overflow) atomicAdd(overflow, 1); }
@@ -158,8 +165,8 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         }
     }
     k_select_problems<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(
-        n_pairs, (int)items, prm->min_matches, prob_item, item_prob, d_count, async_mode ? P : (int)items,
-        async_mode ? c->d_overflow : nullptr);
+        n_pairs, (int)items, prm->min_matches, cand, C, L->d_count, prob_item, item_prob, d_count,
+        async_mode ? P : (int)items, async_mode ? c->d_overflow : nullptr);
     c->launches++;
     if (!async_mode) {
         if ((rc = nclt_pinned_reserve(c, 64))) return rc;

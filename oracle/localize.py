@@ -85,7 +85,7 @@ def localize_frame(landmarks, desc_curr, pts_curr_2d, cand_idx, mode=0, backend=
             continue
         lm = landmarks[li]
         desc_t = lm['descriptors']
-        if desc_t is None or len(desc_t) == 0:
+        if desc_t is None or len(desc_t) < MIN_MATCHES:      # selftest:64-65, matcher:321-322 (skipped BEFORE matching)
             continue
         fr, tr = match(mode, desc_curr, desc_t)
         rec['nmatch'] = len(fr)

@@ -93,15 +93,19 @@ def golden_pnp(count=48, nmax=300):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['match', 'pnp', 'selftest', 'map', 'tick', 'lift', 'reloc', 'hitcount']
+    which = sys.argv[1:] or ['match', 'pnp', 'selftest', 'selftest_short', 'map', 'tick', 'accum', 'lift', 'reloc', 'hitcount']
     if 'match' in which:
         golden_match()
     if 'pnp' in which:
         golden_pnp()
-    if 'selftest' in which or 'map' in which or 'tick' in which or 'lift' in which or 'reloc' in which or 'hitcount' in which:
+    if {'selftest', 'selftest_short', 'accum'} & set(which) or 'map' in which or 'tick' in which or 'lift' in which or 'reloc' in which or 'hitcount' in which:
         from oracle import make_golden_ref      # needs /root/reference
         if 'selftest' in which:
             make_golden_ref.golden_selftest(OUT)
+        if 'selftest_short' in which:
+            make_golden_ref.golden_selftest_short(OUT)
+        if 'accum' in which and hasattr(make_golden_ref, 'golden_accum'):
+            make_golden_ref.golden_accum(OUT)
         if 'map' in which:
             make_golden_ref.golden_map(OUT)
         if 'tick' in which:

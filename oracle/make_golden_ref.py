@@ -146,6 +146,89 @@ def golden_selftest(out_dir):
     print('selftest_golden.npz best slots', [r[0] for r in rows], 'inliers', [r[1] for r in rows])
 
 
+def golden_selftest_short(out_dir):
+    """The same loop body (checkpoint_a_selftest.py:62-103) on a library with 2-, 5-, 9- and 10-row keyframes whose
+    first row attracts dozens of ratio matches from the frame (many-to-one): the reference skips the three
+    keyframes with fewer than MIN_MATCHES rows BEFORE matching (selftest:64-65) although each of them would
+    collect >= MIN_MATCHES `good` matches; the 10-row keyframe is matched and goes to solvePnPRansac."""
+    mods = ros_stubs.import_reference()
+    st = mods['checkpoint_a_selftest']
+    import cv2
+    data = synth.make_library(78, n_kf=8, n_desc=300, ragged=True)
+    rng = np.random.default_rng(7801)
+    short = {1: 2, 2: 5, 3: 9, 4: 10}
+    for k, n in short.items():
+        lm = data['landmarks'][k]
+        for key in ('descriptors', 'keypoints_2d', 'keypoints_3d_cam'):
+            lm[key] = np.ascontiguousarray(lm[key][:n])
+        lm['n_features'] = n
+    rows, descs, pts2, cands, would = [], [], [], [], []
+    for seed in range(4):
+        f = synth.make_frame(data, 7800 + seed, k_star=0 if seed < 2 else 6, n_desc=500, n_planted=200)
+        desc_curr, pts_curr_2d = f['desc'].copy(), f['pts2d']
+        # 30 frame rows per short keyframe = that keyframe's row 0 with a few flipped bits
+        for j, k in enumerate(short):
+            base = data['landmarks'][k]['descriptors'][0]
+            for i in range(30):
+                d = base.copy()
+                for bit in rng.choice(256, size=int(rng.integers(0, 9)), replace=False):
+                    d[bit >> 3] ^= np.uint8(1 << (bit & 7))
+                desc_curr[300 + 30 * j + i] = d
+        cand_idx = [1, 2, f['k_star'], 3, 4]
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+        best = None
+        per = []
+        w = []
+        for li in cand_idx:
+            lm_t = data['landmarks'][li]
+            desc_t = lm_t['descriptors']
+            rec = [0, 0, 0, 0.0, 0, 0, 0, 0, 0, 0]
+            per.append(rec)
+            knn_all = bf.knnMatch(desc_curr, desc_t, k=2)
+            w.append(len([1 for m, n in knn_all if (m.distance < st.LOWE_RATIO * n.distance)]))
+            if desc_t is None or len(desc_t) < st.MIN_MATCHES:
+                continue
+            knn = bf.knnMatch(desc_curr, desc_t, k=2)
+            good = [m for m, n in knn if (m.distance < st.LOWE_RATIO * n.distance)]
+            rec[0] = len(good)
+            if len(good) < st.MIN_MATCHES:
+                continue
+            obj_pts = np.array([lm_t['keypoints_3d_cam'][m.trainIdx] for m in good], dtype=np.float32)
+            img_pts = np.array([pts_curr_2d[m.queryIdx] for m in good], dtype=np.float32)
+            ok, rvec, tvec, inliers = cv2.solvePnPRansac(
+                obj_pts, img_pts, st.K, st.DIST, iterationsCount=st.RANSAC_ITERATIONS,
+                reprojectionError=st.RANSAC_REPROJ_PX, flags=cv2.SOLVEPNP_ITERATIVE)
+            if not ok or inliers is None or len(inliers) < st.MIN_INLIERS:
+                continue
+            proj, _ = cv2.projectPoints(obj_pts[inliers[:, 0]], rvec, tvec, st.K, st.DIST)
+            err = float(np.linalg.norm(proj.reshape(-1, 2) - img_pts[inliers[:, 0]], axis=1).mean())
+            rec[1:] = [1, len(inliers), err] + rvec.ravel().tolist() + tvec.ravel().tolist()
+            if err > st.REPROJ_MAX_PX:
+                continue
+            if best is None or len(inliers) > best[1]:
+                best = (cand_idx.index(li), len(inliers))
+        rows.append((best[0] if best else -1, best[1] if best else 0, per))
+        descs.append(desc_curr)
+        pts2.append(pts_curr_2d)
+        cands.append(cand_idx)
+        would.append(w)
+    would = np.array(would)
+    assert (would[:, [0, 1, 3]] >= st.MIN_MATCHES).all(), would      # the skipped keyframes WOULD pass the count gate
+    lms = data['landmarks']
+    np.savez_compressed(
+        os.path.join(out_dir, 'selftest_short_golden.npz'),
+        counts=np.array([len(lm['descriptors']) for lm in lms], dtype=np.int32),
+        lib_desc=np.concatenate([lm['descriptors'] for lm in lms]),
+        lib_p3d=np.concatenate([lm['keypoints_3d_cam'] for lm in lms]),
+        desc=np.stack(descs), pts2d=np.stack(pts2), cand=np.array(cands, dtype=np.int32),
+        would_match=would.astype(np.int32),
+        best_slot=np.array([r[0] for r in rows], dtype=np.int32), best_inl=np.array([r[1] for r in rows], dtype=np.int32),
+        items=np.array([r[2] for r in rows], dtype=np.float64))
+    print('selftest_short_golden.npz best slots', [r[0] for r in rows], 'inliers', [r[1] for r in rows],
+          'ratio matches the skipped keyframes would have had', would.tolist(), 'items nmatch',
+          [[int(x[0]) for x in r[2]] for r in rows])
+
+
 def golden_tick(out_dir):
     """The production node: VisualLandmarkMatcher._tick (visual_landmark_matcher.py:281-433), run
     unmodified under ROS stubs with a stand-in ORB that returns synthetic keypoints/descriptors.
