@@ -17,6 +17,15 @@ correspondences into one keyframe; every frame is matched against ALL 400 keyfra
 `--impl reference` times only that CPU loop (rank 0), on the same config and metric.
 Under torchrun (N > 1) every rank owns one GPU, the library is replicated and frames are sharded
 (weak scaling, no data-path collective).
+
+`--workload` selects the other BASELINE.json configurations (same JSON contract, same flags):
+  replay     configs[1] (default, above)
+  routes15   configs[3]: 15 independent teach libraries (seeds 100..114) resident on every GPU, (route, frame)
+             units sharded round-robin over the ranks, no collective; a step = one batch of one route
+  map        configs[2]: teach-map build, 640x480 depth frames -> 1950x900 @ 0.1 m log-odds grid along a
+             boustrophedon route (steps x batch frames at 0.05 m spacing; 20 x 2000 = the 40 000-frame 2 km route)
+  crossroute configs[4]: the union of 15 libraries (6.0e6 descriptors) sharded by keyframe range over the ranks,
+             flat global top-2 per query row, ONE NCCL all-gather of the packed keys + local merge (strong scaling)
 """
 import argparse
 import json
@@ -34,7 +43,15 @@ import numpy as np
 
 N_KF, N_DESC, N_QUERY, N_PLANTED = 400, 1000, 1000, 500
 LIB_SEED = 20261018
+ROUTE_SEEDS = list(range(100, 115))          # config 4: 15 independent libraries
 METRIC = 'query frames/s (match+PnP-RANSAC)'
+WORKLOAD_TEXT = {
+    'replay': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
+              'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
+    'routes15': 'configs[3]: 15 routes replayed concurrently, 15 libraries of 400 keyframes x 1000 desc resident per GPU, '
+                '1000-desc frames against all 400 keyframes of their own route, k=2 + Lowe 0.80 + PnP-RANSAC, '
+                '(route, frame) units sharded round-robin over the GPUs, no collective',
+}
 
 
 # stdout carries exactly one JSON line: everything libraries print to fd 1 (NCCL's version banner, ...) is sent to
@@ -60,13 +77,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_inputs(n_frames, seed0, lib=None):
+def make_inputs(n_frames, seed0, lib=None, lib_seed=LIB_SEED, seeds=None):
     import nclt_slam_project_b200  # noqa: F401
     from nclt_slam_project_b200 import synth
     if lib is None:
-        lib = synth.make_library(LIB_SEED, n_kf=N_KF, n_desc=N_DESC)
-    desc, pts2d, kstar, _ = synth.make_frame_batch(lib, range(seed0, seed0 + n_frames), n_desc=N_QUERY,
-                                                   n_planted=N_PLANTED)
+        lib = synth.make_library(lib_seed, n_kf=N_KF, n_desc=N_DESC)
+    if seeds is None:
+        seeds = range(seed0, seed0 + n_frames)
+    desc, pts2d, kstar, _ = synth.make_frame_batch(lib, seeds, n_desc=N_QUERY, n_planted=N_PLANTED)
     return lib, desc, pts2d, kstar
 
 
@@ -147,30 +165,62 @@ def cpu_reference_frames(lib, desc, pts2d, n_frames):
     return time.perf_counter() - t0, n_frames, acc
 
 
+def route_inputs(workload, rank, world, B, n_batches):
+    """-> list of routes: dict(lib, desc [n_batches*B,...], pts2d, kstar).  replay: one library, frames owned by this
+    rank; routes15: 15 libraries (seeds 100..114, replicated on every GPU), this rank's share of the (route, frame)
+    units dealt round-robin by dist.shard_units."""
+    if workload == 'replay':
+        lib, desc, pts2d, kstar = make_inputs(B * n_batches, 1000003 * rank)
+        return [dict(lib=lib, desc=desc, pts2d=pts2d, kstar=kstar)]
+    from nclt_slam_project_b200.dist import shard_units
+    frames_per_route = B * n_batches * world
+    mine = shard_units(len(ROUTE_SEEDS), frames_per_route, rank, world)
+    routes = []
+    for r, seed in enumerate(ROUTE_SEEDS):
+        frames = [f for (rt, f) in mine if rt == r]
+        assert len(frames) == B * n_batches, (len(frames), B, n_batches)
+        lib, desc, pts2d, kstar = make_inputs(0, 0, lib_seed=seed, seeds=[seed * 1000003 + f for f in frames])
+        routes.append(dict(lib=lib, desc=desc, pts2d=pts2d, kstar=kstar))
+    return routes
+
+
+def lib_arrays(lib):
+    lms = lib['landmarks']
+    return [lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.workload in ('map', 'crossroute'):
+        import bench_workloads as bw
+        return (bw.reference_map if args.workload == 'map' else bw.reference_crossroute)(args, emit, log)
     import cv2
     cores = cv2.getNumThreads()
     per_step = args.ref_frames_per_step
-    lib, desc, pts2d, _ = make_inputs(per_step * min(args.steps + args.warmup, 4), 0)
-    nb = desc.shape[0] // per_step
-    for w in range(args.warmup):
-        i = (w % nb) * per_step
-        cpu_reference_frames(lib, desc[i:i + per_step], pts2d[i:i + per_step], per_step)
+    n_routes = 1 if args.workload == 'replay' else len(ROUTE_SEEDS)
+    # replay: one library; routes15: step s replays frames of route s mod 15 against that route's library
+    routes = []
+    for r in range(min(n_routes, args.steps + args.warmup)):
+        seed = LIB_SEED if args.workload == 'replay' else ROUTE_SEEDS[r]
+        lib, desc, pts2d, _ = make_inputs(per_step * (min(args.steps + args.warmup, 4) if n_routes == 1 else 1), 0,
+                                          lib_seed=seed)
+        routes.append((lib, desc, pts2d))
     t = 0.0
-    for s in range(args.steps):
-        i = ((s + args.warmup) % nb) * per_step
+    for s in range(-args.warmup, args.steps):
+        lib, desc, pts2d = routes[(s + args.warmup) % len(routes)]
+        nb = desc.shape[0] // per_step
+        i = ((s + args.warmup) // len(routes) % nb) * per_step
         dt, _, _ = cpu_reference_frames(lib, desc[i:i + per_step], pts2d[i:i + per_step], per_step)
-        t += dt
+        if s >= 0:
+            t += dt
     fps = per_step * args.steps / t
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 match, f64 PnP',
         'data': 'synthetic',
-        'config': {'workload': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
-                               'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
+        'config': {'workload': WORKLOAD_TEXT[args.workload],
                    'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                          'sample': f'{per_step} frames per step x {args.steps} steps; reference-structured loop '
@@ -188,17 +238,26 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=512, help='frames per step per GPU')
+    ap.add_argument('--workload', default='replay', choices=['replay', 'routes15', 'map', 'crossroute'],
+                    help='BASELINE.json configs[1] (default) / [3] / [2] / [4]')
+    ap.add_argument('--batch', type=int, default=None,
+                    help='units per step per GPU (frames; default 512 replay/routes15, 2000 map, 256 crossroute)')
     ap.add_argument('--engine', default='tensor4', choices=['int', 'tensor', 'tensor4'],
                     help='matching engine: integer pipe (LOP3+POPC), tcgen05 fp8 (tensor) or block-scaled fp4 (tensor4); identical results')
-    ap.add_argument('--cpu-frames', type=int, default=16, help='frames in the cpu_baseline sample')
-    ap.add_argument('--ref-frames-per-step', type=int, default=2)
+    ap.add_argument('--cpu-frames', type=int, default=None, help='frames in the cpu_baseline sample')
+    ap.add_argument('--ref-frames-per-step', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--engines', type=int, default=2, help='alternating engines (streams) in the pipelined mode')
     ap.add_argument('--no-pipeline', action='store_true', help='one engine/stream instead of two alternating ones')
     ap.add_argument('--no-graph', action='store_true', help='direct launches instead of CUDA graph replay')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.batch is None:
+        args.batch = {'replay': 512, 'routes15': 512, 'map': 2000, 'crossroute': 256}[args.workload]
+    if args.cpu_frames is None:
+        args.cpu_frames = {'replay': 16, 'routes15': 16, 'map': 300, 'crossroute': 2}[args.workload]
+    if args.ref_frames_per_step is None:
+        args.ref_frames_per_step = {'replay': 2, 'routes15': 2, 'map': 50, 'crossroute': 1}[args.workload]
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -219,20 +278,37 @@ def main():
     dev = torch.device('cuda', local_rank)
 
     import nclt_slam_project_b200  # noqa: F401
+    if args.workload in ('map', 'crossroute'):
+        import bench_workloads as bw
+        tools = dict(emit=emit, log=log, ClockSampler=ClockSampler, rank=rank, world=world, local_rank=local_rank, dev=dev)
+        (bw.run_map if args.workload == 'map' else bw.run_crossroute)(args, tools)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     from nclt_slam_project_b200.pipeline import DeviceLocalizer, StreamingLocalizer, localize_batch
     from nclt_slam_project_b200._lib import LocalizeParams
 
     B = args.batch
-    n_batches = 2                       # distinct input batches, rotated; L2 is flushed between steps
+    multi = args.workload == 'routes15'
+    n_batches = 1 if multi else 2       # distinct input batches per route, rotated; L2 is flushed between steps
     t_gen = time.perf_counter()
-    lib, desc, pts2d, kstar = make_inputs(B * n_batches, 1000003 * rank)
-    log(f'[rank {rank}] generated {B * n_batches} frames in {time.perf_counter() - t_gen:.1f}s')
-    lms = lib['landmarks']
-    eng = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
-                          device=local_rank, params=LocalizeParams(mode=0))
-    eng.ctx.set_engine(args.engine)
-    d_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
-    d_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).to(dev) for i in range(n_batches)]
+    routes = route_inputs(args.workload, rank, world, B, n_batches)
+    R = len(routes)
+    n_slots = R * n_batches             # a slot = (route, batch): step s works on slot s mod n_slots
+    log(f'[rank {rank}] generated {R} librar{"ies" if R > 1 else "y"}, {B * n_batches * R} frames in {time.perf_counter() - t_gen:.1f}s')
+
+    def make_engine():
+        e = DeviceLocalizer(lib_arrays(routes[0]['lib']), device=local_rank, params=LocalizeParams(mode=0))
+        for rt in routes[1:]:
+            e.add_library(lib_arrays(rt['lib']))
+        e.ctx.set_engine(args.engine)
+        return e
+
+    eng = make_engine()
+    slot_route = [k // n_batches for k in range(n_slots)]
+    d_desc = [torch.from_numpy(routes[k // n_batches]['desc'][(k % n_batches) * B:(k % n_batches + 1) * B]).to(dev) for k in range(n_slots)]
+    d_pts = [torch.from_numpy(routes[k // n_batches]['pts2d'][(k % n_batches) * B:(k % n_batches + 1) * B]).to(dev) for k in range(n_slots)]
+    slot_kstar = [routes[k // n_batches]['kstar'][(k % n_batches) * B:(k % n_batches + 1) * B] for k in range(n_slots)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -247,56 +323,61 @@ def main():
     sampler.start()
     time.sleep(0.3)
     torch.cuda.synchronize()
-    stream = eng.stream                   # the stream the C ABI launches on: events must be recorded there
-    for w in range(max(args.warmup, 3)):
-        out = eng.run(d_desc[w % n_batches], d_pts[w % n_batches])
+    n_warm = max(args.warmup, 3, n_slots if multi else 0)      # every library's operand image is built in the warm-up
+    acc_rate, n_prob_warm = 0.0, 0
+    for w in range(n_warm):
+        k = w % n_slots
+        out = eng.run(d_desc[k], d_pts[k], lib=slot_route[k])
+        torch.cuda.synchronize()                    # results are produced on the engine's own stream
+        got = out['best_cand'].cpu().numpy()
+        rate = float((got == slot_kstar[k]).mean())
+        if rate < 0.999:
+            raise SystemExit(f'[rank {rank}] slot {k} (route {slot_route[k]}): only {rate * 100:.2f}% of the frames were '
+                             'localised to their planted keyframe - result invalid')
+        acc_rate, n_prob_warm = rate, out['n_problems']
     torch.cuda.synchronize()
-    got = out['best_cand'].cpu().numpy()
-    i_last = (max(args.warmup, 3) - 1) % n_batches
-    acc_rate = float((got == kstar[i_last * B:(i_last + 1) * B]).mean())
     log(f'[rank {rank}] warm-up ok: {acc_rate * 100:.1f}% of frames localised to their planted keyframe; '
-        f'{out["n_problems"]} PnP problems in the last batch')
+        f'{n_prob_warm} PnP problems in the last batch')
 
     # kernel-only timing of the dominant kernel: CUDA events around its launches (profile mode) over a few
     # direct (non-graph) steps; the timed region below replays CUDA graphs, where such events cannot be read
     eng.ctx.profile(True)
     eng.ctx.profile_read()
     for w in range(4):
-        eng.run(d_desc[w % n_batches], d_pts[w % n_batches], sync_count=False)
+        k = w % n_slots
+        eng.run(d_desc[k], d_pts[k], sync_count=False, lib=slot_route[k])
     k_ms, k_n = eng.ctx.profile_read()
     eng.ctx.profile(False)
-    graphs = None
-    if not args.no_graph:
-        try:
-            graphs = [eng.capture(d_desc[i], d_pts[i]) for i in range(n_batches)]
-        except Exception as e:          # keep measuring with direct launches
-            log(f'[rank {rank}] CUDA graph capture failed ({e!r}); using direct launches')
-            graphs = None
     l0 = eng.ctx.launches
-    eng.run(d_desc[0], d_pts[0], sync_count=False)
+    eng.run(d_desc[0], d_pts[0], sync_count=False, lib=slot_route[0])
     launches_per_step = eng.ctx.launches - l0
-    n_prob = out['n_problems'] * args.steps      # from the (synchronous) warm-up steps: same batches
+    n_prob = n_prob_warm * args.steps      # from the (synchronous) warm-up steps: same batches
     # Steps are fully asynchronous (the PnP problem count stays on the device; capacity overflow is
     # checked below) and replayed as CUDA graphs.  With --pipeline (default) two engines with their own
-    # stream and scratch take the steps alternately, so the tail of step i (verification, PnP) overlaps
-    # the matching kernel of step i+1; the K steps are then bracketed by one pair of events.
+    # stream and scratch take the steps alternately, so the host never waits between steps; the K steps
+    # are bracketed by one pair of events.
     engines = [eng]
-    for k in range(1, 1 if args.no_pipeline else max(args.engines, 1)):
-        eng2 = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
-                               device=local_rank, params=LocalizeParams(mode=0))
-        eng2.ctx.set_engine(args.engine)
-        for w in range(3):
-            eng2.run(d_desc[k % n_batches], d_pts[k % n_batches])
+    for j in range(1, 1 if args.no_pipeline else max(args.engines, 1)):
+        eng2 = make_engine()
+        for w in range(max(3, n_slots if multi else 0)):
+            k = w % n_slots
+            eng2.run(d_desc[k], d_pts[k], lib=slot_route[k])
         engines.append(eng2)
     n_eng = len(engines)
-    step_graph = [None] * n_eng
-    if graphs is not None:
+    # step s: engine s mod n_eng, slot s mod n_slots; one graph per (engine, slot) pair that occurs, captured after
+    # every engine has run every slot once (so no capture can move memory an earlier graph points into -
+    # DeviceLocalizer.replay checks the allocation generation anyway)
+    use_graphs = not args.no_graph
+    graphs = {}
+    if use_graphs:
         try:
-            step_graph = [graphs[0]] + [e.capture(d_desc[i % n_batches], d_pts[i % n_batches])
-                                        for i, e in enumerate(engines) if i > 0]
-        except Exception as e:
+            for s_ in range(args.steps):
+                key = (s_ % n_eng, s_ % n_slots)
+                if key not in graphs:
+                    graphs[key] = engines[key[0]].capture(d_desc[key[1]], d_pts[key[1]], lib=slot_route[key[1]])
+        except Exception as e:          # keep measuring with direct launches
             log(f'[rank {rank}] CUDA graph capture failed ({e!r}); using direct launches')
-            graphs, step_graph = None, [None] * n_eng
+            use_graphs, graphs = False, {}
     ev0 = torch.cuda.Event(enable_timing=True)
     ev_end = [torch.cuda.Event(enable_timing=True) for _ in engines]
     barrier()
@@ -305,14 +386,14 @@ def main():
     for e in engines[1:]:
         e.stream.wait_event(ev0)
     for s in range(args.steps):
-        i = s % n_eng
+        i, k = s % n_eng, s % n_slots
         e = engines[i]
         with torch.cuda.stream(e.stream):
             flush.zero_()                               # evict L2 before every step (inside the timed region)
-            if step_graph[i] is not None:
-                step_graph[i].replay()
+            if use_graphs:
+                e.replay(graphs[(i, k)])
             else:
-                e.run(d_desc[i % n_batches], d_pts[i % n_batches], sync_count=False)
+                e.run(d_desc[k], d_pts[k], sync_count=False, lib=slot_route[k])
     for e, evx in zip(engines, ev_end):
         evx.record(e.stream)
     barrier()
@@ -323,46 +404,60 @@ def main():
         raise SystemExit(f'{overflow} PnP problems exceeded the asynchronous capacity - result invalid')
     total_ms = max(ev0.elapsed_time(evx) for evx in ev_end)
     log(f'[rank {rank}] {args.steps} steps in {total_ms:.2f} ms ({total_ms / args.steps:.2f} ms/step, '
-        f'{n_eng} engine(s), graphs={graphs is not None})')
+        f'{n_eng} engine(s), graphs={use_graphs})')
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = B * args.steps * world / (total_ms_max * 1e-3)
+    for e in engines[1:]:
+        del e
+    engines = [eng]
 
     # ---- end to end through the host-pointer C ABI ------------------------------------------
-    h_desc = [torch.from_numpy(desc[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
-    h_pts = [torch.from_numpy(pts2d[i * B:(i + 1) * B]).pin_memory() for i in range(n_batches)]
+    h_desc = [torch.from_numpy(routes[k // n_batches]['desc'][(k % n_batches) * B:(k % n_batches + 1) * B]).pin_memory() for k in range(n_slots)]
+    h_pts = [torch.from_numpy(routes[k // n_batches]['pts2d'][(k % n_batches) * B:(k % n_batches + 1) * B]).pin_memory() for k in range(n_slots)]
     prm = LocalizeParams(mode=0)
     # the host-buffer replay API: two contexts take the batches alternately through the asynchronous host-pointer
     # C ABI call, so one batch's input / result copies overlap the other's kernels; every step copies its inputs
-    # from pinned host memory and its per-frame results back, inside the timed region
-    sl = StreamingLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]),
-                            device=local_rank, params=prm, engine=args.engine, depth=2)
-    for w in range(3):
-        tk = sl.submit(h_desc[w % n_batches].numpy(), h_pts[w % n_batches].numpy())
-    r = sl.result(tk)
-    i_w = 2 % n_batches
-    if not np.array_equal(r['best_cand'], kstar[i_w * B:(i_w + 1) * B]):
-        log(f'[rank {rank}] WARNING: streaming results differ from the planted keyframes')
-    for s_ in sl.slots:
-        s_['ctx'].sync()
+    # from pinned host memory and its per-frame results back, inside the timed region.  One StreamingLocalizer per
+    # route (each owns that route's library on its two contexts).
+    sls = [StreamingLocalizer(lib_arrays(rt['lib']), device=local_rank, params=prm, engine=args.engine, depth=2) for rt in routes]
+    for w in range(max(3, n_slots if multi else 0)):
+        k = w % n_slots
+        sl = sls[slot_route[k]]
+        r = sl.result(sl.submit(h_desc[k].numpy(), h_pts[k].numpy()))
+        if not np.array_equal(r['best_cand'], slot_kstar[k]):
+            raise SystemExit(f'[rank {rank}] end-to-end results of slot {k} differ from the planted keyframes - result invalid')
+    for sl in sls:
+        for s_ in sl.slots:
+            s_['ctx'].sync()
     barrier()
     t0 = time.perf_counter()
     prev = None
+    n_bad = 0
     for s in range(args.steps):
-        tk = sl.submit(h_desc[s % n_batches].numpy(), h_pts[s % n_batches].numpy())
+        k = s % n_slots
+        sl = sls[slot_route[k]]
+        tk = (sl, sl.submit(h_desc[k].numpy(), h_pts[k].numpy()), k)
         if prev is not None:
-            r = sl.result(prev)           # consume the previous batch's results (host arrays)
+            r = prev[0].result(prev[1])           # consume the previous batch's results (host arrays)
+            n_bad += int((r['best_cand'] != slot_kstar[prev[2]]).sum())
         prev = tk
-    r = sl.result(prev)
-    for s_ in sl.slots:
-        s_['ctx'].sync()
+    r = prev[0].result(prev[1])
+    n_bad += int((r['best_cand'] != slot_kstar[prev[2]]).sum())
+    for sl in sls:
+        for s_ in sl.slots:
+            s_['ctx'].sync()
     e2e_s = time.perf_counter() - t0
-    e2e_overflow = sl.overflow()
-    if e2e_overflow:
-        log(f'[rank {rank}] WARNING: {e2e_overflow} PnP problems over capacity in the streaming run')
-    sl.close()
+    e2e_reruns = sum(sl.reruns for sl in sls)
+    if n_bad:
+        raise SystemExit(f'[rank {rank}] {n_bad} frames of the end-to-end run were not localised to their planted keyframe - result invalid')
+    if e2e_reruns:
+        raise SystemExit(f'[rank {rank}] {e2e_reruns} batches of the end-to-end run overflowed the asynchronous PnP capacity and '
+                         'were re-run synchronously - the timing is not that of the asynchronous path, result invalid')
+    for sl in sls:
+        sl.close()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -413,28 +508,24 @@ def main():
         if not bf16:
             bf16, src = 1400.0, 'fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) x 2 for fp8'
         achieved = cmp_per_s * 512.0 / 1e12
-        # the fp8 tensor peak of THIS GPU at the clock it actually runs this kernel at: an MMA-only probe
-        # (tcgen05.mma kind::f8f6f4 M=128 N=256 back to back on resident tiles, nclt_tc_bench) in this run.
-        # MEASURED_PEAKS.json only carries a cuBLAS bf16 figure (power-capped, ~1.3 GHz); 2 x that is kept
-        # beside it as `peak_measured_peaks_x2` / `frac_vs_measured_peaks_x2`.
+        # the tensor peak of THIS GPU at the clock it actually runs this kernel at: an MMA-only probe of the same
+        # instruction on resident tiles (libnclt_b200_diag.so) in this run.  MEASURED_PEAKS.json only carries a cuBLAS
+        # bf16 figure (power-capped, ~1.3 GHz); 2 x / 4 x that is kept beside it.
         import ctypes as C
-        from nclt_slam_project_b200._lib import lib as _L
-        _L.nclt_tc_bench.restype = C.c_double
-        _L.nclt_tc_bench.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        from nclt_slam_project_b200._lib import diag as _diag
+        _L = _diag()
         cyc = C.c_double()
         if args.engine == 'tensor4':
             # block-scaled fp4: MMA-only probe of tcgen05.mma kind::mxf4 M=128 N=240 (64 comparisons/clk/SM);
             # nominal fp4 dense = 4 x bf16, kept beside it from MEASURED_PEAKS.json
-            _L.nclt_tc_bench_mxf4.restype = C.c_double
-            _L.nclt_tc_bench_mxf4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
             mma_pairs = _L.nclt_tc_bench_mxf4(eng.ctx.h, 240, 4000, 0, C.byref(cyc))
             peak = mma_pairs * 512.0 / 1e12
             roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak,
                         'unit': 'TFLOP/s (fp4 block-scaled, 512 flop per 256-bit comparison)',
                         'frac': achieved / peak if peak > 0 else None, 'kernel': 'k_tc4_top2',
-                        'peak_source': 'MMA-only tcgen05 kind::mxf4 probe on this GPU in this run (64 comparisons/clk/SM); '
-                                       'the kernel is bound by the accumulator hand-over (TMEM read-out of every f32 '
-                                       'cell between MMAs), see DESIGN.md',
+                        'peak_source': 'MMA-only tcgen05 kind::mxf4 probe on this GPU in this run (4 MMAs per 128 x 240 x 256-bit '
+                                       'tile, nothing else); the kernel needs a 5th (bias) MMA per tile and the accumulator '
+                                       'hand-over, see DESIGN.md 4.1c',
                         'peak_measured_peaks_x4': 4.0 * bf16, 'frac_vs_measured_peaks_x4': achieved / (4.0 * bf16),
                         'peak_measured_peaks_source': src.replace('x 2 (fp8 runs at twice', 'x 4 (fp4 runs at four times')}
         else:
@@ -452,25 +543,32 @@ def main():
     if not args.no_cpu_baseline:
         import cv2
         n_cpu = min(args.cpu_frames, B)
-        dt, nf, acc = cpu_reference_frames(lib, desc[:n_cpu], pts2d[:n_cpu], n_cpu)
+        dt, nf, acc = cpu_reference_frames(routes[0]['lib'], routes[0]['desc'][:n_cpu], routes[0]['pts2d'][:n_cpu], n_cpu)
         cpu = {'value': nf / dt, 'unit': 'frames/s', 'cores': cv2.getNumThreads(), 'kind': 'port',
                'sample': f'{nf} frames of the same workload ({dt:.1f} s): reference-structured loop '
                          '(checkpoint_a_selftest.py:62-103 over all 400 keyframes) calling cv2 4.x '
                          'BFMatcher.knnMatch / solvePnPRansac / projectPoints with all host threads'}
 
+    cfg = {'workload': WORKLOAD_TEXT[args.workload],
+           'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY,
+           'frames_per_step_per_gpu': B, 'engine': args.engine, 'cuda_graph': use_graphs,
+           'sharding': f'frames x {world} GPUs, librar{"ies" if multi else "y"} replicated, no collective',
+           'cache': 'L2 flushed (256 MB write) before every step, inside the timed region',
+           'pipelined_engines': n_eng,
+           'pnp_problems_per_step': n_prob / args.steps, 'localised_to_planted_keyframe': acc_rate}
+    if multi:
+        cfg.update(n_libraries=R, library_seeds=ROUTE_SEEDS,
+                   resident_library_bytes_per_engine=R * N_KF * N_DESC * (32 + 12 + (128 if args.engine == 'tensor4' else 256 if args.engine == 'tensor' else 0)),
+                   step_order='step s replays one batch of route s mod 15 (every step meets a library image that the previous '
+                              '14 steps and the L2 flush have evicted)')
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True,
+        'warmup': n_warm, 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32 match, f64 PnP', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: 03_south replay, 400 keyframes x 1000 desc, 1000-desc frames, '
-                               'k=2 + Lowe 0.80 + PnP-RANSAC over all keyframes',
-                   'n_keyframes': N_KF, 'desc_per_keyframe': N_DESC, 'desc_per_frame': N_QUERY,
-                   'frames_per_step_per_gpu': B, 'engine': args.engine, 'cuda_graph': graphs is not None, 'sharding': f'frames x {world} GPUs, library replicated, no collective',
-                   'cache': 'L2 flushed (256 MB write) before every step, inside the timed region',
-                   'pipelined_engines': n_eng,
-                   'pnp_problems_per_step': n_prob / args.steps, 'localised_to_planted_keyframe': acc_rate},
+        'config': cfg,
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'api': 'StreamingLocalizer.submit/result: asynchronous nclt_localize_batch (host pointers), 2 contexts alternate'},
+                'api': 'StreamingLocalizer.submit/result: asynchronous nclt_localize_batch (host pointers), 2 contexts alternate; '
+                       'every frame of every timed step checked against its planted keyframe'},
         'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
     }
     emit(line)

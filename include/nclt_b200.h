@@ -43,6 +43,12 @@ int nclt_ctx_sync(nclt_ctx* ctx);
 const char* nclt_last_error(nclt_ctx* ctx);
 /* kernels launched through this context so far (bench.py's gpu_launches) */
 unsigned long long nclt_ctx_launches(nclt_ctx* ctx);
+/* Generation of the device allocations behind this context: bumped whenever memory that enqueued work may point
+ * into is freed or moved - the scratch arena grows, a tensor-engine library image or work-split table is rebuilt
+ * (different batch size, nclt_lib_append), the library itself grows.  A CUDA graph captured from *_dev calls on this
+ * context holds raw pointers into that memory: record the generation at capture time and re-capture (never replay)
+ * once it has changed (pipeline.py::DeviceLocalizer.capture / replay do exactly that). */
+unsigned long long nclt_ctx_alloc_generation(nclt_ctx* ctx);
 /* asynchronous nclt_localize_batch_dev calls (out_n_problems == NULL) size their PnP buffers for
  * max(4*B, 1024) problems per batch; returns how many problems were dropped since the last reset
  * (>= 0; synchronises the stream). A caller that sees > 0 re-runs those batches synchronously. */
@@ -59,6 +65,9 @@ int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
  * since the last read, and resets. Used by bench.py for the live roofline figure. */
 int nclt_ctx_profile(nclt_ctx* ctx, int enable);
 int nclt_ctx_profile_read(nclt_ctx* ctx, double* ms_total, int* n_launches);
+/* the same per kernel family (8 entries each): 0 Hamming top-2, 1 k_occ_frame (map stage A), 2 k_occ_apply (map stage B),
+ * 3 k_pnp_hypo, 4 k_pnp_score, 5 k_pnp_finish, 6 candidate verification (k_tc_verify), 7 unused; resets like the above */
+int nclt_ctx_profile_read_tags(nclt_ctx* ctx, double* ms_by_tag, int* n_by_tag);
 /* library ABI version, bumped on any signature change */
 int nclt_abi_version(void);
 /* measured POPC32 op/s of a register-only kernel: roofline denominator for the matcher */

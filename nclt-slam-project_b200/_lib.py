@@ -22,7 +22,7 @@ if not os.path.exists(LIB_PATH):
         f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
         '(nvcc, sm_100a). There is no CPU fallback.')
 
-lib = C.CDLL(LIB_PATH)
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)      # RTLD_GLOBAL: the diagnostics library resolves its helpers here
 
 _vp, _i, _u32, _dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_double
 
@@ -40,10 +40,12 @@ _sig('nclt_ctx_destroy', _i, _vp)
 _sig('nclt_ctx_sync', _i, _vp)
 _sig('nclt_last_error', C.c_char_p, _vp)
 _sig('nclt_ctx_launches', C.c_ulonglong, _vp)
+_sig('nclt_ctx_alloc_generation', C.c_ulonglong, _vp)
 _sig('nclt_ctx_set_engine', _i, _vp, _i)
 _sig('nclt_ctx_overflow', _i, _vp, _i)
 _sig('nclt_ctx_profile', _i, _vp, _i)
 _sig('nclt_ctx_profile_read', _i, _vp, C.POINTER(_dbl), C.POINTER(_i))
+_sig('nclt_ctx_profile_read_tags', _i, _vp, C.POINTER(_dbl), C.POINTER(_i))
 _sig('nclt_popc_peak', _dbl, _vp, _i, C.POINTER(C.c_float))
 _sig('nclt_lib_create', _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp))
 _sig('nclt_lib_append', _i, _vp, _vp, _vp, _vp, _i)
@@ -170,6 +172,11 @@ class Context:
     def launches(self):
         return int(lib.nclt_ctx_launches(self.h))
 
+    @property
+    def alloc_generation(self):
+        """Bumped whenever device memory that a captured CUDA graph may point into was freed or moved."""
+        return int(lib.nclt_ctx_alloc_generation(self.h))
+
     def set_engine(self, engine):
         """'int' (LOP3+POPC) or 'tensor' (tcgen05) for all-keyframe ratio matching; same results."""
         code = {'int': 0, 'tensor': 1, 'tensor8': 1, 'tensor4': 2, 0: 0, 1: 1, 2: 2}[engine]
@@ -190,6 +197,21 @@ class Context:
         ms, n = _dbl(), _i()
         self.check(lib.nclt_ctx_profile_read(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    PROF_TAGS = ('hamming_top2', 'occ_frame', 'occ_apply', 'pnp_hypo', 'pnp_score', 'pnp_finish', 'tc_verify', 'other')
+
+    def profile_read_tags(self):
+        """-> {kernel family: (summed device ms, launches)} since the last read (profile mode)."""
+        ms, n = (_dbl * 8)(), (_i * 8)()
+        self.check(lib.nclt_ctx_profile_read_tags(self.h, ms, n))
+        return {name: (ms[k], n[k]) for k, name in enumerate(self.PROF_TAGS)}
+
+    def occ_profile_read(self):
+        """Map builder stages of the calls since the last read: dict(frame_ms, apply_ms, launches) - per launch averages."""
+        t = self.profile_read_tags()
+        fa, na = t['occ_frame']
+        fb, nb = t['occ_apply']
+        return {'frame_ms': fa / na if na else None, 'apply_ms': fb / nb if nb else None, 'launches': na + nb}
 
     def popc_peak(self, iters=4096):
         ms = C.c_float()
@@ -218,3 +240,32 @@ def default_context(device=0):
     if c is None:
         c = _default_ctx[device] = Context(device)
     return c
+
+
+# ---- diagnostics library (include/nclt_b200_diag.h): probes and micro-benchmarks, NOT part of the product path ----
+DIAG_PATH = os.path.join(_HERE, 'libnclt_b200_diag.so')
+_diag = None
+
+
+def diag():
+    """ctypes handle of libnclt_b200_diag.so (tests/test_tc_gpu.py, tools/*.py, bench.py's roofline peak)."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_PATH):
+            raise ImportError(f'{DIAG_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"`')
+        d = C.CDLL(DIAG_PATH, mode=C.RTLD_GLOBAL)
+        d.nclt_tc_probe.restype = _i
+        d.nclt_tc_probe.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp]
+        d.nclt_tc_probe_mxf4.restype = _i
+        d.nclt_tc_probe_mxf4.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+        for name in ('nclt_tc_bench', 'nclt_tc_bench_mxf4'):
+            getattr(d, name).restype = _dbl
+            getattr(d, name).argtypes = [_vp, _i, _i, _i, C.POINTER(_dbl)]
+        d.nclt_tc_bench_mx16.restype = _dbl
+        d.nclt_tc_bench_mx16.argtypes = [_vp, _i, _i, C.POINTER(_dbl)]
+        d.nclt_tmem_bw.restype = _dbl
+        d.nclt_tmem_bw.argtypes = [_vp, _i, _i, _i]
+        d.nclt_tc_bench_two_issuers.restype = _dbl
+        d.nclt_tc_bench_two_issuers.argtypes = [_vp, _i, _i]
+        _diag = d
+    return _diag

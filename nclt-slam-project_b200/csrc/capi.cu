@@ -13,6 +13,7 @@ int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
     if (c->scratch_chunk >= 0 && c->scratch_off + bytes <= c->scratch_bytes) return NCLT_OK;
     const bool idle = c->scratch_chunk < 0 || (c->scratch_chunk == 0 && c->scratch_off == 0);
     if (idle) {
+        c->alloc_gen++;  // frees every chunk: captured graphs are stale from here on
         // top-level call and nothing in use: consolidate into one chunk that fits
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         size_t total = 0;      // the sum: what used to need several chunks then fits one
@@ -51,6 +52,9 @@ int nclt_scratch_reserve(nclt_ctx* c, size_t bytes) {
             return NCLT_OK;
         }
     }
+    // (re-using an idle chunk above moves nothing; a NEW chunk does not invalidate earlier pointers either, but a
+    // graph captured before it existed may be replayed next to calls that now carve from it - stay conservative)
+    c->alloc_gen++;
     void* p = nullptr;
     size_t want = bytes + bytes / 8;
     cudaError_t e = cudaMalloc(&p, want);
@@ -126,6 +130,7 @@ extern "C" int nclt_ctx_sync(nclt_ctx* c) {
 
 extern "C" const char* nclt_last_error(nclt_ctx* c) { return c ? c->err.c_str() : "null context"; }
 extern "C" unsigned long long nclt_ctx_launches(nclt_ctx* c) { return c ? c->launches : 0ull; }
+extern "C" unsigned long long nclt_ctx_alloc_generation(nclt_ctx* c) { return c ? c->alloc_gen : 0ull; }
 
 extern "C" int nclt_ctx_overflow(nclt_ctx* c, int reset) {
     if (!c) return NCLT_ERR_ARG;
@@ -159,10 +164,26 @@ extern "C" int nclt_ctx_profile_read(nclt_ctx* c, double* ms_total, int* n_launc
     int n = 0;
     for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
         float t = 0;
+        if (c->prof_tag.size() > i / 2 && c->prof_tag[i / 2] != 0) continue;
         if (cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]) == cudaSuccess) { ms += t; n++; }
     }
     if (ms_total) *ms_total = ms;
     if (n_launches) *n_launches = n;
+    c->prof_used = 0;
+    return NCLT_OK;
+}
+
+extern "C" int nclt_ctx_profile_read_tags(nclt_ctx* c, double* ms_by_tag, int* n_by_tag) {
+    if (!c || !ms_by_tag || !n_by_tag) return NCLT_ERR_ARG;
+    cudaSetDevice(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < NCLT_PROF_TAGS; ++t) { ms_by_tag[t] = 0; n_by_tag[t] = 0; }
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        float t = 0;
+        int tag = c->prof_tag.size() > i / 2 ? c->prof_tag[i / 2] : 0;
+        if (tag < 0 || tag >= NCLT_PROF_TAGS) continue;
+        if (cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]) == cudaSuccess) { ms_by_tag[tag] += t; n_by_tag[tag]++; }
+    }
     c->prof_used = 0;
     return NCLT_OK;
 }
@@ -181,13 +202,19 @@ static int lib_grow(nclt_ctx* c, nclt_lib* L, int need_desc, int need_kf) {
         int cap = std::max(need_desc, L->cap_desc + L->cap_desc / 2);
         uint4* nd = nullptr;
         float* np = nullptr;
-        CU_TRY(c, cudaMalloc(&nd, (size_t)cap * 32));
-        CU_TRY(c, cudaMalloc(&np, (size_t)cap * 12));
-        if (L->n_desc) {
-            CU_TRY(c, cudaMemcpyAsync(nd, L->d_desc, (size_t)L->n_desc * 32, cudaMemcpyDeviceToDevice, c->stream));
-            CU_TRY(c, cudaMemcpyAsync(np, L->d_pts3d, (size_t)L->n_desc * 12, cudaMemcpyDeviceToDevice, c->stream));
+        cudaError_t e = cudaMalloc(&nd, (size_t)cap * 32);
+        if (e == cudaSuccess) e = cudaMalloc(&np, (size_t)cap * 12);
+        if (e == cudaSuccess && L->n_desc) {
+            e = cudaMemcpyAsync(nd, L->d_desc, (size_t)L->n_desc * 32, cudaMemcpyDeviceToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(np, L->d_pts3d, (size_t)L->n_desc * 12, cudaMemcpyDeviceToDevice, c->stream);
         }
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {      // nothing of the library has been touched yet: drop the new buffers
+            if (nd) cudaFree(nd);
+            if (np) cudaFree(np);
+            return nclt_fail(c, e == cudaErrorMemoryAllocation ? NCLT_ERR_NOMEM : NCLT_ERR_CUDA, "lib_grow (descriptors)", e);
+        }
+        c->alloc_gen++;
         if (L->d_desc) cudaFree(L->d_desc);
         if (L->d_pts3d) cudaFree(L->d_pts3d);
         L->d_desc = nd;
@@ -197,13 +224,19 @@ static int lib_grow(nclt_ctx* c, nclt_lib* L, int need_desc, int need_kf) {
     if (need_kf > L->cap_kf) {
         int cap = std::max(need_kf, L->cap_kf + L->cap_kf / 2 + 16);
         int *ns = nullptr, *nc = nullptr;
-        CU_TRY(c, cudaMalloc(&ns, (size_t)cap * 4));
-        CU_TRY(c, cudaMalloc(&nc, (size_t)cap * 4));
-        if (L->n_kf) {
-            CU_TRY(c, cudaMemcpyAsync(ns, L->d_start, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream));
-            CU_TRY(c, cudaMemcpyAsync(nc, L->d_count, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream));
+        cudaError_t e = cudaMalloc(&ns, (size_t)cap * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&nc, (size_t)cap * 4);
+        if (e == cudaSuccess && L->n_kf) {
+            e = cudaMemcpyAsync(ns, L->d_start, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(nc, L->d_count, (size_t)L->n_kf * 4, cudaMemcpyDeviceToDevice, c->stream);
         }
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            if (ns) cudaFree(ns);
+            if (nc) cudaFree(nc);
+            return nclt_fail(c, e == cudaErrorMemoryAllocation ? NCLT_ERR_NOMEM : NCLT_ERR_CUDA, "lib_grow (keyframe table)", e);
+        }
+        c->alloc_gen++;
         if (L->d_start) cudaFree(L->d_start);
         if (L->d_count) cudaFree(L->d_count);
         L->d_start = ns;
@@ -234,16 +267,23 @@ extern "C" int nclt_lib_create(nclt_ctx* c, int n_kf, const int32_t* kf_offsets,
         L->h_count[k] = cnt;
         L->max_count = std::max(L->max_count, cnt);
     }
+    cudaError_t e = cudaSuccess;
     if (N) {
-        CU_TRY(c, cudaMemcpyAsync(L->d_desc, desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
-        if (pts3d) CU_TRY(c, cudaMemcpyAsync(L->d_pts3d, pts3d, (size_t)N * 12, cudaMemcpyHostToDevice, c->stream));
-        else CU_TRY(c, cudaMemsetAsync(L->d_pts3d, 0, (size_t)N * 12, c->stream));
+        e = cudaMemcpyAsync(L->d_desc, desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess)
+            e = pts3d ? cudaMemcpyAsync(L->d_pts3d, pts3d, (size_t)N * 12, cudaMemcpyHostToDevice, c->stream)
+                      : cudaMemsetAsync(L->d_pts3d, 0, (size_t)N * 12, c->stream);
     }
-    if (n_kf) {
-        CU_TRY(c, cudaMemcpyAsync(L->d_start, L->h_start.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(L->d_count, L->h_count.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream));
+    if (e == cudaSuccess && n_kf) {
+        e = cudaMemcpyAsync(L->d_start, L->h_start.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(L->d_count, L->h_count.data(), (size_t)n_kf * 4, cudaMemcpyHostToDevice, c->stream);
     }
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(c->stream);
+        nclt_lib_destroy(c, L);
+        return nclt_fail(c, NCLT_ERR_CUDA, "lib_create: upload", e);
+    }
     L->n_kf = n_kf;
     L->n_desc = N;
     *out = L;
@@ -462,16 +502,32 @@ static int stage_inputs(nclt_ctx* c, Carver& cv, const uint8_t* q, const int32_t
 static size_t stage_bytes(int B, int Nq, int C) {
     return pad256((size_t)B * Nq * 32) + pad256((size_t)B * 4) + pad256((size_t)B * C * 4);
 }
-static int check_host(nclt_ctx* c, const nclt_lib* L, const void* q, int B, int Nq, int C) {
+// host-pointer entry points: q_n and cand are host arrays, so bad values are rejected here instead of indexing
+// kf_start / kf_count out of bounds on the device
+int nclt_check_host_lists(nclt_ctx* c, const nclt_lib* L, const int32_t* q_n, int B, int Nq, const int32_t* cand, int C) {
+    if (q_n)
+        for (int b = 0; b < B; ++b)
+            if (q_n[b] < 0 || q_n[b] > Nq) return nclt_fail(c, NCLT_ERR_ARG, "q_n entry outside [0, Nq]");
+    if (cand) {
+        const long long n = (long long)B * C;
+        for (long long i = 0; i < n; ++i)
+            if (cand[i] < -1 || cand[i] >= L->n_kf) return nclt_fail(c, NCLT_ERR_ARG, "cand entry outside [-1, n_kf)");
+    }
+    return NCLT_OK;
+}
+static int check_host(nclt_ctx* c, const nclt_lib* L, const void* q, int B, int Nq, int C, const int32_t* q_n = nullptr,
+                      const int32_t* cand = nullptr) {
     if (!c || !L) return nclt_fail(c, NCLT_ERR_ARG, "null handle");
     if (B < 0 || Nq <= 0 || C <= 0 || (B > 0 && !q)) return nclt_fail(c, NCLT_ERR_ARG, "bad B/Nq/C/q");
+    int rc = nclt_check_host_lists(c, L, q_n, B, Nq, cand, C);
+    if (rc) return rc;
     cudaSetDevice(c->device);
     return NCLT_OK;
 }
 
 extern "C" int nclt_match_knn2(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
                                const int32_t* cand, int C, int32_t* out_idx, uint16_t* out_dist) {
-    int rc = check_host(c, L, q, B, Nq, C);
+    int rc = check_host(c, L, q, B, Nq, C, q_n, cand);
     if (rc) return rc;
     if (B == 0) return NCLT_OK;
     ScratchScope scope(c);
@@ -491,7 +547,7 @@ extern "C" int nclt_match_knn2(nclt_ctx* c, const nclt_lib* L, const uint8_t* q,
 
 extern "C" int nclt_match_ratio(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
                                 const int32_t* cand, int C, int num, int den, int32_t* out_pairs, int32_t* out_n) {
-    int rc = check_host(c, L, q, B, Nq, C);
+    int rc = check_host(c, L, q, B, Nq, C, q_n, cand);
     if (rc) return rc;
     if (!out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio outputs null");
     if (B == 0) return NCLT_OK;
@@ -515,7 +571,7 @@ extern "C" int nclt_match_ratio(nclt_ctx* c, const nclt_lib* L, const uint8_t* q
 extern "C" int nclt_match_cross(nclt_ctx* c, const nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq,
                                 const int32_t* cand, int C, int Nmax, int32_t* out_pairs, uint16_t* out_dist,
                                 int32_t* out_n) {
-    int rc = check_host(c, L, q, B, Nq, C);
+    int rc = check_host(c, L, q, B, Nq, C, q_n, cand);
     if (rc) return rc;
     if (!out_pairs || !out_n || Nmax <= 0) return nclt_fail(c, NCLT_ERR_ARG, "cross outputs null");
     if (B == 0) return NCLT_OK;

@@ -36,11 +36,15 @@ struct nclt_ctx {
     int engine = 0;             // 0 = integer pipe (LOP3+POPC), 1 / 2 = tensor cores (fp8 / block-scaled fp4) for all-keyframe ratio matching
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_tag;  // tag of the pair that starts at event 2i (nclt_prof_mark_tag)
     size_t prof_used = 0;
     // async pipeline: PnP problems dropped because a batch produced more than its problem capacity
     int* d_overflow = nullptr;
     unsigned long long* d_tc_clk = nullptr;   // tensor-kernel clock diagnostics (profile mode), 64 x u64
     int tc_clk_launch = 0;
+    // bumped whenever device memory a captured CUDA graph may point into is freed or moved: scratch chunks,
+    // tensor-engine library images / split tables, library growth (nclt_ctx_alloc_generation)
+    unsigned long long alloc_gen = 0;
 };
 
 struct nclt_lib {
@@ -85,16 +89,26 @@ static inline int nclt_fail(nclt_ctx* c, int code, const char* what, cudaError_t
     } while (0)
 
 int nclt_scratch_reserve(nclt_ctx* c, size_t bytes);
-static inline void nclt_prof_mark(nclt_ctx* c) {
+// Profile mode: event pairs around selected launches, summed per tag by nclt_ctx_profile_read[_tags].
+// Tags: 0 Hamming top-2 (the dominant matching kernel), 1 k_occ_frame, 2 k_occ_apply, 3 k_pnp_hypo, 4 k_pnp_score,
+// 5 k_pnp_finish, 6 candidate verification, 7 free.
+#define NCLT_PROF_TAGS 8
+static inline void nclt_prof_mark_tag(nclt_ctx* c, int tag) {
     if (!c->prof) return;
     if (c->prof_used == c->prof_ev.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
         c->prof_ev.push_back(e);
     }
+    if ((c->prof_used & 1) == 0) {
+        if (c->prof_tag.size() <= c->prof_used / 2) c->prof_tag.resize(c->prof_used / 2 + 1);
+        c->prof_tag[c->prof_used / 2] = tag;
+    }
     cudaEventRecord(c->prof_ev[c->prof_used++], c->stream);
 }
+static inline void nclt_prof_mark(nclt_ctx* c) { nclt_prof_mark_tag(c, 0); }
 int nclt_pinned_reserve(nclt_ctx* c, size_t bytes);
+int nclt_check_host_lists(nclt_ctx* c, const nclt_lib* L, const int32_t* q_n, int B, int Nq, const int32_t* cand, int C);
 
 // ---- hamming.cu ----
 struct MatchLaunch {

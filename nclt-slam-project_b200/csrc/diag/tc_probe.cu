@@ -1,11 +1,13 @@
+// libnclt_b200_diag.so - micro-benchmarks and single-tile probes of the tensor-core building blocks (NOT part of the
+// product library libnclt_b200.so; links against it for the context / scratch helpers).  include/nclt_b200_diag.h.
 // Diagnostic: one tcgen05 tile (M = 128 queries x N train rows x K = 256 bits) end to end -
 // validates the operand image layout, the shared-memory / instruction descriptors, the TMEM
 // accumulator layout (f16 and f32) and the packed 16-bit TMEM load against a NumPy popcount
 // (tests/test_tc_gpu.py), and times the building blocks of the tensor-core Hamming path
 // (MMA issue rate, TMEM read rate, half2 min/max rate) for DESIGN.md.
-#include "common.cuh"
-#include "scratch.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../scratch.cuh"
+#include "../tc_common.cuh"
 
 #include <cuda_fp16.h>
 
@@ -241,6 +243,12 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
         uint32_t w = b_bits[r * 8 + (c >> 1)];
         *reinterpret_cast<uint2*>(sB + tc::image_offset4(N, r, c * 8)) = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
     }
+    uint8_t* sAb = sB + (size_t)N * 128;      // bias slabs (magic == 2): 128 x 32 B, N x 32 B
+    uint8_t* sBb = sAb + 4096;
+    if (magic == 2) {
+        tc::mx_fill_bias_slab(sAb, 128, false, tid, 128);
+        tc::mx_fill_bias_slab(sBb, N, true, tid, 128);
+    }
     tc::fence_proxy_async();
     if (tid == 0) { tc::mbar_init(&s_bar, 1); tc::mbar_fence_init(); }
     if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
@@ -250,7 +258,8 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     const uint32_t tmem = s_tmem;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     tc::tmem_st32_const(tmem + lane_base + 480u, 0x7F7F7F7Fu);    // scale factors = 1.0 everywhere
-    if (magic)
+    if (magic == 2) tc::tmem_st16_const(tmem + lane_base + 496u, tc::MX_BIAS_SFA);   // [480,496) = 1.0 (A and B), [496,512) = 2^14
+    if (magic == 1)
         for (int c0 = 0; c0 < N; c0 += 16) tc::tmem_st16_const(tmem + lane_base + (uint32_t)c0, tc::MX_MAGIC);
     tc::tmem_wait_st();
     tc::tc_fence_before();
@@ -259,10 +268,13 @@ __global__ void __launch_bounds__(128) k_tc_probe_mxf4(const uint32_t* __restric
     if (tid == 0) {
         const uint32_t idesc = tc::idesc_mxf4(128, N);
         const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+        if (magic == 2)     // the bias step: constant operands, A scale 2^14
+            tc::mma_mxf4(tmem, tc::smem_desc(tc::smem_u32(sAb), lboA, 128), tc::smem_desc(tc::smem_u32(sBb), lboB, 128), idesc, 0u,
+                         tmem + 496u, tmem + 480u);
         for (int k = 0; k < 4; ++k) {
             uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
             uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
-            tc::mma_mxf4(tmem, da, db, idesc, (k > 0 || magic) ? 1u : 0u, tmem + 480u, tmem + 496u);
+            tc::mma_mxf4(tmem, da, db, idesc, (k > 0 || magic) ? 1u : 0u, tmem + 480u, magic == 2 ? tmem + 480u : tmem + 496u);
         }
         tc::mma_commit(&s_bar);
     }
@@ -295,6 +307,14 @@ __global__ void __launch_bounds__(32 * (4 * NWQ + 2)) k_tc_bench_mxf4(int N, int
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < (16384 + N * 128) / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x2A2A2A2Au, 0xA2A2A2A2u, 0x22AA22AAu, 0xAA22AA22u);
+    uint8_t* sAb = sB + (size_t)N * 128;
+    uint8_t* sBb = sAb + 4096;
+    const bool bias = mode == 8 || mode == 9;
+    if (bias) {
+        tc::mx_fill_bias_slab(sAb, 128, false, tid, blockDim.x);
+        tc::mx_fill_bias_slab(sBb, N, true, tid, blockDim.x);
+        mode = mode == 8 ? 4 : 0;
+    }
     tc::fence_proxy_async();
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 4 * NWQ); }
@@ -308,6 +328,7 @@ __global__ void __launch_bounds__(32 * (4 * NWQ + 2)) k_tc_bench_mxf4(int N, int
     if (warp < 4) {
         const uint32_t lb = (uint32_t)(warp * 32) << 16;
         tc::tmem_st32_const(tmem + lb + 480u, 0x7F7F7F7Fu);
+        if (bias) tc::tmem_st16_const(tmem + lb + 496u, tc::MX_BIAS_SFA);
         if (mode == 2)
             for (int c0 = 0; c0 < 480; c0 += 16) tc::tmem_st16_const(tmem + lb + (uint32_t)c0, tc::MX_MAGIC);
         tc::tmem_wait_st();
@@ -324,10 +345,14 @@ __global__ void __launch_bounds__(32 * (4 * NWQ + 2)) k_tc_bench_mxf4(int N, int
                 int buf = it & 1;
                 if (mode > 0 && it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
                 tc::tc_fence_after();
+                if (bias)
+                    tc::mma_mxf4(tmem + buf * 240, tc::smem_desc(tc::smem_u32(sAb), lboA, 128),
+                                 tc::smem_desc(tc::smem_u32(sBb), lboB, 128), idesc, 0u, tmem + 496u, tmem + 480u);
                 for (int k = 0; k < 4; ++k) {
                     uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
                     uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
-                    tc::mma_mxf4(tmem + buf * 240, da, db, idesc, (k > 0 || mode == 2) ? 1u : 0u, tmem + 480u, tmem + 496u);
+                    tc::mma_mxf4(tmem + buf * 240, da, db, idesc, (k > 0 || mode == 2 || bias) ? 1u : 0u, tmem + 480u,
+                                 bias ? tmem + 480u : tmem + 496u);
                 }
                 tc::mma_commit(&s_full[buf]);
             }
@@ -487,7 +512,7 @@ extern "C" int nclt_tc_probe_mxf4(nclt_ctx* c, const uint8_t* a_desc, const uint
     uint32_t* dout = cv.take<uint32_t>(out_elems);
     CU_TRY(c, cudaMemcpyAsync(da, a_desc, 128 * 32, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(db, b_desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
-    size_t smem = 16384 + (size_t)N * 128;
+    size_t smem = 16384 + (size_t)N * 128 + 4096 + (size_t)N * 32;
     CU_TRY(c, cudaFuncSetAttribute(k_tc_probe_mxf4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tc_probe_mxf4<<<1, 128, smem, c->stream>>>(da, db, N, magic, dout);
     c->launches++;
@@ -505,7 +530,7 @@ extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, do
     long long* cyc = nullptr;
     int blocks = c->sm_count;
     if (cudaMalloc(&sink, 512 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
-    size_t smem = 16384 + (size_t)N * 128;
+    size_t smem = 16384 + (size_t)N * 128 + 4096 + (size_t)N * 32;
     cudaFuncSetAttribute(k_tc_bench_mxf4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_tc_bench_mxf4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_tc_bench_mxf4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -235,6 +235,11 @@ extern "C" int nclt_localize_batch(nclt_ctx* c, const nclt_lib* L, const uint8_t
     if (!out_best_cand || !out_n_inliers || !out_reproj || !out_rvec || !out_tvec)
         return nclt_fail(c, NCLT_ERR_ARG, "localize: null output");
     if (B == 0) { if (out_n_problems) *out_n_problems = 0; return NCLT_OK; }
+    {
+        int rc0 = nclt_check_host_lists(c, L, q_n, B, Nq, cand, C);      // host arrays: reject bad ids before they index device tables
+        if (rc0) return rc0;
+        if (!cand && C > L->n_kf) return nclt_fail(c, NCLT_ERR_ARG, "localize: C exceeds keyframe count with cand == NULL");
+    }
     cudaSetDevice(c->device);
     // host staging lives in its own allocations so that the device pipeline can grow scratch
     const size_t items = (size_t)B * C;

@@ -217,6 +217,32 @@ __device__ __forceinline__ void mma_mxf4(uint32_t tmem_d, uint64_t da, uint64_t 
 // normal fp16 bit pattern that is monotone in -H: .pack::16b loads + half2 max work exactly as on fp16 accumulators.
 constexpr uint32_t MX_MAGIC = 0x4B404000u;
 constexpr uint32_t MX_ZERO16 = 0x4100u;      // low 16 bits at H = 0
+// The same bias produced BY THE TENSOR CORE: one extra K = 64 step whose operands are constant rows
+//   u = 21 x 6.0, 3.0, 1.0, 0...   (A side)      v = 21 x 6.0, 4.0, 1.0, 0...   (B side)
+// so u . v = 21 * 36 + 12 + 1 = 769, with scale factors 2^14 (A, UE8M0 0x8D) x 1.0 (B): 769 * 2^14 = 1.5 * 2^23 + 0x4000.
+// All scale-factor bytes of a region are equal, so the scale-factor layout in TMEM is irrelevant; every partial sum is a
+// multiple of 2^14 below 2^24, i.e. exact whatever the internal alignment of the adder tree.  Issued FIRST (accumulate = 0);
+// the four real steps then add +-1 products to an accumulator of 2^23-magnitude (ulp 1): exact.
+constexpr uint32_t MX_BIAS_SFA = 0x8D8D8D8Du;     // UE8M0 2^14 in every byte
+__host__ __device__ __forceinline__ uint8_t mx_bias_byte(bool b_side, int byte /*0..31 of the 64-nibble row*/) {
+    return byte < 10 ? 0x77 : byte == 10 ? (b_side ? 0x67 : 0x57) : byte == 11 ? 0x02 : 0x00;
+}
+// fills a K = 64 (32 bytes per row) K-major no-swizzle bias slab of `rows` rows; all threads of the CTA
+__device__ __forceinline__ void mx_fill_bias_slab(uint8_t* slab, int rows, bool b_side, int tid, int nthreads) {
+    for (int i = tid; i < rows * 2; i += nthreads) {       // (row, 16-byte k chunk)
+        const int r = i >> 1, kc = i & 1;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v |= (uint32_t)mx_bias_byte(b_side, kc * 16 + j * 4 + b) << (8 * b);
+            w[j] = v;
+        }
+        *reinterpret_cast<uint4*>(slab + (uint32_t)kc * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
 
 // byte offset of element (row r, k-byte k) inside a tile image of `rows` rows
 __host__ __device__ __forceinline__ uint32_t image_offset(int rows, int r, int k) {

@@ -819,6 +819,7 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     if (cch->built_for_kf == L->n_kf && cch->built_for_desc == L->n_desc) return NCLT_OK;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     tc_cache_free(cch);
+    c->alloc_gen++;
     std::vector<LibTile> tiles;
     std::vector<int> row0;
     cch->kf_first_tile.assign(L->n_kf + 1, 0);
@@ -922,6 +923,7 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
         std::vector<int> split_tile(pl->n_splits + 1);
         for (int s = 0; s <= pl->n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / pl->n_splits];
         CU_TRY(c, cudaStreamSynchronize(c->stream));
+        c->alloc_gen++;
         if (cch->d_split) cudaFree(cch->d_split);
         cch->d_split = nullptr;
         CU_TRY(c, cudaMalloc(&cch->d_split, (pl->n_splits + 1) * sizeof(int)));

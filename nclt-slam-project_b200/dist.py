@@ -88,6 +88,9 @@ class ShardedLibrary:
         self.ctx.set_engine(engine)      # tensor engines: per-keyframe top-2 on tcgen05 + exact re-scan of two keyframes
         self.local = LandmarkLibrary(descriptors[lo:hi], None if points3d is None else points3d[lo:hi], ctx=self.ctx)
         self.kf_cum = np.concatenate([[0], np.cumsum(counts)])
+        # set to a list to collect, per call, four CUDA events on self.stream: start, rank-local top-2 done, all-gather
+        # done, merge done (bench.py --workload crossroute reports the collective's share of a step from them)
+        self.timing = None
 
     def flat_top2(self, desc_dev):
         """desc_dev u8[B,Nq,32] CUDA tensor (same on every rank) -> (idx i32[B,Nq,2] global rows,
@@ -104,18 +107,29 @@ class ShardedLibrary:
     def _flat_top2(self, desc_dev, B, Nq):
         from ._lib import lib as _c
         t = self.torch
+        ev = None
+        if self.timing is not None:
+            ev = [t.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(self.stream)
         keys = t.empty((B, Nq, 2), dtype=t.int32, device=self.device)     # u32 payload
         self.ctx.check(_c.nclt_match_flat2_dev(self.ctx.h, self.local.h, desc_dev.data_ptr(), None, B, Nq,
                                                self.row_offset, keys.data_ptr()))
+        if ev:
+            ev[1].record(self.stream)
         if self.world > 1:
             parts = t.empty((self.world, B, Nq, 2), dtype=t.int32, device=self.device)
             self.dist.all_gather_into_tensor(parts, keys)
         else:
             parts = keys[None]
+        if ev:
+            ev[2].record(self.stream)
         idx = t.empty((B, Nq, 2), dtype=t.int32, device=self.device)
         dd = t.empty((B, Nq, 2), dtype=t.int16, device=self.device)       # u16 payload
         self.ctx.check(_c.nclt_merge_top2_dev(self.ctx.h, parts.data_ptr(), parts.shape[0], B * Nq, None,
                                               idx.data_ptr(), dd.data_ptr()))
+        if ev:
+            ev[3].record(self.stream)
+            self.timing.append(tuple(ev))
         return idx, dd.to(t.int32) & 0xFFFF
 
     def row_to_keyframe(self, rows):

@@ -77,12 +77,21 @@ class DeviceLocalizer:
         self.stream = torch.cuda.Stream(self.device)
         self.ctx = _lib.Context(device, self.stream.cuda_stream)
         from .library import LandmarkLibrary
+        self._LandmarkLibrary = LandmarkLibrary
         descs, pts3 = library_arrays
         self.library = LandmarkLibrary(descs, pts3, ctx=self.ctx)
+        self.libraries = [self.library]      # config 4 (15 routes): several libraries share the context's stream and scratch
         self.params = params or LocalizeParams()
         self._out = {}
         self._orb = None
         self._orb_out = None
+
+    def add_library(self, library_arrays):
+        """Another teach library on the same context (one per route, visual_landmark_matcher.py:176-187 loads one
+        pickle per route). Returns its index for run(..., lib=index)."""
+        descs, pts3 = library_arrays
+        self.libraries.append(self._LandmarkLibrary(descs, pts3, ctx=self.ctx))
+        return len(self.libraries) - 1
 
     def _buffers(self, B):
         t = self.torch
@@ -122,18 +131,19 @@ class DeviceLocalizer:
         r.update(n_keypoints=n, keypoints=kp, descriptors=desc)
         return r
 
-    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True, qn_dev=None):
+    def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True, qn_dev=None, lib=0):
         """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors (qn_dev i32[B]: valid rows per frame, default all)
-        -> dict of CUDA tensors + n_problems.
+        -> dict of CUDA tensors + n_problems.  lib: index of the teach library (add_library).
         sync_count=False: fully asynchronous (no host sync; n_problems = -1; check ctx.overflow())."""
         B, Nq = desc_dev.shape[0], desc_dev.shape[1]
+        library = self.libraries[lib]
         Cn = n_cand if cand_dev is None else cand_dev.shape[1]
         if Cn is None:
-            Cn = self.library.n_keyframes
+            Cn = library.n_keyframes
         o = self._buffers(B)
         nprob = C.c_int32(0)
         self.ctx.check(_c.nclt_localize_batch_dev(
-            self.ctx.h, self.library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(),
+            self.ctx.h, library.h, desc_dev.data_ptr(), pts2d_dev.data_ptr(),
             None if qn_dev is None else qn_dev.data_ptr(), B, Nq,
             None if cand_dev is None else cand_dev.data_ptr(), Cn, C.byref(self.params),
             o['best_cand'].data_ptr(), o['n_inliers'].data_ptr(), o['reproj'].data_ptr(), o['rvec'].data_ptr(),
@@ -142,26 +152,47 @@ class DeviceLocalizer:
         r['n_problems'] = int(nprob.value) if sync_count else -1
         return r
 
-    def capture(self, desc_dev, pts2d_dev):
+    def capture(self, desc_dev, pts2d_dev, lib=0):
         """Capture one fully asynchronous localisation step on (desc_dev, pts2d_dev) into a CUDA graph
-        (launch-bound inner loop: ~30 kernels per step).  Returns the torch.cuda.CUDAGraph; replay with
-        `.replay()` on any stream.  The step must have run once before (buffers allocated)."""
+        (launch-bound inner loop: ~30 kernels per step).  Returns the torch.cuda.CUDAGraph; replay it through
+        `self.replay(graph)`.
+
+        The graph's kernel arguments are raw pointers into the context's scratch arena, the tensor-engine library
+        image and its work-split table, and the library arrays.  Ordinary calls on the same context can free or
+        move that memory (a larger batch grows the scratch, a different B rebuilds the split table,
+        nclt_lib_append grows the library and rebuilds its image).  Every such event bumps
+        `ctx.alloc_generation`; the generation is recorded here and `replay` refuses a stale graph."""
         t = self.torch
-        self.run(desc_dev, pts2d_dev, sync_count=False)       # make sure every lazy allocation exists
+        self.run(desc_dev, pts2d_dev, sync_count=False, lib=lib)       # make sure every lazy allocation exists
         t.cuda.synchronize(self.device)
         g = t.cuda.CUDAGraph()
         # 'relaxed': the C ABI makes runtime calls that are not stream operations (cudaSetDevice,
         # cudaFuncSetAttribute, cudaGetLastError) - harmless, but rejected by the default 'global' mode
         with t.cuda.graph(g, stream=self.stream, capture_error_mode='relaxed'):
-            self.run(desc_dev, pts2d_dev, sync_count=False)
+            self.run(desc_dev, pts2d_dev, sync_count=False, lib=lib)
+        gen = self.ctx.alloc_generation
+        g.nclt_generation = gen
+        # the capture pass itself must not have moved anything (it ran once before with the same shapes)
         return g
+
+    def replay(self, graph):
+        """Replay a graph from `capture` on this engine's stream - only if no device allocation it points into has
+        been freed or moved since (otherwise it would run on freed memory and corrupt silently): raises
+        RuntimeError, re-capture then."""
+        if getattr(graph, 'nclt_generation', None) != self.ctx.alloc_generation:
+            raise RuntimeError('stale CUDA graph: the context re-allocated scratch / library memory after the capture '
+                               f'(generation {getattr(graph, "nclt_generation", None)} -> {self.ctx.alloc_generation}); '
+                               're-capture it')
+        graph.replay()
 
 
 class PipelinedLocalizer:
     """Replay engine for BASELINE configs 2/4: two DeviceLocalizers (own CUDA stream and scratch each)
-    take the batches alternately.  The matching kernel of batch i+1 owns the SMs' shared memory, but the
-    tail of batch i (candidate verification, PnP rounds, LM refinement - small-register, no-smem CTAs on
-    the FP64 / integer pipes) co-resides with it, so the tail is hidden behind the next batch's matching.
+    take the batches alternately, so the host never waits between batches and the short kernels of one batch's
+    tail (candidate verification, PnP rounds, LM refinement) are queued behind the other engine's matching kernel.
+    Measured (tools/pipeline_probe.py): the tails do NOT run under the next matching kernel -
+    its 10 warps x 168 registers fill an SM's register file, so no tail CTA fits beside it; what the second
+    engine buys is the removal of host-side gaps, and a step costs matching kernel + tail.
     Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
 
     def __init__(self, library_arrays, device=0, params=None, engine='tensor4'):
@@ -208,6 +239,7 @@ class StreamingLocalizer:
             self.slots.append({'ctx': ctx, 'lib': LandmarkLibrary(descs, pts3, ctx=ctx), 'out': None, 'keep': None,
                                'ticket': -1})
         self.k = 0
+        self.reruns = 0          # batches re-run synchronously because they exceeded the asynchronous PnP capacity
 
     def _pinned(self, shape, dtype):
         t = self.torch.empty(shape, dtype=dtype).pin_memory()
@@ -235,10 +267,18 @@ class StreamingLocalizer:
         if slot['ticket'] != ticket:
             raise ValueError(f'ticket {ticket} has been overwritten (only the last {len(self.slots)} batches are kept)')
         slot['ctx'].sync()
+        # The asynchronous call sizes its PnP buffers for max(4 B, 1024) problems (include/nclt_b200.h); a batch that
+        # produced more (e.g. exp 63's 25 candidates per frame) had the excess dropped and COUNTED.  Such a batch is
+        # run again here synchronously (buffers sized from the real problem count): results are never partial.
+        if slot['ctx'].overflow(reset=True) > 0:
+            desc, pts2d, q_n = slot['keep']
+            localize_batch(slot['lib'], desc, pts2d, q_n=q_n, params=self.params, out=slot['out'], wait=True)
+            self.reruns += 1
         return slot['out']
 
     def overflow(self):
-        return sum(s['ctx'].overflow() for s in self.slots)
+        """Problems dropped by batches whose result() has not been taken yet (result() re-runs such a batch)."""
+        return sum(s['ctx'].overflow(reset=False) for s in self.slots)
 
     def close(self):
         for s in self.slots:

@@ -6,25 +6,39 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    names = set()
-    for h in ('nclt_b200.h', 'nclt_b200_diag.h'):      # the drop-in boundary + the diagnostic entry points
-        src = open(os.path.join(ROOT, 'include', h)).read()
-        src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-        names |= set(re.findall(r'\b(nclt_[a-z0-9_]+)\s*\(', src))
-    return sorted(names)
+def _declared(header):
+    src = open(os.path.join(ROOT, 'include', header)).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(nclt_[a-z0-9_]+)\s*\(', src)))
 
 
 def test_header_symbols_exported():
     path = os.path.join(ROOT, 'nclt-slam-project_b200', 'libnclt_b200.so')
     assert os.path.exists(path), 'build first: python -c "import __graft_entry__ as g; g.build()"'
-    lib = ctypes.CDLL(path)
-    names = _declared()
+    lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    names = _declared('nclt_b200.h')                  # the drop-in boundary
     assert len(names) >= 15
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib.nclt_abi_version.restype = ctypes.c_int
     assert lib.nclt_abi_version() >= 1
+
+
+def test_diagnostics_live_in_their_own_library():
+    """include/nclt_b200_diag.h: the probes / micro-benchmarks are exported by libnclt_b200_diag.so; the product
+    library carries none of them (only the two read-outs of product-kernel state the header marks as such)."""
+    pkg = os.path.join(ROOT, 'nclt-slam-project_b200')
+    lib = ctypes.CDLL(os.path.join(pkg, 'libnclt_b200.so'), mode=ctypes.RTLD_GLOBAL)
+    dpath = os.path.join(pkg, 'libnclt_b200_diag.so')
+    assert os.path.exists(dpath), 'build first: python -c "import __graft_entry__ as g; g.build()"'
+    dlib = ctypes.CDLL(dpath)
+    in_product = {'nclt_ctx_tc_clock', 'nclt_orb_debug_plane'}
+    for n in _declared('nclt_b200_diag.h'):
+        if n in in_product:
+            assert hasattr(lib, n), n
+        else:
+            assert hasattr(dlib, n), n
+            assert not hasattr(lib, n), f'{n} must not ship in the product library'
 
 
 def test_no_cpu_fallback():

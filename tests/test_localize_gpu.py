@@ -105,3 +105,33 @@ def test_streaming_localizer_matches_blocking_call(ctx):
         sl.result(tickets[0])                      # overwritten two submits later
     sl.close()
     lib.close()
+
+
+def test_streaming_localizer_reruns_a_batch_that_overflows(ctx):
+    """The asynchronous call has room for max(4 B, 1024) PnP problems per batch.  A library of 24 identical keyframes
+    makes every frame a problem for every keyframe (64 x 24 = 1536 > 1024): the excess is dropped and counted, and
+    result() must re-run the batch synchronously instead of handing back partial results."""
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import localize_batch, StreamingLocalizer
+    data = synth.make_library(91, n_kf=1, n_desc=120)
+    data['landmarks'] = [dict(data['landmarks'][0]) for _ in range(24)]
+    lms = data['landmarks']
+    desc, pts2d, _, _ = synth.make_frame_batch(data, range(9100, 9164), n_desc=128, n_planted=60)
+    arrays = ([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms])
+    sl = StreamingLocalizer(arrays, engine='int', depth=2)
+    lib = LandmarkLibrary.from_pkl_dict(data, ctx=ctx)
+    want = localize_batch(lib, desc, pts2d)
+    assert want['n_problems'] > 1024
+    t0 = sl.submit(desc, pts2d)
+    t1 = sl.submit(desc[:8], pts2d[:8])               # a batch that fits
+    r0 = {k: np.array(v) for k, v in sl.result(t0).items()}
+    assert sl.reruns == 1
+    r1 = {k: np.array(v) for k, v in sl.result(t1).items()}
+    assert sl.reruns == 1 and sl.overflow() == 0
+    for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
+        assert np.array_equal(r0[k], want[k]), k
+        assert np.array_equal(r1[k], want[k][:8]), k
+    assert (r0['best_cand'] == 0).all()               # identical candidates: the earliest wins (matcher:379)
+    sl.close()
+    lib.close()

@@ -153,3 +153,80 @@ def test_host_path_equals_device_path_and_oracle(ctx, H, W):
     assert a.total_points_integrated == ref.total_points_integrated
     a.close()
     b.close()
+
+
+def _integrate_clouds(m, clouds, tfs):
+    """Several clouds in ONE call (nclt_occ_integrate_points: pts f32[F,Nmax,3], n i32[F], T f64[F,16])."""
+    from nclt_slam_project_b200._lib import lib as _c, ptr
+    nmax = max(max(len(c) for c in clouds), 1)
+    pts = np.zeros((len(clouds), nmax, 3), dtype=np.float32)
+    n = np.array([len(c) for c in clouds], dtype=np.int32)
+    for i, c in enumerate(clouds):
+        pts[i, :len(c)] = c
+    T = np.ascontiguousarray(np.stack([oo.tf_to_matrix(*t) for t in tfs]))
+    m.ctx.check(_c.nclt_occ_integrate_points(m.ctx.h, m.h, ptr(pts), ptr(n), len(clouds), nmax, ptr(T)))
+
+
+def test_fallback_frame_between_fast_frames_keeps_the_order(ctx):
+    """One call: small clouds (fast path), a cloud spanning more than the shared-memory window (exact ray-by-ray
+    path inside the tile gather), small clouds again - all over the same saturating cells."""
+    from nclt_slam_project_b200.mapper import TeachDepthMapper
+    cfg = (-110.0, -45.0, 195.0, 90.0, 0.1)
+    rng = np.random.default_rng(14)
+
+    def cloud(n, reach, side):
+        return np.stack([rng.uniform(0.5, reach, n), rng.uniform(-side, side, n), rng.uniform(-0.2, 1.0, n)], axis=-1).astype(np.float32)
+
+    near = cloud(900, 6, 2)
+    clouds = [near] * 5 + [cloud(6000, 60, 30)] + [near] * 3 + [cloud(900, 6, 2) for _ in range(2)]      # repeated hits saturate
+    tfs = [oo.yaw_tf(-20.0 + (0.05 * i if i > 8 else 0.0), 0.0, 0.2) for i in range(len(clouds))]
+    m = TeachDepthMapper('/tmp/unused', *cfg)
+    ref = oo.OracleMapperInt(*cfg)
+    for c, t in zip(clouds, tfs):
+        ref.cb(c, t)
+    _integrate_clouds(m, clouds, tfs)
+    assert np.array_equal(m.units, ref.grid)
+    assert (ref.grid == 25).any() and (ref.grid == -25).any()
+    assert m.frames_integrated == ref.frames_integrated and m.total_points_integrated == ref.total_points_integrated
+
+
+def test_many_mixed_cells_take_several_bitmap_passes(ctx):
+    """Hits strung along a few bearings: every endpoint cell is also crossed by all the longer rays of its bearing, so
+    hundreds of cells see both passes and hits (more than one 256-cell bitmap pass); order matters in each."""
+    from nclt_slam_project_b200.mapper import TeachDepthMapper
+    cfg = (-30.0, -30.0, 60.0, 60.0, 0.1)
+    rng = np.random.default_rng(15)
+    pts = []
+    for d in np.arange(0.6, 19.0, 0.1):
+        for yaw in (-0.5, -0.2, 0.0, 0.3, 0.6):
+            pts.append((d * np.cos(yaw), d * np.sin(yaw), 0.5))
+    pts = np.array(pts, dtype=np.float32)
+    pts = np.repeat(pts, 4, axis=0)                     # the mapper keeps every 4th point
+    rng.shuffle(pts.reshape(-1, 4, 3))                  # ray order decides the interleaving of passes and hits
+    t = oo.yaw_tf(0.0, 0.0, 0.1)
+    m = TeachDepthMapper('/tmp/unused', *cfg)
+    ref = oo.OracleMapperInt(*cfg)
+    for _ in range(3):
+        ref.cb(pts, t)
+    _integrate_clouds(m, [pts] * 3, [t] * 3)
+    assert np.array_equal(m.units, ref.grid)
+
+
+def test_more_frames_than_one_chunk(ctx):
+    """2100 small frames in one call (stage A / stage B pairs of 2048 frames): grid and counters as the oracle."""
+    from nclt_slam_project_b200.mapper import TeachDepthMapper
+    cfg = (-12.0, -9.0, 40.0, 30.0, 0.1)
+    rng = np.random.default_rng(16)
+    clouds, tfs = [], []
+    for i in range(2100):
+        n = int(rng.integers(0, 60))
+        clouds.append(np.stack([rng.uniform(0.5, 5, n), rng.uniform(-2, 2, n), rng.uniform(-0.3, 1.0, n)], axis=-1).astype(np.float32))
+        tfs.append(oo.yaw_tf(-8.0 + 0.006 * i, 0.002 * i, 0.001 * i))
+    m = TeachDepthMapper('/tmp/unused', *cfg)
+    ref = oo.OracleMapperInt(*cfg)
+    for c, t in zip(clouds, tfs):
+        ref.cb(c, t)
+    _integrate_clouds(m, clouds, tfs)
+    assert np.array_equal(m.units, ref.grid)
+    assert (m.frames_integrated, m.total_points_integrated, m.frames_skipped_empty) == \
+        (ref.frames_integrated, ref.total_points_integrated, ref.frames_skipped_empty)

@@ -68,3 +68,20 @@ def test_integer_model_never_changes_a_class():
         cls_i = 0 if u >= 4 else (254 if u <= -6 else 205)
         assert cls_f == cls_i
         assert abs(float(g) - 0.2 * u) < 2e-5
+
+
+def test_reference_language_restatement(gold):
+    """oracle/occupancy_ref.py (NumPy + the per-cell Python loop, what bench.py's reference arm times for the map
+    workload) against the grids the reference's own modules produced: float32 log-odds bit for bit."""
+    from oracle import occupancy_ref as orf
+    ox, oy, wm, hm, res = gold['cfg'].tolist()
+    m = orf.PyMapper(ox, oy, wm, hm, res)
+    snaps = {int(f): i for i, f in enumerate(gold['grid_snap_frames'])}
+    last = sorted(snaps)[min(1, len(snaps) - 1)]
+    for f in range(last + 1):
+        cloud = orf.depth_to_cloud(_depth(gold, f))
+        n = int(gold['cloud_n'][f])
+        assert np.array_equal(cloud.view(np.uint32), gold['cloud'][f, :n].view(np.uint32)), f
+        m.cb(cloud, oo.tf_to_matrix(*gold['tf'][f]))
+        if f in snaps:
+            assert np.array_equal(m.grid, gold['grid_snaps'][snaps[f]]), f

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _probe(ctx, a, b, c_fmt, ld_mode):
-    from nclt_slam_project_b200._lib import lib
+    from nclt_slam_project_b200._lib import diag
+    lib = diag()
     N = len(b)
     out = np.zeros((128, N // 2 if ld_mode == 1 else N), dtype=np.uint32)
     lib.nclt_tc_probe.restype = C.c_int
@@ -43,7 +44,8 @@ def test_single_tile_matches_popcount(ctx, N):
 def test_single_tile_block_scaled_fp4(ctx, N):
     """kind::mxf4 (+-1.0 as e2m1 nibbles, all scale factors 1.0, f32 accumulators), plain and with the
     accumulators pre-loaded with 1.5 * 2^23 + 0x4000 (the exact integer then sits in the low mantissa bits)."""
-    from nclt_slam_project_b200._lib import lib
+    from nclt_slam_project_b200._lib import diag
+    lib = diag()
     lib.nclt_tc_probe_mxf4.restype = C.c_int
     lib.nclt_tc_probe_mxf4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     rng = np.random.default_rng(1000 + N)
@@ -52,7 +54,7 @@ def test_single_tile_block_scaled_fp4(ctx, N):
     b[:8] = a[:8]                                    # Hamming 0
     b[8:16] = ~a[8:16]                               # Hamming 256
     want = 256 - 2 * oh.hamming_matrix(a, b).astype(np.int64)
-    for magic in (0, 1):
+    for magic in (0, 1, 2):     # 2: the bias comes out of the tensor core itself (an extra K = 64 step with constant operands)
         out = np.zeros((128, N), dtype=np.uint32)
         ctx.check(lib.nclt_tc_probe_mxf4(ctx.h, a.ctypes.data, b.ctypes.data, N, magic, out.ctypes.data))
         if magic:

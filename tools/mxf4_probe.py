@@ -5,7 +5,7 @@ sys.path.insert(0, '/root/repo')
 import nclt_slam_project_b200
 from nclt_slam_project_b200 import _lib
 c = _lib.default_context(0)
-L = _lib.lib
+L = _lib.diag()
 L.nclt_tc_probe_mxf4.restype = C.c_int
 L.nclt_tc_probe_mxf4.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 L.nclt_tc_bench_mxf4.restype = C.c_double
@@ -20,7 +20,7 @@ for trial, N in enumerate((16, 64, 224, 240, 240, 240, 240)):
         a[100:] = 0 if trial == 5 else 255
         b[200:] = rng.integers(0, 2, (N - 200, 32), dtype=np.uint8) * (1 if trial == 5 else 254)
     H = np.unpackbits(a[:, None, :] ^ b[None, :, :], axis=2).sum(2).astype(np.int64)
-    for magic in (0, 1):
+    for magic in (0, 1, 2):
         out = np.zeros((128, N), dtype=np.uint32)
         rc = L.nclt_tc_probe_mxf4(c.h, a.ctypes.data, b.ctypes.data, N, magic, out.ctypes.data)
         if magic:
@@ -31,7 +31,7 @@ for trial, N in enumerate((16, 64, 224, 240, 240, 240, 240)):
         if not ok:
             print(out[:2, :8], (256 - 2 * H)[:2, :8], flush=True)
 for N in (240,):
-    for mode in (0, 4, 5, 6, 7):
+    for mode in (0, 9, 4, 8, 5, 6, 7):
         cyc = C.c_double()
         v = L.nclt_tc_bench_mxf4(c.h, N, 2000, mode, C.byref(cyc))
         print(f'mxf4 N={N} mode={mode}: {v/1e12:.3f} T pairs/s, {cyc.value:.1f} cycles/tile -> {128*N/max(cyc.value,1):.1f} pairs/clk/SM', flush=True)

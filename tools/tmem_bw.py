@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import nclt_slam_project_b200
 from nclt_slam_project_b200 import _lib
 c = _lib.default_context(0)
-L = _lib.lib
+L = _lib.diag()
 L.nclt_tmem_bw.restype = C.c_double
 L.nclt_tmem_bw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
 for with_max in (0, 1):

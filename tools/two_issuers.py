@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import nclt_slam_project_b200
 from nclt_slam_project_b200 import _lib
 c = _lib.default_context(0)
-L = _lib.lib
+L = _lib.diag()
 L.nclt_tc_bench_two_issuers.restype = C.c_double
 L.nclt_tc_bench_two_issuers.argtypes = [C.c_void_p, C.c_int, C.c_int]
 for v in (0, 1):
