@@ -4,7 +4,9 @@
 // checkpoint_a_selftest.py:78-88).  SURVEY.md section 8a rows a5/a6, Appendix A.
 //
 //   k_pnp_sets      one thread per problem: the MWC minimal-set sequence (sequential RNG)
-//   k_pnp_hypo      K3, one thread per (problem, iteration): 5-point EPnP in FP64 -> rvec,tvec
+//   k_pnp_hypo      K3, one lane per (problem, iteration): 5-point EPnP in FP64 -> rvec,tvec; the 12 x 12 Jacobi SVD, the
+//                   6 x 10 system and the small decompositions live in shared memory, one column per lane
+//                   (pnp_epnp_sm.cuh - no local-memory traffic; why not one warp per hypothesis is explained there)
 //   k_pnp_score     K4, one warp per (problem, iteration): project all points in FP64, round to
 //                   float32, float32 squared error <= thr^2, ballot/popc inlier count
 //   k_pnp_finish    K5, one warp per problem: replay OpenCV's sequential best/early-stop rule over
@@ -15,6 +17,7 @@
 // Compiled with -fmad=false: operation order is part of the contract (pnp_math.cuh).
 #include "common.cuh"
 #include "pnp_math.cuh"
+#include "pnp_epnp_sm.cuh"
 
 namespace {
 
@@ -68,6 +71,7 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
 // shrinks as soon as a good model appears) are skipped.
 __global__ void __launch_bounds__(32) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
                                                  int it_lo, int it_cnt, const int* __restrict__ state) {
+    extern __shared__ __align__(16) double sm_cols[];      // [EPNP5_SM_DOUBLES_PER_LANE][32]
     int gg = blockIdx.x * blockDim.x + threadIdx.x;
     if (gg >= eff_P(v) * it_cnt) return;
     int p = gg / it_cnt;
@@ -84,15 +88,18 @@ __global__ void __launch_bounds__(32) k_pnp_hypo(PnpView v, const int* __restric
     const int* idx = sets + (size_t)g * 5;
     const float* obj = v.obj + (size_t)p * v.Nmax * 3;
     const float* img = v.img + (size_t)p * v.Nmax * 2;
-    float so[15], si[10];
+    pnpm::Epnp5In in;
+    in.fu = v.fx; in.fv = v.fy; in.uc = v.cx; in.vc = v.cy;
+#pragma unroll
     for (int i = 0; i < 5; i++) {
         int j = idx[i];
-        so[3 * i] = obj[3 * j]; so[3 * i + 1] = obj[3 * j + 1]; so[3 * i + 2] = obj[3 * j + 2];
-        si[2 * i] = img[2 * j]; si[2 * i + 1] = img[2 * j + 1];
+        in.obj[3 * i] = obj[3 * j]; in.obj[3 * i + 1] = obj[3 * j + 1]; in.obj[3 * i + 2] = obj[3 * j + 2];
+        in.img[2 * i] = img[2 * j]; in.img[2 * i + 1] = img[2 * j + 1];
     }
-    double scratch[pnpm::EPNP5_SCRATCH_DOUBLES];
     double r[3], t[3];
-    pnpm::solvepnp_epnp5(so, si, v.fx, v.fy, v.cx, v.cy, r, t, scratch);
+    const pnpm::SmCol big{sm_cols + threadIdx.x};
+    const pnpm::SmCol aux{sm_cols + pnpm::SM_BIG * pnpm::SM_LANES + threadIdx.x};
+    pnpm::solvepnp_epnp5_sm(in, r, t, big, aux);
     out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
     out[3] = t[0]; out[4] = t[1]; out[5] = t[2];
 }
@@ -428,6 +435,8 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
                unsigned char* ok, double* rvec, double* tvec, int* n_inl, unsigned char* mask, float* mean_err,
                int* best_iter, int* niters, bool score_only) {
     if (P <= 0) return NCLT_OK;
+    // 48.5 KB of dynamic shared memory per 32-lane block (4 blocks per SM); per device, so set on every call
+    CU_TRY(c, cudaFuncSetAttribute(k_pnp_hypo, cudaFuncAttributeMaxDynamicSharedMemorySize, pnpm::EPNP5_SM_BYTES_PER_WARP));
     PnpView v;
     v.obj = obj; v.img = img; v.n = n; v.P = P; v.P_dev = P_dev; v.Nmax = Nmax;
     v.fx = prm->fx; v.fy = prm->fy; v.cx = prm->cx; v.cy = prm->cy;
@@ -455,16 +464,22 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     for (int lo = 0; lo < v.iters; lo += ROUND) {
         int cnt = v.iters - lo < ROUND ? v.iters - lo : ROUND;
         int total = P * cnt;
-        k_pnp_hypo<<<(total + 31) / 32, 32, 0, c->stream>>>(v, buf.sets, buf.models, lo, cnt, buf.state);
+        nclt_prof_mark_tag(c, 3);
+        k_pnp_hypo<<<(total + 31) / 32, 32, pnpm::EPNP5_SM_BYTES_PER_WARP, c->stream>>>(v, buf.sets, buf.models, lo, cnt, buf.state);
+        nclt_prof_mark_tag(c, 3);
         long long threads = (long long)total * 32;
+        nclt_prof_mark_tag(c, 4);
         k_pnp_score<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
+        nclt_prof_mark_tag(c, 4);
         k_pnp_replay<<<(P + 127) / 128, 128, 0, c->stream>>>(v, buf.counts, buf.state, lo + cnt);
         c->launches += 3;
     }
     {
         PnpOut o{ok, rvec, tvec, n_inl, mask, mean_err, best_iter, niters};
         long long threads = (long long)P * 32;
+        nclt_prof_mark_tag(c, 5);
         k_pnp_finish<<<(unsigned)((threads + 31) / 32), 32, 0, c->stream>>>(v, models, buf.state, o);
+        nclt_prof_mark_tag(c, 5);
         c->launches++;
     }
     CU_TRY(c, cudaGetLastError());

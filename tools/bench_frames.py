@@ -67,7 +67,13 @@ def main():
         dl.ctx.check(L.nclt_orb_detect_and_compute_dev(dl.ctx.h, dl._orb._h, q.data_ptr(), 1, B, kp.data_ptr(), desc.data_ptr(), n.data_ptr()))
     torch.cuda.synchronize()
     dt_orb = (time.perf_counter() - t0) / args.steps
-    print(json.dumps({'workload': f'{B} gray 640x480 frames per step vs a {K}-keyframe library taught from images '
+    # one profiled step: device time per kernel family (CUDA events around the launches, nclt_ctx_profile_read_tags)
+    dl.ctx.profile(True)
+    dl.ctx.profile_read_tags()
+    dl.run_frames(q, cand, sync_count=False)
+    fam = {k: {'ms': round(v[0], 4), 'launches': v[1]} for k, v in dl.ctx.profile_read_tags().items() if v[1]}
+    dl.ctx.profile(False)
+    print(json.dumps({'kernel_families_ms_per_step': fam, 'workload': f'{B} gray 640x480 frames per step vs a {K}-keyframe library taught from images '
                                   f'({int(np.mean([len(d) for d in descs]))} landmarks per keyframe), crossCheck against 5 candidate keyframes + PnP-RANSAC',
                       'pnp_problems_per_frame': n_problems / B, 'frames_per_s': B / dt, 'ms_per_step': dt * 1e3, 'orb_share_of_step': dt_orb / dt,
                       'orb_frames_per_s': B / dt_orb, 'localised_to_own_keyframe': ok,
