@@ -32,6 +32,9 @@ int nclt_tc_probe_mxf4(nclt_ctx* ctx, const uint8_t* a_desc, const uint8_t* b_de
 double nclt_tc_bench(nclt_ctx* ctx, int N, int iters, int mode, double* cycles_per_tile);
 double nclt_tc_bench_mxf4(nclt_ctx* ctx, int N, int iters, int mode, double* cycles_per_tile);
 double nclt_tc_bench_mx16(nclt_ctx* ctx, int iters, int variant, double* cycles_per_tile);
+/* the packed design of k_tc4_top2 in isolation (round 2): five MMAs per tile (bias step first), two epilogue sets on
+ * alternate tiles, all 240 columns of a lane quadrant in ONE batch of packed loads (variant 0) or in two (variant 1) */
+double nclt_tc_bench_mxp(nclt_ctx* ctx, int iters, int variant, double* cycles_per_tile);
 /* TMEM read-out: bytes per clock per SM that `warps` warps obtain with `batch` 32-column tcgen05.ld per wait. */
 double nclt_tmem_bw(nclt_ctx* ctx, int warps, int batch, int with_max);
 /* SM clocks per 128 x 240 x 256 mxf4 tile when one thread issues every tile (variant 0) or two warps alternate. */

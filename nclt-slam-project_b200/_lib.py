@@ -261,8 +261,9 @@ def diag():
         for name in ('nclt_tc_bench', 'nclt_tc_bench_mxf4'):
             getattr(d, name).restype = _dbl
             getattr(d, name).argtypes = [_vp, _i, _i, _i, C.POINTER(_dbl)]
-        d.nclt_tc_bench_mx16.restype = _dbl
-        d.nclt_tc_bench_mx16.argtypes = [_vp, _i, _i, C.POINTER(_dbl)]
+        for name in ('nclt_tc_bench_mx16', 'nclt_tc_bench_mxp'):
+            getattr(d, name).restype = _dbl
+            getattr(d, name).argtypes = [_vp, _i, _i, C.POINTER(_dbl)]
         d.nclt_tmem_bw.restype = _dbl
         d.nclt_tmem_bw.argtypes = [_vp, _i, _i, _i]
         d.nclt_tc_bench_two_issuers.restype = _dbl

@@ -104,6 +104,13 @@ extern "C" int nclt_ctx_create(int device, void* stream, nclt_ctx** out) {
         }
         c->own_stream = true;
     }
+    // the capacity-overflow counter of the asynchronous paths (PnP problems, tensor-engine candidates) exists from the
+    // start: allocating it later would not be capturable into a CUDA graph
+    if (cudaMalloc(&c->d_overflow, 4) != cudaSuccess || cudaMemset(c->d_overflow, 0, 4) != cudaSuccess) {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return NCLT_ERR_NOMEM;
+    }
     *out = c;
     return NCLT_OK;
 }
@@ -140,6 +147,16 @@ extern "C" int nclt_ctx_overflow(nclt_ctx* c, int reset) {
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return NCLT_ERR_CUDA;
     if (cudaMemcpy(&v, c->d_overflow, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return NCLT_ERR_CUDA;
     if (reset) cudaMemset(c->d_overflow, 0, 4);
+    return v;
+}
+
+// synchronises, returns the overflow counter and clears it (synchronous entry points that can repair an overflow)
+int nclt_overflow_take(nclt_ctx* c) {
+    if (!c->d_overflow) return 0;
+    int v = 0;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return 0;
+    if (cudaMemcpy(&v, c->d_overflow, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (v) cudaMemset(c->d_overflow, 0, 4);
     return v;
 }
 
@@ -562,6 +579,14 @@ extern "C" int nclt_match_ratio(nclt_ctx* c, const nclt_lib* L, const uint8_t* q
     int32_t* d_pairs = cv.take<int32_t>(rows * 2);
     int32_t* d_n = cv.take<int32_t>(items);
     if ((rc = nclt_match_ratio_dev(c, L, s.d_q, s.d_qn, B, Nq, s.d_cand, C, num, den, d_pairs, d_n))) return rc;
+    if (c->engine == 2 && !cand && nclt_overflow_take(c) > 0) {
+        // the fused fp4 path ran out of candidate capacity (pathological input: most pairs pass the bound test):
+        // this entry point is synchronous, so redo the batch on the integer engine - same results
+        c->engine = 0;
+        rc = nclt_match_ratio_dev(c, L, s.d_q, s.d_qn, B, Nq, s.d_cand, C, num, den, d_pairs, d_n);
+        c->engine = 2;
+        if (rc) return rc;
+    }
     CU_TRY(c, cudaMemcpyAsync(out_pairs, d_pairs, rows * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(out_n, d_n, items * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));

@@ -108,6 +108,7 @@ static inline void nclt_prof_mark_tag(nclt_ctx* c, int tag) {
 }
 static inline void nclt_prof_mark(nclt_ctx* c) { nclt_prof_mark_tag(c, 0); }
 int nclt_pinned_reserve(nclt_ctx* c, size_t bytes);
+int nclt_overflow_take(nclt_ctx* c);
 int nclt_check_host_lists(nclt_ctx* c, const nclt_lib* L, const int32_t* q_n, int B, int Nq, const int32_t* cand, int C);
 
 // ---- hamming.cu ----

@@ -562,6 +562,137 @@ extern "C" double nclt_tc_bench_mxf4(nclt_ctx* c, int N, int iters, int mode, do
     return (double)blocks * iters * 128.0 * N / (ms * 1e-3);
 }
 
+// ---- the packed fp4 design in isolation: five MMAs per 128 x 240 tile (bias step first), two epilogue warp sets that
+// take alternate tiles (set s owns TMEM buffer s), every warp reads ALL 240 columns of its lane quadrant with packed
+// 16-bit loads in ONE batch (120 registers, a single tcgen05.wait::ld), hands the buffer back, then runs the half2 maxima.
+namespace {
+__global__ void __launch_bounds__(320, 1) k_tc_bench_mxp(int iters, int variant, float* sink, long long* cycles) {
+    constexpr int N = 240;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 16384;
+    uint8_t* sAb = sB + (size_t)N * 128;
+    uint8_t* sBb = sAb + 4096;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (16384 + N * 128) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x2A2A2A2Au, 0xA2A2A2A2u, 0x22AA22AAu, 0xAA22AA22u);
+    tc::mx_fill_bias_slab(sAb, 128, false, tid, blockDim.x);
+    tc::mx_fill_bias_slab(sBb, N, true, tid, blockDim.x);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 4); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) { tc::tmem_alloc(&s_tmem, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp < 4) {
+        const uint32_t lb = (uint32_t)(warp * 32) << 16;
+        tc::tmem_st16_const(tmem + lb + 480u, 0x7F7F7F7Fu);
+        tc::tmem_st16_const(tmem + lb + 496u, tc::MX_BIAS_SFA);
+        tc::tmem_wait_st();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    long long t0 = clock64();
+    if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_mxf4(128, N);
+            const uint32_t lboA = 128 * 16, lboB = (uint32_t)N * 16;
+            for (int it = 0; it < iters; ++it) {
+                const int buf = it & 1;
+                if (it >= 2) tc::mbar_wait(&s_empty[buf], ((it >> 1) - 1) & 1);
+                tc::tc_fence_after();
+                tc::mma_mxf4(tmem + buf * 240, tc::smem_desc(tc::smem_u32(sAb), lboA, 128), tc::smem_desc(tc::smem_u32(sBb), lboB, 128),
+                             idesc, 0u, tmem + 496u, tmem + 480u);
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t da = tc::smem_desc(tc::smem_u32(sA) + k * 2 * lboA, lboA, 128);
+                    uint64_t db = tc::smem_desc(tc::smem_u32(sB) + k * 2 * lboB, lboB, 128);
+                    tc::mma_mxf4(tmem + buf * 240, da, db, idesc, 1u, tmem + 480u, tmem + 480u);
+                }
+                tc::mma_commit(&s_full[buf]);
+            }
+        }
+    } else if (warp < 8) {
+        const int quad = warp & 3, set = warp >> 2;
+        const uint32_t lb = (uint32_t)(quad * 32) << 16;
+        __half2 h[4];
+        for (int i = 0; i < 4; ++i) h[i] = __float2half2_rn(0.f);
+        for (int it = set; it < iters; it += 2) {
+            const int buf = set;
+            tc::mbar_wait(&s_full[buf], (it >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t ta = tmem + buf * 240 + lb;
+            uint32_t a[32], b[32], c2[32], d[16], e[8];
+            tc::tmem_ld32_pack16(ta, a);
+            tc::tmem_ld32_pack16(ta + 64, b);
+            if (variant == 1) tc::tmem_wait_ld();          // variant 1: two batches (what 32-bit cells force)
+            tc::tmem_ld32_pack16(ta + 128, c2);
+            tc::tmem_ld16_pack16(ta + 192, d);
+            tc::tmem_ld8_pack16(ta + 224, e);
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s_empty[buf]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                h[j & 3] = __hmax2(h[j & 3], *reinterpret_cast<__half2*>(&a[j]));
+                h[j & 3] = __hmax2(h[j & 3], *reinterpret_cast<__half2*>(&b[j]));
+                h[j & 3] = __hmax2(h[j & 3], *reinterpret_cast<__half2*>(&c2[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j & 3] = __hmax2(h[j & 3], *reinterpret_cast<__half2*>(&d[j]));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j & 3] = __hmax2(h[j & 3], *reinterpret_cast<__half2*>(&e[j]));
+        }
+        float acc = 0;
+        for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); acc += f.x + f.y; }
+        if (acc == 12345.f) sink[tid] = 1.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    long long t1 = clock64();
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" double nclt_tc_bench_mxp(nclt_ctx* c, int iters, int variant, double* cycles_per_tile) {
+    if (!c || iters < 4) return -1.0;
+    cudaSetDevice(c->device);
+    float* sink = nullptr;
+    long long* cyc = nullptr;
+    const int blocks = c->sm_count;
+    if (cudaMalloc(&sink, 512 * 4) != cudaSuccess || cudaMalloc(&cyc, blocks * 8) != cudaSuccess) return -1.0;
+    const size_t smem = 16384 + (size_t)240 * 128 + 4096 + (size_t)240 * 32;
+    cudaFuncSetAttribute(k_tc_bench_mxp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_tc_bench_mxp<<<blocks, 320, smem, c->stream>>>(8, variant, sink, cyc);
+    cudaEventRecord(e0, c->stream);
+    k_tc_bench_mxp<<<blocks, 320, smem, c->stream>>>(iters, variant, sink, cyc);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h = 0;
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    if (cycles_per_tile) *cycles_per_tile = (double)h / iters;
+    c->launches += 2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_mxp", e); return -1.0; }
+    return (double)blocks * iters * 128.0 * 240 / (ms * 1e-3);
+}
+
 // ---- TMEM read-port microbenchmark: NW warps loop tcgen05.ld (32 columns each, `batch` loads per wait) --------
 namespace {
 __global__ void k_tmem_bw(int iters, int batch, int with_max, float* sink, long long* cycles) {

@@ -150,6 +150,15 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
                                   n_pairs);
     }
     if (rc) return rc;
+    if (out_n_problems_host && prm->mode == 0 && c->engine == 2 && !cand && nclt_overflow_take(c) > 0) {
+        // synchronous call and the fused fp4 matcher ran out of candidate capacity: redo the matching on the integer
+        // engine (same results).  The asynchronous mode only counts (nclt_ctx_overflow), as documented.
+        c->engine = 0;
+        rc = nclt_match_ratio_dev(c, L, q, q_n, B, Nq, cand, C, prm->ratio_num, prm->ratio_den,
+                                  reinterpret_cast<int32_t*>(pairs), n_pairs);
+        c->engine = 2;
+        if (rc) return rc;
+    }
     CU_TRY(c, cudaMemsetAsync(d_count, 0, 4, c->stream));
     // The number of PnP problems is data dependent.  Synchronous mode (out_n_problems given): one
     // 4-byte read-back, buffers sized exactly.  Asynchronous mode (out_n_problems == NULL): no host
@@ -159,10 +168,6 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
     int P = 0;
     if (async_mode) {
         P = (int)std::min<size_t>(items, std::max<size_t>((size_t)B * 4, 1024));
-        if (!c->d_overflow) {
-            CU_TRY(c, cudaMalloc(&c->d_overflow, 4));
-            CU_TRY(c, cudaMemsetAsync(c->d_overflow, 0, 4, c->stream));
-        }
     }
     k_select_problems<<<(unsigned)((items + 255) / 256), 256, 0, c->stream>>>(
         n_pairs, (int)items, prm->min_matches, cand, C, L->d_count, prob_item, item_prob, d_count,

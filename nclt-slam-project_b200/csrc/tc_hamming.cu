@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
@@ -322,22 +323,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
 }
 
 // ==============================================================================================
-// Block-scaled fp4 flavour (kind::mxf4, K = 64 per instruction): twice the MMA rate of fp8
-// (64 comparisons/clk/SM at N = 240, tools/mxf4_probe.py), +-1.0 as e2m1 nibbles, all scale factors
-// 1.0, f32 accumulators (the only accumulator type of the block-scaled kinds; exact: |sum| <= 256).
-// The epilogue now reads 32-bit cells, so the TMEM read port (64 cells/clk/SM) is the binding limit:
-// plain three-input f32 maxima (FMNMX3) into 4 disjoint column subsets per thread - with the two
-// column-half warps 8 subsets per (row, keyframe), the same (exact d1, upper bound of d2) contract as
-// the fp8 kernel.  Operand images are half the size (128 B per descriptor): 4 resident query tiles
-// (64 KB) + 3 library stages (3 x 30 KB) leave > 60 KB of shared memory per SM to co-resident kernels.
-// TMEM: accumulator buffers at columns 0 and 240, scale factors at 480..511.
+// Block-scaled fp4 flavour (kind::mxf4, K = 64 per instruction): twice the MMA rate of fp8, +-1.0 as e2m1 nibbles,
+// f32 accumulators (the only accumulator type of the block-scaled kinds; exact: |sum| <= 256).
+//
+// Round-2 design (k_tc4_top2).  The round-1 kernel read 32-bit accumulator cells (two batches of 120 registers per
+// 240-column step, two TMEM round trips while the buffer is held) and spent ~800 clk per step against 480 clk of MMA.
+// Three changes:
+//   1. The bias comes out of the tensor core: a fifth K = 64 step per tile whose operands are constant rows
+//      (tc_common.cuh, mx_bias_byte / MX_BIAS_SFA) adds 1.5 * 2^23 + 0x4000 to every cell, so the LOW 16 bits of the f32
+//      cell are 0x4100 - 2 * Hamming - a positive fp16 bit pattern, monotone in -Hamming.  The epilogue reads with
+//      .pack::16b (two cells per register): all 240 columns of a lane quadrant are 120 registers, ONE batch, and the
+//      maxima are half2 (HMNMX2).  In isolation (tools/mxf4_probe.py, nclt_tc_bench_mxp) this epilogue disappears
+//      behind the five MMAs: 600 clk per tile = the 5-MMA rate itself.
+//   2. The bias row of the LIBRARY side lives in the tile image (2 extra 16-byte K chunks per row, 160 B per row):
+//      padding rows carry a zero bias row, their cells stay 0 - below every valid pattern - so there is no masking
+//      pass and no tcgen05.st in the loop.
+//   3. Tiles are 240 consecutive library rows ACROSS keyframe boundaries (keyframe-aligned tiles wasted a fifth of the
+//      steps on 1000-row keyframes: 4 x 240 + 40; on real 300-row keyframes far more).  The epilogue walks the keyframe
+//      boundaries inside a tile: whole 16-column register groups go to the running maxima of the current keyframe; the
+//      one group a boundary cuts is split per column half.  Tiles restart at "group" boundaries (the first keyframe
+//      boundary after >= 16 tiles' worth of rows), which are the only places a work split may start - so the image
+//      does not depend on the batch size.
+// The kernel either EMITS the Lowe-ratio candidates (row, keyframe) straight from the epilogue (ratio mode: no
+// per-(row, keyframe) plane is ever written) or writes the (d1, d2 bound) plane (flat top-2 mode, config 5).
+// TMEM: accumulator buffers at columns 0 and 240; scale factors 1.0 at [480, 496), 2^14 at [496, 512).
 // ==============================================================================================
 constexpr int MA4 = 4;
 constexpr int A4_TILE_BYTES = 128 * 128;        // 16 KB
 constexpr int B4_ROWS = 240;
-constexpr int B4_STAGE_BYTES = B4_ROWS * 128;   // 30 KB
+constexpr int B4_ROW_BYTES = 160;               // 8 K chunks of the descriptor + 2 of the bias row
+constexpr int B4_STAGE_BYTES = B4_ROWS * B4_ROW_BYTES;   // 38 400
+constexpr int A4_BIAS_BYTES = 128 * 32;         // constant bias slab of the query side
 constexpr int NSTAGE4 = 3;
-constexpr uint32_t SF_COL = 480;
+constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
+constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
+
+// Image row space: every keyframe's rows are padded to a multiple of 16 (zero rows with a zero bias row), so a keyframe
+// boundary always falls between two 16-column register groups of the epilogue.  pstart[k] = first image row of keyframe k.
+struct LibTile4 {
+    uint32_t img_off256;   // byte offset / 256 into the library image
+    uint16_t n;            // rows in the tile image (multiple of 16, <= 240)
+    uint16_t pad_;
+    int prow0;             // image row of column 0
+};
+struct WorkEntry { int item; int q; };
+
+struct Tc4Params {
+    const uint8_t* q_img;      // [n_mtiles][16 KB]
+    const uint8_t* lib_img;
+    const LibTile4* tiles;
+    int n_mtiles, n_groups, n_splits;
+    const int* split_tile;     // [n_splits + 1]
+    const int* split_kf;       // [n_splits + 1] first keyframe of each split
+    const int* kf_pstart;      // [n_kf + 1] image row where every keyframe starts (multiples of 16)
+    const int* kf_count;
+    int n_kf;
+    long long rows_total;      // valid query rows (B * Nq)
+    int Nq;
+    const int* q_n;            // [B] valid rows per frame or null
+    int mode;                  // 0: emit ratio candidates, 1: write the (d1 | d2bound << 16) plane
+    int num, den;
+    WorkEntry* work;
+    int* work_count;           // [0] entries emitted
+    int work_cap;
+    int* overflow;
+    uint32_t* out;             // mode 1: [n_kf][rows_pad]
+    long long rows_pad;
+    unsigned long long* clk;
+    int clk_slot;
+};
 
 __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n_rows, uint8_t* img) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, 16-bit group)
@@ -355,50 +409,139 @@ __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n
     *reinterpret_cast<uint2*>(img + tile * A4_TILE_BYTES + tc::image_offset4(128, r, c * 8)) = v;
 }
 
-__global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile* __restrict__ tiles,
-                                  const int* __restrict__ tile_row0, int n_tiles, uint8_t* img) {
+// tile image: n rows x 160 bytes in the K-major no-swizzle layout (10 K chunks of 16 bytes); chunks 8-9 = bias row
+__global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile4* __restrict__ tiles, int n_tiles,
+                                  const int* __restrict__ kf_pstart, const int* __restrict__ kf_start,
+                                  const int* __restrict__ kf_count, int n_kf, uint8_t* img) {
     int t = blockIdx.x;
     if (t >= n_tiles) return;
-    const LibTile lt = tiles[t];
-    const long long row0 = tile_row0[t];
+    const LibTile4 lt = tiles[t];
     uint8_t* dst = img + (size_t)lt.img_off256 * 256;
-    for (int i = threadIdx.x; i < lt.n * 16; i += blockDim.x) {
-        int r = i >> 4, c = i & 15;
+    for (int i = threadIdx.x; i < lt.n * 20; i += blockDim.x) {
+        const int r = i / 20, g = i % 20;          // g: 8-byte group of the 160-byte row
+        // image row -> (keyframe, row inside it): last keyframe whose image start is <= the row
+        const int pr = lt.prow0 + r;
+        int lo = 0, hi = n_kf;                     // invariant: kf_pstart[lo] <= pr < kf_pstart[hi] (pr < total image rows)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (kf_pstart[mid] <= pr) lo = mid; else hi = mid;
+        }
+        const int local = pr - kf_pstart[lo];
+        const bool valid = pr < kf_pstart[n_kf] && local < kf_count[lo];
+        const size_t src_row = (size_t)kf_start[lo] + local;
         uint2 v = make_uint2(0, 0);
-        if (r < lt.n_valid) {
-            uint32_t w = desc[(row0 + r) * 8 + (c >> 1)];
-            v = tc::expand16_fp4((c & 1) ? (w >> 16) : (w & 0xFFFFu));
-        }
-        *reinterpret_cast<uint2*>(dst + tc::image_offset4(lt.n, r, c * 8)) = v;
-    }
-}
-
-// W accumulator cells of one row -> running maxima of 8 disjoint column subsets
-template <int W>
-__device__ __forceinline__ void max_piece(const uint32_t (&r)[W], float (&M)[8]) {
+        if (valid) {
+            if (g < 16) {
+                uint32_t w = desc[src_row * 8 + (g >> 1)];
+                v = tc::expand16_fp4((g & 1) ? (w >> 16) : (w & 0xFFFFu));
+            } else {
+                uint32_t w[2] = {0, 0};
 #pragma unroll
-    for (int j = 0; j < W; j += 2) M[(j >> 1) & 7] = tc::fmax3(M[(j >> 1) & 7], __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-}
-// Padding columns [valid, cnt) of a keyframe's last tile are overwritten with -inf IN TMEM before the loads, so
-// that the epilogue has a single (unmasked) code path: one copy of the hot loop instead of two per piece.
-__device__ __forceinline__ void premask_padding(uint32_t ta, int valid, int cnt) {
-    int c = valid;
-    while (c < cnt) {
-        if ((c & 7) == 0 && c + 8 <= cnt) {
-            tc::tmem_st8_const(ta + (uint32_t)c, 0xFF800000u);
-            c += 8;
-        } else {
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + (uint32_t)c), "r"(0xFF800000u) : "memory");
-            c += 1;
+                for (int b = 0; b < 8; ++b) w[b >> 2] |= (uint32_t)tc::mx_bias_byte(true, (g - 16) * 8 + b) << (8 * (b & 3));
+                v = make_uint2(w[0], w[1]);
+            }
         }
+        *reinterpret_cast<uint2*>(dst + tc::image_offset4(lt.n, r, g * 8)) = v;
     }
-    tc::tmem_wait_st();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
+// Running maximum of 16-bit patterns (0 or 0x3F00..0x4100) kept in the HIGH half of a 32-bit accumulator.  A packed
+// register holds two patterns (hi : lo); as IEEE f32 bit patterns such words are positive numbers ordered by their high
+// half first, so  acc = max.f32(acc, r, r << 16)  leaves max(acc_hi, hi, lo) in the high half - one shift and one
+// three-input FMNMX per register.  (The packed forms measured ~8 clk per instruction and sub-partition here:
+// HMNMX2 / VHMNMX / VIMNMX.U16x2 made the maxima of a 240-column step cost 1000-2000 clk; FMNMX3 issues every 2 clk.)
+__device__ __forceinline__ uint32_t fmax3u(uint32_t acc, uint32_t x, uint32_t y) {
+    // plain fmaxf (ptxas fuses the pair into one FMNMX3 and is free to schedule it; an inline-asm max is not)
+    return __float_as_uint(fmaxf(fmaxf(__uint_as_float(acc), __uint_as_float(x)), __uint_as_float(y)));
+}
+__device__ __forceinline__ uint32_t fmax2u(uint32_t acc, uint32_t x) {
+    return __float_as_uint(fmaxf(__uint_as_float(acc), __uint_as_float(x)));
+}
+// Two groups of 8 packed registers (32 columns) -> the 8 running maxima.  Pass 1 takes the high halves as they are,
+// then every register is shifted IN PLACE (no temporaries: the kernel sits at its register cap, and ptxas funnels
+// temporaries through one register, serialising shift -> max pairs at ~13 clk each) and pass 2 takes the former low
+// halves.  (The packed 16-bit min / max forms - HMNMX2, VHMNMX, VIMNMX[3].U16x2 - were measured at ~12 clk per
+// instruction and sub-partition; FMNMX3 issues every 2 clk.)
+template <int NA, int NB>
+__device__ __forceinline__ void grp2(uint32_t (&x)[NA], int b0, uint32_t (&y)[NB], int b1, uint32_t (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[b0 + j], y[b1 + j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[b0 + j] <<= 16; y[b1 + j] <<= 16; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[b0 + j], y[b1 + j]);
+}
+template <int NA>
+__device__ __forceinline__ void grp1(uint32_t (&x)[NA], int b0, uint32_t (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[b0 + j], x[b0 + j] << 16);
+}
+
+// Per-warp walk over the keyframe boundaries inside the tiles (all lanes share it; the maxima differ per lane).
+struct SegWalk {
+    int kf;        // keyframe the next column belongs to
+    int end_col;   // first column (tile relative) that is NOT in it any more; INT_MAX once past the split's last keyframe
+};
+struct Acc4 { uint32_t v[4]; };            // running maxima (high halves) of 4 disjoint column subsets
+
+struct Tc4Epilogue {
+    const Tc4Params* p;         // the kernel's __grid_constant__ parameter block (constant bank, no local copy)
+    int kf_stop;            // first keyframe after this split
+    long long row;          // this lane's query row
+    bool row_ok;            // row < rows_total and the step is a real one
+    int lane;
+
+    __device__ __forceinline__ int kf_end_row(int kf) const { return __ldg(p->kf_pstart + kf + 1); }      // image rows
+
+    // Keyframe finished for this lane's row: top-2 of the 8 column-subset maxima -> (exact d1, upper bound of d2).
+    // Inlined at its four call sites only (keyframe advance of the two query tiles, end of split): out-of-line calls
+    // cost a stack frame and a local copy of the parameter block whose dependent loads sat on every step's path.
+    __device__ __forceinline__ void finalize(int kf, const Acc4& a) const {
+        // top-2 of the 4 subset maxima (high halves): second largest of a union = max(min of the maxima, max of the seconds)
+        const uint32_t v0 = a.v[0] >> 16, v1 = a.v[1] >> 16, v2 = a.v[2] >> 16, v3 = a.v[3] >> 16;
+        const uint32_t Ha = max(v0, v1), La = min(v0, v1), Hb = max(v2, v3), Lb = min(v2, v3);
+        const uint32_t m1 = max(Ha, Hb), m2 = max(min(Ha, Hb), max(La, Lb));
+        const uint32_t d1 = m1 ? (tc::MX_ZERO16 - m1) >> 1 : 0xFFFFu;
+        const uint32_t d2 = m2 ? (tc::MX_ZERO16 - m2) >> 1 : 0xFFFFu;
+        if (p->mode == 1) {
+            if (row_ok) p->out[(size_t)kf * p->rows_pad + row] = d1 | (d2 << 16);
+            return;
+        }
+        // ratio mode: the pair can only pass `den * d1 < num * d2` if it passes with the upper bound of d2
+        bool cand = row_ok && d1 != 0xFFFFu && (d2 == 0xFFFFu || (uint32_t)p->den * d1 < (uint32_t)p->num * d2);
+        if (!__any_sync(0xFFFFFFFFu, cand)) return;
+        if (__ldg(p->kf_count + kf) < 2) return;            // knnMatch(k = 2) has no second neighbour: no `good` match
+        int b = 0, q = 0;
+        if (cand) {
+            b = (int)(row / p->Nq);
+            q = (int)(row - (long long)b * p->Nq);
+            if (p->q_n && q >= __ldg(p->q_n + b)) cand = false;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
+        if (!m) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p->work_count, __popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (cand) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < p->work_cap) p->work[pos] = WorkEntry{b * p->n_kf + kf, q};
+            else atomicAdd(p->overflow, 1);
+        }
+    }
+    // next keyframe: finalize the current one for this lane's row, restart the maxima
+    __device__ __forceinline__ void advance(SegWalk& w, Acc4& acc, int row0) const {
+        finalize(w.kf, acc);
+        acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0;
+        ++w.kf;
+        w.end_col = w.kf < kf_stop ? kf_end_row(w.kf) - row0 : INT_MAX;
+    }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constant__ Tc4Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                   // MA4 x 16 KB
-    uint8_t* sB = smem + MA4 * A4_TILE_BYTES;             // NSTAGE4 x 30 KB
+    uint8_t* sAb = sA + MA4 * A4_TILE_BYTES;              // 4 KB bias slab (query side, constant)
+    uint8_t* sB = sAb + A4_BIAS_BYTES;                    // NSTAGE4 x 38 400
     uint8_t* tail = sB + NSTAGE4 * B4_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_full = bars + 0;
@@ -423,6 +566,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
         }
         tc::mbar_fence_init();
     }
+    tc::mx_fill_bias_slab(sAb, 128, false, tid, TC_THREADS);
+    tc::fence_proxy_async();
     if (warp == 0) {
         tc::tmem_alloc(s_tmem, 512);
         tc::tmem_relinquish();
@@ -431,8 +576,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    if (warp < 4) {      // every scale factor = 2^0
-        tc::tmem_st32_const(tmem + ((uint32_t)(warp * 32) << 16) + SF_COL, 0x7F7F7F7Fu);
+    if (warp < 4) {
+        const uint32_t lb = (uint32_t)(warp * 32) << 16;
+        tc::tmem_st16_const(tmem + lb + SF_ONE_COL, 0x7F7F7F7Fu);       // every scale factor of the real steps = 2^0
+        tc::tmem_st16_const(tmem + lb + SF_BIAS_COL, tc::MX_BIAS_SFA);  // query-side scale of the bias step = 2^14
         tc::tmem_wait_st();
     }
     tc::tc_fence_before();
@@ -451,14 +598,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
                 const int split = item / p.n_groups, group = item % p.n_groups;
                 const int m0 = group * MA4;
                 const int ma = min(MA4, p.n_mtiles - m0);
-                tc::mbar_wait(a_empty, (it_cnt & 1) ^ 1);
+                tc::mbar_wait_relaxed(a_empty, (it_cnt & 1) ^ 1);
                 tc::mbar_expect_tx(a_full, (uint32_t)ma * A4_TILE_BYTES);
                 for (int m = 0; m < ma; ++m)
                     tc::bulk_g2s(sA + m * A4_TILE_BYTES, p.q_img + (size_t)(m0 + m) * A4_TILE_BYTES, A4_TILE_BYTES, a_full);
                 for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
-                    const LibTile lt = p.tiles[t];
-                    tc::mbar_wait(&b_empty[s], ph ^ 1);
-                    const uint32_t bytes = (uint32_t)lt.n * 128u;
+                    const LibTile4 lt = p.tiles[t];
+                    tc::mbar_wait_relaxed(&b_empty[s], ph ^ 1);
+                    const uint32_t bytes = (uint32_t)lt.n * B4_ROW_BYTES;
                     tc::mbar_expect_tx(&b_full[s], bytes);
                     tc::bulk_g2s(sB + s * B4_STAGE_BYTES, p.lib_img + (size_t)lt.img_off256 * 256, bytes, &b_full[s]);
                     if (++s == NSTAGE4) { s = 0; ph ^= 1; }
@@ -467,50 +614,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
         }
     } else if (warp == 9) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // The whole warp runs the loops (warp-uniform control flow and operands); one elected lane issues the
+        // tcgen05 instructions.  Descriptors are base + offset: a lone lane building each 64-bit descriptor from
+        // scratch (~22 dependent scalar instructions per MMA, 800 clk per 5-MMA step) was slower than the tensor pipe.
+        {
             uint32_t it_cnt = 0, s = 0, ph = 0, st = 0;
+            const uint64_t da_bias = tc::smem_desc(tc::smem_u32(sAb), 2048u, 128u);
+            const uint64_t da0 = tc::smem_desc(tc::smem_u32(sA), 2048u, 128u);       // + (m * 16 KB + k * 4 KB) / 16
+            const uint64_t db0 = tc::smem_desc(tc::smem_u32(sB), 0u, 128u);          // + stage / 16 + (n << 16) + 2 k n
+#ifdef NCLT_TC_TIMING
+            long long mw[3] = {0, 0, 0}, ml = clock64();
+#define MT(i) { long long now_ = clock64(); mw[i] += now_ - ml; ml = now_; }
+#else
+#define MT(i)
+#endif
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
                 const int split = item / p.n_groups, group = item % p.n_groups;
                 const int ma = min(MA4, p.n_mtiles - group * MA4);
                 tc::mbar_wait(a_full, it_cnt & 1);
                 for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
-                    const int n = p.tiles[t].n;
+                    const uint32_t n = p.tiles[t].n;
+                    MT(2);
                     tc::mbar_wait(&b_full[s], ph);
                     tc::tc_fence_after();
-                    const uint32_t idesc = tc::idesc_mxf4(128, n);
-                    const uint32_t lboB = (uint32_t)n * 16u;
-                    const uint32_t bbase = tc::smem_u32(sB + s * B4_STAGE_BYTES);
+                    MT(0);
+                    const uint32_t idesc = tc::idesc_mxf4(128, (int)n);
+                    // K-major, no swizzle: LBO = n * 16 bytes -> descriptor field n; K chunk pair k starts 2 k n * 16 bytes in
+                    const uint64_t db_tile = db0 + (uint64_t)(s * (B4_STAGE_BYTES >> 4)) + ((uint64_t)n << 16);
+                    const uint64_t db_bias = db_tile + 8u * n;
                     // an odd number of query tiles gets one empty step per library tile: steps per tile stay even,
                     // so epilogue set s always owns accumulator buffer s and sees every phase of its barriers
                     const int ma_pad = (ma + 1) & ~1;
                     for (int m = 0; m < ma_pad; ++m, ++st) {
                         const int buf = st & 1;
+                        MT(2);
                         tc::mbar_wait(&acc_empty[buf], ((st >> 1) & 1) ^ 1);
                         tc::tc_fence_after();
-                        if (m < ma) {
-                            const uint32_t abase = tc::smem_u32(sA + m * A4_TILE_BYTES);
+                        MT(1);
+                        if (tc::elect_one()) {
+                            if (m < ma) {
+                                const uint64_t da_m = da0 + (uint64_t)(m * (A4_TILE_BYTES >> 4));
+                                const uint32_t d = tmem + buf * B4_ROWS;
+                                // bias step first (accumulate = 0): 1.5 * 2^23 + 0x4000 in every cell of a non-padding row
+                                tc::mma_mxf4(d, da_bias, db_bias, idesc, 0u, tmem + SF_BIAS_COL, tmem + SF_ONE_COL);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint64_t da = tc::smem_desc(abase + k * 4096u, 2048u, 128u);
-                                uint64_t db = tc::smem_desc(bbase + k * 2u * lboB, lboB, 128u);
-                                tc::mma_mxf4(tmem + buf * B4_ROWS, da, db, idesc, k > 0 ? 1u : 0u, tmem + SF_COL, tmem + SF_COL + 16u);
+                                for (int k = 0; k < 4; ++k)
+                                    tc::mma_mxf4(d, da_m + (uint64_t)(k * 256), db_tile + (uint64_t)(2u * k * n), idesc, 1u,
+                                                 tmem + SF_ONE_COL, tmem + SF_ONE_COL);
                             }
+                            tc::mma_commit(&acc_full[buf]);
                         }
-                        tc::mma_commit(&acc_full[buf]);
+                        __syncwarp();
                     }
-                    tc::mma_commit(&b_empty[s]);
+                    if (tc::elect_one()) tc::mma_commit(&b_empty[s]);
+                    __syncwarp();
                     if (++s == NSTAGE4) { s = 0; ph ^= 1; }
                 }
-                tc::mma_commit(a_empty);
+                if (tc::elect_one()) tc::mma_commit(a_empty);
+                __syncwarp();
             }
+#ifdef NCLT_TC_TIMING
+            MT(2);
+            if (lane == 0 && blockIdx.x == 0 && p.clk) { p.clk[12] = mw[0]; p.clk[13] = mw[1]; p.clk[14] = mw[2]; }   // waits: b_full, acc_empty; issue
+#endif
         }
     } else {
         // =========================== epilogue (warps 0-7) ===========================
-        // Warps 0-3 take the even steps (query tiles) of every library tile, warps 4-7 the odd ones; warp w reads
-        // TMEM lane quadrant w % 4, ALL columns, in two batches of n/2 columns (<= 120 registers).  The two warps
-        // that share an SM sub-partition are therefore in different phases - one waits on tcgen05.ld while the
-        // other runs its FMNMX3 chain - and each warp has two step periods for its load -> max -> load -> max chain.
-        // A row's 8 subset maxima live in one thread: no cross-warp merge at the end of a keyframe.
+        // Warps 0-3 take the even steps (query tiles) of every library tile, warps 4-7 the odd ones; warp w reads TMEM
+        // lane quadrant w % 4, ALL columns, packed, in one batch, and hands the buffer back before the maxima.
         const int quad = warp & 3, set = warp >> 2;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         uint32_t st_base = 0;
@@ -525,19 +696,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
             const int m0 = group * MA4;
             const int ma = min(MA4, p.n_mtiles - m0);
             const int ma_pad = (ma + 1) & ~1;
-            float M[MA4 / 2][8];
+            Acc4 acc[MA4 / 2];
 #pragma unroll
-            for (int mm = 0; mm < MA4 / 2; ++mm)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) M[mm][k] = -INFINITY;
+            for (int mm = 0; mm < MA4 / 2; ++mm) acc[mm].v[0] = acc[mm].v[1] = acc[mm].v[2] = acc[mm].v[3] = 0;
+            Tc4Epilogue ep{&p, p.split_kf[split + 1], 0, false, lane};
+            int cur_kf = p.split_kf[split];                   // keyframe walk, carried from tile to tile
+            int cur_end_row = cur_kf < ep.kf_stop ? ep.kf_end_row(cur_kf) : INT_MAX;
             const int t_end = p.split_tile[split + 1];
-            LibTile nxt = p.tiles[p.split_tile[split]];
             for (int t = p.split_tile[split]; t < t_end; ++t) {
-                const LibTile lt = nxt;
-                nxt = p.tiles[t + 1];                         // prefetch (the table carries one sentinel entry)
+                LibTile4 lt;                                  // 20 KB table, L1 resident; read while the MMA is still running
+                lt.n = __ldg(&p.tiles[t].n);
+                lt.prow0 = __ldg(&p.tiles[t].prow0);
                 const int n = lt.n;
-                const int cnt = n >> 1;                       // columns per batch: multiple of 8, <= 120
-                const int o16 = cnt & ~31, o8 = cnt & ~15;
+                const int kf0 = cur_kf;
+                const int end0 = cur_end_row == INT_MAX ? INT_MAX : cur_end_row - lt.prow0;
+                SegWalk wk_after{kf0, end0};
 #pragma unroll
                 for (int mm = 0; mm < MA4 / 2; ++mm) {
                     const int m = set + 2 * mm;
@@ -555,62 +728,103 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(TcParams p) {
                         break;
                     }
                     const uint32_t ta = tmem + buf * B4_ROWS + lane_base;
-                    if ((int)lt.n_valid < n) premask_padding(ta, lt.n_valid, n);
                     uint32_t a[32], b[32], c2[32], d[16], e[8];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t th = ta + (uint32_t)(half * cnt);
-                        if (cnt >= 32) tc::tmem_ld32(th, a);
-                        if (cnt >= 64) tc::tmem_ld32(th + 32, b);
-                        if (cnt >= 96) tc::tmem_ld32(th + 64, c2);
-                        if (cnt & 16) tc::tmem_ld16(th + o16, d);
-                        if (cnt & 8) tc::tmem_ld8(th + o8, e);
-                        tc::tmem_wait_ld();
-                        if (half == 1) {
-                            // every column is in registers: hand the buffer back before the last maxima
-                            TT(2);
-                            tc::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-                            TT(3);
-                        }
-                        if (cnt >= 32) max_piece<32>(a, M[mm]);
-                        if (cnt >= 64) max_piece<32>(b, M[mm]);
-                        if (cnt >= 96) max_piece<32>(c2, M[mm]);
-                        if (cnt & 16) max_piece<16>(d, M[mm]);
-                        if (cnt & 8) max_piece<8>(e, M[mm]);
+                    const int o64 = n & ~63, rem = n & 63;
+                    if (n == B4_ROWS) {          // the common full tile: five loads back to back, no branches in between
+                        tc::tmem_ld32_pack16(ta, a);
+                        tc::tmem_ld32_pack16(ta + 64, b);
+                        tc::tmem_ld32_pack16(ta + 128, c2);
+                        tc::tmem_ld16_pack16(ta + 192, d);
+                        tc::tmem_ld8_pack16(ta + 224, e);
+                    } else {
+                        if (n >= 64) tc::tmem_ld32_pack16(ta, a);
+                        if (n >= 128) tc::tmem_ld32_pack16(ta + 64, b);
+                        if (n >= 192) tc::tmem_ld32_pack16(ta + 128, c2);
+                        if (rem & 32) tc::tmem_ld16_pack16(ta + (uint32_t)o64, d);
+                        if (rem & 16) tc::tmem_ld8_pack16(ta + (uint32_t)(o64 + (rem & 32)), e);
                     }
+                    tc::tmem_wait_ld();
+#ifdef NCLT_TC_TIMING
+                    {   // make the loaded registers observably ready before the clock is read
+                        uint32_t probe_ = 0;
+                        if (n >= 64) probe_ ^= a[31];
+                        if (n >= 128) probe_ ^= b[31];
+                        if (n >= 192) probe_ ^= c2[31];
+                        if (rem & 32) probe_ ^= d[15];
+                        if (rem & 16) probe_ ^= e[7];
+                        if (probe_ == 0x12345u) s_tmem[1] = probe_;
+                    }
+#endif
+                    TT(2);
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);     // every column is in registers
+                    TT(3);
+                    ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                    ep.row_ok = ep.row < p.rows_total;
+                    SegWalk wk{kf0, end0};
+                    Acc4& A = acc[mm];
+                    // Keyframes are padded to whole 16-column groups, so a keyframe ends between two register groups:
+                    // groups [g, g_b) go to the running maxima of the current keyframe, then the walk advances.
+#define NCLT_GRP(arr, base) { grp1(arr, (base), A.v); }
+                    if (end0 >= n) {
+                        // no keyframe ends inside this tile (3 tiles in 4 with 1000-row keyframes): straight-line maxima
+                        if (n >= 64) { grp2(a, 0, a, 8, A.v); grp2(a, 16, a, 24, A.v); }
+                        if (n >= 128) { grp2(b, 0, b, 8, A.v); grp2(b, 16, b, 24, A.v); }
+                        if (n >= 192) { grp2(c2, 0, c2, 8, A.v); grp2(c2, 16, c2, 24, A.v); }
+                        if (rem & 32) { grp2(d, 0, d, 8, A.v); }
+                        if (rem & 16) { grp1(e, 0, A.v); }
+                    } else {
+                        // a keyframe ends inside the tile: groups [g_lo, g_b) go to the current keyframe, the walk
+                        // advances, and so on.  a, b, c2 hold the groups below column o64; d / e the tail.
+                        const int n_grp = n >> 4;
+                        const int gd = o64 >> 4, ge = (o64 + (rem & 32)) >> 4;
+                        int g_lo = 0;
+#pragma unroll 1
+                        for (;;) {
+                            const int g_b = wk.end_col >= n ? n_grp : (wk.end_col >> 4);
+#pragma unroll
+                            for (int g = 0; g < 12; ++g) {
+                                if (16 * g < o64 && g >= g_lo && g < g_b) {
+                                    if (g < 4) NCLT_GRP(a, 8 * g)
+                                    else if (g < 8) NCLT_GRP(b, 8 * (g - 4))
+                                    else NCLT_GRP(c2, 8 * (g - 8))
+                                }
+                            }
+                            if (rem & 32) {
+                                if (gd >= g_lo && gd < g_b) NCLT_GRP(d, 0)
+                                if (gd + 1 >= g_lo && gd + 1 < g_b) NCLT_GRP(d, 8)
+                            }
+                            if ((rem & 16) && ge >= g_lo && ge < g_b) NCLT_GRP(e, 0)
+                            if (g_b >= n_grp) break;
+                            g_lo = g_b;
+                            ep.advance(wk, A, lt.prow0);
+                        }
+                    }
+#undef NCLT_GRP
+                    wk_after = wk;
                     TT(4);
                 }
                 st_base += (uint32_t)ma_pad;
-                if (lt.last_of_kf) {
-                    // ---- keyframe finished: top-2 of the 8 subset maxima of each row
+                // every real step of this warp ended its walk in the same state; a warp without a real step does not walk
+                cur_kf = wk_after.kf;
+                cur_end_row = wk_after.end_col == INT_MAX ? INT_MAX : wk_after.end_col + lt.prow0;
+            }
+            // ---- end of the split: the keyframes that are still open (the last one, trailing empty ones)
 #pragma unroll
-                    for (int mm = 0; mm < MA4 / 2; ++mm) {
-                        const int m = set + 2 * mm;
-                        float h[4], l[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            h[k] = fmaxf(M[mm][2 * k], M[mm][2 * k + 1]);
-                            l[k] = fminf(M[mm][2 * k], M[mm][2 * k + 1]);
-                        }
-                        const float ha = fmaxf(h[0], h[1]), la = fmaxf(fminf(h[0], h[1]), h[0] >= h[1] ? l[0] : l[1]);
-                        const float hb = fmaxf(h[2], h[3]), lb = fmaxf(fminf(h[2], h[3]), h[2] >= h[3] ? l[2] : l[3]);
-                        const float g1 = fmaxf(ha, hb), g2 = fmaxf(fminf(ha, hb), ha >= hb ? la : lb);
-                        if (m < ma) {
-                            const long long row = (long long)(m0 + m) * 128 + quad * 32 + lane;
-                            uint32_t d1 = g1 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g1) * 0.5f);
-                            uint32_t d2 = g2 < -300.f ? 0xFFFFu : (uint32_t)((256.f - g2) * 0.5f);
-                            p.out[(size_t)lt.kf * p.rows_pad + row] = d1 | (d2 << 16);   // (exact d1, upper bound of d2)
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) M[mm][k] = -INFINITY;
-                    }
+            for (int mm = 0; mm < MA4 / 2; ++mm) {
+                const int m = set + 2 * mm;
+                if (m >= ma) break;
+                ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                ep.row_ok = ep.row < p.rows_total;
+                for (int kf = cur_kf; kf < ep.kf_stop; ++kf) {
+                    ep.finalize(kf, acc[mm]);
+                    acc[mm].v[0] = acc[mm].v[1] = acc[mm].v[2] = acc[mm].v[3] = 0;
                 }
             }
         }
 #ifdef NCLT_TC_TIMING
-        // phase cycles of epilogue warps 0 and 4 of CTA 0: [other (loop, finalize), wait-full, loads + first maxima, release, last maxima]
+        // phase cycles of epilogue warps 0 and 4 of CTA 0: [other (loop, finalize), wait-full, loads, release, maxima]
         if (blockIdx.x == 0 && lane == 0 && quad == 0 && p.clk)
             for (int i = 0; i < 5; ++i) p.clk[2 + set * 5 + i] = (unsigned long long)tt_acc[i];
 #endif
@@ -768,6 +982,104 @@ __global__ void __launch_bounds__(128) k_tc_compact(int n_items, int Nq, int2* o
     if (lane == 0) out_n[item] = kept;
 }
 
+// ---- fused fp4 ratio path: candidates come straight out of the matching kernel as (item, query row) entries ----------
+//   k_tc4_verify  one warp per entry: exact best (lowest train row on ties) and exact second-best distance over the
+//                 keyframe, exact ratio test; a passing entry sets bit `q` in its item's bitmap and stores the train row.
+//                 Items get a bitmap slot on first use (atomicCAS on the item -> slot map).
+//   k_tc4_emit    one warp per used slot: bitmap -> (queryIdx, trainIdx) pairs in increasing queryIdx, out_n[item]
+struct Tc4Pool {
+    int* item_slot;        // [n_items] -1 = none, -2 = being allocated, else slot
+    int* slot_item;        // [slots]
+    int* slot_count;       // [1]
+    uint32_t* bitmap;      // [slots][nwords]
+    int* tidx;             // [slots][Nq]
+    int slots, nwords;
+};
+
+__global__ void __launch_bounds__(128) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
+                                                    int work_cap, int Nq, int n_kf, int num, int den,
+                                                    const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
+                                                    const int* __restrict__ kf_start, const int* __restrict__ kf_count,
+                                                    Tc4Pool pool, int* overflow) {
+    const int lane = threadIdx.x & 31;
+    const int n_work = min(*work_count, work_cap);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += warps) {
+        const WorkEntry we = work[w];
+        const int b = we.item / n_kf, kf = we.item % n_kf;
+        const int nt = kf_count[kf];
+        const uint4* trows = lib_desc + (size_t)kf_start[kf] * 2;
+        const uint4* qa = q_desc + ((size_t)b * Nq + we.q) * 2;
+        const uint4 a0 = __ldg(qa), a1 = __ldg(qa + 1);
+        uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;      // keys: dist << 16 | train row
+        for (int j = lane; j < nt; j += 32) {
+            const uint4 t0 = __ldg(trows + 2 * j), t1 = __ldg(trows + 2 * j + 1);
+            uint32_t d = __popc(a0.x ^ t0.x) + __popc(a0.y ^ t0.y) + __popc(a0.z ^ t0.z) + __popc(a0.w ^ t0.w) +
+                         __popc(a1.x ^ t1.x) + __popc(a1.y ^ t1.y) + __popc(a1.z ^ t1.z) + __popc(a1.w ^ t1.w);
+            uint32_t key = (d << 16) | (uint32_t)j;
+            uint32_t mx = max(m1, key);
+            m1 = min(m1, key);
+            m2 = min(m2, mx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o);
+            uint32_t lo = min(m1, o1), hi = max(m1, o1);
+            m2 = min(min(m2, o2), hi);
+            m1 = lo;
+        }
+        const bool pass = m2 != 0xFFFFFFFFu && (uint32_t)den * (m1 >> 16) < (uint32_t)num * (m2 >> 16);
+        if (!pass) continue;
+        if (lane == 0) {
+            int slot = atomicCAS(&pool.item_slot[we.item], -1, -2);
+            if (slot == -1) {                               // first passing entry of this item: take a slot
+                slot = atomicAdd(pool.slot_count, 1);
+                if (slot < pool.slots) pool.slot_item[slot] = we.item;
+                else { atomicAdd(overflow, 1); slot = -3; }
+                __threadfence();
+                atomicExch(&pool.item_slot[we.item], slot);
+            } else {
+                while (slot == -2) slot = atomicAdd(&pool.item_slot[we.item], 0);      // the owner publishes within a few instructions
+            }
+            if (slot >= 0) {
+                pool.tidx[(size_t)slot * Nq + we.q] = (int)(m1 & 0xFFFFu);
+                atomicOr(&pool.bitmap[(size_t)slot * pool.nwords + (we.q >> 5)], 1u << (we.q & 31));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_tc4_emit(Tc4Pool pool, int Nq, int2* out_pairs, int* out_n) {
+    const int lane = threadIdx.x & 31;
+    const int n_slots = min(*pool.slot_count, pool.slots);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slots; s += warps) {
+        const int item = pool.slot_item[s];
+        int2* dst = out_pairs + (size_t)item * Nq;
+        const int* tidx = pool.tidx + (size_t)s * Nq;
+        int base = 0;
+        for (int w0 = 0; w0 < pool.nwords; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t bits = w < pool.nwords ? pool.bitmap[(size_t)s * pool.nwords + w] : 0u;
+            int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int pos = base + incl - cnt;
+            while (bits) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int q = w * 32 + bit;
+                dst[pos++] = make_int2(q, tidx[q]);
+            }
+            base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) out_n[item] = base;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -783,16 +1095,27 @@ struct TcLibCache {
     // so that a whole localisation step can be captured into a CUDA graph)
     int* d_split = nullptr;
     int split_groups = -1, split_n = 0;
+    // fp4 flavour: tiles run across keyframe boundaries; a work split may only start where a tile GROUP starts
+    LibTile4* d_tiles4 = nullptr;
+    std::vector<int> grp_tile, grp_kf;   // [n_grp + 1] first tile / first keyframe of every group
+    int* d_split_kf = nullptr;           // [n_splits + 1] beside d_split
+    int* d_pstart = nullptr;             // [n_kf + 1] image row of every keyframe's first row (keyframes padded to 16 rows)
 };
 
 static void tc_cache_free(TcLibCache* cch) {
     if (!cch) return;
     if (cch->d_img) cudaFree(cch->d_img);
     if (cch->d_tiles) cudaFree(cch->d_tiles);
+    if (cch->d_tiles4) cudaFree(cch->d_tiles4);
     if (cch->d_split) cudaFree(cch->d_split);
+    if (cch->d_split_kf) cudaFree(cch->d_split_kf);
+    if (cch->d_pstart) cudaFree(cch->d_pstart);
+    cch->d_pstart = nullptr;
     cch->d_img = nullptr;
     cch->d_tiles = nullptr;
+    cch->d_tiles4 = nullptr;
     cch->d_split = nullptr;
+    cch->d_split_kf = nullptr;
     cch->split_groups = -1;
 }
 
@@ -807,8 +1130,8 @@ void nclt_tc_release(nclt_lib* L) {
     }
 }
 
-// fp4 = false: fp8 images (256 B per descriptor, tiles of <= 256 rows); fp4 = true: e2m1 images (128 B per
-// descriptor, tiles of <= 240 rows, a keyframe's rows spread evenly over its tiles)
+// fp4 = false: fp8 images (256 B per descriptor, keyframe-aligned tiles of <= 256 rows); fp4 = true: e2m1 images
+// (128 B per descriptor + 32 B bias row, 240-row tiles across keyframe boundaries)
 static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     void** slot = fp4 ? &L->tc4_cache : &L->tc_cache;
     TcLibCache* cch = static_cast<TcLibCache*>(*slot);
@@ -820,6 +1143,52 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     tc_cache_free(cch);
     c->alloc_gen++;
+    if (fp4) {
+        // 240-row tiles over the IMAGE row space (every keyframe padded to a multiple of 16 rows), across keyframe
+        // boundaries.  A tile group closes (its last tile is short) at the first keyframe boundary after GROUP_MIN_ROWS
+        // image rows; work splits start at group boundaries.
+        std::vector<int> pstart(L->n_kf + 1, 0);
+        for (int k = 0; k < L->n_kf; ++k) pstart[k + 1] = pstart[k] + ((L->h_count[k] + 15) & ~15);
+        std::vector<LibTile4> tiles;
+        cch->grp_tile.clear();
+        cch->grp_kf.clear();
+        size_t off256 = 0;
+        int k = 0;
+        while (k < L->n_kf) {
+            cch->grp_tile.push_back((int)tiles.size());
+            cch->grp_kf.push_back(k);
+            const int row_a = pstart[k];
+            int row_b = row_a;
+            while (k < L->n_kf && (row_b - row_a < GROUP_MIN_ROWS || L->h_count[k] == 0)) {
+                row_b = pstart[k + 1];
+                ++k;
+            }
+            for (int r = row_a; r < row_b; r += B4_ROWS) {
+                const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 16
+                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, 0, r});
+                off256 += (size_t)n * B4_ROW_BYTES / 256;          // n * 160 bytes = (n / 16) * 2560
+            }
+        }
+        cch->grp_tile.push_back((int)tiles.size());
+        cch->grp_kf.push_back(L->n_kf);
+        cch->n_tiles = (int)tiles.size();
+        tiles.push_back(LibTile4{0, 16, 0, 0});        // sentinel: the epilogue prefetches entry t + 1
+        CU_TRY(c, cudaMalloc(&cch->d_pstart, pstart.size() * sizeof(int)));
+        CU_TRY(c, cudaMemcpyAsync(cch->d_pstart, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if (cch->n_tiles > 0) {
+            CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
+            CU_TRY(c, cudaMalloc(&cch->d_tiles4, tiles.size() * sizeof(LibTile4)));
+            CU_TRY(c, cudaMemcpyAsync(cch->d_tiles4, tiles.data(), tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
+            k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles4,
+                                                                   cch->n_tiles, cch->d_pstart, L->d_start, L->d_count, L->n_kf, cch->d_img);
+            c->launches++;
+            CU_TRY(c, cudaGetLastError());
+        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        cch->built_for_kf = L->n_kf;
+        cch->built_for_desc = L->n_desc;
+        return NCLT_OK;
+    }
     std::vector<LibTile> tiles;
     std::vector<int> row0;
     cch->kf_first_tile.assign(L->n_kf + 1, 0);
@@ -831,22 +1200,17 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
             LibTile t{(uint32_t)off256, 16, 0, k, 1};
             tiles.push_back(t);
             row0.push_back(start);
-            off256 += fp4 ? 8 : 16;
+            off256 += 16;
             continue;
         }
-        int per = 256;
-        if (fp4) {
-            // greedy full tiles: the accumulator hand-over (MMA -> tcgen05.ld -> release -> MMA) has a large fixed
-            // cost per step, so a few 240-column steps plus one short one beat evenly sized steps
-            per = B4_ROWS;
-        }
+        const int per = 256;
         for (int r = 0; r < cnt; r += per) {
             int nv = std::min(per, cnt - r);
             int n = (nv + 15) & ~15;
             LibTile t{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, k, r + per >= cnt ? 1 : 0};
             tiles.push_back(t);
             row0.push_back(start + r);
-            off256 += fp4 ? (size_t)n / 2 : (size_t)n;     // n * (128 | 256) bytes / 256
+            off256 += (size_t)n;     // n * 256 bytes / 256
         }
     }
     cch->kf_first_tile[L->n_kf] = (int)tiles.size();
@@ -859,12 +1223,8 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     CU_TRY(c, cudaMalloc(&d_row0, row0.size() * sizeof(int)));
     CU_TRY(c, cudaMemcpyAsync(cch->d_tiles, tiles.data(), tiles.size() * sizeof(LibTile), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(d_row0, row0.data(), row0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (fp4)
-        k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
-                                                               cch->n_tiles, cch->d_img);
-    else
-        k_expand_library<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
-                                                              cch->n_tiles, cch->d_img);
+    k_expand_library<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles, d_row0,
+                                                          cch->n_tiles, cch->d_img);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -904,7 +1264,8 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
         // ceil(items / SMs) item-times plus ~10 us per item (query-tile reload, pipeline drain and refill), so among
         // the split counts near the target pick the cheapest (e.g. 1000 groups: 4 splits -> 27.03 items per SM -> 28
         // rounds, 3.5 % of the last one idle; 5 splits -> 33.8 -> 34 rounds, 0.6 %: measured 22.5 -> 21.9 ms)
-        const int kf_cap = std::max(n_kf, 1);
+        // fp4: a split starts at a tile-group boundary; fp8: at any keyframe
+        const int kf_cap = fp4 ? std::max((int)cch->grp_tile.size() - 1, 1) : std::max(n_kf, 1);
         const int target = std::max(1, std::min(kf_cap, (c->sm_count * 24 + pl->n_groups - 1) / pl->n_groups));
         int best = target;
         double best_cost = 1e30;
@@ -920,81 +1281,166 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
     pl->d12_bytes = (size_t)n_kf * pl->rows_pad * 4;
     if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
     if (cch->split_groups != pl->n_groups || cch->split_n != pl->n_splits) {
-        std::vector<int> split_tile(pl->n_splits + 1);
-        for (int s = 0; s <= pl->n_splits; ++s) split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / pl->n_splits];
+        std::vector<int> split_tile(pl->n_splits + 1), split_kf(pl->n_splits + 1);
+        const int n_grp = (int)cch->grp_tile.size() - 1;
+        for (int s = 0; s <= pl->n_splits; ++s) {
+            if (fp4) {
+                const int g = (int)((long long)n_grp * s / pl->n_splits);
+                split_tile[s] = cch->grp_tile[g];
+                split_kf[s] = cch->grp_kf[g];
+            } else {
+                split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / pl->n_splits];
+                split_kf[s] = (int)((long long)n_kf * s / pl->n_splits);
+            }
+        }
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         c->alloc_gen++;
         if (cch->d_split) cudaFree(cch->d_split);
-        cch->d_split = nullptr;
+        if (cch->d_split_kf) cudaFree(cch->d_split_kf);
+        cch->d_split = cch->d_split_kf = nullptr;
         CU_TRY(c, cudaMalloc(&cch->d_split, (pl->n_splits + 1) * sizeof(int)));
+        CU_TRY(c, cudaMalloc(&cch->d_split_kf, (pl->n_splits + 1) * sizeof(int)));
         CU_TRY(c, cudaMemcpy(cch->d_split, split_tile.data(), (pl->n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CU_TRY(c, cudaMemcpy(cch->d_split_kf, split_kf.data(), (pl->n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
         cch->split_groups = pl->n_groups;
         cch->split_n = pl->n_splits;
     }
     return NCLT_OK;
 }
 
-// expands the queries into q_img and runs k_tc*_top2: d12[kf * rows_pad + row] = d1 | d2bound << 16
-static int tc_run_top2(nclt_ctx* c, const TcPlan& pl, const uint8_t* q, uint8_t* q_img, uint32_t* d12) {
-    const bool fp4 = pl.fp4;
-    TcLibCache* cch = pl.cch;
-    {
-        long long threads = pl.rows_pad * 16;
-        if (fp4)
-            k_expand_queries4<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
-        else
-            k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
-        c->launches++;
+static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem) {
+    CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
+        int g = atoi(env);
+        if (g > 0) grid = std::min(grid, g);
     }
-    TcParams p;
-    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
-    p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.rows_total = pl.rows; p.out = d12; p.rows_pad = pl.rows_pad;
+    // Highest launch priority: when two engines alternate (PipelinedLocalizer) this kernel's CTAs must be placed
+    // before the small tail CTAs of the previous batch (each of which would otherwise pin some of the shared memory
+    // a matching CTA needs and delay it).
+    static int prio_hi = 1 << 30;
+    if (prio_hi == (1 << 30)) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        prio_hi = greatest;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio_hi;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* args[1] = {params};
+    nclt_prof_mark(c);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
+    nclt_prof_mark(c);
+    c->launches++;
+    if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_CUDA, "tensor matching kernel launch", e);
+    return NCLT_OK;
+}
+
+static int tc_clock_slot(nclt_ctx* c, unsigned long long** clk, int* slot) {
     if (!c->d_tc_clk && c->prof) {      // diagnostics only in profile mode (allocation is not capturable)
         CU_TRY(c, cudaMalloc(&c->d_tc_clk, 512));
         CU_TRY(c, cudaMemsetAsync(c->d_tc_clk, 0, 512, c->stream));
         c->tc_clk_launch = 0;
     }
-    p.clk = c->prof ? c->d_tc_clk : nullptr;
-    p.clk_slot = 0;
-    if (p.clk) {
-        p.clk_slot = c->tc_clk_launch++ % 24;
-        CU_TRY(c, cudaMemsetAsync(p.clk, 0, 128, c->stream));
-        CU_TRY(c, cudaMemsetAsync(p.clk + 16 + 2 * p.clk_slot, 0xFF, 8, c->stream));     // start: atomicMin
-        CU_TRY(c, cudaMemsetAsync(p.clk + 17 + 2 * p.clk_slot, 0, 8, c->stream));        // end: atomicMax
+    *clk = c->prof ? c->d_tc_clk : nullptr;
+    *slot = 0;
+    if (*clk) {
+        *slot = c->tc_clk_launch++ % 24;
+        CU_TRY(c, cudaMemsetAsync(*clk, 0, 128, c->stream));
+        CU_TRY(c, cudaMemsetAsync(*clk + 16 + 2 * *slot, 0xFF, 8, c->stream));     // start: atomicMin
+        CU_TRY(c, cudaMemsetAsync(*clk + 17 + 2 * *slot, 0, 8, c->stream));        // end: atomicMax
     }
-    const size_t smem = fp4 ? (size_t)MA4 * A4_TILE_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 128 + (size_t)4 * MA4 * 32 * 8
-                            : (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
-    CU_TRY(c, cudaFuncSetAttribute(fp4 ? k_tc4_top2 : k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(c->sm_count, pl.n_groups * pl.n_splits);
-    if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
-        int g = atoi(env);
-        if (g > 0) grid = std::min(grid, g);
-    }
-    nclt_prof_mark(c);
+    return NCLT_OK;
+}
+
+// fp4: expands the queries and runs k_tc4_top2 in ratio-candidate mode (mode 0) or plane mode (mode 1)
+static int tc4_run(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8_t* q, const int32_t* q_n, int Nq, uint8_t* q_img,
+                   int mode, int num, int den, WorkEntry* work, int* work_count, int work_cap, uint32_t* d12) {
+    TcLibCache* cch = pl.cch;
     {
-        // Highest launch priority: when two engines alternate (PipelinedLocalizer) this kernel's CTAs must be
-        // placed before the small tail CTAs of the previous batch (each of which would otherwise pin some of
-        // the shared memory a k_tc*_top2 CTA needs and delay it).
-        static int prio_hi = 1 << 30;
-        if (prio_hi == (1 << 30)) {
-            int least = 0, greatest = 0;
-            cudaDeviceGetStreamPriorityRange(&least, &greatest);
-            prio_hi = greatest;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = c->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributePriority;
-        attr[0].val.priority = prio_hi;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CU_TRY(c, cudaLaunchKernelEx(&cfg, fp4 ? k_tc4_top2 : k_tc_top2, p));
+        long long threads = pl.rows_pad * 16;
+        k_expand_queries4<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
+        c->launches++;
     }
-    nclt_prof_mark(c);
-    c->launches++;
+    Tc4Params p{};
+    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles4; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
+    p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.split_kf = cch->d_split_kf;
+    p.kf_pstart = cch->d_pstart; p.kf_count = L->d_count; p.n_kf = L->n_kf;
+    p.rows_total = pl.rows; p.Nq = Nq; p.q_n = q_n; p.mode = mode; p.num = num; p.den = den;
+    p.work = work; p.work_count = work_count; p.work_cap = work_cap; p.overflow = c->d_overflow;
+    p.out = d12; p.rows_pad = pl.rows_pad;
+    int rc;
+    if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + A4_BIAS_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 256;
+    return tc_launch_persistent(c, (const void*)k_tc4_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem);
+}
+
+// fp8: expands the queries into q_img and runs k_tc_top2: d12[kf * rows_pad + row] = d1 | d2bound << 16
+static int tc_run_top2(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8_t* q, int Nq, uint8_t* q_img, uint32_t* d12) {
+    if (pl.fp4) return tc4_run(c, L, pl, q, nullptr, Nq, q_img, 1, 0, 1, nullptr, nullptr, 0, d12);
+    TcLibCache* cch = pl.cch;
+    {
+        long long threads = pl.rows_pad * 16;
+        k_expand_queries<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
+        c->launches++;
+    }
+    TcParams p;
+    p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
+    p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.rows_total = pl.rows; p.out = d12; p.rows_pad = pl.rows_pad;
+    int rc;
+    if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+    const size_t smem = (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
+    return tc_launch_persistent(c, (const void*)k_tc_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem);
+}
+
+// fp4: candidates straight from the matching kernel -> exact verification -> ordered pairs.  No (row, keyframe) plane.
+static int tc4_match_ratio_all(nclt_ctx* c, nclt_lib* L, const TcPlan& pl, const uint8_t* q, const int32_t* q_n, int B, int Nq,
+                               int num, int den, int32_t* out_pairs, int32_t* out_n) {
+    int rc;
+    const int n_kf = L->n_kf;
+    const long long n_items = (long long)B * n_kf;
+    // capacities: the work list takes every pair in small problems and 8 entries per query row otherwise (planted
+    // matches are <= 1 per row; heavy-tie inputs produce more); item slots: 8 per frame.  What does not fit is COUNTED
+    // in the context's overflow counter (nclt_ctx_overflow) - the caller re-runs such a batch on the integer engine.
+    const long long all_pairs = pl.rows * (long long)n_kf;
+    const int work_cap = (int)std::min<long long>(all_pairs, std::max<long long>(pl.rows * 8, 1LL << 20));
+    const int slots = (int)std::min<long long>(n_items, std::max<long long>((long long)B * 8, 4096));
+    const int nwords = (Nq + 31) / 32;
+    ScratchScope scope(c);
+    size_t need = pad256(pl.q_img_bytes) + pad256((size_t)work_cap * sizeof(WorkEntry)) + pad256(16) + pad256((size_t)n_items * 4) +
+                  pad256((size_t)slots * 4) + pad256((size_t)slots * nwords * 4) + pad256((size_t)slots * Nq * 4) + 256;
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    uint8_t* q_img = cv.take<uint8_t>(pl.q_img_bytes);
+    WorkEntry* work = cv.take<WorkEntry>((size_t)work_cap);
+    int* counters = cv.take<int>(4);                       // [0] work entries, [1] slots used
+    Tc4Pool pool;
+    pool.item_slot = cv.take<int>((size_t)n_items);
+    pool.slot_item = cv.take<int>((size_t)slots);
+    pool.bitmap = cv.take<uint32_t>((size_t)slots * nwords);
+    pool.tidx = cv.take<int>((size_t)slots * Nq);
+    pool.slot_count = counters + 1;
+    pool.slots = slots;
+    pool.nwords = nwords;
+    CU_TRY(c, cudaMemsetAsync(counters, 0, 16, c->stream));
+    CU_TRY(c, cudaMemsetAsync(pool.item_slot, 0xFF, (size_t)n_items * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(pool.bitmap, 0, (size_t)slots * nwords * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(out_n, 0, (size_t)n_items * 4, c->stream));
+    if ((rc = tc4_run(c, L, pl, q, q_n, Nq, q_img, 0, num, den, work, counters, work_cap, nullptr))) return rc;
+    nclt_prof_mark_tag(c, 6);
+    k_tc4_verify<<<c->sm_count * 16, 128, 0, c->stream>>>(work, counters, work_cap, Nq, n_kf, num, den,
+                                                         reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start, L->d_count, pool,
+                                                         c->d_overflow);
+    nclt_prof_mark_tag(c, 6);
+    k_tc4_emit<<<c->sm_count * 4, 128, 0, c->stream>>>(pool, Nq, reinterpret_cast<int2*>(out_pairs), out_n);
+    c->launches += 2;
+    CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
 }
 
@@ -1005,7 +1451,12 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     TcPlan pl;
     if ((rc = tc_plan(c, L, B, Nq, fp4, &pl))) return rc;
     const int n_kf = L->n_kf;
-    if (n_kf == 0 || pl.cch->n_tiles == 0) return NCLT_OK;
+    if (n_kf == 0) return NCLT_OK;
+    if (pl.cch->n_tiles == 0) {      // a library of empty keyframes: no matches anywhere
+        CU_TRY(c, cudaMemsetAsync(out_n, 0, (size_t)B * n_kf * 4, c->stream));
+        return NCLT_OK;
+    }
+    if (fp4) return tc4_match_ratio_all(c, L, pl, q, q_n, B, Nq, num, den, out_pairs, out_n);
     ScratchScope scope(c);
     // candidate work list: every (query, keyframe) pair may be a candidate in the worst case
     const long long all_pairs = pl.rows * (long long)n_kf;
@@ -1017,16 +1468,18 @@ int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t
     uint32_t* d12 = cv.take<uint32_t>(pl.d12_bytes / 4);
     WorkItem* work = cv.take<WorkItem>((size_t)work_cap);
     int* work_count = cv.take<int>(1);
-    if ((rc = tc_run_top2(c, pl, q, q_img, d12))) return rc;
+    if ((rc = tc_run_top2(c, L, pl, q, Nq, q_img, d12))) return rc;
     {
         const int n_items = B * n_kf;
         const unsigned blocks = (unsigned)(((long long)n_items * 32 + 127) / 128);
         CU_TRY(c, cudaMemsetAsync(work_count, 0, 4, c->stream));
         k_tc_candidates<<<blocks, 128, 0, c->stream>>>(d12, pl.rows_pad, Nq, q_n, n_kf, n_items, num, den, L->d_count,
                                                       reinterpret_cast<int2*>(out_pairs), out_n, work, work_count, work_cap);
+        nclt_prof_mark_tag(c, 6);
         k_tc_verify<<<c->sm_count * 16, 128, 0, c->stream>>>(work, work_count, work_cap, Nq, n_kf, num, den,
                                                             reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start,
                                                             L->d_count, reinterpret_cast<int2*>(out_pairs));
+        nclt_prof_mark_tag(c, 6);
         k_tc_compact<<<blocks, 128, 0, c->stream>>>(n_items, Nq, reinterpret_cast<int2*>(out_pairs), out_n);
         c->launches += 3;
     }
@@ -1109,7 +1562,7 @@ int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_
     uint32_t* d12 = cv.take<uint32_t>(pl.d12_bytes / 4);
     int2* sel = cv.take<int2>((size_t)pl.rows);
     if (n_kf > 0 && pl.cch->n_tiles > 0) {
-        if ((rc = tc_run_top2(c, pl, q, q_img, d12))) return rc;
+        if ((rc = tc_run_top2(c, L, pl, q, Nq, q_img, d12))) return rc;
     }
     k_flat_select<<<(unsigned)((pl.rows + 255) / 256), 256, 0, c->stream>>>(d12, pl.rows_pad, pl.rows, n_kf, sel);
     k_flat_rescan<<<(unsigned)((pl.rows * 32 + 127) / 128), 128, 0, c->stream>>>(

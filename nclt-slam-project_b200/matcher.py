@@ -33,6 +33,12 @@ RANSAC_ITERATIONS = 200
 MIN_INLIERS = 10
 CONSISTENCY_M = 5.0
 TICK_HZ = 2.0
+# continuous landmark accumulation (visual_landmark_matcher.py:85-89; shipped enabled)
+ACCUM_ENABLE = True
+ACCUM_SILENCE_S = 5.0
+ACCUM_MIN_DIST_M = 5.0
+ACCUM_MIN_KPTS = 30
+ACCUM_SAVE_PKL = True
 # exp 63 global relocalisation (experiments/63_global_reloc/scripts/visual_landmark_matcher.py:82-86)
 RELOC_AGE_S = 20.0
 RELOC_DRIFT_M = 3.0
@@ -128,7 +134,9 @@ class LandmarkMatcher:
     validator's k=2 + Lowe variant (checkpoint_a_selftest.py:62-103, no heading gate, 5 nearest)."""
 
     def __init__(self, pkl_path_or_dict, log_csv=None, mode='crosscheck', ctx=None):
+        self.pkl_path = None
         if isinstance(pkl_path_or_dict, (str, os.PathLike)):
+            self.pkl_path = str(pkl_path_or_dict)
             with open(pkl_path_or_dict, 'rb') as f:
                 data = pickle.load(f)
         else:
@@ -148,6 +156,8 @@ class LandmarkMatcher:
         self.n_attempts = 0
         self.n_published = 0
         self.last_anchor_ts = 0.0
+        self.n_initial_landmarks = len(self.landmarks)
+        self.n_accumulated = 0
         self.log_csv = log_csv
         if log_csv:
             os.makedirs(os.path.dirname(log_csv), exist_ok=True)
@@ -185,6 +195,74 @@ class LandmarkMatcher:
         with open(self.log_csv, 'a') as f:
             f.write(f'{ts:.3f},{vio_xy[0]:.3f},{vio_xy[1]:.3f},{n_tried},{n_in},{err},{ax},{ay},{outcome}\n')
 
+    def accumulate(self, base_pose, desc_curr, pts_curr_2d, depth_mm, ts):
+        """`_maybe_accumulate` (visual_landmark_matcher.py:434-500): after ACCUM_SILENCE_S without an anchor and with no
+        landmark within ACCUM_MIN_DIST_M, the current frame becomes a NEW landmark at the current VIO pose - appended to
+        `landmarks`, to the xy / heading indices AND to the device library (nclt_lib_append), so the very next tick can
+        match against it.  Same arithmetic as the node: np.round to the pixel, float32 millimetres / 1000, float64
+        back-projection rounded to float32, camera pose through the static base -> camera offset.  Returns True when a
+        landmark was added."""
+        if not ACCUM_ENABLE:
+            return False
+        if ts - self.last_anchor_ts < ACCUM_SILENCE_S:
+            return False
+        vio_xy = (base_pose[0], base_pose[1])
+        d = np.linalg.norm(self.xy - np.array(vio_xy), axis=1)
+        if d.min() < ACCUM_MIN_DIST_M:
+            return False
+        if depth_mm is None or pts_curr_2d is None or len(pts_curr_2d) == 0:
+            return False
+        pts = np.asarray(pts_curr_2d)
+        desc_curr = np.asarray(desc_curr)
+        uu = np.round(pts[:, 0]).astype(np.int32)
+        vv = np.round(pts[:, 1]).astype(np.int32)
+        H, W = depth_mm.shape
+        valid = (uu >= 1) & (uu < W - 1) & (vv >= 1) & (vv < H - 1)
+        uu, vv = uu[valid], vv[valid]
+        pts2, desc2 = pts[valid], desc_curr[valid]
+        if len(uu) == 0:
+            return False
+        d_c = depth_mm[vv, uu].astype(np.float32) / 1000.0
+        ok = (d_c > 0.5) & (d_c < 15.0)
+        if ok.sum() < ACCUM_MIN_KPTS:
+            return False
+        uu, vv = uu[ok], vv[ok]
+        kpts2d_kept, desc_kept, d_c = pts2[ok], desc2[ok], d_c[ok]
+        x_cam = (uu - CX) * d_c / FX
+        y_cam = (vv - CY) * d_c / FY
+        kpts_3d_cam = np.stack([x_cam, y_cam, d_c], axis=-1).astype(np.float32)
+        R_wb = quat_to_rot(*base_pose[3:7])
+        cam_xyz = np.array([base_pose[0], base_pose[1], base_pose[2]]) + R_wb @ self.base_to_cam_t
+        R_wc = R_wb @ self.base_to_cam_R
+        from scipy.spatial.transform import Rotation as SR      # the node's own conversion (matcher:478-479)
+        qx, qy, qz, qw = SR.from_matrix(R_wc).as_quat()
+        new_lm = {
+            'pose': (float(cam_xyz[0]), float(cam_xyz[1]), float(cam_xyz[2]), float(qx), float(qy), float(qz), float(qw)),
+            'descriptors': desc_kept, 'keypoints_2d': kpts2d_kept, 'keypoints_3d_cam': kpts_3d_cam,
+            'ts': ts, 'n_features': int(len(kpts_3d_cam)), 'accumulated': True,
+        }
+        self.landmarks.append(new_lm)
+        self.xy = np.vstack([self.xy, [vio_xy[0], vio_xy[1]]])
+        self.heading = np.append(self.heading, self._lm_heading_rad(new_lm))
+        self.library.append(desc_kept, kpts_3d_cam)            # the device library grows with the host one
+        self.n_accumulated += 1
+        return True
+
+    def save_augmented(self, path=None):
+        """The node's SIGTERM handler (matcher:192-202): with accumulated landmarks, pickle the whole dict (same schema)
+        next to the teach pickle as `<name>_augmented.pkl`.  Returns the path written, or None when there is nothing to
+        save."""
+        if not (ACCUM_SAVE_PKL and self.n_accumulated > 0):
+            return None
+        if path is None:
+            if self.pkl_path is None:
+                raise ValueError('save_augmented: the matcher was built from a dict - pass a path')
+            path = self.pkl_path.replace('.pkl', '_augmented.pkl')
+        self.pkl_data['landmarks'] = self.landmarks
+        with open(path, 'wb') as f:
+            pickle.dump(self.pkl_data, f)
+        return path
+
     def reloc_candidates(self, base_pose, desc_curr):
         """exp 63 global relocalisation pool (63_global_reloc/.../visual_landmark_matcher.py:328-345): every
         heading-compatible landmark, scored by its crossCheck match count against the current frame (one batched GPU
@@ -213,11 +291,14 @@ class LandmarkMatcher:
             return self.tick(None, None, base_pose, ts, drift_est)
         return self.tick(desc[0, :m], kp[0, :m, :2], base_pose, ts, drift_est)
 
-    def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0, drift_est=0.0):
+    def tick(self, desc_curr, pts_curr_2d, base_pose, ts=0.0, drift_est=0.0, depth_mm=None):
         """One matcher tick from the ORB output onwards. Returns a dict with 'outcome' (the CSV
         outcome string), and on publish 'anchor_pose', 'std', 'covariance', 'n_inliers',
         'reproj_err', 'lm_idx'.  drift_est: tf_relay's SLAM-vs-encoder disagreement (/tmp/drift_est.txt in exp 63);
-        with the default 0 the tick is the production node's, otherwise exp 63's kidnapped-robot fallback can fire."""
+        with the default 0 the tick is the production node's, otherwise exp 63's kidnapped-robot fallback can fire.
+        depth_mm: the aligned depth image (u16 millimetres, `self.last_depth` of the node); when given, the three
+        outcomes after which the node calls `_maybe_accumulate` (no_candidates, no_pnp_accept, consistency_fail) do the
+        same here and report it as res['accumulated']."""
         self.n_attempts += 1
         vio_xy = (base_pose[0], base_pose[1])
         cand_idx = self.select_candidates(base_pose)
@@ -231,7 +312,8 @@ class LandmarkMatcher:
             relocating = True
         if not cand_idx:
             self._log(ts, vio_xy, 0, 0, '', None, 'no_candidates')
-            return {'outcome': 'no_candidates', 'candidates': cand_idx}
+            acc = depth_mm is not None and self.accumulate(base_pose, desc_curr, pts_curr_2d, depth_mm, ts)
+            return {'outcome': 'no_candidates', 'candidates': cand_idx, 'accumulated': acc}
         cand = np.full((1, max(MAX_CANDIDATES, len(cand_idx))), -1, dtype=np.int32)
         cand[0, :len(cand_idx)] = cand_idx
         params = self.params
@@ -243,7 +325,8 @@ class LandmarkMatcher:
         slot = int(out['best_cand'][0])
         if slot < 0:
             self._log(ts, vio_xy, len(cand_idx), 0, '', None, 'no_pnp_accept')
-            return {'outcome': 'no_pnp_accept', 'candidates': cand_idx}
+            acc = depth_mm is not None and self.accumulate(base_pose, desc_curr, pts_curr_2d, depth_mm, ts)
+            return {'outcome': 'no_pnp_accept', 'candidates': cand_idx, 'accumulated': acc}
         lm_idx = cand_idx[slot]
         n_inliers = int(out['n_inliers'][0])
         reproj_err = float(out['reproj'][0])
@@ -255,6 +338,7 @@ class LandmarkMatcher:
         if not relocating and consistency_d > CONSISTENCY_M:     # the jump is the point of a relocalisation (exp 63)
             res['outcome'] = f'consistency_fail_{consistency_d:.1f}m'
             self._log(ts, vio_xy, len(cand_idx), n_inliers, f'{reproj_err:.2f}', anchor_pose[:2], res['outcome'])
+            res['accumulated'] = depth_mm is not None and self.accumulate(base_pose, desc_curr, pts_curr_2d, depth_mm, ts)
             return res
         std = anchor_std(n_inliers)
         res.update(std=std, covariance=anchor_covariance(std),

@@ -305,6 +305,121 @@ def golden_tick(out_dir):
     print('tick_golden.npz', [t[0]['csv'][-1] for t in ticks])
 
 
+def golden_accum(out_dir):
+    """The production node WITH continuous accumulation (visual_landmark_matcher.py:85 ACCUM_ENABLE = True, the shipped
+    default; _maybe_accumulate :434-500): ticks far from every teach landmark after the silence period append the
+    current frame as a new landmark; later ticks near it localise against the ACCUMULATED landmark.  The SIGTERM
+    handler's augmented pickle (:192-202) is produced by invoking the node's own registered handler."""
+    import pickle
+    import signal
+    mods = ros_stubs.import_reference()
+    vm = mods['visual_landmark_matcher']
+    vm.ACCUM_ENABLE = True
+    data = synth.make_library(56, n_kf=20, n_desc=300, ragged=True, route_len_m=40.0)
+    tmp = tempfile.mkdtemp()
+    pkl = os.path.join(tmp, 'south_landmarks.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump(data, f)
+    csv = os.path.join(tmp, 'log', 'anchor_matches.csv')
+    node = vm.VisualLandmarkMatcher(pkl, csv)
+    node.last_rgb = np.zeros((480, 640, 3), dtype=np.uint8)
+
+    class _Kp:
+        def __init__(self, pt):
+            self.pt = (float(pt[0]), float(pt[1]))
+
+    class _Orb:
+        next = None
+
+        def detectAndCompute(self, gray, mask):
+            d, p = self.next
+            return [_Kp(q) for q in p], d
+
+    node.orb = _Orb()
+    rng = np.random.default_rng(19)
+    # a new place 30 m off the route: every frame shows the same scene (planted from a hidden "scene" keyframe with
+    # known 3-D points, seen from slightly different poses), depth consistent with those points
+    scene = synth.make_library(5601, n_kf=1, n_desc=400)
+    ticks = []
+    plan = [('near_route', 0.0), ('off_route_early', 3.0), ('off_route', 9.0), ('off_route_again', 10.0),
+            ('few_depth', 16.0), ('off_route_second_site', 22.0), ('back_at_new_site', 30.0), ('back_at_new_site', 31.0)]
+    for i, (kind, ts) in enumerate(plan):
+        fr = synth.make_frame(scene, 5600 + i, k_star=0, n_desc=500, n_planted=260)
+        desc, pts = fr['desc'], fr['pts2d']
+        if kind == 'near_route':
+            k = 7
+            fr = synth.make_frame(data, 5650, k_star=k, n_desc=500, n_planted=200)
+            desc, pts = fr['desc'], fr['pts2d']
+            lm = data['landmarks'][k]
+            bx, by, yaw = lm['pose'][0] - 0.35, lm['pose'][1], 0.0
+        elif kind == 'off_route_second_site':
+            bx, by, yaw = 10.0, -42.0, 0.4
+        else:
+            bx, by, yaw = 12.0 + 0.05 * i, 30.0, 0.1
+        # depth image (mm): the planted points' depths at their pixels, a wall elsewhere; some zeros
+        depth = np.full((480, 640), 4000, dtype=np.uint16)
+        if kind == 'few_depth':
+            depth[:] = 200                                  # closer than 0.5 m: fewer than ACCUM_MIN_KPTS valid points
+        uu = np.clip(np.round(pts[:, 0]).astype(int), 0, 639)
+        vv = np.clip(np.round(pts[:, 1]).astype(int), 0, 479)
+        if kind != 'few_depth':
+            depth[vv, uu] = rng.integers(400, 16500, len(uu)).astype(np.uint16)
+            if kind != 'near_route':
+                # planted keypoints: the depth the scene point really has in THIS camera, so that the landmark
+                # accumulated from this frame is geometrically consistent with the later frames of the same place
+                X = scene['landmarks'][0]['keypoints_3d_cam'][fr['t_idx']].astype(np.float64)
+                Xc = X @ synth.rodrigues(fr['rvec']).T + np.asarray(fr['tvec']).reshape(1, 3)
+                z_mm = np.clip(np.round(Xc[:, 2] * 1000.0), 0, 65535).astype(np.uint16)
+                depth[vv[fr['q_slots']], uu[fr['q_slots']]] = z_mm
+            depth[vv[::17], uu[::17]] = 0
+        node.last_depth = depth
+        base_pose = (float(bx), float(by), 0.0, 0.0, 0.0, float(np.sin(yaw / 2)), float(np.cos(yaw / 2)))
+        node.orb.next = (desc, pts)
+        node._read_pose = (lambda bp=base_pose: bp)
+        real_time = vm.time.time
+        vm.time.time = (lambda t=ts: 1000.0 + t)            # the node stamps ticks with time.time()
+        n_lm_before = len(node.landmarks)
+        n_before = len(node.anchor_pub.sent)
+        try:
+            node._tick()
+        finally:
+            vm.time.time = real_time
+        line = open(csv).read().strip().split('\n')[-1].split(',')
+        rec = {'kind': kind, 'ts': 1000.0 + ts, 'base_pose': base_pose, 'csv': line[1:], 'depth': depth,
+               'published': len(node.anchor_pub.sent) > n_before, 'n_landmarks': len(node.landmarks),
+               'appended': len(node.landmarks) > n_lm_before}
+        if rec['published']:
+            m = node.anchor_pub.sent[-1]
+            p_, o_ = m.pose.pose.position, m.pose.pose.orientation
+            rec['anchor'] = [p_.x, p_.y, p_.z, o_.x, o_.y, o_.z, o_.w]
+        ticks.append((rec, desc, pts))
+    # the SIGTERM handler the node registered: writes <pkl>_augmented.pkl and exits
+    try:
+        signal.getsignal(signal.SIGTERM)()
+    except SystemExit:
+        pass
+    aug = pickle.load(open(pkl.replace('.pkl', '_augmented.pkl'), 'rb'))
+    new = [lm for lm in aug['landmarks'] if lm.get('accumulated')]
+    assert len(new) == node.n_accumulated and len(new) >= 2, (len(new), node.n_accumulated)
+    np.savez_compressed(
+        os.path.join(out_dir, 'accum_golden.npz'), lib_seed=np.int64(56),
+        kinds=np.array([t[0]['kind'] for t in ticks]), ts=np.array([t[0]['ts'] for t in ticks]),
+        base_pose=np.array([t[0]['base_pose'] for t in ticks]),
+        csv=np.array([','.join(t[0]['csv']) for t in ticks]), published=np.array([t[0]['published'] for t in ticks]),
+        appended=np.array([t[0]['appended'] for t in ticks]), n_landmarks=np.array([t[0]['n_landmarks'] for t in ticks]),
+        anchor=np.array([t[0].get('anchor', [0] * 7) for t in ticks], dtype=np.float64),
+        desc=np.stack([t[1] for t in ticks]), pts2d=np.stack([t[2] for t in ticks]),
+        depth=np.stack([t[0]['depth'] for t in ticks]),
+        n_aug_landmarks=np.int64(len(aug['landmarks'])), aug_keys=np.array(sorted(aug.keys())),
+        new_pose=np.array([lm['pose'] for lm in new], dtype=np.float64), new_ts=np.array([lm['ts'] for lm in new]),
+        new_n=np.array([lm['n_features'] for lm in new], dtype=np.int64),
+        new_desc=np.concatenate([lm['descriptors'] for lm in new]),
+        new_kp2d=np.concatenate([lm['keypoints_2d'] for lm in new]),
+        new_kp3d=np.concatenate([lm['keypoints_3d_cam'] for lm in new]))
+    print('accum_golden.npz', [t[0]['csv'][-1] for t in ticks], 'landmarks', [t[0]['n_landmarks'] for t in ticks],
+          'new n_features', [lm['n_features'] for lm in new])
+
+
 def _lift_depth(rng, kind):
     """Synthetic aligned depth in millimetres: a ground ramp below the horizon, boxes at other ranges
     (depth discontinuities), holes (0), far background beyond the 15 m gate."""

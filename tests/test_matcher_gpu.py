@@ -163,3 +163,48 @@ def test_short_keyframes_every_engine_and_mode(ctx, mode, engine):
         for c, it in enumerate(ref['items']):
             assert out['item_nmatch'][b, c] == it['nmatch'], (b, c)
             assert bool(out['item_ok'][b, c]) == it['ok'] and out['item_ninl'][b, c] == it['n_in'], (b, c)
+
+
+def test_accumulation_against_reference_node(ctx, tmp_path):
+    """ACCUM_ENABLE = True (the shipped default): ticks far from the route after the silence period append the frame as
+    a new landmark (host lists, xy / heading indices and the DEVICE library), later ticks localise against the
+    accumulated landmark, and the augmented pickle equals the one the node's own SIGTERM handler wrote.
+    Golden: the unmodified node under ROS stubs (oracle/make_golden_ref.py::golden_accum)."""
+    import pickle
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.matcher import LandmarkMatcher
+    g = np.load(os.path.join(GD, 'accum_golden.npz'))
+    data = synth.make_library(int(g['lib_seed']), n_kf=20, n_desc=300, ragged=True, route_len_m=40.0)
+    pkl = str(tmp_path / 'south_landmarks.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump(data, f)
+    csv = str(tmp_path / 'log' / 'anchor_matches.csv')
+    m = LandmarkMatcher(pkl, csv, mode='crosscheck')
+    for i in range(len(g['kinds'])):
+        r = m.tick(g['desc'][i], g['pts2d'][i], tuple(g['base_pose'][i]), ts=float(g['ts'][i]), depth_mm=g['depth'][i])
+        ref = str(g['csv'][i]).split(',')
+        got = open(csv).read().strip().split('\n')[-1].split(',')[1:]
+        assert got[-1] == ref[-1], (i, got, ref)            # outcome incl. std / shift
+        assert got[:5] == ref[:5], (i, got, ref)            # vio, candidates tried, inliers, reprojection error
+        assert bool(r.get('accumulated', False)) == bool(g['appended'][i]), i
+        assert len(m.landmarks) == int(g['n_landmarks'][i]) == m.library.n_keyframes
+        assert bool(g['published'][i]) == r['outcome'].startswith('published')
+        if g['published'][i]:
+            a = np.array(r['anchor_pose'])
+            assert np.abs(a[:3] - g['anchor'][i, :3]).max() < 1e-3 and np.abs(a[3:] - g['anchor'][i, 3:]).max() < 1e-4
+    assert m.n_accumulated == len(g['new_n']) >= 2
+    assert any(r_ for r_ in g['published'][3:])             # an anchor came from an ACCUMULATED landmark
+    # the landmarks that were appended, bit for bit
+    new = [lm for lm in m.landmarks if lm.get('accumulated')]
+    offs = np.concatenate([[0], np.cumsum(g['new_n'])])
+    for k, lm in enumerate(new):
+        sl = slice(offs[k], offs[k + 1])
+        assert lm['n_features'] == int(g['new_n'][k]) and lm['ts'] == float(g['new_ts'][k])
+        assert np.array_equal(lm['descriptors'], g['new_desc'][sl])
+        assert np.array_equal(lm['keypoints_2d'].view(np.uint32), g['new_kp2d'][sl].view(np.uint32))
+        assert np.array_equal(lm['keypoints_3d_cam'].view(np.uint32), g['new_kp3d'][sl].view(np.uint32))
+        assert np.allclose(lm['pose'], g['new_pose'][k], rtol=0, atol=1e-12)
+    out = m.save_augmented()
+    assert out == pkl.replace('.pkl', '_augmented.pkl')
+    aug = pickle.load(open(out, 'rb'))
+    assert sorted(aug.keys()) == g['aug_keys'].tolist() and len(aug['landmarks']) == int(g['n_aug_landmarks'])

@@ -41,3 +41,9 @@ for variant in (0, 1):
     cyc = C.c_double()
     v = L.nclt_tc_bench_mx16(c.h, 2000, variant, C.byref(cyc))
     print(f'mx16 variant={variant}: {v/1e12:.3f} T pairs/s, {cyc.value:.1f} cycles/tile -> {128*240/max(cyc.value,1):.1f} pairs/clk/SM', flush=True)
+L.nclt_tc_bench_mxp.restype = C.c_double
+L.nclt_tc_bench_mxp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+for variant in (0, 1):
+    cyc = C.c_double()
+    v = L.nclt_tc_bench_mxp(c.h, 2000, variant, C.byref(cyc))
+    print(f'mxp (5 MMAs, two sets, packed, {"one batch" if variant == 0 else "two batches"}): {v/1e12:.3f} T pairs/s, {cyc.value:.1f} cycles/tile -> {128*240/max(cyc.value,1):.1f} pairs/clk/SM', flush=True)

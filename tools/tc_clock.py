@@ -28,6 +28,9 @@ for engine in sys.argv[1:] or ('tensor', 'tensor4'):
         if raw[2:12].any():      # built with -DNCLT_TC_TIMING
             for part in (0, 1):
                 v = raw[2 + 5 * part: 7 + 5 * part].astype(np.float64)
+                if part == 0 and raw[12:15].any():
+                    mv = raw[12:15].astype(np.float64)
+                    print(f'   MMA issuer: total {mv.sum()/1e6:.2f} Mcyc: wait b_full {100*mv[0]/mv.sum():.1f}%, wait acc_empty {100*mv[1]/mv.sum():.1f}%, issue+other {100*mv[2]/mv.sum():.1f}%', flush=True)
                 print(f'   epilogue part {part}: total {v.sum()/1e6:.2f} Mcyc: ' + ', '.join(
                     f'{n} {100*x/v.sum():.1f}%' for n, x in zip(('other', 'wait-full', 'loads', 'release', 'maxima'), v)), flush=True)
     eng.ctx.profile(False)
