@@ -248,6 +248,7 @@ def main():
     ap.add_argument('--ref-frames-per-step', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--engines', type=int, default=2, help='alternating engines (streams) in the pipelined mode')
+    ap.add_argument('--tail-sms', type=int, default=4, help='SMs the matching kernel leaves to the other engine\'s tail kernels')
     ap.add_argument('--no-pipeline', action='store_true', help='one engine/stream instead of two alternating ones')
     ap.add_argument('--no-graph', action='store_true', help='direct launches instead of CUDA graph replay')
     args = ap.parse_args()
@@ -302,6 +303,8 @@ def main():
         for rt in routes[1:]:
             e.add_library(lib_arrays(rt['lib']))
         e.ctx.set_engine(args.engine)
+        if not args.no_pipeline and args.engines > 1:
+            e.ctx.set_tail_sms(args.tail_sms)      # the other engine's tail kernels run on these SMs
         return e
 
     eng = make_engine()
@@ -554,7 +557,7 @@ def main():
            'frames_per_step_per_gpu': B, 'engine': args.engine, 'cuda_graph': use_graphs,
            'sharding': f'frames x {world} GPUs, librar{"ies" if multi else "y"} replicated, no collective',
            'cache': 'L2 flushed (256 MB write) before every step, inside the timed region',
-           'pipelined_engines': n_eng,
+           'pipelined_engines': n_eng, 'tail_sms': args.tail_sms if n_eng > 1 else 0,
            'pnp_problems_per_step': n_prob / args.steps, 'localised_to_planted_keyframe': acc_rate}
     if multi:
         cfg.update(n_libraries=R, library_seeds=ROUTE_SEEDS,

@@ -60,6 +60,10 @@ int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
  * Used by nclt_match_ratio[_dev] / nclt_localize_batch[_dev] with cand == NULL and by
  * nclt_match_flat2_dev; candidate-list and crossCheck matching always use the integer pipe. */
 int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
+/* The tensor-engine matching kernel is persistent (one CTA per SM) and fills every SM it runs on.  When two contexts
+ * take batches alternately, leaving n SMs free lets the short tail kernels (candidate verification, PnP-RANSAC) of one
+ * batch run beside the matching kernel of the next instead of after it.  Default 0. */
+int nclt_ctx_set_tail_sms(nclt_ctx* ctx, int n);
 /* enable/disable CUDA-event timing of the dominant kernel (the Hamming top-2 launches) on this
  * context; nclt_ctx_profile_read synchronises, returns the summed device time and launch count
  * since the last read, and resets. Used by bench.py for the live roofline figure. */

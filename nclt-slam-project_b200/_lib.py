@@ -42,6 +42,7 @@ _sig('nclt_last_error', C.c_char_p, _vp)
 _sig('nclt_ctx_launches', C.c_ulonglong, _vp)
 _sig('nclt_ctx_alloc_generation', C.c_ulonglong, _vp)
 _sig('nclt_ctx_set_engine', _i, _vp, _i)
+_sig('nclt_ctx_set_tail_sms', _i, _vp, _i)
 _sig('nclt_ctx_overflow', _i, _vp, _i)
 _sig('nclt_ctx_profile', _i, _vp, _i)
 _sig('nclt_ctx_profile_read', _i, _vp, C.POINTER(_dbl), C.POINTER(_i))
@@ -181,6 +182,10 @@ class Context:
         """'int' (LOP3+POPC) or 'tensor' (tcgen05) for all-keyframe ratio matching; same results."""
         code = {'int': 0, 'tensor': 1, 'tensor8': 1, 'tensor4': 2, 0: 0, 1: 1, 2: 2}[engine]
         self.check(lib.nclt_ctx_set_engine(self.h, code))
+
+    def set_tail_sms(self, n):
+        """SMs the persistent matching kernel leaves to the tail kernels of an alternating context (default 0)."""
+        self.check(lib.nclt_ctx_set_tail_sms(self.h, int(n)))
 
     def overflow(self, reset=True):
         """PnP problems dropped by asynchronous localisation calls since the last reset."""

@@ -166,6 +166,12 @@ extern "C" int nclt_ctx_set_engine(nclt_ctx* c, int engine) {
     return NCLT_OK;
 }
 
+extern "C" int nclt_ctx_set_tail_sms(nclt_ctx* c, int n) {
+    if (!c || n < 0 || n >= c->sm_count) return nclt_fail(c, NCLT_ERR_ARG, "tail_sms must be in [0, SM count)");
+    c->tail_sms = n;
+    return NCLT_OK;
+}
+
 extern "C" int nclt_ctx_profile(nclt_ctx* c, int enable) {
     if (!c) return NCLT_ERR_ARG;
     c->prof = enable != 0;

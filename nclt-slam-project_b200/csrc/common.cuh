@@ -45,6 +45,7 @@ struct nclt_ctx {
     // bumped whenever device memory a captured CUDA graph may point into is freed or moved: scratch chunks,
     // tensor-engine library images / split tables, library growth (nclt_ctx_alloc_generation)
     unsigned long long alloc_gen = 0;
+    int tail_sms = 0;           // SMs the persistent matching kernel leaves free for the tail kernels of another context
 };
 
 struct nclt_lib {

@@ -454,9 +454,6 @@ __device__ __forceinline__ uint32_t fmax3u(uint32_t acc, uint32_t x, uint32_t y)
     // plain fmaxf (ptxas fuses the pair into one FMNMX3 and is free to schedule it; an inline-asm max is not)
     return __float_as_uint(fmaxf(fmaxf(__uint_as_float(acc), __uint_as_float(x)), __uint_as_float(y)));
 }
-__device__ __forceinline__ uint32_t fmax2u(uint32_t acc, uint32_t x) {
-    return __float_as_uint(fmaxf(__uint_as_float(acc), __uint_as_float(x)));
-}
 // Two groups of 8 packed registers (32 columns) -> the 8 running maxima.  Pass 1 takes the high halves as they are,
 // then every register is shifted IN PLACE (no temporaries: the kernel sits at its register cap, and ptxas funnels
 // temporaries through one register, serialising shift -> max pairs at ~13 clk each) and pass 2 takes the former low
@@ -1310,7 +1307,12 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
 
 static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem) {
     CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob: leave some SMs to co-running tail kernels
+    // Two contexts that alternate batches (PipelinedLocalizer, bench.py): the short tail kernels of one batch
+    // (verification, PnP) cannot co-reside with a matching CTA (its 10 warps x 168 registers fill an SM's register
+    // file), so the matching kernel of the other context leaves `tail_sms` SMs to them (nclt_ctx_set_tail_sms).
+    // Measured at 512-frame steps: 4 SMs hide ~half of the tail (+1.5 % frames/s), 12 SMs all of it (+-0 %).
+    grid = std::max(1, std::min(grid, c->sm_count - c->tail_sms));
+    if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob
         int g = atoi(env);
         if (g > 0) grid = std::min(grid, g);
     }

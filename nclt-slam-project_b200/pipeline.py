@@ -195,10 +195,11 @@ class PipelinedLocalizer:
     engine buys is the removal of host-side gaps, and a step costs matching kernel + tail.
     Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
 
-    def __init__(self, library_arrays, device=0, params=None, engine='tensor4'):
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', tail_sms=4):
         self.engines = [DeviceLocalizer(library_arrays, device, params) for _ in range(2)]
         for e in self.engines:
             e.ctx.set_engine(engine)
+            e.ctx.set_tail_sms(tail_sms)      # the matching kernel leaves these SMs to the other engine's tail kernels
         self.k = 0
 
     def submit(self, desc_dev, pts2d_dev):
@@ -226,7 +227,7 @@ class StreamingLocalizer:
         res = sl.result(ticket)                           # dict of NumPy arrays, valid until `depth` submits later
     """
 
-    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', depth=2):
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', depth=2, tail_sms=4):
         import torch
         from .library import LandmarkLibrary
         self.torch = torch
@@ -236,6 +237,8 @@ class StreamingLocalizer:
         for _ in range(depth):
             ctx = _lib.Context(device)
             ctx.set_engine(engine)
+            if depth > 1:
+                ctx.set_tail_sms(tail_sms)
             self.slots.append({'ctx': ctx, 'lib': LandmarkLibrary(descs, pts3, ctx=ctx), 'out': None, 'keep': None,
                                'ticket': -1})
         self.k = 0
