@@ -120,8 +120,10 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, iteratio
     """cv2.solvePnPRansac as called at visual_landmark_matcher.py:342-346.
 
     Returns (ok, rvec f64[3,1], tvec f64[3,1], inliers i32[m,1] | None).  Fewer than 4 points
-    raises `error` like cv2; exactly 4 points is cv2's P3P branch, which the reference can never
-    reach (MIN_MATCHES = 10, matcher:330) and is not implemented."""
+    raises `error` like cv2.  Exactly 4 points: cv2 takes its P3P branch and returns ok=True with 4
+    inliers; that branch is not restated here, and the call returns ok=False (inliers None) instead
+    of raising - for both call sites the outcome is the same `continue`, because they reject anything
+    below MIN_INLIERS = 10 (matcher:349, selftest:83) and never pass fewer than MIN_MATCHES = 10 points."""
     from .pnp import pnp_ransac_batch
     from ._lib import PnpParams
     if flags != SOLVEPNP_ITERATIVE:
@@ -130,8 +132,8 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, iteratio
     img = np.ascontiguousarray(imagePoints, dtype=np.float32).reshape(-1, 2)
     if len(obj) != len(img) or len(obj) < 4:
         raise error('solvePnPRansac needs >= 4 matching object/image points')
-    if len(obj) == 4:
-        raise error('4-point (P3P) problems are outside the reference call sites and not implemented')
+    if len(obj) == 4:        # documented divergence: cv2's P3P branch (ok=True, 4 inliers) is reported as "no model"
+        return False, np.zeros((3, 1)), np.zeros((3, 1)), None
     fx, fy, cx, cy = _intrinsics(cameraMatrix, distCoeffs)
     prm = PnpParams(fx, fy, cx, cy, int(iterationsCount), float(reprojectionError), float(confidence), 1)
     o = pnp_ransac_batch(obj[None], img[None], None, prm, ctx=ctx)
