@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
     tc::tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const int n_items = p.n_groups * p.n_splits;
+#ifdef NCLT_TC_TRACE
+#define TR(st_, k_) { const uint32_t s__ = (st_) - 2000u; if (s__ < 128u && blockIdx.x == 0 && p.clk) p.clk[64 + s__ * 8 + (k_)] = clock64(); }
+#else
+#define TR(st_, k_)
+#endif
     const long long clk0 = clock64();
     unsigned long long ns0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
@@ -355,6 +360,7 @@ constexpr int B4_ROW_BYTES = 160;               // 8 K chunks of the descriptor 
 constexpr int B4_STAGE_BYTES = B4_ROWS * B4_ROW_BYTES;   // 38 400
 constexpr int A4_BIAS_BYTES = 128 * 32;         // constant bias slab of the query side
 constexpr int NSTAGE4 = 3;
+constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MMA issuers
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
 constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
 
@@ -476,9 +482,15 @@ __device__ __forceinline__ void grp1(uint32_t (&x)[NA], int b0, uint32_t (&acc)[
 
 // Per-warp walk over the keyframe boundaries inside the tiles (all lanes share it; the maxima differ per lane).
 struct SegWalk {
-    int kf;        // keyframe the next column belongs to
-    int end_col;   // first column (tile relative) that is NOT in it any more; INT_MAX once past the split's last keyframe
+    int kf;            // keyframe the next column belongs to
+    int end_col;       // first column (tile relative) that is NOT in it any more; INT_MAX once past the split's last keyframe
+    int next_end_row;  // image row where keyframe kf + 1 ends (INT_MAX past the split), loaded one boundary ahead
 };
+// The walk is the same in every lane, but it is computed from loaded values, which ptxas has to treat as divergent:
+// every `if (group in range)` around the maxima then costs a BSSY / BSYNC pair and a branch-resolution stall (~60 % of a
+// boundary tile's time in the ncu source view).  A REDUX result is warp-uniform by construction and lives in a uniform
+// register, so the same branches become plain uniform ones.
+__device__ __forceinline__ int warp_uniform(int x) { return __reduce_max_sync(0xFFFFFFFFu, x); }
 struct Acc4 { uint32_t v[4]; };            // running maxima (high halves) of 4 disjoint column subsets
 
 struct Tc4Epilogue {
@@ -530,11 +542,12 @@ struct Tc4Epilogue {
         finalize(w.kf, acc);
         acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0;
         ++w.kf;
-        w.end_col = w.kf < kf_stop ? kf_end_row(w.kf) - row0 : INT_MAX;
+        w.end_col = warp_uniform(w.next_end_row == INT_MAX ? INT_MAX : w.next_end_row - row0);
+        w.next_end_row = w.kf + 1 < kf_stop ? kf_end_row(w.kf + 1) : INT_MAX;     // not needed before the next boundary
     }
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constant__ Tc4Params p) {
+__global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_constant__ Tc4Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                   // MA4 x 16 KB
     uint8_t* sAb = sA + MA4 * A4_TILE_BYTES;              // 4 KB bias slab (query side, constant)
@@ -552,10 +565,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(a_full, 1);
-        tc::mbar_init(a_empty, 1);
+        tc::mbar_init(a_empty, 2);                 // one tcgen05.commit per issuer
         for (int s = 0; s < NSTAGE4; ++s) {
             tc::mbar_init(&b_full[s], 1);
-            tc::mbar_init(&b_empty[s], 1);
+            tc::mbar_init(&b_empty[s], 2);
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
         }
         tc::mbar_fence_init();
     }
-    tc::mx_fill_bias_slab(sAb, 128, false, tid, TC_THREADS);
+    tc::mx_fill_bias_slab(sAb, 128, false, tid, TC4_THREADS);
     tc::fence_proxy_async();
     if (warp == 0) {
         tc::tmem_alloc(s_tmem, 512);
@@ -583,6 +596,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
     __syncthreads();
     tc::tc_fence_after();
     const int n_items = p.n_groups * p.n_splits;
+#ifdef NCLT_TC_TRACE
+#define TR(st_, k_) { const uint32_t s__ = (st_) - 2000u; if (s__ < 128u && blockIdx.x == 0 && p.clk) p.clk[64 + s__ * 8 + (k_)] = clock64(); }
+#else
+#define TR(st_, k_)
+#endif
     const long long clk0 = clock64();
     unsigned long long ns0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
@@ -609,49 +627,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
                 }
             }
         }
-    } else if (warp == 9) {
-        // =========================== MMA issuer ===========================
-        // The whole warp runs the loops (warp-uniform control flow and operands); one elected lane issues the
-        // tcgen05 instructions.  Descriptors are base + offset: a lone lane building each 64-bit descriptor from
-        // scratch (~22 dependent scalar instructions per MMA, 800 clk per 5-MMA step) was slower than the tensor pipe.
+    } else if (warp >= 9) {
+        // =========================== MMA issuers (warps 9 and 10) ===========================
+        // Issuer i owns accumulator buffer i: the even steps (query tiles) of every library tile go to warp 9, the odd
+        // ones to warp 10.  One warp per buffer because an issuer's own path per step - mbarrier try_wait, five
+        // tcgen05.mma, tcgen05.commit - measured 650-700 clk while the tensor pipe is saturating shared memory (each
+        // mbarrier operation ~250 clk then), more than the 600 clk the five MMAs execute in: a single issuer left the
+        // pipe idle 40 % of the time.  The whole warp runs the loops (warp-uniform control flow and operands); one
+        // elected lane issues the tcgen05 instructions.  Descriptors are base + offset.
         {
+            const int iss = warp - 9;
             uint32_t it_cnt = 0, s = 0, ph = 0, st = 0;
             const uint64_t da_bias = tc::smem_desc(tc::smem_u32(sAb), 2048u, 128u);
             const uint64_t da0 = tc::smem_desc(tc::smem_u32(sA), 2048u, 128u);       // + (m * 16 KB + k * 4 KB) / 16
             const uint64_t db0 = tc::smem_desc(tc::smem_u32(sB), 0u, 128u);          // + stage / 16 + (n << 16) + 2 k n
-#ifdef NCLT_TC_TIMING
-            long long mw[3] = {0, 0, 0}, ml = clock64();
-#define MT(i) { long long now_ = clock64(); mw[i] += now_ - ml; ml = now_; }
-#else
-#define MT(i)
-#endif
+            const uint32_t d = tmem + iss * B4_ROWS;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
                 const int split = item / p.n_groups, group = item % p.n_groups;
                 const int ma = min(MA4, p.n_mtiles - group * MA4);
+                // an odd number of query tiles gets one empty step per library tile: steps per tile stay even,
+                // so issuer / epilogue set s always owns accumulator buffer s and sees every phase of its barriers
+                const int ma_pad = (ma + 1) & ~1;
                 tc::mbar_wait(a_full, it_cnt & 1);
                 for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
                     const uint32_t n = p.tiles[t].n;
-                    MT(2);
                     tc::mbar_wait(&b_full[s], ph);
                     tc::tc_fence_after();
-                    MT(0);
                     const uint32_t idesc = tc::idesc_mxf4(128, (int)n);
                     // K-major, no swizzle: LBO = n * 16 bytes -> descriptor field n; K chunk pair k starts 2 k n * 16 bytes in
                     const uint64_t db_tile = db0 + (uint64_t)(s * (B4_STAGE_BYTES >> 4)) + ((uint64_t)n << 16);
                     const uint64_t db_bias = db_tile + 8u * n;
-                    // an odd number of query tiles gets one empty step per library tile: steps per tile stay even,
-                    // so epilogue set s always owns accumulator buffer s and sees every phase of its barriers
-                    const int ma_pad = (ma + 1) & ~1;
-                    for (int m = 0; m < ma_pad; ++m, ++st) {
-                        const int buf = st & 1;
-                        MT(2);
-                        tc::mbar_wait(&acc_empty[buf], ((st >> 1) & 1) ^ 1);
+                    for (int m = iss; m < ma_pad; m += 2) {
+                        const uint32_t stm = st + (uint32_t)m;                   // global step number, stm & 1 == iss
+                        tc::mbar_wait(&acc_empty[iss], ((stm >> 1) & 1) ^ 1);
                         tc::tc_fence_after();
-                        MT(1);
+                        TR(stm, 0);
                         if (tc::elect_one()) {
                             if (m < ma) {
                                 const uint64_t da_m = da0 + (uint64_t)(m * (A4_TILE_BYTES >> 4));
-                                const uint32_t d = tmem + buf * B4_ROWS;
                                 // bias step first (accumulate = 0): 1.5 * 2^23 + 0x4000 in every cell of a non-padding row
                                 tc::mma_mxf4(d, da_bias, db_bias, idesc, 0u, tmem + SF_BIAS_COL, tmem + SF_ONE_COL);
 #pragma unroll
@@ -659,21 +672,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
                                     tc::mma_mxf4(d, da_m + (uint64_t)(k * 256), db_tile + (uint64_t)(2u * k * n), idesc, 1u,
                                                  tmem + SF_ONE_COL, tmem + SF_ONE_COL);
                             }
-                            tc::mma_commit(&acc_full[buf]);
+                            TR(stm, 1);
+                            tc::mma_commit(&acc_full[iss]);
                         }
                         __syncwarp();
+                        TR(stm, 2);
                     }
-                    if (tc::elect_one()) tc::mma_commit(&b_empty[s]);
+                    st += (uint32_t)ma_pad;
+                    if (tc::elect_one()) tc::mma_commit(&b_empty[s]);      // this issuer's MMAs on the stage are done
                     __syncwarp();
                     if (++s == NSTAGE4) { s = 0; ph ^= 1; }
                 }
                 if (tc::elect_one()) tc::mma_commit(a_empty);
                 __syncwarp();
             }
-#ifdef NCLT_TC_TIMING
-            MT(2);
-            if (lane == 0 && blockIdx.x == 0 && p.clk) { p.clk[12] = mw[0]; p.clk[13] = mw[1]; p.clk[14] = mw[2]; }   // waits: b_full, acc_empty; issue
-#endif
         }
     } else {
         // =========================== epilogue (warps 0-7) ===========================
@@ -696,18 +708,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
             Acc4 acc[MA4 / 2];
 #pragma unroll
             for (int mm = 0; mm < MA4 / 2; ++mm) acc[mm].v[0] = acc[mm].v[1] = acc[mm].v[2] = acc[mm].v[3] = 0;
-            Tc4Epilogue ep{&p, p.split_kf[split + 1], 0, false, lane};
-            int cur_kf = p.split_kf[split];                   // keyframe walk, carried from tile to tile
+            Tc4Epilogue ep{&p, warp_uniform(p.split_kf[split + 1]), 0, false, lane};
+            int cur_kf = warp_uniform(p.split_kf[split]);     // keyframe walk, carried from tile to tile
             int cur_end_row = cur_kf < ep.kf_stop ? ep.kf_end_row(cur_kf) : INT_MAX;
+            int cur_next_end = cur_kf + 1 < ep.kf_stop ? ep.kf_end_row(cur_kf + 1) : INT_MAX;
             const int t_end = p.split_tile[split + 1];
             for (int t = p.split_tile[split]; t < t_end; ++t) {
                 LibTile4 lt;                                  // 20 KB table, L1 resident; read while the MMA is still running
                 lt.n = __ldg(&p.tiles[t].n);
                 lt.prow0 = __ldg(&p.tiles[t].prow0);
-                const int n = lt.n;
+                const int n = warp_uniform(lt.n);
                 const int kf0 = cur_kf;
-                const int end0 = cur_end_row == INT_MAX ? INT_MAX : cur_end_row - lt.prow0;
-                SegWalk wk_after{kf0, end0};
+                const int end0 = warp_uniform(cur_end_row == INT_MAX ? INT_MAX : cur_end_row - lt.prow0);
+                SegWalk wk_after{kf0, end0, cur_next_end};
 #pragma unroll
                 for (int mm = 0; mm < MA4 / 2; ++mm) {
                     const int m = set + 2 * mm;
@@ -718,6 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
                     tc::mbar_wait(&acc_full[buf], (st >> 1) & 1);
                     tc::tc_fence_after();
                     TT(1);
+                    if (quad == 0) TR(st, 3);
                     if (m >= ma) {                            // the empty step of an odd group: just hand it back
                         tc::tc_fence_before();
                         __syncwarp();
@@ -757,9 +771,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);     // every column is in registers
                     TT(3);
+                    TR(st, 4 + quad);
                     ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
                     ep.row_ok = ep.row < p.rows_total;
-                    SegWalk wk{kf0, end0};
+                    SegWalk wk{kf0, end0, cur_next_end};
                     Acc4& A = acc[mm];
                     // Keyframes are padded to whole 16-column groups, so a keyframe ends between two register groups:
                     // groups [g, g_b) go to the running maxima of the current keyframe, then the walk advances.
@@ -806,6 +821,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc4_top2(const __grid_constan
                 // every real step of this warp ended its walk in the same state; a warp without a real step does not walk
                 cur_kf = wk_after.kf;
                 cur_end_row = wk_after.end_col == INT_MAX ? INT_MAX : wk_after.end_col + lt.prow0;
+                cur_next_end = wk_after.next_end_row;
             }
             // ---- end of the split: the keyframes that are still open (the last one, trailing empty ones)
 #pragma unroll
@@ -1305,7 +1321,7 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
     return NCLT_OK;
 }
 
-static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem) {
+static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem, int threads) {
     CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // Two contexts that alternate batches (PipelinedLocalizer, bench.py): the short tail kernels of one batch
     // (verification, PnP) cannot co-reside with a matching CTA (its 10 warps x 168 registers fill an SM's register
@@ -1327,7 +1343,7 @@ static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, i
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -1346,8 +1362,8 @@ static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, i
 
 static int tc_clock_slot(nclt_ctx* c, unsigned long long** clk, int* slot) {
     if (!c->d_tc_clk && c->prof) {      // diagnostics only in profile mode (allocation is not capturable)
-        CU_TRY(c, cudaMalloc(&c->d_tc_clk, 512));
-        CU_TRY(c, cudaMemsetAsync(c->d_tc_clk, 0, 512, c->stream));
+        CU_TRY(c, cudaMalloc(&c->d_tc_clk, 512 + 8192));
+        CU_TRY(c, cudaMemsetAsync(c->d_tc_clk, 0, 512 + 8192, c->stream));
         c->tc_clk_launch = 0;
     }
     *clk = c->prof ? c->d_tc_clk : nullptr;
@@ -1380,7 +1396,7 @@ static int tc4_run(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8
     int rc;
     if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
     const size_t smem = (size_t)MA4 * A4_TILE_BYTES + A4_BIAS_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 256;
-    return tc_launch_persistent(c, (const void*)k_tc4_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem);
+    return tc_launch_persistent(c, (const void*)k_tc4_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS);
 }
 
 // fp8: expands the queries into q_img and runs k_tc_top2: d12[kf * rows_pad + row] = d1 | d2bound << 16
@@ -1398,7 +1414,7 @@ static int tc_run_top2(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const u
     int rc;
     if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
     const size_t smem = (size_t)MA * A_TILE_BYTES + (size_t)NSTAGE * B_STAGE_BYTES + 1024;
-    return tc_launch_persistent(c, (const void*)k_tc_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem);
+    return tc_launch_persistent(c, (const void*)k_tc_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC_THREADS);
 }
 
 // fp4: candidates straight from the matching kernel -> exact verification -> ordered pairs.  No (row, keyframe) plane.
@@ -1576,6 +1592,15 @@ int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_
 }
 
 // SM clock the last profiled k_tc*_top2 launch actually ran at (cycles / wall time of its longest CTA)
+#ifdef NCLT_TC_TRACE
+// diagnostics build only: clock64 stamps of steps 2000..2127 of CTA 0 (tools/tc_clock.py prints them)
+extern "C" int nclt_ctx_tc_trace(nclt_ctx* c, unsigned long long* out1024) {
+    if (!c || !c->d_tc_clk) return NCLT_ERR_ARG;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaMemcpy(out1024, c->d_tc_clk + 64, 8192, cudaMemcpyDeviceToHost));
+    return NCLT_OK;
+}
+#endif
 extern "C" int nclt_ctx_tc_clock(nclt_ctx* c, double* mhz, double* kernel_ms, unsigned long long* raw64) {
     if (!c) return NCLT_ERR_ARG;
     unsigned long long h[64] = {0};

@@ -1,5 +1,5 @@
 """SM clock the tensor-core matching kernel really runs at (clock64 vs globaltimer inside the kernel)."""
-import ctypes as C, sys
+import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, '/root/repo')
 import nclt_slam_project_b200
@@ -11,6 +11,11 @@ L.nclt_ctx_tc_clock.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c
 data = synth.make_library(1, n_kf=400, n_desc=1000)
 B = 256
 desc, pts2d, kstar, _ = synth.make_frame_batch(data, range(100, 100 + B), n_desc=1000, n_planted=400)
+FILL = os.environ.get('TC_CLOCK_FILL')      # '0' / '255' / '170': constant descriptor bytes (the tensor pipe's speed does not depend on the data)
+if FILL is not None:
+    desc[:] = int(FILL)
+    for lm in data['landmarks']:
+        lm['descriptors'][:] = int(FILL)
 for engine in sys.argv[1:] or ('tensor', 'tensor4'):
     lms = data['landmarks']
     eng = DeviceLocalizer(([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms]), 0)
@@ -34,3 +39,12 @@ for engine in sys.argv[1:] or ('tensor', 'tensor4'):
                 print(f'   epilogue part {part}: total {v.sum()/1e6:.2f} Mcyc: ' + ', '.join(
                     f'{n} {100*x/v.sum():.1f}%' for n, x in zip(('other', 'wait-full', 'loads', 'release', 'maxima'), v)), flush=True)
     eng.ctx.profile(False)
+    if engine == 'tensor4' and hasattr(L, 'nclt_ctx_tc_trace'):      # built with -DNCLT_TC_TRACE
+        tr = np.zeros(1024, dtype=np.uint64)
+        L.nclt_ctx_tc_trace.argtypes = [C.c_void_p, C.c_void_p]
+        L.nclt_ctx_tc_trace(eng.ctx.h, tr.ctypes.data)
+        tr = tr.reshape(128, 8).astype(np.int64)
+        t0 = tr[0, 0]
+        print('step: acc_empty-ok  mma-issued  commit-ret | full-seen(q0)  released q0 q1 q2 q3   (clk rel.)')
+        for i in range(40):
+            print(f'{i:3d}: ' + '  '.join(f'{int(x - t0):7d}' for x in tr[i, :8]))
