@@ -343,12 +343,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
 //   2. The bias row of the LIBRARY side lives in the tile image (2 extra 16-byte K chunks per row, 160 B per row):
 //      padding rows carry a zero bias row, their cells stay 0 - below every valid pattern - so there is no masking
 //      pass and no tcgen05.st in the loop.
-//   3. Tiles are 240 consecutive library rows ACROSS keyframe boundaries (keyframe-aligned tiles wasted a fifth of the
-//      steps on 1000-row keyframes: 4 x 240 + 40; on real 300-row keyframes far more).  The epilogue walks the keyframe
-//      boundaries inside a tile: whole 16-column register groups go to the running maxima of the current keyframe; the
-//      one group a boundary cuts is split per column half.  Tiles restart at "group" boundaries (the first keyframe
-//      boundary after >= 16 tiles' worth of rows), which are the only places a work split may start - so the image
-//      does not depend on the batch size.
+//   3. Tiles never cross a keyframe: a keyframe of c rows (padded to 16) becomes ceil(c / 240) tiles of EQUAL size
+//      (1000 rows -> 5 x 208, 300 rows -> 2 x 160), and its last tile carries a flag: the epilogue closes the keyframe's
+//      running maxima there.  (An intermediate design ran 240-row tiles across keyframe boundaries to save the padding:
+//      the boundary walk inside the epilogue - a branch per 16-column register group, BSSY / BSYNC around each because
+//      ptxas cannot see that the walk is warp-uniform - made a boundary tile 3.6 x as expensive as a plain one, +35 % on
+//      the whole kernel with 1000-row keyframes; a step is latency-bound, so more, smaller steps cost less than that.)
 // The kernel either EMITS the Lowe-ratio candidates (row, keyframe) straight from the epilogue (ratio mode: no
 // per-(row, keyframe) plane is ever written) or writes the (d1, d2 bound) plane (flat top-2 mode, config 5).
 // TMEM: accumulator buffers at columns 0 and 240; scale factors 1.0 at [480, 496), 2^14 at [496, 512).
@@ -362,15 +362,13 @@ constexpr int A4_BIAS_BYTES = 128 * 32;         // constant bias slab of the que
 constexpr int NSTAGE4 = 3;
 constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MMA issuers
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
-constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
 
-// Image row space: every keyframe's rows are padded to a multiple of 16 (zero rows with a zero bias row), so a keyframe
-// boundary always falls between two 16-column register groups of the epilogue.  pstart[k] = first image row of keyframe k.
 struct LibTile4 {
     uint32_t img_off256;   // byte offset / 256 into the library image
     uint16_t n;            // rows in the tile image (multiple of 16, <= 240)
-    uint16_t pad_;
-    int prow0;             // image row of column 0
+    uint16_t nv;           // valid rows (the rest is zero padding with a zero bias row)
+    int kf_last;           // keyframe << 1 | (last tile of the keyframe)
+    int src_row0;          // library row of image row 0
 };
 struct WorkEntry { int item; int q; };
 
@@ -379,9 +377,7 @@ struct Tc4Params {
     const uint8_t* lib_img;
     const LibTile4* tiles;
     int n_mtiles, n_groups, n_splits;
-    const int* split_tile;     // [n_splits + 1]
-    const int* split_kf;       // [n_splits + 1] first keyframe of each split
-    const int* kf_pstart;      // [n_kf + 1] image row where every keyframe starts (multiples of 16)
+    const int* split_tile;     // [n_splits + 1] first tile of each split (a keyframe's first tile)
     const int* kf_count;
     int n_kf;
     long long rows_total;      // valid query rows (B * Nq)
@@ -417,28 +413,17 @@ __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n
 
 // tile image: n rows x 160 bytes in the K-major no-swizzle layout (10 K chunks of 16 bytes); chunks 8-9 = bias row
 __global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile4* __restrict__ tiles, int n_tiles,
-                                  const int* __restrict__ kf_pstart, const int* __restrict__ kf_start,
-                                  const int* __restrict__ kf_count, int n_kf, uint8_t* img) {
+                                  uint8_t* img) {
     int t = blockIdx.x;
     if (t >= n_tiles) return;
     const LibTile4 lt = tiles[t];
     uint8_t* dst = img + (size_t)lt.img_off256 * 256;
     for (int i = threadIdx.x; i < lt.n * 20; i += blockDim.x) {
         const int r = i / 20, g = i % 20;          // g: 8-byte group of the 160-byte row
-        // image row -> (keyframe, row inside it): last keyframe whose image start is <= the row
-        const int pr = lt.prow0 + r;
-        int lo = 0, hi = n_kf;                     // invariant: kf_pstart[lo] <= pr < kf_pstart[hi] (pr < total image rows)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (kf_pstart[mid] <= pr) lo = mid; else hi = mid;
-        }
-        const int local = pr - kf_pstart[lo];
-        const bool valid = pr < kf_pstart[n_kf] && local < kf_count[lo];
-        const size_t src_row = (size_t)kf_start[lo] + local;
         uint2 v = make_uint2(0, 0);
-        if (valid) {
+        if (r < lt.nv) {
             if (g < 16) {
-                uint32_t w = desc[src_row * 8 + (g >> 1)];
+                uint32_t w = desc[((size_t)lt.src_row0 + r) * 8 + (g >> 1)];
                 v = tc::expand16_fp4((g & 1) ? (w >> 16) : (w & 0xFFFFu));
             } else {
                 uint32_t w[2] = {0, 0};
@@ -480,30 +465,16 @@ __device__ __forceinline__ void grp1(uint32_t (&x)[NA], int b0, uint32_t (&acc)[
     for (int j = 0; j < 8; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[b0 + j], x[b0 + j] << 16);
 }
 
-// Per-warp walk over the keyframe boundaries inside the tiles (all lanes share it; the maxima differ per lane).
-struct SegWalk {
-    int kf;            // keyframe the next column belongs to
-    int end_col;       // first column (tile relative) that is NOT in it any more; INT_MAX once past the split's last keyframe
-    int next_end_row;  // image row where keyframe kf + 1 ends (INT_MAX past the split), loaded one boundary ahead
-};
-// The walk is the same in every lane, but it is computed from loaded values, which ptxas has to treat as divergent:
-// every `if (group in range)` around the maxima then costs a BSSY / BSYNC pair and a branch-resolution stall (~60 % of a
-// boundary tile's time in the ncu source view).  A REDUX result is warp-uniform by construction and lives in a uniform
-// register, so the same branches become plain uniform ones.
-__device__ __forceinline__ int warp_uniform(int x) { return __reduce_max_sync(0xFFFFFFFFu, x); }
 struct Acc4 { uint32_t v[4]; };            // running maxima (high halves) of 4 disjoint column subsets
 
 struct Tc4Epilogue {
     const Tc4Params* p;         // the kernel's __grid_constant__ parameter block (constant bank, no local copy)
-    int kf_stop;            // first keyframe after this split
     long long row;          // this lane's query row
     bool row_ok;            // row < rows_total and the step is a real one
     int lane;
 
-    __device__ __forceinline__ int kf_end_row(int kf) const { return __ldg(p->kf_pstart + kf + 1); }      // image rows
-
     // Keyframe finished for this lane's row: top-2 of the 8 column-subset maxima -> (exact d1, upper bound of d2).
-    // Inlined at its four call sites only (keyframe advance of the two query tiles, end of split): out-of-line calls
+    // Inlined at its two call sites (one per query tile of the epilogue set): out-of-line calls
     // cost a stack frame and a local copy of the parameter block whose dependent loads sat on every step's path.
     __device__ __forceinline__ void finalize(int kf, const Acc4& a) const {
         // top-2 of the 4 subset maxima (high halves): second largest of a union = max(min of the maxima, max of the seconds)
@@ -536,14 +507,6 @@ struct Tc4Epilogue {
             if (pos < p->work_cap) p->work[pos] = WorkEntry{b * p->n_kf + kf, q};
             else atomicAdd(p->overflow, 1);
         }
-    }
-    // next keyframe: finalize the current one for this lane's row, restart the maxima
-    __device__ __forceinline__ void advance(SegWalk& w, Acc4& acc, int row0) const {
-        finalize(w.kf, acc);
-        acc.v[0] = acc.v[1] = acc.v[2] = acc.v[3] = 0;
-        ++w.kf;
-        w.end_col = warp_uniform(w.next_end_row == INT_MAX ? INT_MAX : w.next_end_row - row0);
-        w.next_end_row = w.kf + 1 < kf_stop ? kf_end_row(w.kf + 1) : INT_MAX;     // not needed before the next boundary
     }
 };
 
@@ -708,19 +671,12 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
             Acc4 acc[MA4 / 2];
 #pragma unroll
             for (int mm = 0; mm < MA4 / 2; ++mm) acc[mm].v[0] = acc[mm].v[1] = acc[mm].v[2] = acc[mm].v[3] = 0;
-            Tc4Epilogue ep{&p, warp_uniform(p.split_kf[split + 1]), 0, false, lane};
-            int cur_kf = warp_uniform(p.split_kf[split]);     // keyframe walk, carried from tile to tile
-            int cur_end_row = cur_kf < ep.kf_stop ? ep.kf_end_row(cur_kf) : INT_MAX;
-            int cur_next_end = cur_kf + 1 < ep.kf_stop ? ep.kf_end_row(cur_kf + 1) : INT_MAX;
+            Tc4Epilogue ep{&p, 0, false, lane};
             const int t_end = p.split_tile[split + 1];
             for (int t = p.split_tile[split]; t < t_end; ++t) {
-                LibTile4 lt;                                  // 20 KB table, L1 resident; read while the MMA is still running
-                lt.n = __ldg(&p.tiles[t].n);
-                lt.prow0 = __ldg(&p.tiles[t].prow0);
-                const int n = warp_uniform(lt.n);
-                const int kf0 = cur_kf;
-                const int end0 = warp_uniform(cur_end_row == INT_MAX ? INT_MAX : cur_end_row - lt.prow0);
-                SegWalk wk_after{kf0, end0, cur_next_end};
+                // 16-byte table entries, L1 resident; read while the MMA is still running
+                const int n = (int)__ldg(&p.tiles[t].n);
+                const int kf_last = __ldg(&p.tiles[t].kf_last);
 #pragma unroll
                 for (int mm = 0; mm < MA4 / 2; ++mm) {
                     const int m = set + 2 * mm;
@@ -741,7 +697,7 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                     const uint32_t ta = tmem + buf * B4_ROWS + lane_base;
                     uint32_t a[32], b[32], c2[32], d[16], e[8];
                     const int o64 = n & ~63, rem = n & 63;
-                    if (n == B4_ROWS) {          // the common full tile: five loads back to back, no branches in between
+                    if (n == B4_ROWS) {          // a full tile: five loads back to back, no branches in between
                         tc::tmem_ld32_pack16(ta, a);
                         tc::tmem_ld32_pack16(ta + 64, b);
                         tc::tmem_ld32_pack16(ta + 128, c2);
@@ -772,68 +728,21 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                     if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);     // every column is in registers
                     TT(3);
                     TR(st, 4 + quad);
-                    ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
-                    ep.row_ok = ep.row < p.rows_total;
-                    SegWalk wk{kf0, end0, cur_next_end};
                     Acc4& A = acc[mm];
-                    // Keyframes are padded to whole 16-column groups, so a keyframe ends between two register groups:
-                    // groups [g, g_b) go to the running maxima of the current keyframe, then the walk advances.
-#define NCLT_GRP(arr, base) { grp1(arr, (base), A.v); }
-                    if (end0 >= n) {
-                        // no keyframe ends inside this tile (3 tiles in 4 with 1000-row keyframes): straight-line maxima
-                        if (n >= 64) { grp2(a, 0, a, 8, A.v); grp2(a, 16, a, 24, A.v); }
-                        if (n >= 128) { grp2(b, 0, b, 8, A.v); grp2(b, 16, b, 24, A.v); }
-                        if (n >= 192) { grp2(c2, 0, c2, 8, A.v); grp2(c2, 16, c2, 24, A.v); }
-                        if (rem & 32) { grp2(d, 0, d, 8, A.v); }
-                        if (rem & 16) { grp1(e, 0, A.v); }
-                    } else {
-                        // a keyframe ends inside the tile: groups [g_lo, g_b) go to the current keyframe, the walk
-                        // advances, and so on.  a, b, c2 hold the groups below column o64; d / e the tail.
-                        const int n_grp = n >> 4;
-                        const int gd = o64 >> 4, ge = (o64 + (rem & 32)) >> 4;
-                        int g_lo = 0;
-#pragma unroll 1
-                        for (;;) {
-                            const int g_b = wk.end_col >= n ? n_grp : (wk.end_col >> 4);
-#pragma unroll
-                            for (int g = 0; g < 12; ++g) {
-                                if (16 * g < o64 && g >= g_lo && g < g_b) {
-                                    if (g < 4) NCLT_GRP(a, 8 * g)
-                                    else if (g < 8) NCLT_GRP(b, 8 * (g - 4))
-                                    else NCLT_GRP(c2, 8 * (g - 8))
-                                }
-                            }
-                            if (rem & 32) {
-                                if (gd >= g_lo && gd < g_b) NCLT_GRP(d, 0)
-                                if (gd + 1 >= g_lo && gd + 1 < g_b) NCLT_GRP(d, 8)
-                            }
-                            if ((rem & 16) && ge >= g_lo && ge < g_b) NCLT_GRP(e, 0)
-                            if (g_b >= n_grp) break;
-                            g_lo = g_b;
-                            ep.advance(wk, A, lt.prow0);
-                        }
+                    if (n >= 64) { grp2(a, 0, a, 8, A.v); grp2(a, 16, a, 24, A.v); }
+                    if (n >= 128) { grp2(b, 0, b, 8, A.v); grp2(b, 16, b, 24, A.v); }
+                    if (n >= 192) { grp2(c2, 0, c2, 8, A.v); grp2(c2, 16, c2, 24, A.v); }
+                    if (rem & 32) { grp2(d, 0, d, 8, A.v); }
+                    if (rem & 16) { grp1(e, 0, A.v); }
+                    if (kf_last & 1) {                        // the keyframe ends with this tile
+                        ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                        ep.row_ok = ep.row < p.rows_total;
+                        ep.finalize(kf_last >> 1, A);
+                        A.v[0] = A.v[1] = A.v[2] = A.v[3] = 0;
                     }
-#undef NCLT_GRP
-                    wk_after = wk;
                     TT(4);
                 }
                 st_base += (uint32_t)ma_pad;
-                // every real step of this warp ended its walk in the same state; a warp without a real step does not walk
-                cur_kf = wk_after.kf;
-                cur_end_row = wk_after.end_col == INT_MAX ? INT_MAX : wk_after.end_col + lt.prow0;
-                cur_next_end = wk_after.next_end_row;
-            }
-            // ---- end of the split: the keyframes that are still open (the last one, trailing empty ones)
-#pragma unroll
-            for (int mm = 0; mm < MA4 / 2; ++mm) {
-                const int m = set + 2 * mm;
-                if (m >= ma) break;
-                ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
-                ep.row_ok = ep.row < p.rows_total;
-                for (int kf = cur_kf; kf < ep.kf_stop; ++kf) {
-                    ep.finalize(kf, acc[mm]);
-                    acc[mm].v[0] = acc[mm].v[1] = acc[mm].v[2] = acc[mm].v[3] = 0;
-                }
             }
         }
 #ifdef NCLT_TC_TIMING
@@ -1108,11 +1017,7 @@ struct TcLibCache {
     // so that a whole localisation step can be captured into a CUDA graph)
     int* d_split = nullptr;
     int split_groups = -1, split_n = 0;
-    // fp4 flavour: tiles run across keyframe boundaries; a work split may only start where a tile GROUP starts
-    LibTile4* d_tiles4 = nullptr;
-    std::vector<int> grp_tile, grp_kf;   // [n_grp + 1] first tile / first keyframe of every group
-    int* d_split_kf = nullptr;           // [n_splits + 1] beside d_split
-    int* d_pstart = nullptr;             // [n_kf + 1] image row of every keyframe's first row (keyframes padded to 16 rows)
+    LibTile4* d_tiles4 = nullptr;        // fp4 flavour
 };
 
 static void tc_cache_free(TcLibCache* cch) {
@@ -1121,14 +1026,10 @@ static void tc_cache_free(TcLibCache* cch) {
     if (cch->d_tiles) cudaFree(cch->d_tiles);
     if (cch->d_tiles4) cudaFree(cch->d_tiles4);
     if (cch->d_split) cudaFree(cch->d_split);
-    if (cch->d_split_kf) cudaFree(cch->d_split_kf);
-    if (cch->d_pstart) cudaFree(cch->d_pstart);
-    cch->d_pstart = nullptr;
     cch->d_img = nullptr;
     cch->d_tiles = nullptr;
     cch->d_tiles4 = nullptr;
     cch->d_split = nullptr;
-    cch->d_split_kf = nullptr;
     cch->split_groups = -1;
 }
 
@@ -1144,7 +1045,7 @@ void nclt_tc_release(nclt_lib* L) {
 }
 
 // fp4 = false: fp8 images (256 B per descriptor, keyframe-aligned tiles of <= 256 rows); fp4 = true: e2m1 images
-// (128 B per descriptor + 32 B bias row, 240-row tiles across keyframe boundaries)
+// (128 B per descriptor + 32 B bias row, keyframe-aligned tiles of <= 240 rows, equal sizes within a keyframe)
 static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     void** slot = fp4 ? &L->tc4_cache : &L->tc_cache;
     TcLibCache* cch = static_cast<TcLibCache*>(*slot);
@@ -1157,43 +1058,32 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     tc_cache_free(cch);
     c->alloc_gen++;
     if (fp4) {
-        // 240-row tiles over the IMAGE row space (every keyframe padded to a multiple of 16 rows), across keyframe
-        // boundaries.  A tile group closes (its last tile is short) at the first keyframe boundary after GROUP_MIN_ROWS
-        // image rows; work splits start at group boundaries.
-        std::vector<int> pstart(L->n_kf + 1, 0);
-        for (int k = 0; k < L->n_kf; ++k) pstart[k + 1] = pstart[k] + ((L->h_count[k] + 15) & ~15);
+        // keyframe-aligned tiles of equal size: c rows (padded to 16) -> ceil(c16 / 240) tiles of ceil16(c16 / tiles) rows
         std::vector<LibTile4> tiles;
-        cch->grp_tile.clear();
-        cch->grp_kf.clear();
-        size_t off256 = 0;
-        int k = 0;
-        while (k < L->n_kf) {
-            cch->grp_tile.push_back((int)tiles.size());
-            cch->grp_kf.push_back(k);
-            const int row_a = pstart[k];
-            int row_b = row_a;
-            while (k < L->n_kf && (row_b - row_a < GROUP_MIN_ROWS || L->h_count[k] == 0)) {
-                row_b = pstart[k + 1];
-                ++k;
-            }
-            for (int r = row_a; r < row_b; r += B4_ROWS) {
-                const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 16
-                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, 0, r});
-                off256 += (size_t)n * B4_ROW_BYTES / 256;          // n * 160 bytes = (n / 16) * 2560
+        cch->kf_first_tile.assign(L->n_kf + 1, 0);
+        size_t off256 = 0;      // a tile image is n * 160 bytes = (n / 16) * 2560: always a multiple of 256
+        for (int k = 0; k < L->n_kf; ++k) {
+            cch->kf_first_tile[k] = (int)tiles.size();
+            const int cnt = L->h_count[k], start = L->h_start[k];
+            const int c16 = std::max(16, (cnt + 15) & ~15);       // an empty keyframe owns one all-padding tile
+            const int nt = (c16 + B4_ROWS - 1) / B4_ROWS;
+            const int per = (((c16 + nt - 1) / nt) + 15) & ~15;
+            for (int r = 0; r < c16; r += per) {
+                const int n = std::min(per, c16 - r);
+                const int nv = std::max(0, std::min(n, cnt - r));
+                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, (k << 1) | (r + per >= c16 ? 1 : 0), start + r});
+                off256 += (size_t)n * B4_ROW_BYTES / 256;
             }
         }
-        cch->grp_tile.push_back((int)tiles.size());
-        cch->grp_kf.push_back(L->n_kf);
+        cch->kf_first_tile[L->n_kf] = (int)tiles.size();
         cch->n_tiles = (int)tiles.size();
-        tiles.push_back(LibTile4{0, 16, 0, 0});        // sentinel: the epilogue prefetches entry t + 1
-        CU_TRY(c, cudaMalloc(&cch->d_pstart, pstart.size() * sizeof(int)));
-        CU_TRY(c, cudaMemcpyAsync(cch->d_pstart, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        tiles.push_back(LibTile4{0, 16, 0, 0, 0});     // sentinel
         if (cch->n_tiles > 0) {
             CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
             CU_TRY(c, cudaMalloc(&cch->d_tiles4, tiles.size() * sizeof(LibTile4)));
             CU_TRY(c, cudaMemcpyAsync(cch->d_tiles4, tiles.data(), tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
             k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles4,
-                                                                   cch->n_tiles, cch->d_pstart, L->d_start, L->d_count, L->n_kf, cch->d_img);
+                                                                   cch->n_tiles, cch->d_img);
             c->launches++;
             CU_TRY(c, cudaGetLastError());
         }
@@ -1277,8 +1167,7 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
         // ceil(items / SMs) item-times plus ~10 us per item (query-tile reload, pipeline drain and refill), so among
         // the split counts near the target pick the cheapest (e.g. 1000 groups: 4 splits -> 27.03 items per SM -> 28
         // rounds, 3.5 % of the last one idle; 5 splits -> 33.8 -> 34 rounds, 0.6 %: measured 22.5 -> 21.9 ms)
-        // fp4: a split starts at a tile-group boundary; fp8: at any keyframe
-        const int kf_cap = fp4 ? std::max((int)cch->grp_tile.size() - 1, 1) : std::max(n_kf, 1);
+        const int kf_cap = std::max(n_kf, 1);       // a split starts at a keyframe's first tile
         const int target = std::max(1, std::min(kf_cap, (c->sm_count * 24 + pl->n_groups - 1) / pl->n_groups));
         int best = target;
         double best_cost = 1e30;
@@ -1294,27 +1183,25 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
     pl->d12_bytes = (size_t)n_kf * pl->rows_pad * 4;
     if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
     if (cch->split_groups != pl->n_groups || cch->split_n != pl->n_splits) {
-        std::vector<int> split_tile(pl->n_splits + 1), split_kf(pl->n_splits + 1);
-        const int n_grp = (int)cch->grp_tile.size() - 1;
+        // split s starts at the keyframe whose first tile is nearest to tile n_tiles * s / n_splits (equal tile counts,
+        // not equal keyframe counts: ragged libraries stay balanced)
+        std::vector<int> split_tile(pl->n_splits + 1);
+        const std::vector<int>& kft = cch->kf_first_tile;
         for (int s = 0; s <= pl->n_splits; ++s) {
-            if (fp4) {
-                const int g = (int)((long long)n_grp * s / pl->n_splits);
-                split_tile[s] = cch->grp_tile[g];
-                split_kf[s] = cch->grp_kf[g];
-            } else {
-                split_tile[s] = cch->kf_first_tile[(long long)n_kf * s / pl->n_splits];
-                split_kf[s] = (int)((long long)n_kf * s / pl->n_splits);
-            }
+            const int want = (int)((long long)cch->n_tiles * s / pl->n_splits);
+            int k = (int)(std::lower_bound(kft.begin(), kft.end(), want) - kft.begin());      // first kf with first tile >= want
+            if (k > 0 && (k > n_kf || want - kft[k - 1] < kft[k] - want)) --k;
+            split_tile[s] = kft[std::min(k, n_kf)];
         }
+        split_tile[0] = 0;
+        split_tile[pl->n_splits] = cch->n_tiles;
+        for (int s = 1; s <= pl->n_splits; ++s) split_tile[s] = std::max(split_tile[s], split_tile[s - 1]);
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         c->alloc_gen++;
         if (cch->d_split) cudaFree(cch->d_split);
-        if (cch->d_split_kf) cudaFree(cch->d_split_kf);
-        cch->d_split = cch->d_split_kf = nullptr;
+        cch->d_split = nullptr;
         CU_TRY(c, cudaMalloc(&cch->d_split, (pl->n_splits + 1) * sizeof(int)));
-        CU_TRY(c, cudaMalloc(&cch->d_split_kf, (pl->n_splits + 1) * sizeof(int)));
         CU_TRY(c, cudaMemcpy(cch->d_split, split_tile.data(), (pl->n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        CU_TRY(c, cudaMemcpy(cch->d_split_kf, split_kf.data(), (pl->n_splits + 1) * sizeof(int), cudaMemcpyHostToDevice));
         cch->split_groups = pl->n_groups;
         cch->split_n = pl->n_splits;
     }
@@ -1388,8 +1275,8 @@ static int tc4_run(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8
     }
     Tc4Params p{};
     p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles4; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
-    p.n_splits = pl.n_splits; p.split_tile = cch->d_split; p.split_kf = cch->d_split_kf;
-    p.kf_pstart = cch->d_pstart; p.kf_count = L->d_count; p.n_kf = L->n_kf;
+    p.n_splits = pl.n_splits; p.split_tile = cch->d_split;
+    p.kf_count = L->d_count; p.n_kf = L->n_kf;
     p.rows_total = pl.rows; p.Nq = Nq; p.q_n = q_n; p.mode = mode; p.num = num; p.den = den;
     p.work = work; p.work_count = work_count; p.work_cap = work_cap; p.overflow = c->d_overflow;
     p.out = d12; p.rows_pad = pl.rows_pad;
