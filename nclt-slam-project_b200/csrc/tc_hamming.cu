@@ -343,12 +343,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
 //   2. The bias row of the LIBRARY side lives in the tile image (2 extra 16-byte K chunks per row, 160 B per row):
 //      padding rows carry a zero bias row, their cells stay 0 - below every valid pattern - so there is no masking
 //      pass and no tcgen05.st in the loop.
-//   3. Tiles never cross a keyframe: a keyframe of c rows (padded to 16) becomes ceil(c / 240) tiles of EQUAL size
-//      (1000 rows -> 5 x 208, 300 rows -> 2 x 160), and its last tile carries a flag: the epilogue closes the keyframe's
-//      running maxima there.  (An intermediate design ran 240-row tiles across keyframe boundaries to save the padding:
-//      the boundary walk inside the epilogue - a branch per 16-column register group, BSSY / BSYNC around each because
-//      ptxas cannot see that the walk is warp-uniform - made a boundary tile 3.6 x as expensive as a plain one, +35 % on
-//      the whole kernel with 1000-row keyframes; a step is latency-bound, so more, smaller steps cost less than that.)
+//   3. Tiles are 240 consecutive library rows ACROSS keyframe boundaries, with every keyframe padded to whole 48-row
+//      segments (five per tile): the tensor pipe takes ~118 clk per MMA for ANY N <= 240, so only full tiles run at its
+//      rate (keyframe-aligned tiles: 1000 rows = 5 steps; running across: 4.2).  A keyframe can then only end at one
+//      of five places in a tile, and the host precomputes where (`endmask`): the epilogue's straight-line maxima get
+//      one `if` per segment in the tiles that have a boundary, nothing in the others.  (A first version padded to 16
+//      rows and walked the boundaries in the kernel - a branch per 16-column register group, BSSY / BSYNC around each
+//      because ptxas cannot see that the walk is warp-uniform: a boundary tile cost 3.6 x a plain one, +35 % on the
+//      whole kernel.)  Tiles restart at "group" boundaries (the first keyframe boundary after >= 16 tiles' worth of
+//      rows), the only places a work split may start - so the image does not depend on the batch size.
 // The kernel either EMITS the Lowe-ratio candidates (row, keyframe) straight from the epilogue (ratio mode: no
 // per-(row, keyframe) plane is ever written) or writes the (d1, d2 bound) plane (flat top-2 mode, config 5).
 // TMEM: accumulator buffers at columns 0 and 240; scale factors 1.0 at [480, 496), 2^14 at [496, 512).
@@ -363,12 +366,19 @@ constexpr int NSTAGE4 = 3;
 constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MMA issuers
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
 
+constexpr int SEG4 = 48;                        // keyframes are padded to whole 48-row segments; a tile is <= 5 segments
+constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
+
+// Image row space: every keyframe's rows are padded to a multiple of SEG4 (zero rows with a zero bias row; an empty
+// keyframe owns one all-padding segment), and tiles are 240 consecutive image rows ACROSS keyframe boundaries, so a
+// keyframe can only end at a segment boundary of a tile.  The host precomputes where: bit s of `endmask` says that a
+// keyframe ends with segment s; keyframes inside a tile are consecutive, starting at kf0.
 struct LibTile4 {
     uint32_t img_off256;   // byte offset / 256 into the library image
-    uint16_t n;            // rows in the tile image (multiple of 16, <= 240)
-    uint16_t nv;           // valid rows (the rest is zero padding with a zero bias row)
-    int kf_last;           // keyframe << 1 | (last tile of the keyframe)
-    int src_row0;          // library row of image row 0
+    uint16_t n;            // rows in the tile image (multiple of 48, <= 240)
+    uint16_t endmask;      // bit s: a keyframe ends at tile column 48 * (s + 1)
+    int kf0;               // keyframe of column 0
+    int prow0;             // image row of column 0
 };
 struct WorkEntry { int item; int q; };
 
@@ -413,17 +423,26 @@ __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n
 
 // tile image: n rows x 160 bytes in the K-major no-swizzle layout (10 K chunks of 16 bytes); chunks 8-9 = bias row
 __global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile4* __restrict__ tiles, int n_tiles,
-                                  uint8_t* img) {
+                                  const int* __restrict__ kf_pstart, const int* __restrict__ kf_start,
+                                  const int* __restrict__ kf_count, int n_kf, uint8_t* img) {
     int t = blockIdx.x;
     if (t >= n_tiles) return;
     const LibTile4 lt = tiles[t];
     uint8_t* dst = img + (size_t)lt.img_off256 * 256;
     for (int i = threadIdx.x; i < lt.n * 20; i += blockDim.x) {
         const int r = i / 20, g = i % 20;          // g: 8-byte group of the 160-byte row
+        // image row -> (keyframe, row inside it): last keyframe whose image start is <= the row
+        const int pr = lt.prow0 + r;
+        int lo = 0, hi = n_kf;                     // invariant: kf_pstart[lo] <= pr < kf_pstart[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (kf_pstart[mid] <= pr) lo = mid; else hi = mid;
+        }
+        const int local = pr - kf_pstart[lo];
         uint2 v = make_uint2(0, 0);
-        if (r < lt.nv) {
+        if (local < kf_count[lo]) {
             if (g < 16) {
-                uint32_t w = desc[((size_t)lt.src_row0 + r) * 8 + (g >> 1)];
+                uint32_t w = desc[((size_t)kf_start[lo] + local) * 8 + (g >> 1)];
                 v = tc::expand16_fp4((g & 1) ? (w >> 16) : (w & 0xFFFFu));
             } else {
                 uint32_t w[2] = {0, 0};
@@ -463,6 +482,15 @@ template <int NA>
 __device__ __forceinline__ void grp1(uint32_t (&x)[NA], int b0, uint32_t (&acc)[4]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[b0 + j], x[b0 + j] << 16);
+}
+// One 48-column segment = 24 packed registers -> the 4 running maxima, same two-pass scheme.
+__device__ __forceinline__ void seg24(uint32_t* x, uint32_t (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[j], x[j + 12]);
+#pragma unroll
+    for (int j = 0; j < 24; ++j) x[j] <<= 16;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j & 3] = fmax3u(acc[j & 3], x[j], x[j + 12]);
 }
 
 struct Acc4 { uint32_t v[4]; };            // running maxima (high halves) of 4 disjoint column subsets
@@ -675,8 +703,10 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
             const int t_end = p.split_tile[split + 1];
             for (int t = p.split_tile[split]; t < t_end; ++t) {
                 // 16-byte table entries, L1 resident; read while the MMA is still running
-                const int n = (int)__ldg(&p.tiles[t].n);
-                const int kf_last = __ldg(&p.tiles[t].kf_last);
+                const uint32_t nm = __ldg(reinterpret_cast<const uint32_t*>(&p.tiles[t].n));     // n | endmask << 16
+                const int n = (int)(nm & 0xFFFFu);
+                const uint32_t endmask = nm >> 16;
+                const int kf0 = __ldg(&p.tiles[t].kf0);
 #pragma unroll
                 for (int mm = 0; mm < MA4 / 2; ++mm) {
                     const int m = set + 2 * mm;
@@ -695,32 +725,17 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                         break;
                     }
                     const uint32_t ta = tmem + buf * B4_ROWS + lane_base;
-                    uint32_t a[32], b[32], c2[32], d[16], e[8];
-                    const int o64 = n & ~63, rem = n & 63;
-                    if (n == B4_ROWS) {          // a full tile: five loads back to back, no branches in between
-                        tc::tmem_ld32_pack16(ta, a);
-                        tc::tmem_ld32_pack16(ta + 64, b);
-                        tc::tmem_ld32_pack16(ta + 128, c2);
-                        tc::tmem_ld16_pack16(ta + 192, d);
-                        tc::tmem_ld8_pack16(ta + 224, e);
-                    } else {
-                        if (n >= 64) tc::tmem_ld32_pack16(ta, a);
-                        if (n >= 128) tc::tmem_ld32_pack16(ta + 64, b);
-                        if (n >= 192) tc::tmem_ld32_pack16(ta + 128, c2);
-                        if (rem & 32) tc::tmem_ld16_pack16(ta + (uint32_t)o64, d);
-                        if (rem & 16) tc::tmem_ld8_pack16(ta + (uint32_t)(o64 + (rem & 32)), e);
-                    }
+                    // all 240 columns of the lane quadrant, packed: 120 registers, five loads back to back, no branches
+                    // in between (columns beyond a short tile's n hold stale cells that are never looked at)
+                    uint32_t r[120];
+                    tc::tmem_ld32_pack16(ta, r);
+                    tc::tmem_ld32_pack16(ta + 64, r + 32);
+                    tc::tmem_ld32_pack16(ta + 128, r + 64);
+                    tc::tmem_ld16_pack16(ta + 192, r + 96);
+                    tc::tmem_ld8_pack16(ta + 224, r + 112);
                     tc::tmem_wait_ld();
 #ifdef NCLT_TC_TIMING
-                    {   // make the loaded registers observably ready before the clock is read
-                        uint32_t probe_ = 0;
-                        if (n >= 64) probe_ ^= a[31];
-                        if (n >= 128) probe_ ^= b[31];
-                        if (n >= 192) probe_ ^= c2[31];
-                        if (rem & 32) probe_ ^= d[15];
-                        if (rem & 16) probe_ ^= e[7];
-                        if (probe_ == 0x12345u) s_tmem[1] = probe_;
-                    }
+                    if ((r[31] ^ r[63] ^ r[95] ^ r[111] ^ r[119]) == 0x12345u) s_tmem[1] = r[0];   // registers observably ready
 #endif
                     TT(2);
                     tc::tc_fence_before();
@@ -729,16 +744,25 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                     TT(3);
                     TR(st, 4 + quad);
                     Acc4& A = acc[mm];
-                    if (n >= 64) { grp2(a, 0, a, 8, A.v); grp2(a, 16, a, 24, A.v); }
-                    if (n >= 128) { grp2(b, 0, b, 8, A.v); grp2(b, 16, b, 24, A.v); }
-                    if (n >= 192) { grp2(c2, 0, c2, 8, A.v); grp2(c2, 16, c2, 24, A.v); }
-                    if (rem & 32) { grp2(d, 0, d, 8, A.v); }
-                    if (rem & 16) { grp1(e, 0, A.v); }
-                    if (kf_last & 1) {                        // the keyframe ends with this tile
+                    if (endmask == 0) {
+                        // no keyframe ends inside this tile (3 tiles in 4 with 1000-row keyframes; such a tile is full)
+#pragma unroll
+                        for (int sg = 0; sg < 5; ++sg) seg24(r + 24 * sg, A.v);
+                    } else {
                         ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
                         ep.row_ok = ep.row < p.rows_total;
-                        ep.finalize(kf_last >> 1, A);
-                        A.v[0] = A.v[1] = A.v[2] = A.v[3] = 0;
+                        int kf = kf0;
+#pragma unroll
+                        for (int sg = 0; sg < 5; ++sg) {
+                            if (SEG4 * sg < n) {
+                                seg24(r + 24 * sg, A.v);
+                                if ((endmask >> sg) & 1u) {       // a keyframe ends with this segment
+                                    ep.finalize(kf, A);
+                                    A.v[0] = A.v[1] = A.v[2] = A.v[3] = 0;
+                                    ++kf;
+                                }
+                            }
+                        }
                     }
                     TT(4);
                 }
@@ -1017,7 +1041,9 @@ struct TcLibCache {
     // so that a whole localisation step can be captured into a CUDA graph)
     int* d_split = nullptr;
     int split_groups = -1, split_n = 0;
-    LibTile4* d_tiles4 = nullptr;        // fp4 flavour
+    // fp4 flavour: tiles run across keyframe boundaries; a work split may only start where a tile GROUP starts
+    LibTile4* d_tiles4 = nullptr;
+    std::vector<int> grp_tile;           // [n_grp + 1] first tile of every group
 };
 
 static void tc_cache_free(TcLibCache* cch) {
@@ -1045,7 +1071,7 @@ void nclt_tc_release(nclt_lib* L) {
 }
 
 // fp4 = false: fp8 images (256 B per descriptor, keyframe-aligned tiles of <= 256 rows); fp4 = true: e2m1 images
-// (128 B per descriptor + 32 B bias row, keyframe-aligned tiles of <= 240 rows, equal sizes within a keyframe)
+// (128 B per descriptor + 32 B bias row, 240-row tiles across keyframe boundaries, keyframes padded to 48 rows)
 static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     void** slot = fp4 ? &L->tc4_cache : &L->tc_cache;
     TcLibCache* cch = static_cast<TcLibCache*>(*slot);
@@ -1058,36 +1084,49 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     tc_cache_free(cch);
     c->alloc_gen++;
     if (fp4) {
-        // keyframe-aligned tiles of equal size: c rows (padded to 16) -> ceil(c16 / 240) tiles of ceil16(c16 / tiles) rows
+        // 240-row tiles over the IMAGE row space (every keyframe padded to whole 48-row segments), across keyframe
+        // boundaries.  A tile group closes (its last tile is short) at the first keyframe boundary after GROUP_MIN_ROWS
+        // image rows; work splits start at group boundaries, so the image does not depend on the batch size.
+        std::vector<int> pstart(L->n_kf + 1, 0);
+        for (int k = 0; k < L->n_kf; ++k)
+            pstart[k + 1] = pstart[k] + std::max(SEG4, (L->h_count[k] + SEG4 - 1) / SEG4 * SEG4);
         std::vector<LibTile4> tiles;
-        cch->kf_first_tile.assign(L->n_kf + 1, 0);
-        size_t off256 = 0;      // a tile image is n * 160 bytes = (n / 16) * 2560: always a multiple of 256
-        for (int k = 0; k < L->n_kf; ++k) {
-            cch->kf_first_tile[k] = (int)tiles.size();
-            const int cnt = L->h_count[k], start = L->h_start[k];
-            const int c16 = std::max(16, (cnt + 15) & ~15);       // an empty keyframe owns one all-padding tile
-            const int nt = (c16 + B4_ROWS - 1) / B4_ROWS;
-            const int per = (((c16 + nt - 1) / nt) + 15) & ~15;
-            for (int r = 0; r < c16; r += per) {
-                const int n = std::min(per, c16 - r);
-                const int nv = std::max(0, std::min(n, cnt - r));
-                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, (uint16_t)nv, (k << 1) | (r + per >= c16 ? 1 : 0), start + r});
-                off256 += (size_t)n * B4_ROW_BYTES / 256;
+        cch->grp_tile.clear();
+        size_t off256 = 0;
+        int k = 0;
+        while (k < L->n_kf) {
+            cch->grp_tile.push_back((int)tiles.size());
+            const int k_a = k, row_a = pstart[k];
+            int row_b = row_a;
+            while (k < L->n_kf && row_b - row_a < GROUP_MIN_ROWS) row_b = pstart[++k];
+            int kf = k_a;                                          // keyframe of the tile's column 0
+            for (int r = row_a; r < row_b; r += B4_ROWS) {
+                const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 48
+                while (pstart[kf + 1] <= r) ++kf;
+                uint16_t endmask = 0;
+                for (int q = kf; q < k && pstart[q + 1] <= r + n; ++q) endmask |= (uint16_t)(1u << ((pstart[q + 1] - r) / SEG4 - 1));
+                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, endmask, kf, r});
+                off256 += (size_t)n * B4_ROW_BYTES / 256;          // n * 160 bytes = (n / 48) * 7680
             }
         }
-        cch->kf_first_tile[L->n_kf] = (int)tiles.size();
+        cch->grp_tile.push_back((int)tiles.size());
         cch->n_tiles = (int)tiles.size();
-        tiles.push_back(LibTile4{0, 16, 0, 0, 0});     // sentinel
+        tiles.push_back(LibTile4{0, 48, 0, 0, 0});     // sentinel
         if (cch->n_tiles > 0) {
+            int* d_pstart = nullptr;
+            CU_TRY(c, cudaMalloc(&d_pstart, pstart.size() * sizeof(int)));
+            CU_TRY(c, cudaMemcpyAsync(d_pstart, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
             CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
             CU_TRY(c, cudaMalloc(&cch->d_tiles4, tiles.size() * sizeof(LibTile4)));
             CU_TRY(c, cudaMemcpyAsync(cch->d_tiles4, tiles.data(), tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
             k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles4,
-                                                                   cch->n_tiles, cch->d_img);
+                                                                   cch->n_tiles, d_pstart, L->d_start, L->d_count, L->n_kf, cch->d_img);
             c->launches++;
-            CU_TRY(c, cudaGetLastError());
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            cudaFree(d_pstart);
+            if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_CUDA, "k_expand_library4", e);
         }
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
         cch->built_for_kf = L->n_kf;
         cch->built_for_desc = L->n_desc;
         return NCLT_OK;
@@ -1167,7 +1206,8 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
         // ceil(items / SMs) item-times plus ~10 us per item (query-tile reload, pipeline drain and refill), so among
         // the split counts near the target pick the cheapest (e.g. 1000 groups: 4 splits -> 27.03 items per SM -> 28
         // rounds, 3.5 % of the last one idle; 5 splits -> 33.8 -> 34 rounds, 0.6 %: measured 22.5 -> 21.9 ms)
-        const int kf_cap = std::max(n_kf, 1);       // a split starts at a keyframe's first tile
+        // a split starts at a keyframe's first tile (fp8) / at a tile group (fp4)
+        const int kf_cap = fp4 ? std::max((int)cch->grp_tile.size() - 1, 1) : std::max(n_kf, 1);
         const int target = std::max(1, std::min(kf_cap, (c->sm_count * 24 + pl->n_groups - 1) / pl->n_groups));
         int best = target;
         double best_cost = 1e30;
@@ -1183,15 +1223,16 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
     pl->d12_bytes = (size_t)n_kf * pl->rows_pad * 4;
     if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
     if (cch->split_groups != pl->n_groups || cch->split_n != pl->n_splits) {
-        // split s starts at the keyframe whose first tile is nearest to tile n_tiles * s / n_splits (equal tile counts,
-        // not equal keyframe counts: ragged libraries stay balanced)
+        // split s starts at the legal start (a keyframe's first tile / a group's first tile) nearest to tile
+        // n_tiles * s / n_splits: equal tile counts, not equal keyframe counts, so ragged libraries stay balanced
         std::vector<int> split_tile(pl->n_splits + 1);
-        const std::vector<int>& kft = cch->kf_first_tile;
+        const std::vector<int>& kft = fp4 ? cch->grp_tile : cch->kf_first_tile;
+        const int n_starts = (int)kft.size() - 1;
         for (int s = 0; s <= pl->n_splits; ++s) {
             const int want = (int)((long long)cch->n_tiles * s / pl->n_splits);
-            int k = (int)(std::lower_bound(kft.begin(), kft.end(), want) - kft.begin());      // first kf with first tile >= want
-            if (k > 0 && (k > n_kf || want - kft[k - 1] < kft[k] - want)) --k;
-            split_tile[s] = kft[std::min(k, n_kf)];
+            int k = (int)(std::lower_bound(kft.begin(), kft.end(), want) - kft.begin());      // first start >= want
+            if (k > 0 && (k > n_starts || want - kft[k - 1] < kft[k] - want)) --k;
+            split_tile[s] = kft[std::min(k, n_starts)];
         }
         split_tile[0] = 0;
         split_tile[pl->n_splits] = cch->n_tiles;
