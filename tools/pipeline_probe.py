@@ -11,6 +11,7 @@ from nclt_slam_project_b200._lib import LocalizeParams
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 n_eng = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 steps = 12
+tail_sms = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 lib, desc, pts2d, kstar = bench.make_inputs(B, 0)
 lms = lib['landmarks']
 arrs = ([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms])
@@ -19,6 +20,7 @@ dev = torch.device('cuda', 0)
 d_desc = torch.from_numpy(desc).to(dev); d_pts = torch.from_numpy(pts2d).to(dev)
 for e in engs:
     e.ctx.set_engine('tensor4')
+    e.ctx.set_tail_sms(tail_sms)
     for _ in range(2):
         e.run(d_desc, d_pts)
 torch.cuda.synchronize()
@@ -51,4 +53,4 @@ for st, en, i in spans:
     gap = '' if prev_end is None else f'  gap since previous matching kernel ended: {(st - prev_end) / 1e6:6.2f} ms'
     print(f'  engine {i}: matching kernel [{(st - t00) / 1e6:8.2f}, {(en - t00) / 1e6:8.2f}] ms{gap}')
     prev_end = en
-print(f'B={B} engines={n_eng}: {wall:.2f} ms per step (wall), matching kernel {tot_ms / max(tot_n, 1):.2f} ms avg over {tot_n} launches', flush=True)
+print(f'B={B} engines={n_eng} tail_sms={tail_sms}: {wall:.2f} ms per step (wall), matching kernel {tot_ms / max(tot_n, 1):.2f} ms avg over {tot_n} launches', flush=True)
