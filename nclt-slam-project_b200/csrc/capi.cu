@@ -432,6 +432,10 @@ extern "C" int nclt_match_cross_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if (!out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "cross outputs null");
     if (Nmax < L->max_count) return nclt_fail(c, NCLT_ERR_ARG, "Nmax smaller than the largest keyframe");
     if (B == 0) return NCLT_OK;
+    // every frame against every keyframe (exp 63's whole-library ranking): both directions on the tensor cores
+    // (tc_hamming.cu, index-carrying cells), same outputs
+    if (c->engine == 2 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30) && L->n_desc < (1 << 23))
+        return tc4_match_cross_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, Nmax, out_pairs, out_dist, out_n);
     ScratchScope scope(c);
     size_t items = (size_t)B * C;
     if ((rc = nclt_scratch_reserve(c, pad256(items * Nmax * sizeof(uint2)) + pad256(items * Nq * sizeof(uint2)))))

@@ -62,6 +62,7 @@ struct nclt_lib {
     int max_count = 0;
     void* tc_cache = nullptr;   // tensor-core operand images + tile table (tc_hamming.cu), built lazily
     void* tc4_cache = nullptr;  // same for the block-scaled fp4 flavour
+    void* tc4x_cache = nullptr; // same for the crossCheck flavour (index-carrying cells, 192-byte rows)
 };
 
 // A ragged set of 32-byte descriptors on the device.
@@ -140,6 +141,8 @@ double run_popc_peak(nclt_ctx* c, int iters, float* ms_out);
 void nclt_tc_release(nclt_lib* L);
 int tc_match_ratio_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int num, int den,
                        int32_t* out_pairs, int32_t* out_n, bool fp4);
+int tc4_match_cross_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int Nmax,
+                        int32_t* out_pairs, uint16_t* out_dist, int32_t* out_n);
 int tc_match_flat2(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, uint32_t idx_offset,
                    uint32_t* out_keys, bool fp4);
 

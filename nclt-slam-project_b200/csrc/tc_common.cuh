@@ -243,6 +243,50 @@ constexpr uint32_t MX_BIAS_SFA = 0x8D8D8D8Du;     // UE8M0 2^14 in every byte
 __host__ __device__ __forceinline__ uint8_t mx_bias_byte(bool b_side, int byte /*0..31 of the 64-nibble row*/) {
     return byte < 10 ? 0x77 : byte == 10 ? (b_side ? 0x67 : 0x57) : byte == 11 ? 0x02 : 0x00;
 }
+// ---- index-carrying cells (crossCheck on the tensor core) ---------------------------------------------------------
+// cell = 2^23 + 256 * (256 - H) + (255 - column): the row maximum is the nearest library row of the tile AND its column,
+// lowest column on ties (cv2's tie rule).  Six K = 64 steps per tile: a bias step with u . v = 257 at A-scale 2^15
+// (= 2^23 + 2^15), an index step whose library-side row for column c sums to 255 - c (A side all 1.0, scales 1.0), and
+// the four data steps at A-scale 2^7 (128 * (256 - 2 H) = 256 * (256 - H) - 2^15).  Every partial sum is an integer
+// multiple of its scale below 2^24: exact.  Decode: x = bits - 0x4B000000; H = 256 - (x >> 8); column = 255 - (x & 255).
+constexpr uint32_t MX_X_SFA_DATA = 0x86868686u;     // UE8M0 2^7 in every byte
+constexpr uint32_t MX_X_SFA_BIAS = 0x8E8E8E8Eu;     // UE8M0 2^15
+constexpr uint32_t MX_X_BASE = 0x4B000000u;         // f32 bits of 2^23
+// u = 7 x 6.0, 4.0, 1.0    v = 7 x 6.0, 1.0, 1.0     u . v = 252 + 4 + 1 = 257
+__host__ __device__ __forceinline__ uint8_t mx_xbias_byte(bool b_side, int byte /*0..31*/) {
+    return byte < 3 ? 0x77 : byte == 3 ? (b_side ? 0x27 : 0x67) : byte == 4 ? 0x02 : 0x00;
+}
+// library-side index row of column c: e2m1 values summing to n = 255 - c (sixes, then the remainder as 4 / 3 / 2 / 1 [+ 1])
+__host__ __device__ __forceinline__ uint8_t mx_index_byte(int n, int byte /*0..31*/) {
+    const int n6 = n / 6, rem = n - 6 * n6;
+    uint8_t out = 0;
+    for (int h = 0; h < 2; ++h) {
+        const int e = 2 * byte + h - n6;          // position after the sixes
+        uint8_t code = 0;
+        if (e < 0) code = 7;                      // 6.0
+        else if (e == 0) code = rem == 0 ? 0 : rem == 1 ? 2 : rem == 2 ? 4 : rem == 3 ? 5 : 6;   // 1, 2, 3, 4 (5 = 4 + 1)
+        else if (e == 1) code = rem == 5 ? 2 : 0;
+        out |= (uint8_t)(code << (4 * h));
+    }
+    return out;
+}
+// query-side constant slab of the crossCheck kernel: rows of K = 64: which = 0 bias (u above), 1 index (all 1.0)
+__device__ __forceinline__ void mx_fill_xslab(uint8_t* slab, int rows, int which, int tid, int nthreads) {
+    for (int i = tid; i < rows * 2; i += nthreads) {       // (row, 16-byte k chunk)
+        const int r = i >> 1, kc = i & 1;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v |= (uint32_t)(which ? 0x22 : mx_xbias_byte(false, kc * 16 + j * 4 + b)) << (8 * b);
+            w[j] = v;
+        }
+        *reinterpret_cast<uint4*>(slab + (uint32_t)kc * (uint32_t)rows * 16u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // fills a K = 64 (32 bytes per row) K-major no-swizzle bias slab of `rows` rows; all threads of the CTA
 __device__ __forceinline__ void mx_fill_bias_slab(uint8_t* slab, int rows, bool b_side, int tid, int nthreads) {
     for (int i = tid; i < rows * 2; i += nthreads) {       // (row, 16-byte k chunk)

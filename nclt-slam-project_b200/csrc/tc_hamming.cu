@@ -361,10 +361,13 @@ constexpr int A4_TILE_BYTES = 128 * 128;        // 16 KB
 constexpr int B4_ROWS = 240;
 constexpr int B4_ROW_BYTES = 160;               // 8 K chunks of the descriptor + 2 of the bias row
 constexpr int B4_STAGE_BYTES = B4_ROWS * B4_ROW_BYTES;   // 38 400
+constexpr int BX_ROW_BYTES = 192;               // crossCheck image: + 2 chunks of the column-index row (tc_common.cuh)
+constexpr int BX_STAGE_BYTES = B4_ROWS * BX_ROW_BYTES;   // 46 080
 constexpr int A4_BIAS_BYTES = 128 * 32;         // constant bias slab of the query side
 constexpr int NSTAGE4 = 3;
 constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MMA issuers
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
+constexpr uint32_t SFX_DATA_COL = 496, SFX_BIAS_COL = 504;     // crossCheck kernel: 2^7 at [496, 504), 2^15 at [504, 512)
 
 constexpr int SEG4 = 48;                        // keyframes are padded to whole 48-row segments; a tile is <= 5 segments
 constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
@@ -401,6 +404,14 @@ struct Tc4Params {
     int* overflow;
     uint32_t* out;             // mode 1: [n_kf][rows_pad]
     long long rows_pad;
+    // crossCheck kernel (k_tc4<true>): nearest tile-side row WITH its index for every (query-side row, tile-side keyframe)
+    int xpass;                 // 1: A = frame rows, B = library;  2: A = library rows, B = the frames (one "keyframe" each)
+    uint32_t* x_out;           // uint2-strided key arrays of launch_cross_combine: bwd (pass 1) / fwd (pass 2); .x is written
+    int x_stride;              // rows per item in x_out (Nq / Nmax)
+    int x_n_kf;                // teach keyframes (item = frame * x_n_kf + teach keyframe)
+    const int* b_pstart;       // [B-side keyframes + 1] image row where each B-side keyframe starts
+    const int* a_row_kf;       // pass 2: teach keyframe of every library row
+    const int* a_kf_start;     // pass 2: first library row of every teach keyframe
     unsigned long long* clk;
     int clk_slot;
 };
@@ -422,15 +433,19 @@ __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n
 }
 
 // tile image: n rows x 160 bytes in the K-major no-swizzle layout (10 K chunks of 16 bytes); chunks 8-9 = bias row
+// xc: crossCheck image (192-byte rows: bias row of the index-carrying encoding + the column-index row); kf_count may be
+// null (every keyframe has kf_stride rows: the frames of a batch as a library) and kf_start null (keyframe k starts at
+// k * kf_stride)
 __global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTile4* __restrict__ tiles, int n_tiles,
                                   const int* __restrict__ kf_pstart, const int* __restrict__ kf_start,
-                                  const int* __restrict__ kf_count, int n_kf, uint8_t* img) {
+                                  const int* __restrict__ kf_count, int kf_stride, int n_kf, uint8_t* img, int xc) {
     int t = blockIdx.x;
     if (t >= n_tiles) return;
     const LibTile4 lt = tiles[t];
     uint8_t* dst = img + (size_t)lt.img_off256 * 256;
-    for (int i = threadIdx.x; i < lt.n * 20; i += blockDim.x) {
-        const int r = i / 20, g = i % 20;          // g: 8-byte group of the 160-byte row
+    const int gpr = xc ? 24 : 20;                  // 8-byte groups per row
+    for (int i = threadIdx.x; i < lt.n * gpr; i += blockDim.x) {
+        const int r = i / gpr, g = i % gpr;        // g: 8-byte group of the 160- / 192-byte row
         // image row -> (keyframe, row inside it): last keyframe whose image start is <= the row
         const int pr = lt.prow0 + r;
         int lo = 0, hi = n_kf;                     // invariant: kf_pstart[lo] <= pr < kf_pstart[hi]
@@ -440,14 +455,19 @@ __global__ void k_expand_library4(const uint32_t* __restrict__ desc, const LibTi
         }
         const int local = pr - kf_pstart[lo];
         uint2 v = make_uint2(0, 0);
-        if (local < kf_count[lo]) {
+        if (local < (kf_count ? kf_count[lo] : kf_stride)) {
             if (g < 16) {
-                uint32_t w = desc[((size_t)kf_start[lo] + local) * 8 + (g >> 1)];
+                const size_t src = (kf_start ? (size_t)kf_start[lo] : (size_t)lo * kf_stride) + local;
+                uint32_t w = desc[src * 8 + (g >> 1)];
                 v = tc::expand16_fp4((g & 1) ? (w >> 16) : (w & 0xFFFFu));
             } else {
                 uint32_t w[2] = {0, 0};
 #pragma unroll
-                for (int b = 0; b < 8; ++b) w[b >> 2] |= (uint32_t)tc::mx_bias_byte(true, (g - 16) * 8 + b) << (8 * (b & 3));
+                for (int b = 0; b < 8; ++b) {
+                    const int kb = (g & 3) * 8 + b;      // byte of the 32-byte constant row
+                    const uint8_t by = !xc ? tc::mx_bias_byte(true, kb) : g < 20 ? tc::mx_xbias_byte(true, kb) : tc::mx_index_byte(255 - r, kb);
+                    w[b >> 2] |= (uint32_t)by << (8 * (b & 3));
+                }
                 v = make_uint2(w[0], w[1]);
             }
         }
@@ -501,6 +521,24 @@ struct Tc4Epilogue {
     bool row_ok;            // row < rows_total and the step is a real one
     int lane;
 
+    // crossCheck kernel: the tile-side keyframe `kf` is finished for this lane's row.  best = largest index-carrying cell
+    // (0: the keyframe has no valid row), row0 = image row of column 0 of the tile it was found in.
+    __device__ __forceinline__ void xfinalize(int kf, uint32_t best, int row0) const {
+        if (!row_ok || best == 0u) return;
+        const uint32_t x = best - tc::MX_X_BASE;
+        const uint32_t dist = 256u - (x >> 8);
+        const int idx = row0 + 255 - (int)(x & 255u) - __ldg(p->b_pstart + kf);       // row inside the tile-side keyframe
+        const uint32_t key = (dist << NCLT_KEY_SHIFT) | (uint32_t)idx;
+        if (p->xpass == 1) {                 // frame rows against the library: bwd[(frame, keyframe)][frame row]
+            const int b = (int)(row / p->Nq), j = (int)(row - (long long)b * p->Nq);
+            if (p->q_n && j >= __ldg(p->q_n + b)) return;
+            p->x_out[2 * (((size_t)b * p->x_n_kf + kf) * p->x_stride + j)] = key;
+        } else {                             // library rows against the frames: fwd[(frame, keyframe)][teach row]
+            const int ka = __ldg(p->a_row_kf + row);
+            const int i = (int)row - __ldg(p->a_kf_start + ka);
+            p->x_out[2 * (((size_t)kf * p->x_n_kf + ka) * p->x_stride + i)] = key;
+        }
+    }
     // Keyframe finished for this lane's row: top-2 of the 8 column-subset maxima -> (exact d1, upper bound of d2).
     // Inlined at its two call sites (one per query tile of the epilogue set): out-of-line calls
     // cost a stack frame and a local copy of the parameter block whose dependent loads sat on every step's path.
@@ -538,12 +576,19 @@ struct Tc4Epilogue {
     }
 };
 
+// XC = false: the matcher (ratio candidates / (d1, d2 bound) plane).  XC = true: the crossCheck flavour - index-carrying
+// f32 cells (tc_common.cuh), six MMAs per step, the epilogue keeps the nearest tile-side row AND its index per
+// (query-side row, tile-side keyframe) and writes launch_cross_combine's key arrays directly.
+template <bool XC>
 __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_constant__ Tc4Params p) {
+    constexpr int STAGE_BYTES = XC ? BX_STAGE_BYTES : B4_STAGE_BYTES;
+    constexpr int ROW_BYTES = XC ? BX_ROW_BYTES : B4_ROW_BYTES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                   // MA4 x 16 KB
     uint8_t* sAb = sA + MA4 * A4_TILE_BYTES;              // 4 KB bias slab (query side, constant)
-    uint8_t* sB = sAb + A4_BIAS_BYTES;                    // NSTAGE4 x 38 400
-    uint8_t* tail = sB + NSTAGE4 * B4_STAGE_BYTES;
+    uint8_t* sAi = sAb + A4_BIAS_BYTES;                   // XC: 4 KB index slab (all 1.0)
+    uint8_t* sB = sAi + (XC ? A4_BIAS_BYTES : 0);         // NSTAGE4 x 38 400 (46 080)
+    uint8_t* tail = sB + NSTAGE4 * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 1;
@@ -567,7 +612,12 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
         }
         tc::mbar_fence_init();
     }
-    tc::mx_fill_bias_slab(sAb, 128, false, tid, TC4_THREADS);
+    if (XC) {
+        tc::mx_fill_xslab(sAb, 128, 0, tid, TC4_THREADS);
+        tc::mx_fill_xslab(sAi, 128, 1, tid, TC4_THREADS);
+    } else {
+        tc::mx_fill_bias_slab(sAb, 128, false, tid, TC4_THREADS);
+    }
     tc::fence_proxy_async();
     if (warp == 0) {
         tc::tmem_alloc(s_tmem, 512);
@@ -580,7 +630,12 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
     if (warp < 4) {
         const uint32_t lb = (uint32_t)(warp * 32) << 16;
         tc::tmem_st16_const(tmem + lb + SF_ONE_COL, 0x7F7F7F7Fu);       // every scale factor of the real steps = 2^0
-        tc::tmem_st16_const(tmem + lb + SF_BIAS_COL, tc::MX_BIAS_SFA);  // query-side scale of the bias step = 2^14
+        if (XC) {
+            tc::tmem_st8_const(tmem + lb + SFX_DATA_COL, tc::MX_X_SFA_DATA);    // query-side scale of the data steps = 2^7
+            tc::tmem_st8_const(tmem + lb + SFX_BIAS_COL, tc::MX_X_SFA_BIAS);    // query-side scale of the bias step = 2^15
+        } else {
+            tc::tmem_st16_const(tmem + lb + SF_BIAS_COL, tc::MX_BIAS_SFA);  // query-side scale of the bias step = 2^14
+        }
         tc::tmem_wait_st();
     }
     tc::tc_fence_before();
@@ -611,9 +666,9 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                 for (int t = p.split_tile[split]; t < p.split_tile[split + 1]; ++t) {
                     const LibTile4 lt = p.tiles[t];
                     tc::mbar_wait_relaxed(&b_empty[s], ph ^ 1);
-                    const uint32_t bytes = (uint32_t)lt.n * B4_ROW_BYTES;
+                    const uint32_t bytes = (uint32_t)lt.n * ROW_BYTES;
                     tc::mbar_expect_tx(&b_full[s], bytes);
-                    tc::bulk_g2s(sB + s * B4_STAGE_BYTES, p.lib_img + (size_t)lt.img_off256 * 256, bytes, &b_full[s]);
+                    tc::bulk_g2s(sB + s * STAGE_BYTES, p.lib_img + (size_t)lt.img_off256 * 256, bytes, &b_full[s]);
                     if (++s == NSTAGE4) { s = 0; ph ^= 1; }
                 }
             }
@@ -646,7 +701,7 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                     tc::tc_fence_after();
                     const uint32_t idesc = tc::idesc_mxf4(128, (int)n);
                     // K-major, no swizzle: LBO = n * 16 bytes -> descriptor field n; K chunk pair k starts 2 k n * 16 bytes in
-                    const uint64_t db_tile = db0 + (uint64_t)(s * (B4_STAGE_BYTES >> 4)) + ((uint64_t)n << 16);
+                    const uint64_t db_tile = db0 + (uint64_t)(s * (STAGE_BYTES >> 4)) + ((uint64_t)n << 16);
                     const uint64_t db_bias = db_tile + 8u * n;
                     for (int m = iss; m < ma_pad; m += 2) {
                         const uint32_t stm = st + (uint32_t)m;                   // global step number, stm & 1 == iss
@@ -656,12 +711,23 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                         if (tc::elect_one()) {
                             if (m < ma) {
                                 const uint64_t da_m = da0 + (uint64_t)(m * (A4_TILE_BYTES >> 4));
-                                // bias step first (accumulate = 0): 1.5 * 2^23 + 0x4000 in every cell of a non-padding row
-                                tc::mma_mxf4(d, da_bias, db_bias, idesc, 0u, tmem + SF_BIAS_COL, tmem + SF_ONE_COL);
+                                if (XC) {
+                                    // bias step first (accumulate = 0): 2^23 + 2^15; then 255 - column; then 128 x the +-1 products
+                                    tc::mma_mxf4(d, da_bias, db_bias, idesc, 0u, tmem + SFX_BIAS_COL, tmem + SF_ONE_COL);
+                                    tc::mma_mxf4(d, da_bias + (A4_BIAS_BYTES >> 4), db_tile + 10u * n, idesc, 1u, tmem + SF_ONE_COL,
+                                                 tmem + SF_ONE_COL);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    tc::mma_mxf4(d, da_m + (uint64_t)(k * 256), db_tile + (uint64_t)(2u * k * n), idesc, 1u,
-                                                 tmem + SF_ONE_COL, tmem + SF_ONE_COL);
+                                    for (int k = 0; k < 4; ++k)
+                                        tc::mma_mxf4(d, da_m + (uint64_t)(k * 256), db_tile + (uint64_t)(2u * k * n), idesc, 1u,
+                                                     tmem + SFX_DATA_COL, tmem + SF_ONE_COL);
+                                } else {
+                                    // bias step first (accumulate = 0): 1.5 * 2^23 + 0x4000 in every cell of a non-padding row
+                                    tc::mma_mxf4(d, da_bias, db_bias, idesc, 0u, tmem + SF_BIAS_COL, tmem + SF_ONE_COL);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc::mma_mxf4(d, da_m + (uint64_t)(k * 256), db_tile + (uint64_t)(2u * k * n), idesc, 1u,
+                                                     tmem + SF_ONE_COL, tmem + SF_ONE_COL);
+                                }
                             }
                             TR(stm, 1);
                             tc::mma_commit(&acc_full[iss]);
@@ -707,6 +773,7 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                 const int n = (int)(nm & 0xFFFFu);
                 const uint32_t endmask = nm >> 16;
                 const int kf0 = __ldg(&p.tiles[t].kf0);
+                const int prow0 = XC ? __ldg(&p.tiles[t].prow0) : 0;
 #pragma unroll
                 for (int mm = 0; mm < MA4 / 2; ++mm) {
                     const int m = set + 2 * mm;
@@ -725,6 +792,57 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
                         break;
                     }
                     const uint32_t ta = tmem + buf * B4_ROWS + lane_base;
+                    if constexpr (XC) {
+                        // 32-bit cells do not pack: three batches of 96 / 96 / 48 columns (2 + 2 + 1 segments), the buffer
+                        // goes back after the last batch that holds columns of this tile
+                        Acc4& A = acc[mm];           // v[0]: best cell so far, v[1]: image row of column 0 of its tile
+                        ep.row = (long long)(m0 + m) * 128 + quad * 32 + lane;
+                        ep.row_ok = ep.row < p.rows_total;
+                        int kf = kf0;
+                        uint32_t r[96];
+#pragma unroll
+                        for (int bt = 0; bt < 3; ++bt) {
+                            const int c0 = 96 * bt;
+                            if (c0 < n) {
+                                tc::tmem_ld32(ta + c0, r);
+                                if (bt < 2) {
+                                    tc::tmem_ld32(ta + c0 + 32, r + 32);
+                                    tc::tmem_ld32(ta + c0 + 64, r + 64);
+                                } else {
+                                    tc::tmem_ld16(ta + c0 + 32, r + 32);
+                                }
+                                tc::tmem_wait_ld();
+                                if (c0 + 96 >= n) {
+                                    tc::tc_fence_before();
+                                    __syncwarp();
+                                    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+                                    TR(st, 4 + quad);
+                                }
+#pragma unroll
+                                for (int h = 0; h < (bt < 2 ? 2 : 1); ++h) {
+                                    const int sg = 2 * bt + h;
+                                    if (SEG4 * sg < n) {
+                                        uint32_t m0_ = 0, m1_ = 0;
+#pragma unroll
+                                        for (int j = 0; j < 24; j += 2) {
+                                            m0_ = fmax3u(m0_, r[48 * h + j], r[48 * h + 24 + j]);
+                                            m1_ = fmax3u(m1_, r[48 * h + j + 1], r[48 * h + 24 + j + 1]);
+                                        }
+                                        const uint32_t mx = max(m0_, m1_);     // positive floats of one exponent: integer order
+                                        // inside a segment the column bits break ties (lowest column); between segments
+                                        // and tiles only the distance counts, strictly: the earlier rows keep a tie
+                                        if ((mx >> 8) > (A.v[0] >> 8)) { A.v[0] = mx; A.v[1] = (uint32_t)prow0; }
+                                        if ((endmask >> sg) & 1u) {
+                                            ep.xfinalize(kf, A.v[0], (int)A.v[1]);
+                                            A.v[0] = 0;
+                                            ++kf;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     // all 240 columns of the lane quadrant, packed: 120 registers, five loads back to back, no branches
                     // in between (columns beyond a short tile's n hold stale cells that are never looked at)
                     uint32_t r[120];
@@ -1044,6 +1162,10 @@ struct TcLibCache {
     // fp4 flavour: tiles run across keyframe boundaries; a work split may only start where a tile GROUP starts
     LibTile4* d_tiles4 = nullptr;
     std::vector<int> grp_tile;           // [n_grp + 1] first tile of every group
+    int* d_pstart = nullptr;             // [n_kf + 1] image row where every keyframe starts
+    // crossCheck flavour only: the library rows as the query side of pass 2
+    uint8_t* d_aimg = nullptr;           // A-tile image of all library rows (128 B per row)
+    int* d_row_kf = nullptr;             // keyframe of every library row
 };
 
 static void tc_cache_free(TcLibCache* cch) {
@@ -1052,6 +1174,11 @@ static void tc_cache_free(TcLibCache* cch) {
     if (cch->d_tiles) cudaFree(cch->d_tiles);
     if (cch->d_tiles4) cudaFree(cch->d_tiles4);
     if (cch->d_split) cudaFree(cch->d_split);
+    if (cch->d_pstart) cudaFree(cch->d_pstart);
+    if (cch->d_aimg) cudaFree(cch->d_aimg);
+    if (cch->d_row_kf) cudaFree(cch->d_row_kf);
+    cch->d_pstart = cch->d_row_kf = nullptr;
+    cch->d_aimg = nullptr;
     cch->d_img = nullptr;
     cch->d_tiles = nullptr;
     cch->d_tiles4 = nullptr;
@@ -1061,7 +1188,7 @@ static void tc_cache_free(TcLibCache* cch) {
 
 void nclt_tc_release(nclt_lib* L) {
     if (!L) return;
-    for (void** slot : {&L->tc_cache, &L->tc4_cache}) {
+    for (void** slot : {&L->tc_cache, &L->tc4_cache, &L->tc4x_cache}) {
         if (*slot) {
             tc_cache_free(static_cast<TcLibCache*>(*slot));
             delete static_cast<TcLibCache*>(*slot);
@@ -1072,8 +1199,41 @@ void nclt_tc_release(nclt_lib* L) {
 
 // fp4 = false: fp8 images (256 B per descriptor, keyframe-aligned tiles of <= 256 rows); fp4 = true: e2m1 images
 // (128 B per descriptor + 32 B bias row, 240-row tiles across keyframe boundaries, keyframes padded to 48 rows)
-static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
-    void** slot = fp4 ? &L->tc4_cache : &L->tc_cache;
+// Tile table of an fp4 image: 240-row tiles over the IMAGE row space (every keyframe padded to whole 48-row segments; an
+// empty keyframe owns one all-padding segment), across keyframe boundaries.  A tile group closes (its last tile is short)
+// at the first keyframe boundary after GROUP_MIN_ROWS image rows; work splits start at group boundaries, so the image does
+// not depend on the batch size.  counts == nullptr: every keyframe has `stride` rows (the frames of a batch as a library).
+struct Tiles4 {
+    std::vector<LibTile4> tiles;
+    std::vector<int> pstart, grp_tile;
+    size_t off256 = 0;
+};
+static void build_tiles4(const int* counts, int n_kf, int row_bytes, Tiles4& o, int stride = 0) {
+    o.pstart.assign(n_kf + 1, 0);
+    for (int k = 0; k < n_kf; ++k)
+        o.pstart[k + 1] = o.pstart[k] + std::max(SEG4, ((counts ? counts[k] : stride) + SEG4 - 1) / SEG4 * SEG4);
+    const std::vector<int>& pstart = o.pstart;
+    int k = 0;
+    while (k < n_kf) {
+        o.grp_tile.push_back((int)o.tiles.size());
+        const int k_a = k, row_a = pstart[k];
+        int row_b = row_a;
+        while (k < n_kf && row_b - row_a < GROUP_MIN_ROWS) row_b = pstart[++k];
+        int kf = k_a;                                          // keyframe of the tile's column 0
+        for (int r = row_a; r < row_b; r += B4_ROWS) {
+            const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 48
+            while (pstart[kf + 1] <= r) ++kf;
+            uint16_t endmask = 0;
+            for (int q = kf; q < k && pstart[q + 1] <= r + n; ++q) endmask |= (uint16_t)(1u << ((pstart[q + 1] - r) / SEG4 - 1));
+            o.tiles.push_back(LibTile4{(uint32_t)o.off256, (uint16_t)n, endmask, kf, r});
+            o.off256 += (size_t)n * row_bytes / 256;           // 48 rows x 160 (192) bytes = 30 (36) x 256
+        }
+    }
+    o.grp_tile.push_back((int)o.tiles.size());
+}
+
+static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4, bool xc = false) {
+    void** slot = xc ? &L->tc4x_cache : fp4 ? &L->tc4_cache : &L->tc_cache;
     TcLibCache* cch = static_cast<TcLibCache*>(*slot);
     if (!cch) {
         cch = new TcLibCache();
@@ -1084,49 +1244,38 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4) {
     tc_cache_free(cch);
     c->alloc_gen++;
     if (fp4) {
-        // 240-row tiles over the IMAGE row space (every keyframe padded to whole 48-row segments), across keyframe
-        // boundaries.  A tile group closes (its last tile is short) at the first keyframe boundary after GROUP_MIN_ROWS
-        // image rows; work splits start at group boundaries, so the image does not depend on the batch size.
-        std::vector<int> pstart(L->n_kf + 1, 0);
-        for (int k = 0; k < L->n_kf; ++k)
-            pstart[k + 1] = pstart[k] + std::max(SEG4, (L->h_count[k] + SEG4 - 1) / SEG4 * SEG4);
-        std::vector<LibTile4> tiles;
-        cch->grp_tile.clear();
-        size_t off256 = 0;
-        int k = 0;
-        while (k < L->n_kf) {
-            cch->grp_tile.push_back((int)tiles.size());
-            const int k_a = k, row_a = pstart[k];
-            int row_b = row_a;
-            while (k < L->n_kf && row_b - row_a < GROUP_MIN_ROWS) row_b = pstart[++k];
-            int kf = k_a;                                          // keyframe of the tile's column 0
-            for (int r = row_a; r < row_b; r += B4_ROWS) {
-                const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 48
-                while (pstart[kf + 1] <= r) ++kf;
-                uint16_t endmask = 0;
-                for (int q = kf; q < k && pstart[q + 1] <= r + n; ++q) endmask |= (uint16_t)(1u << ((pstart[q + 1] - r) / SEG4 - 1));
-                tiles.push_back(LibTile4{(uint32_t)off256, (uint16_t)n, endmask, kf, r});
-                off256 += (size_t)n * B4_ROW_BYTES / 256;          // n * 160 bytes = (n / 48) * 7680
+        Tiles4 tb;
+        build_tiles4(L->h_count.data(), L->n_kf, xc ? BX_ROW_BYTES : B4_ROW_BYTES, tb);
+        cch->grp_tile = tb.grp_tile;
+        cch->n_tiles = (int)tb.tiles.size();
+        tb.tiles.push_back(LibTile4{0, 48, 0, 0, 0});     // sentinel
+        if (cch->n_tiles > 0) {
+            CU_TRY(c, cudaMalloc(&cch->d_pstart, tb.pstart.size() * sizeof(int)));
+            CU_TRY(c, cudaMemcpyAsync(cch->d_pstart, tb.pstart.data(), tb.pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(c, cudaMalloc(&cch->d_img, tb.off256 * 256));
+            CU_TRY(c, cudaMalloc(&cch->d_tiles4, tb.tiles.size() * sizeof(LibTile4)));
+            CU_TRY(c, cudaMemcpyAsync(cch->d_tiles4, tb.tiles.data(), tb.tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
+            k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles4,
+                                                                   cch->n_tiles, cch->d_pstart, L->d_start, L->d_count, 0, L->n_kf,
+                                                                   cch->d_img, xc ? 1 : 0);
+            c->launches++;
+            CU_TRY(c, cudaGetLastError());
+            if (xc) {
+                // pass 2 of the crossCheck: the library rows are the QUERY side - A-tile image of all rows + row -> keyframe
+                const long long rows_pad = ((long long)L->n_desc + 127) / 128 * 128;
+                CU_TRY(c, cudaMalloc(&cch->d_aimg, (size_t)rows_pad * 128));
+                k_expand_queries4<<<(unsigned)((rows_pad * 16 + 255) / 256), 256, 0, c->stream>>>(
+                    reinterpret_cast<const uint32_t*>(L->d_desc), L->n_desc, cch->d_aimg);
+                std::vector<int> row_kf((size_t)std::max(L->n_desc, 1), 0);
+                for (int k = 0; k < L->n_kf; ++k)
+                    for (int r = 0; r < L->h_count[k]; ++r) row_kf[(size_t)L->h_start[k] + r] = k;
+                CU_TRY(c, cudaMalloc(&cch->d_row_kf, row_kf.size() * sizeof(int)));
+                CU_TRY(c, cudaMemcpyAsync(cch->d_row_kf, row_kf.data(), row_kf.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                c->launches++;
+                CU_TRY(c, cudaStreamSynchronize(c->stream));      // row_kf is a local
             }
         }
-        cch->grp_tile.push_back((int)tiles.size());
-        cch->n_tiles = (int)tiles.size();
-        tiles.push_back(LibTile4{0, 48, 0, 0, 0});     // sentinel
-        if (cch->n_tiles > 0) {
-            int* d_pstart = nullptr;
-            CU_TRY(c, cudaMalloc(&d_pstart, pstart.size() * sizeof(int)));
-            CU_TRY(c, cudaMemcpyAsync(d_pstart, pstart.data(), pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-            CU_TRY(c, cudaMalloc(&cch->d_img, off256 * 256));
-            CU_TRY(c, cudaMalloc(&cch->d_tiles4, tiles.size() * sizeof(LibTile4)));
-            CU_TRY(c, cudaMemcpyAsync(cch->d_tiles4, tiles.data(), tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
-            k_expand_library4<<<cch->n_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(L->d_desc), cch->d_tiles4,
-                                                                   cch->n_tiles, d_pstart, L->d_start, L->d_count, L->n_kf, cch->d_img);
-            c->launches++;
-            cudaError_t e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            cudaFree(d_pstart);
-            if (e != cudaSuccess) return nclt_fail(c, NCLT_ERR_CUDA, "k_expand_library4", e);
-        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
         cch->built_for_kf = L->n_kf;
         cch->built_for_desc = L->n_desc;
         return NCLT_OK;
@@ -1186,10 +1335,43 @@ struct TcPlan {
 };
 
 // library image + work split table for a batch of B x Nq query rows; no kernel launches, no scratch
-static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl) {
+// items = n_groups x n_splits are dealt round-robin to one persistent CTA per SM: the kernel lasts
+// ceil(items / SMs) item-times plus ~10 us per item (query-tile reload, pipeline drain and refill), so among
+// the split counts near the target (>= ~24 items per SM) pick the cheapest (e.g. 1000 groups: 4 splits -> 27.03 items
+// per SM -> 28 rounds, 3.5 % of the last one idle; 5 splits -> 33.8 -> 34 rounds, 0.6 %: measured 22.5 -> 21.9 ms)
+static int tc_choose_splits(int sm_count, int n_groups, int cap) {
+    const int target = std::max(1, std::min(cap, (sm_count * 24 + n_groups - 1) / n_groups));
+    int best = target;
+    double best_cost = 1e30;
+    for (int sp = std::max(1, target / 2); sp <= std::min(cap, 2 * target); ++sp) {
+        const long long items = (long long)n_groups * sp;
+        const long long rounds = (items + sm_count - 1) / sm_count;
+        const double cost = (double)rounds * (1.0 / sp + 0.005);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = sp; }
+    }
+    return best;
+}
+// split s starts at the legal start (a keyframe's first tile / a group's first tile) nearest to tile
+// n_tiles * s / n_splits: equal tile counts, not equal keyframe counts, so ragged libraries stay balanced
+static std::vector<int> tc_split_table(const std::vector<int>& starts, int n_tiles, int n_splits) {
+    std::vector<int> split_tile(n_splits + 1);
+    const int n_starts = (int)starts.size() - 1;
+    for (int s = 0; s <= n_splits; ++s) {
+        const int want = (int)((long long)n_tiles * s / n_splits);
+        int k = (int)(std::lower_bound(starts.begin(), starts.end(), want) - starts.begin());      // first start >= want
+        if (k > 0 && (k > n_starts || want - starts[k - 1] < starts[k] - want)) --k;
+        split_tile[s] = starts[std::min(k, n_starts)];
+    }
+    split_tile[0] = 0;
+    split_tile[n_splits] = n_tiles;
+    for (int s = 1; s <= n_splits; ++s) split_tile[s] = std::max(split_tile[s], split_tile[s - 1]);
+    return split_tile;
+}
+
+static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl, bool xc = false) {
     int rc;
-    if ((rc = tc_build_library(c, L, fp4))) return rc;
-    TcLibCache* cch = static_cast<TcLibCache*>(fp4 ? L->tc4_cache : L->tc_cache);
+    if ((rc = tc_build_library(c, L, fp4, xc))) return rc;
+    TcLibCache* cch = static_cast<TcLibCache*>(xc ? L->tc4x_cache : fp4 ? L->tc4_cache : L->tc_cache);
     const int ma_tiles = fp4 ? MA4 : MA;
     const size_t a_tile_bytes = fp4 ? A4_TILE_BYTES : A_TILE_BYTES;
     const int n_kf = L->n_kf;
@@ -1199,44 +1381,13 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
     pl->n_mtiles = (int)((pl->rows + 127) / 128);
     pl->rows_pad = (long long)pl->n_mtiles * 128;
     pl->n_groups = (pl->n_mtiles + ma_tiles - 1) / ma_tiles;
-    // keyframe-aligned splits of the tile range, enough items to balance the persistent grid
-    // >= ~24 items per SM so that the last (partial) wave of the static round-robin costs a few percent
-    {
-        // items = n_groups x n_splits are dealt round-robin to one persistent CTA per SM: the kernel lasts
-        // ceil(items / SMs) item-times plus ~10 us per item (query-tile reload, pipeline drain and refill), so among
-        // the split counts near the target pick the cheapest (e.g. 1000 groups: 4 splits -> 27.03 items per SM -> 28
-        // rounds, 3.5 % of the last one idle; 5 splits -> 33.8 -> 34 rounds, 0.6 %: measured 22.5 -> 21.9 ms)
-        // a split starts at a keyframe's first tile (fp8) / at a tile group (fp4)
-        const int kf_cap = fp4 ? std::max((int)cch->grp_tile.size() - 1, 1) : std::max(n_kf, 1);
-        const int target = std::max(1, std::min(kf_cap, (c->sm_count * 24 + pl->n_groups - 1) / pl->n_groups));
-        int best = target;
-        double best_cost = 1e30;
-        for (int sp = std::max(1, target / 2); sp <= std::min(kf_cap, 2 * target); ++sp) {
-            const long long items = (long long)pl->n_groups * sp;
-            const long long rounds = (items + c->sm_count - 1) / c->sm_count;
-            const double cost = (double)rounds * (1.0 / sp + 0.005);
-            if (cost < best_cost - 1e-12) { best_cost = cost; best = sp; }
-        }
-        pl->n_splits = best;
-    }
+    // a split starts at a keyframe's first tile (fp8) / at a tile group (fp4)
+    pl->n_splits = tc_choose_splits(c->sm_count, pl->n_groups, fp4 ? std::max((int)cch->grp_tile.size() - 1, 1) : std::max(n_kf, 1));
     pl->q_img_bytes = (size_t)pl->n_mtiles * a_tile_bytes;
     pl->d12_bytes = (size_t)n_kf * pl->rows_pad * 4;
     if (n_kf == 0 || cch->n_tiles == 0) return NCLT_OK;
     if (cch->split_groups != pl->n_groups || cch->split_n != pl->n_splits) {
-        // split s starts at the legal start (a keyframe's first tile / a group's first tile) nearest to tile
-        // n_tiles * s / n_splits: equal tile counts, not equal keyframe counts, so ragged libraries stay balanced
-        std::vector<int> split_tile(pl->n_splits + 1);
-        const std::vector<int>& kft = fp4 ? cch->grp_tile : cch->kf_first_tile;
-        const int n_starts = (int)kft.size() - 1;
-        for (int s = 0; s <= pl->n_splits; ++s) {
-            const int want = (int)((long long)cch->n_tiles * s / pl->n_splits);
-            int k = (int)(std::lower_bound(kft.begin(), kft.end(), want) - kft.begin());      // first start >= want
-            if (k > 0 && (k > n_starts || want - kft[k - 1] < kft[k] - want)) --k;
-            split_tile[s] = kft[std::min(k, n_starts)];
-        }
-        split_tile[0] = 0;
-        split_tile[pl->n_splits] = cch->n_tiles;
-        for (int s = 1; s <= pl->n_splits; ++s) split_tile[s] = std::max(split_tile[s], split_tile[s - 1]);
+        const std::vector<int> split_tile = tc_split_table(fp4 ? cch->grp_tile : cch->kf_first_tile, cch->n_tiles, pl->n_splits);
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         c->alloc_gen++;
         if (cch->d_split) cudaFree(cch->d_split);
@@ -1324,7 +1475,88 @@ static int tc4_run(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8
     int rc;
     if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
     const size_t smem = (size_t)MA4 * A4_TILE_BYTES + A4_BIAS_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 256;
-    return tc_launch_persistent(c, (const void*)k_tc4_top2, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS);
+    return tc_launch_persistent(c, (const void*)k_tc4_top2<false>, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS);
+}
+
+// ---- crossCheck of every frame against every keyframe on the tensor cores ----------------------------------------
+// cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match(desc_t, desc_curr) (visual_landmark_matcher.py:211,327; exp 63's
+// whole-library ranking, experiments/63_global_reloc/scripts/visual_landmark_matcher.py:314-345): pair (i, j) iff j is the
+// nearest frame row of teach row i (lowest j on ties) and i the nearest teach row of j (lowest i on ties).  Two passes of
+// k_tc4_top2<true> with the roles swapped - the index-carrying cells give argmin and distance exactly, no verification
+// pass - fill the same fwd / bwd key arrays the integer path fills, and launch_cross_combine (hamming.cu) does the rest.
+int tc4_match_cross_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_t* q_n, int B, int Nq, int Nmax,
+                        int32_t* out_pairs, uint16_t* out_dist, int32_t* out_n) {
+    TcPlan pl;
+    int rc;
+    if ((rc = tc_plan(c, L, B, Nq, true, &pl, true))) return rc;
+    const int n_kf = L->n_kf;
+    if (n_kf == 0) return NCLT_OK;
+    TcLibCache* cch = pl.cch;
+    const size_t items = (size_t)B * n_kf;
+    // pass 2 geometry: the library rows are the query side, the frames the tile side (every frame = Nq rows; rows past
+    // q_n[b] become zero image rows)
+    Tiles4 ft;
+    build_tiles4(nullptr, B, BX_ROW_BYTES, ft, Nq);
+    const int f_tiles = (int)ft.tiles.size();
+    const long long a_rows = L->n_desc;
+    const int a_mtiles = (int)((a_rows + 127) / 128), a_groups = (a_mtiles + MA4 - 1) / MA4;
+    const int f_splits = tc_choose_splits(c->sm_count, std::max(a_groups, 1), std::max((int)ft.grp_tile.size() - 1, 1));
+    const std::vector<int> f_split = tc_split_table(ft.grp_tile, f_tiles, f_splits);
+    ft.tiles.push_back(LibTile4{0, 48, 0, 0, 0});     // sentinel
+
+    ScratchScope scope(c);
+    const size_t fwd_bytes = pad256(items * Nmax * sizeof(uint2)), bwd_bytes = pad256(items * Nq * sizeof(uint2));
+    const size_t f_img_bytes = pad256(ft.off256 * 256);
+    size_t need = fwd_bytes + bwd_bytes + pad256(pl.q_img_bytes) + f_img_bytes + pad256(ft.tiles.size() * sizeof(LibTile4)) +
+                  pad256(ft.pstart.size() * sizeof(int)) + pad256(f_split.size() * sizeof(int)) + 256;
+    if ((rc = nclt_scratch_reserve(c, need))) return rc;
+    Carver cv(c);
+    uint2* fwd = cv.take<uint2>(items * Nmax);
+    uint2* bwd = cv.take<uint2>(items * Nq);
+    uint8_t* q_img = cv.take<uint8_t>(pl.q_img_bytes);
+    uint8_t* f_img = cv.take<uint8_t>(ft.off256 * 256);
+    LibTile4* f_tiles_d = cv.take<LibTile4>(ft.tiles.size());
+    int* f_pstart_d = cv.take<int>(ft.pstart.size());
+    int* f_split_d = cv.take<int>(f_split.size());
+    // synchronous copies: the sources are locals (this entry point is not meant for graph capture)
+    CU_TRY(c, cudaMemcpyAsync(f_tiles_d, ft.tiles.data(), ft.tiles.size() * sizeof(LibTile4), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(f_pstart_d, ft.pstart.data(), ft.pstart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(f_split_d, f_split.data(), f_split.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaMemsetAsync(fwd, 0xFF, items * Nmax * sizeof(uint2), c->stream));       // NCLT_KEY_INVALID
+    CU_TRY(c, cudaMemsetAsync(bwd, 0xFF, items * Nq * sizeof(uint2), c->stream));
+    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + 2 * A4_BIAS_BYTES + (size_t)NSTAGE4 * BX_STAGE_BYTES + 256;
+    // ---- pass 1: frame rows against the library -> bwd[(frame, keyframe)][frame row] = nearest teach row
+    if (cch->n_tiles > 0) {
+        k_expand_queries4<<<(unsigned)((pl.rows_pad * 16 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
+        c->launches++;
+        Tc4Params p{};
+        p.q_img = q_img; p.lib_img = cch->d_img; p.tiles = cch->d_tiles4; p.n_mtiles = pl.n_mtiles; p.n_groups = pl.n_groups;
+        p.n_splits = pl.n_splits; p.split_tile = cch->d_split;
+        p.kf_count = L->d_count; p.n_kf = n_kf; p.rows_total = pl.rows; p.Nq = Nq; p.q_n = q_n;
+        p.xpass = 1; p.x_out = reinterpret_cast<uint32_t*>(bwd); p.x_stride = Nq; p.x_n_kf = n_kf; p.b_pstart = cch->d_pstart;
+        if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+        if ((rc = tc_launch_persistent(c, (const void*)k_tc4_top2<true>, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS)))
+            return rc;
+    }
+    // ---- pass 2: teach rows against the frames -> fwd[(frame, keyframe)][teach row] = nearest frame row
+    if (a_rows > 0 && f_tiles > 0) {
+        k_expand_library4<<<f_tiles, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), f_tiles_d, f_tiles, f_pstart_d, nullptr, q_n,
+                                                         Nq, B, f_img, 1);
+        c->launches++;
+        Tc4Params p{};
+        p.q_img = cch->d_aimg; p.lib_img = f_img; p.tiles = f_tiles_d; p.n_mtiles = a_mtiles; p.n_groups = a_groups;
+        p.n_splits = f_splits; p.split_tile = f_split_d;
+        p.kf_count = nullptr; p.n_kf = B; p.rows_total = a_rows; p.Nq = Nq; p.q_n = nullptr;
+        p.xpass = 2; p.x_out = reinterpret_cast<uint32_t*>(fwd); p.x_stride = Nmax; p.x_n_kf = n_kf; p.b_pstart = f_pstart_d;
+        p.a_row_kf = cch->d_row_kf; p.a_kf_start = L->d_start;
+        if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+        if ((rc = tc_launch_persistent(c, (const void*)k_tc4_top2<true>, &p, std::min(c->sm_count, a_groups * f_splits), smem, TC4_THREADS)))
+            return rc;
+    }
+    CU_TRY(c, cudaGetLastError());
+    return launch_cross_combine(c, fwd, bwd, SegView{L->d_desc, L->d_start, L->d_count, 0}, nullptr, B, n_kf, Nmax, Nq,
+                                reinterpret_cast<int2*>(out_pairs), out_dist, out_n, Nmax);
 }
 
 // fp8: expands the queries into q_img and runs k_tc_top2: d12[kf * rows_pad + row] = d1 | d2bound << 16
