@@ -182,6 +182,7 @@ class Context:
         """'int' (LOP3+POPC) or 'tensor' (tcgen05) for all-keyframe ratio matching; same results."""
         code = {'int': 0, 'tensor': 1, 'tensor8': 1, 'tensor4': 2, 0: 0, 1: 1, 2: 2}[engine]
         self.check(lib.nclt_ctx_set_engine(self.h, code))
+        self.engine = code
 
     def set_tail_sms(self, n):
         """SMs the persistent matching kernel leaves to the tail kernels of an alternating context (default 0)."""

@@ -274,8 +274,15 @@ class LandmarkMatcher:
                 if self.library.counts[i] >= MIN_MATCHES]
         if not pool:
             return []
-        _, _, n = self.library.cross(np.asarray(desc_curr)[None], None, np.asarray(pool, dtype=np.int32)[None])
-        scored = [(int(c), li) for c, li in zip(n[0], pool) if c >= MIN_MATCHES]
+        if getattr(self.library.ctx, 'engine', 0) == 2 and 4 * len(pool) >= self.library.n_keyframes:
+            # a large pool on the fp4 tensor engine: crossCheck against the WHOLE library in two tcgen05 passes
+            # (nclt_match_cross with cand == NULL) and read the pool's counts - identical counts, keyframes are independent
+            _, _, n_all = self.library.cross(np.asarray(desc_curr)[None], None, None)
+            counts = n_all[0, pool]
+        else:
+            _, _, n = self.library.cross(np.asarray(desc_curr)[None], None, np.asarray(pool, dtype=np.int32)[None])
+            counts = n[0]
+        scored = [(int(c), li) for c, li in zip(counts, pool) if c >= MIN_MATCHES]
         scored.sort(reverse=True)
         return [li for _, li in scored[:RELOC_MAX_CANDIDATES]]
 

@@ -81,15 +81,20 @@ def test_match_golden_from_cv2(ctx):
         assert np.array_equal(np.array(rows, dtype=np.int32), g[f'{tag}_cross'])
 
 
-def test_global_relocalisation_against_exp63_node(ctx, tmp_path):
+@pytest.mark.parametrize('engine', ['int', 'tensor4'])
+def test_global_relocalisation_against_exp63_node(ctx, tmp_path, engine):
     """exp 63's kidnapped-robot fallback (whole-library crossCheck ranking -> top 25 -> PnP with
-    18 inliers / 1.5 px, no consistency gate) against the exp 63 node itself (tests/golden/reloc_golden.npz)."""
-    from nclt_slam_project_b200 import synth
+    18 inliers / 1.5 px, no consistency gate) against the exp 63 node itself (tests/golden/reloc_golden.npz).  With
+    engine tensor4 the ranking runs on the tensor cores (crossCheck against the whole library, nclt_match_cross with
+    cand == NULL); same outcomes."""
+    from nclt_slam_project_b200 import synth, _lib
     from nclt_slam_project_b200.matcher import LandmarkMatcher
     g = np.load(os.path.join(GD, 'reloc_golden.npz'))
     data = synth.make_library(int(g['lib_seed']), n_kf=60, n_desc=300, ragged=True, route_len_m=120.0)
     csv = str(tmp_path / 'log' / 'anchor_matches.csv')
-    m = LandmarkMatcher(data, csv, mode='crosscheck')
+    ectx = _lib.Context(0)
+    ectx.set_engine(engine)
+    m = LandmarkMatcher(data, csv, mode='crosscheck', ctx=ectx)
     kinds = [str(k) for k in g['kinds']]
     n_reloc = 0
     for i, kind in enumerate(kinds):
