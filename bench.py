@@ -248,7 +248,7 @@ def main():
     ap.add_argument('--ref-frames-per-step', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--engines', type=int, default=2, help='alternating engines (streams) in the pipelined mode')
-    ap.add_argument('--tail-sms', type=int, default=4, help='SMs the matching kernel leaves to the other engine\'s tail kernels')
+    ap.add_argument('--tail-sms', type=int, default=0, help='SMs the matching kernel leaves to the other engine\'s tail kernels')
     ap.add_argument('--no-pipeline', action='store_true', help='one engine/stream instead of two alternating ones')
     ap.add_argument('--no-graph', action='store_true', help='direct launches instead of CUDA graph replay')
     args = ap.parse_args()
@@ -426,7 +426,9 @@ def main():
     # from pinned host memory and its per-frame results back, inside the timed region.  One StreamingLocalizer per
     # route (each owns that route's library on its two contexts).
     sls = [StreamingLocalizer(lib_arrays(rt['lib']), device=local_rank, params=prm, engine=args.engine, depth=2) for rt in routes]
-    for w in range(max(3, n_slots if multi else 0)):
+    # warm-up: every route's localizer alternates two contexts, and each context builds its own operand image of the
+    # route's library on first use - two passes over the slots touch both
+    for w in range(max(3, 2 * n_slots if multi else 0)):
         k = w % n_slots
         sl = sls[slot_route[k]]
         r = sl.result(sl.submit(h_desc[k].numpy(), h_pts[k].numpy()))

@@ -58,7 +58,9 @@ int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
  * accumulators in TMEM, 2 = tcgen05 block-scaled fp4 (kind::mxf4) +-1 operands with f32 accumulators
  * (the fastest); all three produce identical results (exact index recovery on the integer pipe).
  * Used by nclt_match_ratio[_dev] / nclt_localize_batch[_dev] with cand == NULL and by
- * nclt_match_flat2_dev; candidate-list and crossCheck matching always use the integer pipe. */
+ * nclt_match_flat2_dev; with engine 2 also by nclt_match_cross[_dev] with cand == NULL (crossCheck of every
+ * frame against every keyframe: both directions on tcgen05 with index-carrying cells, no verification pass).
+ * Candidate-list matching (cand != NULL) always uses the integer pipe. */
 int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
 /* The tensor-engine matching kernel is persistent (one CTA per SM) and fills every SM it runs on.  When two contexts
  * take batches alternately, leaving n SMs free lets the short tail kernels (candidate verification, PnP-RANSAC) of one
@@ -115,7 +117,8 @@ int nclt_match_ratio_dev(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, c
 /* replaces cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match(desc_t, desc_curr)
  * (scripts/common/visual_landmark_matcher.py:211,327).  out_pairs i32[B,C,Nmax,2] =
  * (queryIdx = teach row, trainIdx = frame row) in increasing queryIdx, out_dist u16[B,C,Nmax],
- * out_n i32[B,C]; Nmax >= the largest candidate keyframe. */
+ * out_n i32[B,C]; Nmax >= the largest candidate keyframe.  cand == NULL, C == keyframe count: every keyframe (exp 63's
+ * whole-library ranking, experiments/63_global_reloc/scripts/visual_landmark_matcher.py:314-345). */
 int nclt_match_cross(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const int32_t* q_n, int B,
                      int Nq, const int32_t* cand, int C, int Nmax, int32_t* out_pairs, uint16_t* out_dist,
                      int32_t* out_n);

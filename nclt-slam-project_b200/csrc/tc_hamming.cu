@@ -1402,10 +1402,10 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
 
 static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem, int threads) {
     CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Two contexts that alternate batches (PipelinedLocalizer, bench.py): the short tail kernels of one batch
-    // (verification, PnP) cannot co-reside with a matching CTA (its 10 warps x 168 registers fill an SM's register
-    // file), so the matching kernel of the other context leaves `tail_sms` SMs to them (nclt_ctx_set_tail_sms).
-    // Measured at 512-frame steps: 4 SMs hide ~half of the tail (+1.5 % frames/s), 12 SMs all of it (+-0 %).
+    // Two contexts that alternate batches (PipelinedLocalizer, bench.py) can make the matching kernel of one leave
+    // `tail_sms` SMs to the short tail kernels of the other (nclt_ctx_set_tail_sms).  Measured with the final kernel
+    // (512-frame steps, 0 / 4 / 8 / 12 / 20 SMs): 26.2-26.8k frames/s, no trend - the tail is ~400 SM-ms of
+    // throughput-bound work per step, so the SMs it gets cost the matching kernel what they save.  Default 0.
     grid = std::max(1, std::min(grid, c->sm_count - c->tail_sms));
     if (const char* env = getenv("NCLT_TC_GRID")) {      // experiment knob
         int g = atoi(env);

@@ -190,12 +190,13 @@ class PipelinedLocalizer:
     """Replay engine for BASELINE configs 2/4: two DeviceLocalizers (own CUDA stream and scratch each)
     take the batches alternately, so the host never waits between batches and the short kernels of one batch's
     tail (candidate verification, PnP rounds, LM refinement) are queued behind the other engine's matching kernel.
-    Measured (tools/pipeline_probe.py): the tails do NOT run under the next matching kernel -
-    its 10 warps x 168 registers fill an SM's register file, so no tail CTA fits beside it; what the second
-    engine buys is the removal of host-side gaps, and a step costs matching kernel + tail.
+    Measured (tools/pipeline_probe.py): the tails do NOT hide under the next matching kernel - they
+    are ~400 SM-ms of throughput-bound work per 512-frame step, and SMs left to them (`tail_sms`) cost the matching
+    kernel as much as they save (0 / 4 / 8 / 12 / 20 SMs: 26.2-26.8k frames/s, no trend); what the second engine buys
+    is the removal of host-side gaps, and a step costs matching kernel + tail.
     Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
 
-    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', tail_sms=4):
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', tail_sms=0):
         self.engines = [DeviceLocalizer(library_arrays, device, params) for _ in range(2)]
         for e in self.engines:
             e.ctx.set_engine(engine)
@@ -227,7 +228,7 @@ class StreamingLocalizer:
         res = sl.result(ticket)                           # dict of NumPy arrays, valid until `depth` submits later
     """
 
-    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', depth=2, tail_sms=4):
+    def __init__(self, library_arrays, device=0, params=None, engine='tensor4', depth=2, tail_sms=0):
         import torch
         from .library import LandmarkLibrary
         self.torch = torch
