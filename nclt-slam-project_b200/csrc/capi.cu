@@ -406,7 +406,8 @@ extern "C" int nclt_match_ratio_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if (num <= 0 || den <= 0 || !out_pairs || !out_n) return nclt_fail(c, NCLT_ERR_ARG, "ratio args");
     if (B == 0) return NCLT_OK;
     // every frame against every keyframe: the tensor-core path (tc_hamming.cu), same outputs
-    if (c->engine >= 1 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30))
+    // (the tensor path's verification packs (distance << 16 | row): keyframes of 65 536 rows or more stay on the integer pipe)
+    if (c->engine >= 1 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30) && L->max_count < 65536)
         return tc_match_ratio_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, num, den, out_pairs, out_n, c->engine == 2);
     ScratchScope scope(c);
     size_t items = (size_t)B * C;
@@ -434,7 +435,7 @@ extern "C" int nclt_match_cross_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if (B == 0) return NCLT_OK;
     // every frame against every keyframe (exp 63's whole-library ranking): both directions on the tensor cores
     // (tc_hamming.cu, index-carrying cells), same outputs
-    if (c->engine == 2 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30) && L->n_desc < (1 << 23))
+    if (c->engine == 2 && !cand && C == L->n_kf && (long long)B * Nq < (1LL << 30) && L->n_desc < (1 << 23) && Nq < (1 << 23))
         return tc4_match_cross_all(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, Nmax, out_pairs, out_dist, out_n);
     ScratchScope scope(c);
     size_t items = (size_t)B * C;
@@ -469,7 +470,7 @@ extern "C" int nclt_match_flat2_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     if (B == 0) return NCLT_OK;
     // tensor engines: per-keyframe (d1, d2 bound) on tcgen05, then an exact re-scan of the two keyframes that can
     // hold the global top-2 (tc_hamming.cu); identical keys
-    if (c->engine >= 1 && L->n_kf > 0 && L->n_kf < 65536 && (long long)B * Nq < (1LL << 30))
+    if (c->engine >= 1 && L->n_kf > 0 && L->n_kf < 65536 && (long long)B * Nq < (1LL << 30) && L->max_count < 65536)
         return tc_match_flat2(c, const_cast<nclt_lib*>(L), q, q_n, B, Nq, idx_offset, out_keys, c->engine == 2);
     // the whole library is one segment; split its rows so that the grid fills the GPU
     int want = (c->sm_count * 8 + B - 1) / B;

@@ -1619,6 +1619,13 @@ static int tc4_match_ratio_all(nclt_ctx* c, nclt_lib* L, const TcPlan& pl, const
     k_tc4_emit<<<c->sm_count * 4, 128, 0, c->stream>>>(pool, Nq, reinterpret_cast<int2*>(out_pairs), out_n);
     c->launches += 2;
     CU_TRY(c, cudaGetLastError());
+    if (getenv("NCLT_DEBUG_WORK")) {       // diagnostics: candidates the epilogue emitted vs item slots used
+        int h[2] = {0, 0};
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(h, counters, 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[nclt] ratio candidates: %d work entries (cap %d) for %lld query rows x %d keyframes, %d item slots\n", h[0],
+                work_cap, pl.rows, n_kf, h[1]);
+    }
     return NCLT_OK;
 }
 
