@@ -1067,8 +1067,14 @@ __global__ void __launch_bounds__(128) k_tc4_verify(const WorkEntry* __restrict_
                                                     Tc4Pool pool, int* overflow) {
     const int lane = threadIdx.x & 31;
     const int n_work = min(*work_count, work_cap);
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += warps) {
+    // An epilogue warp appends its candidates of one (32 query rows, keyframe) together, so neighbouring entries mostly
+    // share the keyframe: a CTA walks a run of VERIFY_RUN consecutive entries, its warps side by side, and the keyframe's
+    // rows (32 KB) are served by L1 instead of being streamed from L2 once per entry (the kernel was bound by L2 bandwidth:
+    // 207 k entries x 32 KB = 6.6 GB per 512-frame step)
+    constexpr int VERIFY_RUN = 64;
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int base = blockIdx.x * VERIFY_RUN; base < n_work; base += gridDim.x * VERIFY_RUN)
+    for (int w = base + wib; w < min(base + VERIFY_RUN, n_work); w += wpb) {
         const WorkEntry we = work[w];
         const int b = we.item / n_kf, kf = we.item % n_kf;
         const int nt = kf_count[kf];
