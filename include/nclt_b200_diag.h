@@ -50,6 +50,12 @@ int nclt_ctx_tc_clock(nclt_ctx* ctx, double* mhz, double* kernel_ms, unsigned lo
  * out: HOST u8[h,w] of that level (nclt_orb_levels gives w, h). */
 int nclt_orb_debug_plane(nclt_ctx* ctx, nclt_orb* orb, int what, int frame, int level, uint8_t* out);
 
+/* CPU-callable hooks for the host logic of the fp4 engines (no GPU needed; tests/test_tc_tiles_cpu.py): the tile table
+ * of a library image (csrc/tc_tiles.h) and the constant operand rows of the bias / index encodings (csrc/tc_common.cuh) */
+int nclt_diag_tiles4(const int* counts, int n_kf, int stride, int row_bytes, int cap, unsigned* img_off256, int* n,
+                     int* endmask, int* kf0, int* prow0, int* pstart, int* grp_tile, int grp_cap, int* n_grp);
+int nclt_diag_mx_row(int which, int arg, unsigned char* out32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -982,3 +982,29 @@ extern "C" double nclt_tc_bench_two_issuers(nclt_ctx* c, int iters, int variant)
     if (e != cudaSuccess) { nclt_fail(c, NCLT_ERR_CUDA, "tc_bench_two_issuers", e); return -1.0; }
     return (double)h / iters;
 }
+
+// ---- CPU-callable hooks for the host logic of the fp4 engines (no GPU needed; tests/test_tc_tiles_cpu.py) -------------
+#include "../tc_tiles.h"
+// tile table of a library (counts[n_kf], or every keyframe `stride` rows when counts == NULL): fills the first `cap`
+// entries of the per-tile arrays, pstart[n_kf + 1] and grp_tile[<= grp_cap]; returns the number of tiles
+extern "C" int nclt_diag_tiles4(const int* counts, int n_kf, int stride, int row_bytes, int cap, unsigned* img_off256, int* n,
+                                int* endmask, int* kf0, int* prow0, int* pstart, int* grp_tile, int grp_cap, int* n_grp) {
+    nclt_tc4::Tiles4 t;
+    nclt_tc4::build_tiles4(counts, n_kf, row_bytes, t, stride);
+    for (int i = 0; i < (int)t.tiles.size() && i < cap; ++i) {
+        img_off256[i] = t.tiles[i].img_off256; n[i] = t.tiles[i].n; endmask[i] = t.tiles[i].endmask;
+        kf0[i] = t.tiles[i].kf0; prow0[i] = t.tiles[i].prow0;
+    }
+    for (int k = 0; k <= n_kf; ++k) pstart[k] = t.pstart[k];
+    for (int g = 0; g < (int)t.grp_tile.size() && g < grp_cap; ++g) grp_tile[g] = t.grp_tile[g];
+    if (n_grp) *n_grp = (int)t.grp_tile.size();
+    return (int)t.tiles.size();
+}
+// the 32-byte (64 e2m1 nibbles) constant rows of the encodings: which = 0 / 1 matcher bias row (query / library side),
+// 2 / 3 crossCheck bias row (query / library side), 4 crossCheck index row of value `arg`
+extern "C" int nclt_diag_mx_row(int which, int arg, unsigned char* out32) {
+    for (int b = 0; b < 32; ++b)
+        out32[b] = which == 0 ? tc::mx_bias_byte(false, b) : which == 1 ? tc::mx_bias_byte(true, b) : which == 2 ? tc::mx_xbias_byte(false, b)
+                 : which == 3 ? tc::mx_xbias_byte(true, b) : tc::mx_index_byte(arg, b);
+    return 0;
+}

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "scratch.cuh"
 #include "tc_common.cuh"
+#include "tc_tiles.h"
 
 #include <algorithm>
 #include <climits>
@@ -29,6 +30,8 @@
 #include <cstring>
 #include <cuda_fp16.h>
 #include <vector>
+
+using namespace nclt_tc4;
 
 namespace {
 
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_top2(TcParams p) {
 constexpr int MA4 = 4;
 constexpr int A4_TILE_BYTES = 128 * 128;        // 16 KB
 constexpr int B4_ROWS = 240;
+static_assert(B4_ROWS == TILE_ROWS, "tc_tiles.h builds the table for this tile height");
 constexpr int B4_ROW_BYTES = 160;               // 8 K chunks of the descriptor + 2 of the bias row
 constexpr int B4_STAGE_BYTES = B4_ROWS * B4_ROW_BYTES;   // 38 400
 constexpr int BX_ROW_BYTES = 192;               // crossCheck image: + 2 chunks of the column-index row (tc_common.cuh)
@@ -369,20 +373,7 @@ constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MM
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
 constexpr uint32_t SFX_DATA_COL = 496, SFX_BIAS_COL = 504;     // crossCheck kernel: 2^7 at [496, 504), 2^15 at [504, 512)
 
-constexpr int SEG4 = 48;                        // keyframes are padded to whole 48-row segments; a tile is <= 5 segments
-constexpr int GROUP_MIN_ROWS = 16 * B4_ROWS;    // a tile group closes at the first keyframe boundary after this many rows
-
-// Image row space: every keyframe's rows are padded to a multiple of SEG4 (zero rows with a zero bias row; an empty
-// keyframe owns one all-padding segment), and tiles are 240 consecutive image rows ACROSS keyframe boundaries, so a
-// keyframe can only end at a segment boundary of a tile.  The host precomputes where: bit s of `endmask` says that a
-// keyframe ends with segment s; keyframes inside a tile are consecutive, starting at kf0.
-struct LibTile4 {
-    uint32_t img_off256;   // byte offset / 256 into the library image
-    uint16_t n;            // rows in the tile image (multiple of 48, <= 240)
-    uint16_t endmask;      // bit s: a keyframe ends at tile column 48 * (s + 1)
-    int kf0;               // keyframe of column 0
-    int prow0;             // image row of column 0
-};
+// SEG4, GROUP_MIN_ROWS, LibTile4, Tiles4, build_tiles4: tc_tiles.h (host + device; the tile table is unit-tested on the CPU)
 struct WorkEntry { int item; int q; };
 
 struct Tc4Params {
@@ -1205,39 +1196,6 @@ void nclt_tc_release(nclt_lib* L) {
 
 // fp4 = false: fp8 images (256 B per descriptor, keyframe-aligned tiles of <= 256 rows); fp4 = true: e2m1 images
 // (128 B per descriptor + 32 B bias row, 240-row tiles across keyframe boundaries, keyframes padded to 48 rows)
-// Tile table of an fp4 image: 240-row tiles over the IMAGE row space (every keyframe padded to whole 48-row segments; an
-// empty keyframe owns one all-padding segment), across keyframe boundaries.  A tile group closes (its last tile is short)
-// at the first keyframe boundary after GROUP_MIN_ROWS image rows; work splits start at group boundaries, so the image does
-// not depend on the batch size.  counts == nullptr: every keyframe has `stride` rows (the frames of a batch as a library).
-struct Tiles4 {
-    std::vector<LibTile4> tiles;
-    std::vector<int> pstart, grp_tile;
-    size_t off256 = 0;
-};
-static void build_tiles4(const int* counts, int n_kf, int row_bytes, Tiles4& o, int stride = 0) {
-    o.pstart.assign(n_kf + 1, 0);
-    for (int k = 0; k < n_kf; ++k)
-        o.pstart[k + 1] = o.pstart[k] + std::max(SEG4, ((counts ? counts[k] : stride) + SEG4 - 1) / SEG4 * SEG4);
-    const std::vector<int>& pstart = o.pstart;
-    int k = 0;
-    while (k < n_kf) {
-        o.grp_tile.push_back((int)o.tiles.size());
-        const int k_a = k, row_a = pstart[k];
-        int row_b = row_a;
-        while (k < n_kf && row_b - row_a < GROUP_MIN_ROWS) row_b = pstart[++k];
-        int kf = k_a;                                          // keyframe of the tile's column 0
-        for (int r = row_a; r < row_b; r += B4_ROWS) {
-            const int n = std::min(B4_ROWS, row_b - r);        // a multiple of 48
-            while (pstart[kf + 1] <= r) ++kf;
-            uint16_t endmask = 0;
-            for (int q = kf; q < k && pstart[q + 1] <= r + n; ++q) endmask |= (uint16_t)(1u << ((pstart[q + 1] - r) / SEG4 - 1));
-            o.tiles.push_back(LibTile4{(uint32_t)o.off256, (uint16_t)n, endmask, kf, r});
-            o.off256 += (size_t)n * row_bytes / 256;           // 48 rows x 160 (192) bytes = 30 (36) x 256
-        }
-    }
-    o.grp_tile.push_back((int)o.tiles.size());
-}
-
 static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4, bool xc = false) {
     void** slot = xc ? &L->tc4x_cache : fp4 ? &L->tc4_cache : &L->tc_cache;
     TcLibCache* cch = static_cast<TcLibCache*>(*slot);
