@@ -1227,9 +1227,11 @@ static int tc_build_library(nclt_ctx* c, nclt_lib* L, bool fp4, bool xc = false)
             if (xc) {
                 // pass 2 of the crossCheck: the library rows are the QUERY side - A-tile image of all rows + row -> keyframe
                 const long long rows_pad = ((long long)L->n_desc + 127) / 128 * 128;
-                CU_TRY(c, cudaMalloc(&cch->d_aimg, (size_t)rows_pad * 128));
-                k_expand_queries4<<<(unsigned)((rows_pad * 16 + 255) / 256), 256, 0, c->stream>>>(
-                    reinterpret_cast<const uint32_t*>(L->d_desc), L->n_desc, cch->d_aimg);
+                if (rows_pad > 0) {
+                    CU_TRY(c, cudaMalloc(&cch->d_aimg, (size_t)rows_pad * 128));
+                    k_expand_queries4<<<(unsigned)((rows_pad * 16 + 255) / 256), 256, 0, c->stream>>>(
+                        reinterpret_cast<const uint32_t*>(L->d_desc), L->n_desc, cch->d_aimg);
+                }
                 std::vector<int> row_kf((size_t)std::max(L->n_desc, 1), 0);
                 for (int k = 0; k < L->n_kf; ++k)
                     for (int r = 0; r < L->h_count[k]; ++r) row_kf[(size_t)L->h_start[k] + r] = k;

@@ -90,3 +90,14 @@ def test_cross_tensor_many_frames_span_groups(ctx):
     for b in range(12):
         q[b, :60] = kfs[2 * b][:60]
     assert _check(kfs, q, None) > 12 * 60
+
+
+def test_cross_tensor_degenerate_libraries(ctx):
+    """only empty keyframes; a single one-row keyframe; a one-row frame"""
+    rng = np.random.default_rng(6)
+    q = rng.integers(0, 256, (2, 40, 32), dtype=np.uint8)
+    e = np.zeros((0, 32), dtype=np.uint8)
+    assert _check([e, e, e], q, None) == 0
+    one = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    assert _check([one], q, None) == 2
+    assert _check([one, e, rng.integers(0, 256, (300, 32), dtype=np.uint8)], q[:, :1], None) == 2 * 2
