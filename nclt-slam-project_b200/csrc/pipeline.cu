@@ -34,6 +34,57 @@ __global__ void k_select_problems(int* __restrict__ n_pairs, int n_items, int mi
     item_prob[i] = slot;
 }
 
+// ---- pruned candidate loop (candidate lists, no per-item outputs requested) -------------------------------------------
+// The reference tries every candidate of a tick in turn and keeps the FIRST one with the MOST inliers among those that pass
+// the gates (matcher:318-380).  A candidate cannot have more inliers than matches, so once one candidate has been accepted
+// with X inliers, a candidate with fewer than X matches - or with exactly X from a later slot - cannot become the result
+// and its 200 RANSAC iterations need not run.  Pass A solves, per frame, the eligible candidate with the most matches
+// (lowest slot on ties); pass B whatever can still win.  Same best candidate / pose / inliers / error as the full loop
+// (tests/test_localize_gpu.py::test_pruned_candidate_loop_equals_full_loop); four of five candidates of a production
+// tick are wrong keyframes that run all 200 iterations, so this is most of the tick's PnP work.
+__global__ void k_select_top(int* __restrict__ n_pairs, int B, int C, int min_matches, const int* __restrict__ cand,
+                             const int* __restrict__ kf_count, int* prob_item, int* item_prob, int* top_c, int* count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int best = -1, bn = -1;
+    for (int c = 0; c < C; ++c) {
+        const int i = b * C + c, kf = cand[i];
+        if (kf < 0 || kf_count[kf] < min_matches) n_pairs[i] = 0;
+        item_prob[i] = -1;
+        const int np = n_pairs[i];
+        if (kf >= 0 && np >= min_matches && np > bn) { bn = np; best = c; }
+    }
+    top_c[b] = best;
+    if (best >= 0) {
+        const int slot = atomicAdd(count, 1);        // <= B: always fits
+        prob_item[slot] = b * C + best;
+        item_prob[b * C + best] = slot;
+    }
+}
+
+__global__ void k_select_rest(const int* __restrict__ n_pairs, int B, int C, int min_matches, const int* __restrict__ cand,
+                              const int* __restrict__ top_c, const unsigned char* __restrict__ ok, const int* __restrict__ n_inl,
+                              const float* __restrict__ mean_err, int min_inliers, float reproj_max, int base, int* prob_item,
+                              int* item_prob, int* count, int cap, int* overflow) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int ca = top_c[b];
+    if (ca < 0) return;
+    const int pa = item_prob[b * C + ca];
+    int X = -1;                                      // inliers of the accepted pass-A result, -1: not accepted
+    if (ok[pa] && n_inl[pa] >= min_inliers && mean_err[pa] <= reproj_max) X = n_inl[pa];
+    for (int c = 0; c < C; ++c) {
+        if (c == ca) continue;
+        const int i = b * C + c, np = n_pairs[i];    // 0 for empty slots and short keyframes (k_select_top)
+        if (cand[i] < 0 || np < min_matches) continue;
+        if (np > X || (np == X && c < ca)) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) { prob_item[slot] = i; item_prob[i] = base + slot; }
+            else if (overflow) atomicAdd(overflow, 1);
+        }
+    }
+}
+
 // a4: obj_pts = keypoints_3d_cam[teach row], img_pts = pts_curr_2d[frame row]
 __global__ void __launch_bounds__(256) k_gather_problems(const int* __restrict__ prob_item, const int2* __restrict__ pairs,
                                                          const int* __restrict__ n_pairs, int pair_stride, int mode,
@@ -134,7 +185,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
     const int Nrow = prm->mode == 0 ? Nq : (L->max_count > 0 ? L->max_count : 1);
     int rc;
     // stage 1 scratch: pairs + counts + problem tables (the match entry points reserve their own)
-    size_t need1 = pad256(items * Nrow * 8) + 3 * pad256(items * 4) + 4096;
+    size_t need1 = pad256(items * Nrow * 8) + 4 * pad256(items * 4) + pad256((size_t)B * 4) + 4096;
     if ((rc = nclt_scratch_reserve(c, need1))) return rc;
     Carver cv(c);
     int2* pairs = cv.take<int2>(items * Nrow);
@@ -159,12 +210,82 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         c->engine = 2;
         if (rc) return rc;
     }
+    const bool async_mode = out_n_problems_host == nullptr;
+    if (cand && C > 1 && !out_item_ok && !out_item_ninl && !out_item_err && !out_item_rvec && !out_item_tvec) {
+        // ---- pruned candidate loop: pass A (<= B problems, capacity known: no read-back), pass B (what can still win)
+        const int PA = B;
+        const int capB = (int)std::min<size_t>(items - (size_t)B, std::max<size_t>((size_t)B * 4, 1024));
+        const int iters = prm->pnp.iterations;
+        int* prob_item2 = cv.take<int>(items);
+        int* top_c = cv.take<int>(B);
+        int* d_count2 = cv.take<int>(1);
+        CU_TRY(c, cudaMemsetAsync(d_count, 0, 4, c->stream));
+        CU_TRY(c, cudaMemsetAsync(d_count2, 0, 4, c->stream));
+        k_select_top<<<(B + 127) / 128, 128, 0, c->stream>>>(n_pairs, B, C, prm->min_matches, cand, L->d_count, prob_item, item_prob,
+                                                            top_c, d_count);
+        c->launches++;
+        const int Pm = std::max(PA, capB), Pt = PA + capB;
+        size_t h = (size_t)Pm * iters;
+        size_t need2 = pad256((size_t)Pm * Nrow * 12) + pad256((size_t)Pm * Nrow * 8) + pad256((size_t)Pm * 4) +
+                       pad256((size_t)Pm * Nrow) + pad256((size_t)Pt) + 2 * pad256((size_t)Pt * 24) + 2 * pad256((size_t)Pt * 4) +
+                       pad256(h * 20) + pad256(h * 48) + pad256(h * 4) + pad256((size_t)Pm * 16);
+        if ((rc = nclt_scratch_reserve(c, need2))) return rc;   // never moves what is already carved
+        Carver cv2(c);
+        float* obj = cv2.take<float>((size_t)Pm * Nrow * 3);
+        float* img = cv2.take<float>((size_t)Pm * Nrow * 2);
+        int* pn = cv2.take<int>(Pm);
+        unsigned char* mask = cv2.take<unsigned char>((size_t)Pm * Nrow);
+        unsigned char* p_ok = cv2.take<unsigned char>(Pt);
+        double* p_r = cv2.take<double>((size_t)Pt * 3);
+        double* p_t = cv2.take<double>((size_t)Pt * 3);
+        int* p_inl = cv2.take<int>(Pt);
+        float* p_err = cv2.take<float>(Pt);
+        PnpBuffers buf;
+        buf.sets = cv2.take<int>(h * 5);
+        buf.models = cv2.take<double>(h * 6);
+        buf.counts = cv2.take<int>(h);
+        buf.state = cv2.take<int>((size_t)Pm * 4);
+        k_gather_problems<<<PA, 256, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start, L->d_pts3d,
+                                                     q_pts2d, Nq, obj, img, pn, Nrow, d_count);
+        c->launches++;
+        if ((rc = launch_pnp(c, obj, img, pn, PA, d_count, Nrow, &prm->pnp, buf, nullptr, p_ok, p_r, p_t, p_inl, mask, p_err,
+                             nullptr, nullptr, false)))
+            return rc;
+        k_select_rest<<<(B + 127) / 128, 128, 0, c->stream>>>(n_pairs, B, C, prm->min_matches, cand, top_c, p_ok, p_inl, p_err,
+                                                             prm->min_inliers, prm->reproj_max_px, PA, prob_item2, item_prob,
+                                                             d_count2, capB, async_mode ? c->d_overflow : nullptr);
+        c->launches++;
+        int PB = capB;
+        if (!async_mode) {
+            if ((rc = nclt_pinned_reserve(c, 64))) return rc;
+            int* hp = static_cast<int*>(c->pinned);
+            CU_TRY(c, cudaMemcpyAsync(hp, d_count, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(hp + 1, d_count2, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            PB = std::min(hp[1], capB);
+            if (hp[1] > capB) return nclt_fail(c, NCLT_ERR_STATE, "localize: pass-B problem capacity exceeded");
+            *out_n_problems_host = hp[0] + PB;
+        }
+        if (PB > 0) {
+            k_gather_problems<<<PB, 256, 0, c->stream>>>(prob_item2, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
+                                                         L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow, d_count2);
+            c->launches++;
+            if ((rc = launch_pnp(c, obj, img, pn, PB, d_count2, Nrow, &prm->pnp, buf, nullptr, p_ok + PA, p_r + 3 * (size_t)PA,
+                                 p_t + 3 * (size_t)PA, p_inl + PA, mask, p_err + PA, nullptr, nullptr, false)))
+                return rc;
+        }
+        k_reduce_frames<<<(B + 127) / 128, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t, prm->min_inliers,
+                                                                prm->reproj_max_px, out_best_cand, out_n_inliers, out_reproj,
+                                                                out_rvec, out_tvec);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        return NCLT_OK;
+    }
     CU_TRY(c, cudaMemsetAsync(d_count, 0, 4, c->stream));
     // The number of PnP problems is data dependent.  Synchronous mode (out_n_problems given): one
     // 4-byte read-back, buffers sized exactly.  Asynchronous mode (out_n_problems == NULL): no host
     // sync at all - buffers sized for `cap` problems, kernels read the count on the device, and a
     // per-context overflow counter (nclt_ctx_overflow) reports batches that needed more.
-    const bool async_mode = out_n_problems_host == nullptr;
     int P = 0;
     if (async_mode) {
         P = (int)std::min<size_t>(items, std::max<size_t>((size_t)B * 4, 1024));

@@ -135,3 +135,58 @@ def test_streaming_localizer_reruns_a_batch_that_overflows(ctx):
     assert (r0['best_cand'] == 0).all()               # identical candidates: the earliest wins (matcher:379)
     sl.close()
     lib.close()
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_pruned_candidate_loop_equals_full_loop(ctx, mode):
+    """Without per-item outputs a candidate LIST is solved in two passes (the candidate with the most matches first, then
+    only what can still beat it, csrc/pipeline.cu): best candidate, inliers, error and pose must be bit-identical to the
+    full loop (per_item=True runs every candidate), also when several candidates are good (duplicated keyframes, partial
+    copies with fewer rows) in every slot order, synchronously and through the asynchronous device path."""
+    import torch
+    from nclt_slam_project_b200 import synth
+    from nclt_slam_project_b200.library import LandmarkLibrary
+    from nclt_slam_project_b200.pipeline import localize_batch, DeviceLocalizer
+    from nclt_slam_project_b200._lib import LocalizeParams
+    data = synth.make_library(23, n_kf=6, n_desc=400)
+    lms = data['landmarks']
+    # keyframes 6, 7: exact copies of 0 and 1; 8: the first 250 rows of keyframe 2; 9: the first 120 rows of keyframe 0
+    for src, rows in ((0, 400), (1, 400), (2, 250), (0, 120)):
+        lm = dict(lms[src])
+        lm['descriptors'] = lms[src]['descriptors'][:rows].copy()
+        lm['keypoints_3d_cam'] = lms[src]['keypoints_3d_cam'][:rows].copy()
+        lm['keypoints_2d'] = lms[src]['keypoints_2d'][:rows].copy() if 'keypoints_2d' in lm else None
+        lms.append(lm)
+    B = 24
+    desc, pts2d, kstar, _ = synth.make_frame_batch(data, [2300 + i for i in range(B)], n_desc=500, n_planted=220)
+    kfs = ([lm['descriptors'] for lm in lms], [lm['keypoints_3d_cam'] for lm in lms])
+    lib = LandmarkLibrary(kfs[0], kfs[1])
+    rng = np.random.default_rng(5)
+    alias = {0: [0, 6, 9], 1: [1, 7], 2: [2, 8]}
+    cand = np.full((B, 5), -1, dtype=np.int32)
+    for b in range(B):
+        k = int(kstar[b])
+        pool = list(alias.get(k, [k])) + [int(x) for x in rng.choice(10, 3, replace=False)]
+        pool = list(dict.fromkeys(pool))[:5]
+        rng.shuffle(pool)
+        cand[b, :len(pool)] = pool
+        if b % 7 == 0:
+            cand[b, rng.integers(0, 5)] = -1
+    prm = LocalizeParams(mode=mode)
+    full = localize_batch(lib, desc, pts2d, None, cand, prm, per_item=True)
+    pruned = localize_batch(lib, desc, pts2d, None, cand, prm, per_item=False)
+    assert (full['best_cand'] >= 0).sum() >= B - 4
+    # several candidates pass the gates in many frames (otherwise the test proves nothing)
+    good = (full['item_ok'].astype(bool) & (full['item_ninl'] >= 10)).sum(axis=1)
+    assert (good >= 2).sum() >= 5
+    for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
+        assert np.array_equal(full[k], pruned[k]), k
+    assert int(pruned['n_problems']) < int(full['n_problems'])
+    # asynchronous device-resident path (problem counts stay on the device)
+    eng = DeviceLocalizer(kfs, 0, params=prm)
+    o = eng.run(torch.from_numpy(desc).cuda(), torch.from_numpy(pts2d).cuda(), cand_dev=torch.from_numpy(cand).cuda(), sync_count=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(o['best_cand'].cpu().numpy(), full['best_cand'])
+    assert np.array_equal(o['n_inliers'].cpu().numpy(), full['n_inliers'])
+    assert np.array_equal(o['rvec'].cpu().numpy(), full['rvec']) and np.array_equal(o['tvec'].cpu().numpy(), full['tvec'])
+    assert eng.ctx.overflow() == 0
