@@ -204,7 +204,11 @@ typedef struct nclt_localize_params {
  * nclt_ctx_sync().  Two contexts used alternately overlap one batch's copies with the other's kernels.
  * Optional per (frame, candidate) outputs (NULL ok): out_item_nmatch i32[B,C] matches after the
  * ratio / crossCheck filter, out_item_ok u8[B,C], out_item_ninl i32[B,C], out_item_err f32[B,C],
- * out_item_rvec/out_item_tvec f64[B,C,3] (valid where nmatch >= min_matches). */
+ * out_item_rvec/out_item_tvec f64[B,C,3] (valid where nmatch >= min_matches).
+ * With a candidate list (cand != NULL) and none of out_item_ok / _ninl / _err / _rvec / _tvec requested, candidates
+ * that cannot become the frame's result are not solved: PnP runs first on the candidate with the most matches, then
+ * only on those with more matches than its accepted inlier count (or as many, from an earlier slot).  The per-frame
+ * outputs are those of the full loop; out_n_problems counts the problems actually solved. */
 int nclt_localize_batch(nclt_ctx* ctx, const nclt_lib* lib, const uint8_t* q, const float* q_pts2d,
                         const int32_t* q_n, int B, int Nq, const int32_t* cand, int C,
                         const nclt_localize_params* prm, int32_t* out_best_cand, int32_t* out_n_inliers,
