@@ -115,31 +115,40 @@ __global__ void __launch_bounds__(256) k_gather_problems(const int* __restrict__
     if (threadIdx.x == 0) n_out[p] = n;
 }
 
-// a6 + a7: gates and "first candidate with the most inliers wins" (matcher:349-359,379-380)
-__global__ void k_reduce_frames(const int* __restrict__ item_prob, int B, int C, const unsigned char* __restrict__ ok,
-                                const int* __restrict__ n_inl, const float* __restrict__ mean_err,
-                                const double* __restrict__ rvec, const double* __restrict__ tvec, int min_inliers,
-                                float reproj_max, int* best_cand, int* best_inl, float* best_err, double* best_rvec,
-                                double* best_tvec) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+// a6 + a7: gates and "first candidate with the most inliers wins" (matcher:349-359,379-380).  One warp per frame: the
+// lanes stride over the C candidates (400 in the all-keyframes replay: a single thread walking them took 63 us per
+// 512 frames), then a shuffle reduction on (most inliers, earliest slot).
+__global__ void __launch_bounds__(128) k_reduce_frames(const int* __restrict__ item_prob, int B, int C,
+                                                       const unsigned char* __restrict__ ok, const int* __restrict__ n_inl,
+                                                       const float* __restrict__ mean_err, const double* __restrict__ rvec,
+                                                       const double* __restrict__ tvec, int min_inliers, float reproj_max,
+                                                       int* best_cand, int* best_inl, float* best_err, double* best_rvec,
+                                                       double* best_tvec) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     int bc = -1, bi = 0, bp = -1;
-    float be = 0.f;
-    for (int c = 0; c < C; c++) {
-        int p = item_prob[b * C + c];
+    for (int c = lane; c < C; c += 32) {             // a lane sees its slots in increasing order: strict > keeps the earliest
+        const int p = item_prob[b * C + c];
         if (p < 0 || !ok[p]) continue;
-        int ni = n_inl[p];
+        const int ni = n_inl[p];
         if (ni < min_inliers) continue;
-        float e = mean_err[p];
-        if (e > reproj_max) continue;
-        if (bc < 0 || ni > bi) { bc = c; bi = ni; be = e; bp = p; }
+        if (mean_err[p] > reproj_max) continue;
+        if (bc < 0 || ni > bi) { bc = c; bi = ni; bp = p; }
     }
-    best_cand[b] = bc;
-    best_inl[b] = bi;
-    best_err[b] = be;
-    for (int k = 0; k < 3; k++) {
-        best_rvec[b * 3 + k] = bp >= 0 ? rvec[bp * 3 + k] : 0.0;
-        best_tvec[b * 3 + k] = bp >= 0 ? tvec[bp * 3 + k] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int oc = __shfl_xor_sync(0xFFFFFFFFu, bc, o), oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o),
+                  op = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
+        if (oc >= 0 && (bc < 0 || oi > bi || (oi == bi && oc < bc))) { bc = oc; bi = oi; bp = op; }
+    }
+    if (lane == 0) {
+        best_cand[b] = bc;
+        best_inl[b] = bi;
+        best_err[b] = bp >= 0 ? mean_err[bp] : 0.f;
+    }
+    if (lane < 3) {
+        best_rvec[b * 3 + lane] = bp >= 0 ? rvec[bp * 3 + lane] : 0.0;
+        best_tvec[b * 3 + lane] = bp >= 0 ? tvec[bp * 3 + lane] : 0.0;
     }
 }
 
@@ -274,7 +283,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
                                  p_t + 3 * (size_t)PA, p_inl + PA, mask, p_err + PA, nullptr, nullptr, false)))
                 return rc;
         }
-        k_reduce_frames<<<(B + 127) / 128, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t, prm->min_inliers,
+        k_reduce_frames<<<(B + 3) / 4, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t, prm->min_inliers,
                                                                 prm->reproj_max_px, out_best_cand, out_n_inliers, out_reproj,
                                                                 out_rvec, out_tvec);
         c->launches++;
@@ -335,7 +344,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
                              p_r, p_t, p_inl, mask, p_err, nullptr, nullptr, false)))
             return rc;
     }
-    k_reduce_frames<<<(B + 127) / 128, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t,
+    k_reduce_frames<<<(B + 3) / 4, 128, 0, c->stream>>>(item_prob, B, C, p_ok, p_inl, p_err, p_r, p_t,
                                                             prm->min_inliers, prm->reproj_max_px, out_best_cand,
                                                             out_n_inliers, out_reproj, out_rvec, out_tvec);
     c->launches++;
