@@ -1051,7 +1051,10 @@ struct Tc4Pool {
     int slots, nwords;
 };
 
-__global__ void __launch_bounds__(128) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
+// measured per 512-frame replay step (207 k entries; an epilogue warp appends ~13 candidates of one keyframe together):
+// strided over all warps 0.85 ms, runs of 64 0.67, 32 0.57, 16 0.54, 8 0.54; 256-thread CTAs with runs of 128 0.72
+constexpr int VERIFY_THREADS = 128, VERIFY_RUN = 16;
+__global__ void __launch_bounds__(VERIFY_THREADS) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
                                                     int work_cap, int Nq, int n_kf, int num, int den,
                                                     const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
                                                     const int* __restrict__ kf_start, const int* __restrict__ kf_count,
@@ -1059,10 +1062,9 @@ __global__ void __launch_bounds__(128) k_tc4_verify(const WorkEntry* __restrict_
     const int lane = threadIdx.x & 31;
     const int n_work = min(*work_count, work_cap);
     // An epilogue warp appends its candidates of one (32 query rows, keyframe) together, so neighbouring entries mostly
-    // share the keyframe: a CTA walks a run of VERIFY_RUN consecutive entries, its warps side by side, and the keyframe's
+    // share the keyframe: a CTA walks runs of VERIFY_RUN consecutive entries, its warps side by side, and the keyframe's
     // rows (32 KB) are served by L1 instead of being streamed from L2 once per entry (the kernel was bound by L2 bandwidth:
     // 207 k entries x 32 KB = 6.6 GB per 512-frame step)
-    constexpr int VERIFY_RUN = 64;
     const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int base = blockIdx.x * VERIFY_RUN; base < n_work; base += gridDim.x * VERIFY_RUN)
     for (int w = base + wib; w < min(base + VERIFY_RUN, n_work); w += wpb) {
@@ -1578,7 +1580,7 @@ static int tc4_match_ratio_all(nclt_ctx* c, nclt_lib* L, const TcPlan& pl, const
     CU_TRY(c, cudaMemsetAsync(out_n, 0, (size_t)n_items * 4, c->stream));
     if ((rc = tc4_run(c, L, pl, q, q_n, Nq, q_img, 0, num, den, work, counters, work_cap, nullptr))) return rc;
     nclt_prof_mark_tag(c, 6);
-    k_tc4_verify<<<c->sm_count * 16, 128, 0, c->stream>>>(work, counters, work_cap, Nq, n_kf, num, den,
+    k_tc4_verify<<<c->sm_count * (2048 / VERIFY_THREADS), VERIFY_THREADS, 0, c->stream>>>(work, counters, work_cap, Nq, n_kf, num, den,
                                                          reinterpret_cast<const uint4*>(q), L->d_desc, L->d_start, L->d_count, pool,
                                                          c->d_overflow);
     nclt_prof_mark_tag(c, 6);
