@@ -521,47 +521,61 @@ __device__ __forceinline__ int retain_any(RespIdx* v, int n, int n_points, unsig
     return m;
 }
 
-__global__ void __launch_bounds__(256) k_orb_select1(OrbGeom g, LevelTab lt, int* __restrict__ rowcnt, const unsigned short* __restrict__ hx,
+constexpr int kSel1Threads = 1024;
+__global__ void __launch_bounds__(kSel1Threads) k_orb_select1(OrbGeom g, LevelTab lt, int* __restrict__ rowcnt, const unsigned short* __restrict__ hx,
                                                      const uint8_t* __restrict__ hs, uint32_t* __restrict__ key,
                                                      RespIdx* __restrict__ work, unsigned short* __restrict__ lists,
                                                      int* __restrict__ kept1, int* __restrict__ flags) {
     extern __shared__ RespIdx sel_smem[];
     __shared__ int soff[kLevels + 1];
     __shared__ int counts[kLevels];
-    const int f = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool selector = warp < kLevels;            // warps 0..7 own a level each; the other 24 only help with the gather
+    const int l = selector ? warp : 0;
     const size_t ob = (size_t)f * lt.cand_per_frame + lt.cand_off[l];
-    const int rows = max(g.h[l] - 2 * kEdge, 0);
-    int* rc = rowcnt + (size_t)f * lt.rows_total + lt.row_off[l];
+    int* rc_frame = rowcnt + (size_t)f * lt.rows_total;
     // per-row counts -> exclusive offsets, in place; n = survivors of the level
     int n = 0;
-    for (int r0 = 0; r0 < rows; r0 += 32) {
-        const int r = r0 + lane;
-        const int c = r < rows ? rc[r] : 0;
-        int incl = c;
+    if (selector) {
+        const int rows = max(g.h[l] - 2 * kEdge, 0);
+        int* rc = rc_frame + lt.row_off[l];
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int r = r0 + lane;
+            const int c = r < rows ? rc[r] : 0;
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (r < rows) rc[r] = n + incl - c;
+            n += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (r < rows) rc[r] = n + incl - c;
-        n += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (lane == 0) counts[l] = n;
     }
-    if (lane == 0) counts[l] = n;
     __syncthreads();
     bool in_smem;
     RespIdx* v = sel_buffer(sel_smem, soff, counts, l, work + ob, in_smem);
-    unsigned short* Ls = in_smem ? reinterpret_cast<unsigned short*>(sel_smem + kSelSmemEntries) + 2 * soff[l] : lists + 2 * ob;
-    unsigned short* Rs = Ls + n;
-    // gather in row-major order: one lane per row
-    for (int r = lane; r < rows; r += 32) {
-        const int o = rc[r], e = (r + 1 < rows) ? rc[r + 1] : n;
-        const size_t hb = ((size_t)f * lt.rows_total + lt.row_off[l] + r) * lt.hit_stride;
+    // gather in row-major order: one thread per row of the frame (all levels), the whole CTA
+    for (int R = threadIdx.x; R < lt.rows_total; R += kSel1Threads) {
+        int lr = 0;
+#pragma unroll
+        for (int k = 1; k < kLevels; ++k) lr += (R >= lt.row_off[k]) ? 1 : 0;
+        const int r = R - lt.row_off[lr];
+        const int rows = max(g.h[lr] - 2 * kEdge, 0);
+        const int o = rc_frame[R], e = (r + 1 < rows) ? rc_frame[R + 1] : counts[lr];
+        const size_t obr = (size_t)f * lt.cand_per_frame + lt.cand_off[lr];
+        RespIdx* vr = in_smem ? sel_smem + soff[lr] : work + obr;
+        const size_t hb = ((size_t)f * lt.rows_total + R) * lt.hit_stride;
         for (int k = 0; k < e - o; ++k) {
-            v[o + k] = RespIdx{(float)hs[hb + k], o + k};
-            key[ob + o + k] = (uint32_t)((r + kEdge) << 16 | hx[hb + k]);
+            vr[o + k] = RespIdx{(float)hs[hb + k], o + k};
+            key[obr + o + k] = (uint32_t)((r + kEdge) << 16 | hx[hb + k]);
         }
     }
-    __syncwarp();
+    __syncthreads();
+    if (!selector) return;
+    unsigned short* Ls = in_smem ? reinterpret_cast<unsigned short*>(sel_smem + kSelSmemEntries) + 2 * soff[l] : lists + 2 * ob;
+    unsigned short* Rs = Ls + n;
     int m = retain_any(v, n, 2 * lt.n_level[l], Ls, Rs);
     if (m < 0) {
         if (lane == 0) atomicOr(flags, 1);
@@ -988,7 +1002,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         // everything stays on the device; one read of (flags, n_out) at the end
         k_orb_nms_rows<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt, o->d_hx, o->d_hs);
         const size_t sel_smem = (size_t)kSelSmemBytes;
-        k_orb_select1<<<F, 256, sel_smem, st>>>(g, o->lt, o->d_rowcnt, o->d_hx, o->d_hs, o->d_key, o->d_work, o->d_lists, o->d_kept1,
+        k_orb_select1<<<F, kSel1Threads, sel_smem, st>>>(g, o->lt, o->d_rowcnt, o->d_hx, o->d_hs, o->d_key, o->d_work, o->d_lists, o->d_kept1,
                                                 o->d_flags);
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
         k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_lists, o->d_sel, o->out_cap, o->d_nout,
