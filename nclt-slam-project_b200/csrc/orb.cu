@@ -881,15 +881,15 @@ extern "C" int nclt_orb_levels(const nclt_orb* o, int32_t* out_w, int32_t* out_h
 // phase 1, common to both selection modes: pyramid, FAST score map, blurred pyramid
 // The blur needs only the pyramid.  It is queued on the side stream behind `after` (an event on the main stream) so
 // that it runs beside the selection kernels, which occupy one lane per level and leave the SMs idle.
-static int orb_blur_beside(nclt_ctx* c, nclt_orb* o, int F) {
-    CU_TRY(c, cudaEventRecord(o->ev_pyr, c->stream));
+static int orb_blur_beside(nclt_ctx* c, nclt_orb* o, int F, bool record = true) {
+    if (record) CU_TRY(c, cudaEventRecord(o->ev_pyr, c->stream));
     CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
     k_orb_blur<<<dim3(o->bm_blur.first[kLevels], F), 256, 0, o->side>>>(o->d_pyr, o->g, o->bm_blur, o->d_blur);
     CU_TRY(c, cudaEventRecord(o->ev_blur, o->side));
     return NCLT_OK;
 }
 
-static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channels, int F) {
+static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channels, int F, bool blur_later = false) {
     const OrbGeom& g = o->g;
     int rc_blur = 0;
     cudaStream_t st = c->stream;
@@ -908,7 +908,8 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
     if (nb0 > 0) k_orb_fast<<<dim3(nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, 0, o->d_score);
     CU_TRY(c, cudaStreamWaitEvent(st, o->ev_rs, 0));
     if (nb > nb0) k_orb_fast<<<dim3(nb - nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, nb0, o->d_score);
-    if ((rc_blur = orb_blur_beside(c, o, F))) return rc_blur;       // beside the light kernels that follow (NMS, selection)
+    // beside the light kernels that follow; the device-selection path queues it itself, behind the NMS pass
+    if (!blur_later && (rc_blur = orb_blur_beside(c, o, F))) return rc_blur;
     c->launches += 11;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
@@ -994,7 +995,7 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
             d_img = o->d_in;
         }
     }
-    int rc = orb_front(c, o, d_img, channels, F);
+    int rc = orb_front(c, o, d_img, channels, F, o->select_mode != 1);
     if (rc) return rc;
     float* d_kp = out_on_device ? out_kp : o->d_kp;
     uint8_t* d_desc = out_on_device ? out_desc : o->d_desc;
@@ -1002,8 +1003,13 @@ static int orb_run(nclt_ctx* c, nclt_orb* o, const uint8_t* img, bool img_on_dev
         // everything stays on the device; one read of (flags, n_out) at the end
         k_orb_nms_rows<<<dim3(o->bm_rows.first[kLevels], F), 256, 0, st>>>(o->d_score, g, o->lt, o->bm_rows, o->d_rowcnt, o->d_hx, o->d_hs);
         const size_t sel_smem = (size_t)kSelSmemBytes;
+        // the blur (throughput-bound, needs only the pyramid) starts when the NMS pass is through: it runs beside the two
+        // selection kernels, whose few warps leave the SMs idle, instead of sharing the SMs with the NMS pass.  select1 is
+        // queued first so that its CTAs are placed before the blur's fill the machine.
+        CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
         k_orb_select1<<<F, kSel1Threads, sel_smem, st>>>(g, o->lt, o->d_rowcnt, o->d_hx, o->d_hs, o->d_key, o->d_work, o->d_lists, o->d_kept1,
                                                 o->d_flags);
+        if ((rc = orb_blur_beside(c, o, F, false))) return rc;
         k_orb_harris<<<dim3(kLevels * 8, F), 256, 0, st>>>(o->d_pyr, g, o->lt, o->harris_scale4, o->d_key, o->d_kept1, o->d_work);
         k_orb_select2<<<F, 256, sel_smem, st>>>(o->lt, o->d_key, o->d_kept1, o->d_work, o->d_lists, o->d_sel, o->out_cap, o->d_nout,
                                                 o->d_flags);

@@ -217,6 +217,35 @@ class PipelinedLocalizer:
         return sum(e.ctx.overflow() for e in self.engines)
 
 
+class PipelinedFrameLocalizer:
+    """The production tick (visual_landmark_matcher.py:293-380) for batches of camera frames, two DeviceLocalizers
+    taking the batches alternately: frames -> ORB(500) -> crossCheck against the candidate keyframes -> PnP-RANSAC ->
+    gates, all on the device.  The PnP tail of a batch is a chain of latency-bound launches (EPnP rounds, LM finish:
+    a few warps per SM) and the ORB kernels are small CTAs, so - unlike the whole-SM tensor matching kernel of the
+    replay workload - they do share the SMs: the tail of one batch runs beside the ORB extraction of the next
+    (tools/bench_frames.py: 34.5k -> 48.0k frames/s at 128-frame batches, 50.4k -> 59.0k at 400).
+    Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
+
+    def __init__(self, library_arrays, device=0, params=None):
+        prm = params or LocalizeParams(mode=MODE_CROSSCHECK)
+        self.engines = [DeviceLocalizer(library_arrays, device, prm) for _ in range(2)]
+        self.k = 0
+
+    def submit(self, frames_dev, cand_dev):
+        """Enqueue one batch (no host wait for the PnP problem count; the ORB call still ends with its 4-byte flag read,
+        during which the other engine's tail keeps running). Returns (engine, result dict of CUDA tensors)."""
+        e = self.engines[self.k & 1]
+        self.k += 1
+        return e, e.run_frames(frames_dev, cand_dev, sync_count=False)
+
+    def synchronize(self):
+        for e in self.engines:
+            e.ctx.sync()
+
+    def overflow(self):
+        return sum(e.ctx.overflow() for e in self.engines)
+
+
 class StreamingLocalizer:
     """Host-buffer replay API: batches of host (ideally page-locked) arrays in, per-frame results in page-locked
     host arrays out, through the host-pointer C ABI in its asynchronous mode.  `depth` contexts (own CUDA stream,

@@ -72,3 +72,44 @@ def test_device_resident_frames_to_poses(ctx, tmp_path):
         assert int(ref['best_cand'][0]) == f and int(ref['n_inliers'][0]) == int(out['n_inliers'][b])
         assert np.allclose(ref['rvec'][0], out['rvec'][b].cpu().numpy(), atol=1e-12)
         assert np.allclose(ref['tvec'][0], out['tvec'][b].cpu().numpy(), atol=1e-12)
+
+
+def test_pipelined_frames_equal_the_single_engine(ctx, tmp_path):
+    """PipelinedFrameLocalizer (two engines alternate, no host wait for the problem count) returns, batch for batch,
+    what one DeviceLocalizer.run_frames returns - with candidate lists (the pruned candidate loop of the node's tick)."""
+    import torch
+    from nclt_slam_project_b200.pipeline import DeviceLocalizer, LocalizeParams, PipelinedFrameLocalizer
+    from nclt_slam_project_b200.recorder import LandmarkRecorder
+    rec = LandmarkRecorder(str(tmp_path / 'teach' / 'landmarks.pkl'), ctx=ctx)
+    frames = np.stack([synth.make_camera_frame(90 + i) for i in range(4)])
+    rng = np.random.default_rng(5)
+    depth = (5000 + 3 * rng.standard_normal((480, 640))).astype(np.uint16)
+    for i in range(4):
+        assert rec.tick_image(frames[i], depth, (3.0 * i, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0), float(i)) is not None
+    arrays = ([lm['descriptors'] for lm in rec.landmarks], [lm['keypoints_3d_cam'] for lm in rec.landmarks])
+    prm = LocalizeParams(mode=1)
+    dl = DeviceLocalizer(arrays, params=prm)
+    pfl = PipelinedFrameLocalizer(arrays, params=prm)
+    batches = [[2, 0, 3, 1], [1, 1, 0, 2], [3, 2, 1, 0]]
+    cands = [np.array([[f, (f + 1) % 4, -1] for f in b], np.int32) for b in batches]
+    cands[1] = np.array([[(f + 2) % 4, f, (f + 1) % 4] for f in batches[1]], np.int32)      # the right keyframe in slot 1
+    got = []
+    for b, c in zip(batches, cands):
+        q = torch.from_numpy(frames[b]).to(dl.device)
+        e, o = pfl.submit(q, torch.from_numpy(c).to(dl.device))
+        got.append((e, {k: o[k] for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec')}))
+        if len(got) >= 2:          # an engine's buffers are reused by its next batch: take a batch before that
+            e0, o0 = got[-2]
+            e0.ctx.sync()
+            got[-2] = (e0, {k: v.cpu().numpy().copy() for k, v in o0.items()})
+    pfl.synchronize()
+    assert pfl.overflow() == 0
+    got[-1] = (got[-1][0], {k: v.cpu().numpy().copy() for k, v in got[-1][1].items()})
+    for (b, c), (_, o) in zip(zip(batches, cands), got):
+        q = torch.from_numpy(frames[b]).to(dl.device)
+        ref = dl.run_frames(q, torch.from_numpy(c).to(dl.device))
+        torch.cuda.synchronize()
+        want_slot = [list(ci).index(f) for f, ci in zip(b, c)]
+        assert ref['best_cand'].cpu().tolist() == want_slot
+        for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
+            assert np.array_equal(ref[k].cpu().numpy(), o[k]), k
