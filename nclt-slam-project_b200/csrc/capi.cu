@@ -444,18 +444,9 @@ extern "C" int nclt_match_cross_dev(nclt_ctx* c, const nclt_lib* L, const uint8_
     Carver cv(c);
     uint2* fwd = cv.take<uint2>(items * Nmax);
     uint2* bwd = cv.take<uint2>(items * Nq);
-    MatchLaunch m{};
-    // forward: teach rows (query side of match(desc_t, desc_curr)) against the frame
-    m.A = lib_view(L);
-    m.B = frame_view(q, q_n, Nq);
-    m.cand = cand; m.n_outer = B; m.C = C; m.swap = 1; m.a_rows_max = Nmax; m.nsplit = 1; m.b_seg_fixed = -1;
-    m.out_keys = fwd;
-    if ((rc = launch_hamming_top2(c, m, 0u))) return rc;
-    // backward: frame rows against the teach keyframe
-    m.A = frame_view(q, q_n, Nq);
-    m.B = lib_view(L);
-    m.swap = 0; m.a_rows_max = Nq; m.out_keys = bwd;
-    if ((rc = launch_hamming_top2(c, m, 0u))) return rc;
+    // both directions from one pass over each item's distance matrix (hamming.cu, k_hamming_cross): fwd = teach rows
+    // (the query side of match(desc_t, desc_curr)) -> nearest frame row, bwd = frame rows -> nearest teach row
+    if ((rc = launch_hamming_cross(c, frame_view(q, q_n, Nq), lib_view(L), cand, B, C, Nq, Nmax, fwd, bwd))) return rc;
     return launch_cross_combine(c, fwd, bwd, lib_view(L), cand, B, C, Nmax, Nq,
                                 reinterpret_cast<int2*>(out_pairs), out_dist, out_n, Nmax);
 }

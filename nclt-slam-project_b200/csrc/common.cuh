@@ -128,6 +128,8 @@ struct MatchLaunch {
     ushort2* out_dist;       // [n_items, a_rows_max] or nullptr
 };
 int launch_hamming_top2(nclt_ctx* c, const MatchLaunch& m, uint32_t idx_offset);
+int launch_hamming_cross(nclt_ctx* c, const SegView& frames, const SegView& lib, const int* cand, int n_outer, int C, int Nq,
+                         int fwd_rows_max, uint2* fwd, uint2* bwd);
 int launch_merge_top2(nclt_ctx* c, const uint2* parts, int n_items, int nparts, int rows, long long part_stride,
                       long long item_stride, uint2* out_keys, int2* out_idx, ushort2* out_dist);
 int launch_cross_combine(nclt_ctx* c, const uint2* fwd_keys, const uint2* bwd_keys, const SegView& Lib,

@@ -174,6 +174,112 @@ __global__ void __launch_bounds__(TB) k_hamming_top2(KParams p) {
     }
 }
 
+// K1' fused: both directions of crossCheck from ONE pass over the distance matrix of an item (frame x candidate keyframe).
+// A = frame rows in registers (R per thread), B = the keyframe's rows streamed through shared memory as above.
+//   bwd[item][frame row].x = min over teach rows of (d << 23 | teach row)   - the thread's running minimum
+//   fwd[item][teach row].x = min over frame rows of (d << 23 | frame row)   - per teach row: minimum over the thread's R
+//                            rows, REDUX.MIN over the warp, one shared-memory slot per (warp, teach row), the CTA's 8
+//                            slots folded when the chunk is through, atomicMin into fwd (preset to INVALID; several
+//                            CTAs when the frame has more than TB * R rows)
+// min() on the packed key is the reference's tie rule in both directions (lowest index).  Half the POPC work of the
+// two directional launches it replaces (visual_landmark_matcher.py:327 runs this against <= 5 candidates per tick).
+constexpr int XCHUNK = 256;
+template <int R>
+__global__ void __launch_bounds__(TB) k_hamming_cross(KParams p, uint2* __restrict__ fwd, int fwd_rows_max) {
+    __shared__ __align__(128) uint4 sB[2][XCHUNK * 2];
+    __shared__ uint32_t s_col[TB / 32][XCHUNK];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int item = blockIdx.x, achunk = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = item / p.C;
+    const int cand = p.cand ? p.cand[item] : item % p.C;
+    const int row0 = achunk * (TB * R);
+    const size_t out_base = (size_t)item * p.a_rows_max;
+    uint32_t m1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) m1[r] = NCLT_KEY_INVALID;
+    int a_cnt = 0;
+    if (cand >= 0) {
+        const int a_start = p.A.start ? p.A.start[b] : b * p.A.stride;
+        a_cnt = p.A.count ? p.A.count[b] : p.A.stride;
+        const int b_start = p.B.start ? p.B.start[cand] : cand * p.B.stride;
+        const int nrows = p.B.count ? p.B.count[cand] : p.B.stride;
+        const int nch = (nrows + XCHUNK - 1) / XCHUNK;
+        const uint4* bsrc = p.B.base + (size_t)b_start * 2;
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && nch > 0) {
+            uint32_t bytes = (uint32_t)min(XCHUNK, nrows) * 32u;
+            mbar_expect_tx(&mbar[0], bytes);
+            tma_bulk_g2s(&sB[0][0], bsrc, bytes, &mbar[0]);
+        }
+        uint4 q0[R], q1[R];
+        uint32_t rowkey[R];          // the frame row, or all ones for rows past the frame's end (their keys stay INVALID)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r * TB + tid;
+            if (row < a_cnt) {
+                const uint4* src = p.A.base + (size_t)(a_start + row) * 2;
+                q0[r] = __ldg(src);
+                q1[r] = __ldg(src + 1);
+                rowkey[r] = (uint32_t)row;
+            } else {
+                q0[r] = make_uint4(0, 0, 0, 0);
+                q1[r] = make_uint4(0, 0, 0, 0);
+                rowkey[r] = NCLT_KEY_INVALID;
+            }
+        }
+        uint2* fwd_item = fwd + (size_t)item * fwd_rows_max;
+        for (int ch = 0; ch < nch; ++ch) {
+            const int st = ch & 1;
+            if (tid == 0 && ch + 1 < nch) {
+                const int nst = st ^ 1;
+                uint32_t bytes = (uint32_t)min(XCHUNK, nrows - (ch + 1) * XCHUNK) * 32u;
+                mbar_expect_tx(&mbar[nst], bytes);
+                tma_bulk_g2s(&sB[nst][0], bsrc + (size_t)(ch + 1) * XCHUNK * 2, bytes, &mbar[nst]);
+            }
+            mbar_wait(&mbar[st], (ch >> 1) & 1);
+            const int n = min(XCHUNK, nrows - ch * XCHUNK);
+            const uint4* sb = &sB[st][0];
+            uint32_t jkey = (uint32_t)(ch * XCHUNK);
+#pragma unroll 2
+            for (int j = 0; j < n; ++j, ++jkey) {
+                const uint4 t0 = sb[2 * j];
+                const uint4 t1 = sb[2 * j + 1];
+                uint32_t col = NCLT_KEY_INVALID;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t d = __popc(q0[r].x ^ t0.x) + __popc(q0[r].y ^ t0.y) + __popc(q0[r].z ^ t0.z) +
+                                       __popc(q0[r].w ^ t0.w) + __popc(q1[r].x ^ t1.x) + __popc(q1[r].y ^ t1.y) +
+                                       __popc(q1[r].z ^ t1.z) + __popc(q1[r].w ^ t1.w);
+                    const uint32_t dk = d << NCLT_KEY_SHIFT;
+                    m1[r] = min(m1[r], dk + jkey);
+                    col = min(col, dk | rowkey[r]);
+                }
+                col = __reduce_min_sync(0xFFFFFFFFu, col);
+                if (lane == 0) s_col[warp][j] = col;
+            }
+            __syncthreads();
+            if (tid < n) {
+                uint32_t v = s_col[0][tid];
+#pragma unroll
+                for (int w = 1; w < TB / 32; ++w) v = min(v, s_col[w][tid]);
+                if (v != NCLT_KEY_INVALID) atomicMin(&fwd_item[ch * XCHUNK + tid].x, v);
+            }
+            __syncthreads();   // stage st and s_col are free again
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * TB + tid;
+        if (row >= p.a_rows_max) continue;
+        p.out_keys[out_base + row] = make_uint2(row < a_cnt ? m1[r] : NCLT_KEY_INVALID, NCLT_KEY_INVALID);
+    }
+}
+
 // Merge `nparts` partial top-2 lists per (item,row) into one (flat mode: B-row splits on one
 // GPU, then library shards gathered from all ranks).
 __global__ void k_merge_top2(const uint2* __restrict__ parts, int n_items, int nparts, int rows,
@@ -319,6 +425,27 @@ int launch_hamming_top2(nclt_ctx* c, const MatchLaunch& m, uint32_t idx_offset) 
     if (R == 4) k_hamming_top2<4><<<grid, TB, 0, c->stream>>>(p);
     else if (R == 2) k_hamming_top2<2><<<grid, TB, 0, c->stream>>>(p);
     else k_hamming_top2<1><<<grid, TB, 0, c->stream>>>(p);
+    nclt_prof_mark(c);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return NCLT_OK;
+}
+
+// crossCheck against candidate lists: fwd[item][teach row] / bwd[item][frame row] top-1 keys from one pass (see the kernel)
+int launch_hamming_cross(nclt_ctx* c, const SegView& frames, const SegView& lib, const int* cand, int n_outer, int C, int Nq,
+                         int fwd_rows_max, uint2* fwd, uint2* bwd) {
+    const int n_items = n_outer * C;
+    if (n_items <= 0 || Nq <= 0) return NCLT_OK;
+    KParams p{};
+    p.A = frames; p.B = lib; p.cand = cand; p.C = C; p.swap = 0; p.a_rows_max = Nq; p.nsplit = 1; p.b_seg_fixed = -1;
+    p.idx_offset = 0; p.out_keys = bwd;
+    CU_TRY(c, cudaMemsetAsync(fwd, 0xFF, (size_t)n_items * fwd_rows_max * sizeof(uint2), c->stream));
+    const int R = Nq > 2 * TB ? 4 : (Nq > TB ? 2 : 1);
+    dim3 grid(n_items, 1, (Nq + TB * R - 1) / (TB * R));
+    nclt_prof_mark(c);
+    if (R == 4) k_hamming_cross<4><<<grid, TB, 0, c->stream>>>(p, fwd, fwd_rows_max);
+    else if (R == 2) k_hamming_cross<2><<<grid, TB, 0, c->stream>>>(p, fwd, fwd_rows_max);
+    else k_hamming_cross<1><<<grid, TB, 0, c->stream>>>(p, fwd, fwd_rows_max);
     nclt_prof_mark(c);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
