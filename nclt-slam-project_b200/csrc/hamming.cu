@@ -184,12 +184,62 @@ __global__ void __launch_bounds__(TB) k_hamming_top2(KParams p) {
 // min() on the packed key is the reference's tie rule in both directions (lowest index).  Half the POPC work of the
 // two directional launches it replaces (visual_landmark_matcher.py:327 runs this against <= 5 candidates per tick).
 constexpr int XCHUNK = 256;
+struct CrossShared {
+    uint4 sB[2][XCHUNK * 2];
+    uint32_t s_col[TB / 32][XCHUNK];
+    uint64_t mbar[2];
+};
+
+// the pass over the keyframe's rows with RL of the thread's R register rows in use (the frame may have far fewer rows
+// than the row stride Nq the launch was sized for: ORB returns <= 500 keypoints in a 512-row buffer)
+template <int R, int RL>
+__device__ __forceinline__ void cross_pass(CrossShared& sh, const uint4* __restrict__ bsrc, int nrows, int nch, const uint4 (&q0)[R],
+                                           const uint4 (&q1)[R], const uint32_t (&rowkey)[R], uint32_t (&m1)[R], uint2* fwd_item) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int st = ch & 1;
+        if (tid == 0 && ch + 1 < nch) {
+            const int nst = st ^ 1;
+            uint32_t bytes = (uint32_t)min(XCHUNK, nrows - (ch + 1) * XCHUNK) * 32u;
+            mbar_expect_tx(&sh.mbar[nst], bytes);
+            tma_bulk_g2s(&sh.sB[nst][0], bsrc + (size_t)(ch + 1) * XCHUNK * 2, bytes, &sh.mbar[nst]);
+        }
+        mbar_wait(&sh.mbar[st], (ch >> 1) & 1);
+        const int n = min(XCHUNK, nrows - ch * XCHUNK);
+        const uint4* sb = &sh.sB[st][0];
+        uint32_t jkey = (uint32_t)(ch * XCHUNK);
+#pragma unroll 2
+        for (int j = 0; j < n; ++j, ++jkey) {
+            const uint4 t0 = sb[2 * j];
+            const uint4 t1 = sb[2 * j + 1];
+            uint32_t col = NCLT_KEY_INVALID;
+#pragma unroll
+            for (int r = 0; r < RL; ++r) {
+                const uint32_t d = __popc(q0[r].x ^ t0.x) + __popc(q0[r].y ^ t0.y) + __popc(q0[r].z ^ t0.z) +
+                                   __popc(q0[r].w ^ t0.w) + __popc(q1[r].x ^ t1.x) + __popc(q1[r].y ^ t1.y) +
+                                   __popc(q1[r].z ^ t1.z) + __popc(q1[r].w ^ t1.w);
+                const uint32_t dk = d << NCLT_KEY_SHIFT;
+                m1[r] = min(m1[r], dk + jkey);
+                col = min(col, dk | rowkey[r]);
+            }
+            col = __reduce_min_sync(0xFFFFFFFFu, col);
+            if (lane == 0) sh.s_col[warp][j] = col;
+        }
+        __syncthreads();
+        if (tid < n) {
+            uint32_t v = sh.s_col[0][tid];
+#pragma unroll
+            for (int w = 1; w < TB / 32; ++w) v = min(v, sh.s_col[w][tid]);
+            if (v != NCLT_KEY_INVALID) atomicMin(&fwd_item[ch * XCHUNK + tid].x, v);
+        }
+        __syncthreads();   // stage st and s_col are free again
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(TB) k_hamming_cross(KParams p, uint2* __restrict__ fwd, int fwd_rows_max) {
-    __shared__ __align__(128) uint4 sB[2][XCHUNK * 2];
-    __shared__ uint32_t s_col[TB / 32][XCHUNK];
-    __shared__ __align__(8) uint64_t mbar[2];
-    const int item = blockIdx.x, achunk = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(128) CrossShared sh;
+    const int item = blockIdx.x, achunk = blockIdx.z, tid = threadIdx.x;
     const int b = item / p.C;
     const int cand = p.cand ? p.cand[item] : item % p.C;
     const int row0 = achunk * (TB * R);
@@ -203,18 +253,19 @@ __global__ void __launch_bounds__(TB) k_hamming_cross(KParams p, uint2* __restri
         a_cnt = p.A.count ? p.A.count[b] : p.A.stride;
         const int b_start = p.B.start ? p.B.start[cand] : cand * p.B.stride;
         const int nrows = p.B.count ? p.B.count[cand] : p.B.stride;
-        const int nch = (nrows + XCHUNK - 1) / XCHUNK;
+        const int live = min(R, (a_cnt - row0 + TB - 1) / TB);       // register rows of this CTA that hold frame rows
+        const int nch = live > 0 ? (nrows + XCHUNK - 1) / XCHUNK : 0;
         const uint4* bsrc = p.B.base + (size_t)b_start * 2;
         if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
+            mbar_init(&sh.mbar[0], 1);
+            mbar_init(&sh.mbar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (tid == 0 && nch > 0) {
             uint32_t bytes = (uint32_t)min(XCHUNK, nrows) * 32u;
-            mbar_expect_tx(&mbar[0], bytes);
-            tma_bulk_g2s(&sB[0][0], bsrc, bytes, &mbar[0]);
+            mbar_expect_tx(&sh.mbar[0], bytes);
+            tma_bulk_g2s(&sh.sB[0][0], bsrc, bytes, &sh.mbar[0]);
         }
         uint4 q0[R], q1[R];
         uint32_t rowkey[R];          // the frame row, or all ones for rows past the frame's end (their keys stay INVALID)
@@ -233,44 +284,10 @@ __global__ void __launch_bounds__(TB) k_hamming_cross(KParams p, uint2* __restri
             }
         }
         uint2* fwd_item = fwd + (size_t)item * fwd_rows_max;
-        for (int ch = 0; ch < nch; ++ch) {
-            const int st = ch & 1;
-            if (tid == 0 && ch + 1 < nch) {
-                const int nst = st ^ 1;
-                uint32_t bytes = (uint32_t)min(XCHUNK, nrows - (ch + 1) * XCHUNK) * 32u;
-                mbar_expect_tx(&mbar[nst], bytes);
-                tma_bulk_g2s(&sB[nst][0], bsrc + (size_t)(ch + 1) * XCHUNK * 2, bytes, &mbar[nst]);
-            }
-            mbar_wait(&mbar[st], (ch >> 1) & 1);
-            const int n = min(XCHUNK, nrows - ch * XCHUNK);
-            const uint4* sb = &sB[st][0];
-            uint32_t jkey = (uint32_t)(ch * XCHUNK);
-#pragma unroll 2
-            for (int j = 0; j < n; ++j, ++jkey) {
-                const uint4 t0 = sb[2 * j];
-                const uint4 t1 = sb[2 * j + 1];
-                uint32_t col = NCLT_KEY_INVALID;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t d = __popc(q0[r].x ^ t0.x) + __popc(q0[r].y ^ t0.y) + __popc(q0[r].z ^ t0.z) +
-                                       __popc(q0[r].w ^ t0.w) + __popc(q1[r].x ^ t1.x) + __popc(q1[r].y ^ t1.y) +
-                                       __popc(q1[r].z ^ t1.z) + __popc(q1[r].w ^ t1.w);
-                    const uint32_t dk = d << NCLT_KEY_SHIFT;
-                    m1[r] = min(m1[r], dk + jkey);
-                    col = min(col, dk | rowkey[r]);
-                }
-                col = __reduce_min_sync(0xFFFFFFFFu, col);
-                if (lane == 0) s_col[warp][j] = col;
-            }
-            __syncthreads();
-            if (tid < n) {
-                uint32_t v = s_col[0][tid];
-#pragma unroll
-                for (int w = 1; w < TB / 32; ++w) v = min(v, s_col[w][tid]);
-                if (v != NCLT_KEY_INVALID) atomicMin(&fwd_item[ch * XCHUNK + tid].x, v);
-            }
-            __syncthreads();   // stage st and s_col are free again
-        }
+        if (R >= 4 && live == 4) cross_pass<R, (R >= 4 ? 4 : R)>(sh, bsrc, nrows, nch, q0, q1, rowkey, m1, fwd_item);
+        else if (R >= 3 && live == 3) cross_pass<R, (R >= 3 ? 3 : R)>(sh, bsrc, nrows, nch, q0, q1, rowkey, m1, fwd_item);
+        else if (R >= 2 && live == 2) cross_pass<R, (R >= 2 ? 2 : R)>(sh, bsrc, nrows, nch, q0, q1, rowkey, m1, fwd_item);
+        else if (live == 1) cross_pass<R, 1>(sh, bsrc, nrows, nch, q0, q1, rowkey, m1, fwd_item);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -440,7 +457,9 @@ int launch_hamming_cross(nclt_ctx* c, const SegView& frames, const SegView& lib,
     p.A = frames; p.B = lib; p.cand = cand; p.C = C; p.swap = 0; p.a_rows_max = Nq; p.nsplit = 1; p.b_seg_fixed = -1;
     p.idx_offset = 0; p.out_keys = bwd;
     CU_TRY(c, cudaMemsetAsync(fwd, 0xFF, (size_t)n_items * fwd_rows_max * sizeof(uint2), c->stream));
-    const int R = Nq > 2 * TB ? 4 : (Nq > TB ? 2 : 1);
+    // rows per thread: 4 for 1000-row frames; 2 (and a second, usually empty, CTA per item) for ORB's 640-row buffers that
+    // hold <= 500 keypoints - 40 registers instead of 64, six CTAs per SM
+    const int R = Nq > 3 * TB ? 4 : (Nq > TB ? 2 : 1);
     dim3 grid(n_items, 1, (Nq + TB * R - 1) / (TB * R));
     nclt_prof_mark(c);
     if (R == 4) k_hamming_cross<4><<<grid, TB, 0, c->stream>>>(p, fwd, fwd_rows_max);

@@ -226,15 +226,15 @@ class PipelinedFrameLocalizer:
     (tools/bench_frames.py: 34.5k -> 48.0k frames/s at 128-frame batches, 50.4k -> 59.0k at 400).
     Results of a batch live in the buffers of the engine that ran it until that engine's next batch."""
 
-    def __init__(self, library_arrays, device=0, params=None):
+    def __init__(self, library_arrays, device=0, params=None, depth=2):
         prm = params or LocalizeParams(mode=MODE_CROSSCHECK)
-        self.engines = [DeviceLocalizer(library_arrays, device, prm) for _ in range(2)]
+        self.engines = [DeviceLocalizer(library_arrays, device, prm) for _ in range(depth)]
         self.k = 0
 
     def submit(self, frames_dev, cand_dev):
         """Enqueue one batch (no host wait for the PnP problem count; the ORB call still ends with its 4-byte flag read,
-        during which the other engine's tail keeps running). Returns (engine, result dict of CUDA tensors)."""
-        e = self.engines[self.k & 1]
+        during which the other engines' tails keep running). Returns (engine, result dict of CUDA tensors)."""
+        e = self.engines[self.k % len(self.engines)]
         self.k += 1
         return e, e.run_frames(frames_dev, cand_dev, sync_count=False)
 
