@@ -338,6 +338,13 @@ long long nclt_orb_host_fallbacks(const nclt_orb* orb);
 int nclt_orb_submit(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F, float* out_kp,
                     uint8_t* out_desc, int32_t* out_n);
 int nclt_orb_wait(nclt_ctx* ctx, nclt_orb* orb);
+/* nclt_orb_submit with DEVICE pointers (img, out_kp, out_desc, out_n): nothing but kernels and one device-to-device
+ * copy are enqueued, the call returns at once and work queued behind it on the context's stream (nclt_localize_batch_dev
+ * on the descriptors) may consume the outputs.  nclt_orb_wait later synchronises and checks the selection flags; when
+ * it had to hand the selection over to the host (nclt_orb_host_fallbacks grew - never seen on camera images) it
+ * rewrites the outputs, and whatever consumed them meanwhile has to be run again (pipeline.py does). */
+int nclt_orb_submit_dev(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F, float* out_kp,
+                        uint8_t* out_desc, int32_t* out_n);
 /* img, out_kp, out_desc, out_n are DEVICE pointers */
 int nclt_orb_detect_and_compute_dev(nclt_ctx* ctx, nclt_orb* orb, const uint8_t* img, int channels, int F,
                                     float* out_kp, uint8_t* out_desc, int32_t* out_n);

@@ -115,6 +115,7 @@ _sig('nclt_orb_levels', _i, _vp, _vp, _vp, _vp, _vp)
 for _n in ('nclt_orb_detect_and_compute', 'nclt_orb_detect_and_compute_dev'):
     _sig(_n, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp)
 _sig('nclt_orb_submit', _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp)
+_sig('nclt_orb_submit_dev', _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp)
 _sig('nclt_orb_wait', _i, _vp, _vp)
 _sig('nclt_orb_set_select', _i, _vp, _vp, _i)
 _sig('nclt_orb_host_fallbacks', C.c_longlong, _vp)

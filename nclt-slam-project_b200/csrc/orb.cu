@@ -1084,6 +1084,10 @@ extern "C" int nclt_orb_submit(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int
                                int32_t* out_n) {
     return orb_run(c, o, img, false, channels, F, out_kp, out_desc, out_n, false, true);
 }
+extern "C" int nclt_orb_submit_dev(nclt_ctx* c, nclt_orb* o, const uint8_t* img, int channels, int F, float* out_kp,
+                                   uint8_t* out_desc, int32_t* out_n) {
+    return orb_run(c, o, img, true, channels, F, out_kp, out_desc, out_n, true, true);
+}
 extern "C" int nclt_orb_wait(nclt_ctx* c, nclt_orb* o) {
     if (!c) return NCLT_ERR_ARG;
     if (!o) return nclt_fail(c, NCLT_ERR_ARG, "orb_wait: null handle");

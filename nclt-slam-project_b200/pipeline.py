@@ -105,13 +105,18 @@ class DeviceLocalizer:
             self._out[B] = o
         return o
 
-    def run_frames(self, frames_dev, cand_dev=None, n_cand=None, sync_count=True):
+    def run_frames(self, frames_dev, cand_dev=None, n_cand=None, sync_count=True, defer_orb_check=False):
         """Camera frames in, poses out, nothing leaves the device in between: frames_dev u8[B,H,W] (gray) or
         u8[B,H,W,3] (BGR) CUDA tensor -> ORB(500) (orb.py / nclt_orb_detect_and_compute_dev, bit-identical to the cv2
         call at matcher:305-306) -> `run` on its descriptors and keypoint positions (matcher:310-380).
-        Returns run()'s dict plus 'n_keypoints' i32[B], 'keypoints' f32[B,cap,6], 'descriptors' u8[B,cap,32]."""
+        Returns run()'s dict plus 'n_keypoints' i32[B], 'keypoints' f32[B,cap,6], 'descriptors' u8[B,cap,32].
+        defer_orb_check=True (with sync_count=False): the host does not wait for the ORB call's selection flags either
+        (nclt_orb_submit_dev); `finish_frames()` must be called before the results are used or the engine takes its
+        next batch - it waits, and in the (never observed) case that the ORB selection had to be redone on the host it
+        runs the localisation again on the corrected keypoints."""
         t = self.torch
         from .orb import ORB
+        self.finish_frames()
         B, H, W = frames_dev.shape[0], frames_dev.shape[1], frames_dev.shape[2]
         ch = 3 if frames_dev.dim() == 4 else 1
         orb = getattr(self, '_orb', None)
@@ -124,12 +129,37 @@ class DeviceLocalizer:
                              t.empty(B, dtype=t.int32, device=self.device))
         kp, desc, n = self._orb_out
         with t.cuda.stream(self.stream):
-            self.ctx.check(_c.nclt_orb_detect_and_compute_dev(self.ctx.h, orb._h, frames_dev.data_ptr(), ch, B,
-                                                              kp.data_ptr(), desc.data_ptr(), n.data_ptr()))
+            if defer_orb_check:
+                if sync_count:
+                    raise ValueError('defer_orb_check needs sync_count=False')
+                self.ctx.check(_c.nclt_orb_submit_dev(self.ctx.h, orb._h, frames_dev.data_ptr(), ch, B,
+                                                      kp.data_ptr(), desc.data_ptr(), n.data_ptr()))
+                self._pending_frames = (frames_dev, cand_dev, n_cand, orb.host_fallbacks)
+            else:
+                self.ctx.check(_c.nclt_orb_detect_and_compute_dev(self.ctx.h, orb._h, frames_dev.data_ptr(), ch, B,
+                                                                  kp.data_ptr(), desc.data_ptr(), n.data_ptr()))
             pts2d = kp[:, :, :2].contiguous()
             r = self.run(desc, pts2d, cand_dev, n_cand, sync_count, qn_dev=n)
         r.update(n_keypoints=n, keypoints=kp, descriptors=desc)
         return r
+
+    def finish_frames(self):
+        """Second half of run_frames(defer_orb_check=True): wait for the batch, look at the ORB selection flags; returns
+        True when the localisation had to be run again (host fall-back of the ORB selection).  No-op otherwise."""
+        pend = getattr(self, '_pending_frames', None)
+        if pend is None:
+            return False
+        self._pending_frames = None
+        _frames, cand_dev, n_cand, fallbacks_before = pend
+        t = self.torch
+        self.ctx.check(_c.nclt_orb_wait(self.ctx.h, self._orb._h))
+        if self._orb.host_fallbacks == fallbacks_before:
+            return False
+        kp, desc, n = self._orb_out        # rewritten by the host selection: localise again on the corrected keypoints
+        with t.cuda.stream(self.stream):
+            self.run(desc, kp[:, :, :2].contiguous(), cand_dev, n_cand, False, qn_dev=n)
+        self.ctx.sync()
+        return True
 
     def run(self, desc_dev, pts2d_dev, cand_dev=None, n_cand=None, sync_count=True, qn_dev=None, lib=0):
         """desc_dev u8[B,Nq,32], pts2d_dev f32[B,Nq,2] CUDA tensors (qn_dev i32[B]: valid rows per frame, default all)
@@ -230,16 +260,20 @@ class PipelinedFrameLocalizer:
         prm = params or LocalizeParams(mode=MODE_CROSSCHECK)
         self.engines = [DeviceLocalizer(library_arrays, device, prm) for _ in range(depth)]
         self.k = 0
+        self.reruns = 0          # batches localised again because the ORB selection fell back to the host
 
     def submit(self, frames_dev, cand_dev):
-        """Enqueue one batch (no host wait for the PnP problem count; the ORB call still ends with its 4-byte flag read,
-        during which the other engines' tails keep running). Returns (engine, result dict of CUDA tensors)."""
+        """Enqueue one batch: no host wait at all (the PnP problem count stays on the device, the ORB selection flags are
+        looked at when the engine is used again or in synchronize()). Returns (engine, result dict of CUDA tensors),
+        valid after engine.finish_frames() / synchronize()."""
         e = self.engines[self.k % len(self.engines)]
         self.k += 1
-        return e, e.run_frames(frames_dev, cand_dev, sync_count=False)
+        self.reruns += int(e.finish_frames())          # the engine's previous batch (its buffers are reused now)
+        return e, e.run_frames(frames_dev, cand_dev, sync_count=False, defer_orb_check=True)
 
     def synchronize(self):
         for e in self.engines:
+            self.reruns += int(e.finish_frames())
             e.ctx.sync()
 
     def overflow(self):

@@ -100,7 +100,7 @@ def test_pipelined_frames_equal_the_single_engine(ctx, tmp_path):
         got.append((e, {k: o[k] for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec')}))
         if len(got) >= 2:          # an engine's buffers are reused by its next batch: take a batch before that
             e0, o0 = got[-2]
-            e0.ctx.sync()
+            assert e0.finish_frames() is False
             got[-2] = (e0, {k: v.cpu().numpy().copy() for k, v in o0.items()})
     pfl.synchronize()
     assert pfl.overflow() == 0
@@ -113,3 +113,34 @@ def test_pipelined_frames_equal_the_single_engine(ctx, tmp_path):
         assert ref['best_cand'].cpu().tolist() == want_slot
         for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec'):
             assert np.array_equal(ref[k].cpu().numpy(), o[k]), k
+
+
+def test_deferred_orb_check_reruns_after_a_host_fallback(ctx, tmp_path):
+    """run_frames(defer_orb_check=True) queues the localisation behind the ORB call without looking at its selection
+    flags; when the selection falls back to the host (forced here, select='force_fallback'), finish_frames() localises
+    again on the rewritten keypoints: same results as the synchronous call."""
+    import torch
+    from nclt_slam_project_b200.orb import ORB
+    from nclt_slam_project_b200.pipeline import DeviceLocalizer, LocalizeParams
+    from nclt_slam_project_b200.recorder import LandmarkRecorder
+    rec = LandmarkRecorder(str(tmp_path / 'teach' / 'landmarks.pkl'), ctx=ctx)
+    frames = np.stack([synth.make_camera_frame(40 + i) for i in range(3)])
+    rng = np.random.default_rng(6)
+    depth = (5000 + 3 * rng.standard_normal((480, 640))).astype(np.uint16)
+    for i in range(3):
+        assert rec.tick_image(frames[i], depth, (3.0 * i, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0), float(i)) is not None
+    arrays = ([lm['descriptors'] for lm in rec.landmarks], [lm['keypoints_3d_cam'] for lm in rec.landmarks])
+    prm = LocalizeParams(mode=1)
+    ref_dl = DeviceLocalizer(arrays, params=prm)
+    dl = DeviceLocalizer(arrays, params=prm)
+    dl._orb = ORB(max_frames=3, ctx=dl.ctx, select='force_fallback')
+    q = torch.from_numpy(frames[[1, 2, 0]]).to(dl.device)
+    cand = torch.from_numpy(np.array([[0, 1, 2]] * 3, np.int32)).to(dl.device)
+    ref = ref_dl.run_frames(q, cand)
+    torch.cuda.synchronize()
+    assert ref['best_cand'].cpu().tolist() == [1, 2, 0]
+    out = dl.run_frames(q, cand, sync_count=False, defer_orb_check=True)
+    assert dl.finish_frames() is True and dl._orb.host_fallbacks == 1
+    assert dl.finish_frames() is False
+    for k in ('best_cand', 'n_inliers', 'reproj', 'rvec', 'tvec', 'n_keypoints'):
+        assert np.array_equal(ref[k].cpu().numpy(), out[k].cpu().numpy()), k
