@@ -416,36 +416,30 @@ __device__ __forceinline__ bool nms_max(const uint8_t* sc, int p) {
     return s > max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
 }
 
-// NMS over four pixels at once: one 32-bit read of the score row (almost always zero), neighbours only for corners.
-// row = first byte of the score row (16-byte aligned), wi = word index; bit k of the result = pixel 4 wi + k survives.
-__device__ __forceinline__ unsigned nms_word_hits(const uint8_t* row, int p, int wi, int xlo, int xhi) {
-    const uint32_t wv = *reinterpret_cast<const uint32_t*>(row + 4 * wi);
-    if (wv == 0) return 0;
-    unsigned hits = 0;
-    uint32_t m = wv;
-    while (m) {                                  // only the non-zero bytes (corners) are looked at
-        const int k = (__ffs(m) - 1) >> 3;
-        m &= ~(0xFFu << (8 * k));
-        const int x = 4 * wi + k;
-        if (x >= xlo && x < xhi && nms_max(row + x, p)) hits |= 1u << k;
-    }
-    return hits;
-}
-
 // NMS survivors of every (frame, level), one warp per row: the row's survivors in ascending x (position, FAST score)
 // go to the row's slot of `hx` / `hs` (hit_stride entries per row: a row holds at most one strict maximum per two
 // pixels), their number to rowcnt.  FAST's row-major order is then "rows in order, hits in order" - k_orb_select1
 // turns the per-row counts into offsets and gathers.  rowcnt: [F][rows_total], rows of level l start at lt.row_off[l].
 constexpr int kNmsRowsPerCta = 32;
+// bit k of the result: byte k of w is non-zero
+__device__ __forceinline__ unsigned nz_nibble(uint32_t w) {
+    const uint32_t t = (w | ((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;
+    return ((t >> 7) * 0x10204080u) >> 28;
+}
 __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict__ score, OrbGeom g, LevelTab lt, BlockMap bm,
                                                       int* __restrict__ rowcnt, unsigned short* __restrict__ hx,
                                                       uint8_t* __restrict__ hs) {
+    __shared__ unsigned short corner_list[8][512];     // per warp: the corners of one 512-pixel step of its row
     const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l, bx, by;
     block_of(bm, blockIdx.x, l, bx, by);
     const int w = g.w[l], h = g.h[l], p = g.pitch[l];
     const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
-    if (cols <= 0) return;
+    if (cols <= 0) {        // a level too narrow for any keypoint still owns row slots: their counts must read 0
+        for (int r = by * kNmsRowsPerCta + (int)threadIdx.x; r < min((by + 1) * kNmsRowsPerCta, rows); r += 256)
+            rowcnt[(size_t)f * lt.rows_total + lt.row_off[l] + r] = 0;
+        return;
+    }
     for (int r = by * kNmsRowsPerCta + warp; r < min((by + 1) * kNmsRowsPerCta, rows); r += 8) {     // short rows: several per warp
     const uint8_t* row = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p;
     const size_t slot = (size_t)f * lt.rows_total + lt.row_off[l] + r;
@@ -453,19 +447,22 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
     uint8_t* os = hs + slot * lt.hit_stride;
     const int vi_max = (w - kEdge - 1) / 16;                 // 16 scores (one uint4) per lane and step
     const uint4* rowv = reinterpret_cast<const uint4*>(row);
+    const int xlo = kEdge, xhi = w - kEdge;
+    unsigned short* list = corner_list[warp];
     int pos = 0;
     for (int vi0 = kEdge / 16; vi0 <= vi_max; vi0 += 32) {
         const int vi = vi0 + lane;
         uint4 q = make_uint4(0u, 0u, 0u, 0u);
         if (vi <= vi_max) q = rowv[vi];
-        unsigned hits = 0;                                   // bit k: pixel 16 vi + k survives
+        // bit k: pixel 16 vi + k is a corner (non-zero score) inside the border
+        unsigned nz = 0;
         if (q.x | q.y | q.z | q.w) {
-            if (q.x) hits |= nms_word_hits(row, p, 4 * vi, kEdge, w - kEdge);
-            if (q.y) hits |= nms_word_hits(row, p, 4 * vi + 1, kEdge, w - kEdge) << 4;
-            if (q.z) hits |= nms_word_hits(row, p, 4 * vi + 2, kEdge, w - kEdge) << 8;
-            if (q.w) hits |= nms_word_hits(row, p, 4 * vi + 3, kEdge, w - kEdge) << 12;
+            nz = nz_nibble(q.x) | nz_nibble(q.y) << 4 | nz_nibble(q.z) << 8 | nz_nibble(q.w) << 12;
+            const int xb = 16 * vi;
+            if (xb < xlo) nz &= (xlo - xb < 16) ? ~((1u << (xlo - xb)) - 1u) : 0u;
+            if (xb + 16 > xhi) nz &= (xhi > xb) ? ((1u << (xhi - xb)) - 1u) : 0u;
         }
-        const int c = __popc(hits);
+        const int c = __popc(nz);
         if (__ballot_sync(0xFFFFFFFFu, c > 0) == 0) continue;
         int incl = c;                                   // lanes hold ascending x: exclusive scan of the per-lane counts
 #pragma unroll
@@ -473,15 +470,33 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
             const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += u;
         }
-        int o = pos + incl - c;
-        while (hits) {
-            const int k = __ffs(hits) - 1;
-            hits &= hits - 1;
-            ox[o] = (unsigned short)(16 * vi + k);
-            os[o] = row[16 * vi + k];
-            ++o;
+        // corners cluster (a lane may hold six while most hold none): they go to a list in ascending x first, and the
+        // 3x3 test - eight neighbour loads per corner - then runs on the list with all lanes busy
+        int o = incl - c;
+        while (nz) {
+            const int k = __ffs(nz) - 1;
+            nz &= nz - 1;
+            list[o++] = (unsigned short)(16 * vi + k);
         }
-        pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            int x = 0;
+            bool hit = false;
+            if (i < total) {
+                x = list[i];
+                hit = nms_max(row + x, p);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hit) {
+                const int at = pos + __popc(m & ((1u << lane) - 1u));
+                ox[at] = (unsigned short)x;
+                os[at] = row[x];
+            }
+            pos += __popc(m);
+        }
+        __syncwarp();
     }
     if (lane == 0) rowcnt[slot] = pos;
     }

@@ -127,6 +127,21 @@ def test_large_frames_and_more_than_65535_candidates(ctx):
     assert o.host_fallbacks == 0
 
 
+def test_tall_narrow_frame_with_a_level_too_narrow_for_keypoints(ctx):
+    """220 x 900: level 7 is 61 px wide - inside the 31 px border nothing can be a keypoint, yet the level owns row slots
+    (its row counts must read 0, not whatever the allocation held)."""
+    from nclt_slam_project_b200.orb import ORB
+    o = ORB(width=220, height=900, max_frames=2, ctx=ctx)
+    frames = np.stack([synth.make_camera_frame(77, 900, 220, n_rect=300), synth.make_camera_frame(78, 900, 220, n_rect=200)])
+    for _ in range(2):          # the second call sees the first call's scan results in the count array
+        kp, desc, n = o.detect_and_compute_batch(frames)
+        for f in range(2):
+            rk, rd = oo.detect_and_compute(frames[f])
+            assert (rk[:, 5] == 7).sum() == 0
+            _check(kp, desc, n, f, rk, rd, f'frame {f}')
+    assert o.host_fallbacks == 0
+
+
 @pytest.mark.parametrize('select', ['device', 'host'])
 def test_out_cap_overflow_is_an_error(ctx, select):
     """The tiled frame yields 514 keypoints (ties at the Harris cut): out_cap = 500 must fail loudly, not truncate."""
