@@ -45,14 +45,18 @@ struct OrbGeom {
 __constant__ __align__(16) signed char c_pattern[256 * 4];
 
 // One launch covers all levels without empty CTAs: blockIdx.x runs over the tiles of level 0, then level 1, ...
-struct BlockMap { int first[kLevels + 1]; int bx[kLevels]; };
+// The decode is a table in device memory, one int4 {level, bx, by, 0} per block, and the level's geometry another
+// {w, h, pitch, byte offset}: two broadcast loads per thread.  (Computed from `first` / `bx` - a compare chain, a dynamic
+// index into kernel parameters, which ptxas expands into predicated loads, and an integer division - it was 200 of the
+// 975 instructions a FAST warp executes, ncu source view of round 2.)
+struct BlockMap { int first[kLevels + 1]; int bx[kLevels]; const int4* tab; const int4* lev; };
 __device__ __forceinline__ void block_of(const BlockMap& m, int b, int& l, int& bx, int& by) {
-    l = 0;
-#pragma unroll
-    for (int k = 1; k < kLevels; ++k) l += (b >= m.first[k]) ? 1 : 0;
-    const int t = b - m.first[l];
-    by = t / m.bx[l];
-    bx = t - by * m.bx[l];
+    const int4 e = __ldg(m.tab + b);
+    l = e.x; bx = e.y; by = e.z;
+}
+__device__ __forceinline__ void level_of(const BlockMap& m, int l, int& w, int& h, int& pitch, long long& off) {
+    const int4 e = __ldg(m.lev + l);
+    w = e.x; h = e.y; pitch = e.z; off = e.w;
 }
 
 struct Cand { uint32_t tag, key; float score, harris; };          // tag = frame * 8 + level, key = y << 16 | x
@@ -121,33 +125,43 @@ __global__ void __launch_bounds__(256, 6) k_orb_fast(const uint8_t* __restrict__
     const int f = blockIdx.y;
     int l, bx, by;
     block_of(bm, blockIdx.x + block0, l, bx, by);
-    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    int w, h, p;
+    long long loff;
+    level_of(bm, l, w, h, p, loff);
     const int x0 = bx * kFastTile + kEdge - 1, y0 = by * kFastTile + kEdge - 1;      // first pixel of the tile
     const int xe = w - kEdge, ye = h - kEdge;                                        // last pixel scored (inclusive)
-    const size_t base = (size_t)f * g.frame_bytes + g.off[l];
+    const size_t base = (size_t)f * g.frame_bytes + loff;
     if (threadIdx.x == 0) n_list = 0;
     const int tx = threadIdx.x & 31;
     // staging with 32-bit loads (rows are 16-byte aligned, x0 - 6 = 32 bx + 24); the clamps only touch pixels that are
     // never scored
-    for (int i = threadIdx.x; i < (kFastTile + 6) * 11; i += 256) {
-        const int r = i / 11, k = i - r * 11;
-        const uint8_t* row = pyr + base + (size_t)min(y0 + r - 3, h - 1) * p;
+    {   // 16 threads per tile row (11 words), 16 rows per pass: no index division
+        const int k = threadIdx.x & 15;
         const int xw = min(x0 - 6 + 4 * k, p - 4);
-        *reinterpret_cast<uint32_t*>(&tile[r][4 * k]) = *reinterpret_cast<const uint32_t*>(row + xw);
+#pragma unroll
+        for (int r = threadIdx.x >> 4; r < kFastTile + 6; r += 16) {
+            if (k < 11) {
+                const uint8_t* row = pyr + base + (size_t)min(y0 + r - 3, h - 1) * p;
+                *reinterpret_cast<uint32_t*>(&tile[r][4 * k]) = *reinterpret_cast<const uint32_t*>(row + xw);
+            }
+        }
     }
     __syncthreads();
+    {
+        const int x = x0 + tx;
+        uint8_t* srow = score + base + (size_t)(y0 + (int)(threadIdx.x >> 5)) * p + x;     // this thread's pixel of row ty
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int ty = (threadIdx.x >> 5) + 8 * r;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x > xe || y > ye) continue;
-        const uint8_t* c = &tile[ty + 3][tx + 6];
-        const int v = c[0];
-        const int e0 = v - c[3 * kFastPitch], e8 = v - c[-3 * kFastPitch], e4 = v - c[3], e12 = v - c[-3];
-        const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
-        const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
-        if (in0 || in4) score[base + (size_t)y * p + x] = 0;
-        else list[atomicAdd(&n_list, 1)] = (unsigned short)(ty * kFastTile + tx);
+        for (int r = 0; r < 4; ++r, srow += 8 * p) {
+            const int ty = (threadIdx.x >> 5) + 8 * r;
+            if (x > xe || y0 + ty > ye) continue;
+            const uint8_t* c = &tile[ty + 3][tx + 6];
+            const int v = c[0];
+            const int e0 = v - c[3 * kFastPitch], e8 = v - c[-3 * kFastPitch], e4 = v - c[3], e12 = v - c[-3];
+            const bool in0 = (e0 <= kFastThr && e0 >= -kFastThr) && (e8 <= kFastThr && e8 >= -kFastThr);
+            const bool in4 = (e4 <= kFastThr && e4 >= -kFastThr) && (e12 <= kFastThr && e12 >= -kFastThr);
+            if (in0 || in4) *srow = 0;
+            else list[atomicAdd(&n_list, 1)] = (unsigned short)(ty * kFastTile + tx);
+        }
     }
     __syncthreads();
     const int n = n_list;
@@ -242,10 +256,12 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
     const int f = blockIdx.y;
     int l, bx, by;
     block_of(bm, blockIdx.x, l, bx, by);
-    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    int w, h, p;
+    long long loff;
+    level_of(bm, l, w, h, p, loff);
     const int x0 = bx * 32, y0 = by * kBlurH;
-    const uint8_t* src = pyr + (size_t)f * g.frame_bytes + g.off[l];
-    uint8_t* dst = blur + (size_t)f * g.frame_bytes + g.off[l];
+    const uint8_t* src = pyr + (size_t)f * g.frame_bytes + loff;
+    uint8_t* dst = blur + (size_t)f * g.frame_bytes + loff;
     __shared__ float tile[kBlurH + 6][45];          // column c holds pixel x0 - 4 + c (44 staged, 11 words per row)
     __shared__ float rowp[kBlurH + 6][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -433,7 +449,9 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
     const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int l, bx, by;
     block_of(bm, blockIdx.x, l, bx, by);
-    const int w = g.w[l], h = g.h[l], p = g.pitch[l];
+    int w, h, p;
+    long long loff;
+    level_of(bm, l, w, h, p, loff);
     const int rows = h - 2 * kEdge, cols = w - 2 * kEdge;
     if (cols <= 0) {        // a level too narrow for any keypoint still owns row slots: their counts must read 0
         for (int r = by * kNmsRowsPerCta + (int)threadIdx.x; r < min((by + 1) * kNmsRowsPerCta, rows); r += 256)
@@ -441,7 +459,7 @@ __global__ void __launch_bounds__(256) k_orb_nms_rows(const uint8_t* __restrict_
         return;
     }
     for (int r = by * kNmsRowsPerCta + warp; r < min((by + 1) * kNmsRowsPerCta, rows); r += 8) {     // short rows: several per warp
-    const uint8_t* row = score + (size_t)f * g.frame_bytes + g.off[l] + (size_t)(r + kEdge) * p;
+    const uint8_t* row = score + (size_t)f * g.frame_bytes + loff + (size_t)(r + kEdge) * p;
     const size_t slot = (size_t)f * lt.rows_total + lt.row_off[l] + r;
     unsigned short* ox = hx + slot * lt.hit_stride;
     uint8_t* os = hs + slot * lt.hit_stride;
@@ -715,6 +733,7 @@ struct nclt_orb {
     unsigned short* d_lists = nullptr;     // stopper lists of the warp partitions when a frame does not fit shared memory
     int *d_nout = nullptr, *d_flags = nullptr, *d_rowcnt = nullptr;
     BlockMap bm_fast, bm_blur, bm_rows;
+    int4* d_tabs = nullptr;       // block / level tables the three maps point into
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
     int* h_pinned = nullptr;      // [0] flags, [1..] n_out
@@ -733,7 +752,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     cudaFree(o->d_pyr); cudaFree(o->d_blur); cudaFree(o->d_score); cudaFree(o->d_in); cudaFree(o->d_cand);
     cudaFree(o->d_ncand); cudaFree(o->d_sel); cudaFree(o->d_kp); cudaFree(o->d_desc);
     cudaFree(o->d_key); cudaFree(o->d_hx); cudaFree(o->d_hs); cudaFree(o->d_kept1); cudaFree(o->d_work); cudaFree(o->d_lists);
-    cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt);
+    cudaFree(o->d_nout); cudaFree(o->d_flags); cudaFree(o->d_rowcnt); cudaFree(o->d_tabs);
     if (o->side) cudaStreamDestroy(o->side);
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
     if (o->ev_blur) cudaEventDestroy(o->ev_blur);
@@ -787,6 +806,26 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     }
     g.frame_bytes = (off + 255) & ~255LL;
     o->cand_cap_per_frame = cand_cap;
+    {   // device tables of the three block maps + the level geometry (block_of / level_of)
+        std::vector<int4> tabs;
+        size_t at[3];
+        BlockMap* maps[3] = {&o->bm_fast, &o->bm_blur, &o->bm_rows};
+        for (int m = 0; m < 3; ++m) {
+            at[m] = tabs.size();
+            for (int l = 0; l < kLevels; ++l) {
+                const int n = maps[m]->first[l + 1] - maps[m]->first[l], nbx = std::max(maps[m]->bx[l], 1);
+                for (int t = 0; t < n; ++t) tabs.push_back(make_int4(l, t % nbx, t / nbx, 0));
+            }
+        }
+        const size_t lev_at = tabs.size();
+        for (int l = 0; l < kLevels; ++l) tabs.push_back(make_int4(g.w[l], g.h[l], g.pitch[l], (int)g.off[l]));
+        if (cudaMalloc((void**)&o->d_tabs, tabs.size() * sizeof(int4)) != cudaSuccess ||
+            cudaMemcpy(o->d_tabs, tabs.data(), tabs.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) {
+            nclt_orb_destroy(c, o);
+            return nclt_fail(c, NCLT_ERR_NOMEM, "orb_create: block tables");
+        }
+        for (int m = 0; m < 3; ++m) { maps[m]->tab = o->d_tabs + at[m]; maps[m]->lev = o->d_tabs + lev_at; }
+    }
     // features per level (ORB_Impl::detectAndCompute)
     {
         const float factor = (float)(1.0 / scale_factor);
