@@ -267,16 +267,21 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // staging with 32-bit loads; clamped reads: only pixels >= 9 px inside the level are ever sampled, the clamps just
     // keep the reads inside the row
-    for (int i = threadIdx.x; i < (kBlurH + 6) * 11; i += 256) {
-        const int r = i / 11, k = i - r * 11;
-        const uint8_t* row = src + (size_t)min(max(y0 + r - 3, 0), h - 1) * p;
+    {   // 16 threads per tile row (11 words), 16 rows per pass: no index division
+        const int k = threadIdx.x & 15;
         const int xw = min(max(x0 - 4 + 4 * k, 0), p - 4);
-        const uint32_t q = *reinterpret_cast<const uint32_t*>(row + xw);
-        float* t = &tile[r][4 * k];
-        t[0] = (float)(q & 0xFFu);
-        t[1] = (float)((q >> 8) & 0xFFu);
-        t[2] = (float)((q >> 16) & 0xFFu);
-        t[3] = (float)(q >> 24);
+        if (k < 11) {
+#pragma unroll
+            for (int r = threadIdx.x >> 4; r < kBlurH + 6; r += 16) {
+                const uint8_t* row = src + (size_t)min(max(y0 + r - 3, 0), h - 1) * p;
+                const uint32_t q = *reinterpret_cast<const uint32_t*>(row + xw);
+                float* t = &tile[r][4 * k];
+                t[0] = (float)(q & 0xFFu);
+                t[1] = (float)((q >> 8) & 0xFFu);
+                t[2] = (float)((q >> 16) & 0xFFu);
+                t[3] = (float)(q >> 24);
+            }
+        }
     }
     __syncthreads();
     // row pass: four adjacent outputs per task from ten loaded values (each output keeps its own sequential FMA chain)
@@ -304,16 +309,17 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
     float c[14];
 #pragma unroll
     for (int j = 0; j < 14; ++j) c[j] = rowp[ty * 8 + j][tx];
+    uint8_t* out = dst + (size_t)(y0 + ty * 8) * p + x;
+    const int nj = min(8, h - (y0 + ty * 8));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int y = y0 + ty * 8 + j;
-        if (y >= h) break;
+    for (int j = 0; j < 8; ++j, out += p) {
+        if (j >= nj) break;
         float s = __fmul_rn(g.gk[0], c[j + 3]);
         s = fmaf(g.gk[1], __fadd_rn(c[j + 4], c[j + 2]), s);
         s = fmaf(g.gk[2], __fadd_rn(c[j + 5], c[j + 1]), s);
         s = fmaf(g.gk[3], __fadd_rn(c[j + 6], c[j]), s);
         const int v = __float2int_rn(s);
-        dst[(size_t)y * p + x] = (uint8_t)min(max(v, 0), 255);
+        *out = (uint8_t)min(max(v, 0), 255);
     }
 }
 
@@ -359,9 +365,11 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
     int m01 = 0, m10 = 0;
     {
         const int u = lane - kHalfPatch, au = u < 0 ? -u : u;
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+        const uint8_t* cr = c - kHalfPatch * p + u;
+#pragma unroll          // static index into g.umax (a dynamic one is a chain of predicated parameter loads per row)
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v, cr += p) {
             if (lane <= 2 * kHalfPatch && au <= g.umax[v < 0 ? -v : v]) {
-                const int val = c[v * p + u];
+                const int val = *cr;
                 m10 += u * val;
                 m01 += v * val;
             }
