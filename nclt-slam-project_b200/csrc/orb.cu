@@ -744,6 +744,7 @@ struct nclt_orb {
     int4* d_tabs = nullptr;       // block / level tables the three maps point into
     cudaStream_t side = nullptr;       // the blur runs beside FAST / NMS / selection
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_rs = nullptr;
+    cudaEvent_t ev_lvl[kLevels] = {};      // level l of the pyramid exists (recorded on the side stream)
     int* h_pinned = nullptr;      // [0] flags, [1..] n_out
     unsigned long long host_fallbacks = 0;
     // a submitted, not yet awaited call (nclt_orb_submit / nclt_orb_wait)
@@ -765,6 +766,7 @@ extern "C" int nclt_orb_destroy(nclt_ctx* c, nclt_orb* o) {
     if (o->ev_pyr) cudaEventDestroy(o->ev_pyr);
     if (o->ev_blur) cudaEventDestroy(o->ev_blur);
     if (o->ev_rs) cudaEventDestroy(o->ev_rs);
+    for (int l = 0; l < kLevels; ++l) if (o->ev_lvl[l]) cudaEventDestroy(o->ev_lvl[l]);
     if (o->h_pinned) cudaFreeHost(o->h_pinned);
     for (int l = 0; l < kLevels; ++l) cudaFree(o->d_tab[l]);
     delete o;
@@ -891,6 +893,7 @@ extern "C" int nclt_orb_create(nclt_ctx* c, int W, int H, int max_frames, int ou
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_pyr, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_blur, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_rs, cudaEventDisableTiming);
+    for (int l = 1; l < kLevels; ++l) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&o->ev_lvl[l], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&o->h_pinned, (size_t)(max_frames + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(o->d_flags, 0, 256);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_orb_select1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes);
@@ -961,18 +964,24 @@ static int orb_front(nclt_ctx* c, nclt_orb* o, const uint8_t* d_img, int channel
     // works on level 0 (45 % of all pixels); FAST of levels 1-7 follows when the chain is done
     CU_TRY(c, cudaEventRecord(o->ev_pyr, st));
     CU_TRY(c, cudaStreamWaitEvent(o->side, o->ev_pyr, 0));
-    for (int l = 1; l < kLevels; ++l)
+    for (int l = 1; l < kLevels; ++l) {
         k_orb_resize<<<dim3((g.w[l] + 255) / 256, (g.h[l] + kResizeRows - 1) / kResizeRows, F), 256, 0, o->side>>>(o->d_pyr + g.off[l - 1], g.w[l - 1], g.h[l - 1],
                                                                                   g.pitch[l - 1], o->d_pyr + g.off[l], g.w[l], g.h[l],
                                                                                   g.pitch[l], g.frame_bytes, o->d_tab[l]);
-    CU_TRY(c, cudaEventRecord(o->ev_rs, o->side));
-    const int nb0 = o->bm_fast.first[1], nb = o->bm_fast.first[kLevels];
-    if (nb0 > 0) k_orb_fast<<<dim3(nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, 0, o->d_score);
-    CU_TRY(c, cudaStreamWaitEvent(st, o->ev_rs, 0));
-    if (nb > nb0) k_orb_fast<<<dim3(nb - nb0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, nb0, o->d_score);
+        if (l == 1 || l == 2 || l == kLevels - 1) CU_TRY(c, cudaEventRecord(o->ev_lvl[l], o->side));
+    }
+    // FAST in four launches - level 0 at once, levels 1 and 2 as soon as each exists, levels 3-7 when the chain is
+    // through (by then FAST has been busy for longer than the chain takes): the main stream no longer idles at the end of
+    // level 0 waiting for level 7
+    const int fast_from[5] = {0, 1, 2, 3, kLevels};
+    for (int q = 0; q < 4; ++q) {
+        const int b0 = o->bm_fast.first[fast_from[q]], b1 = o->bm_fast.first[fast_from[q + 1]];
+        if (q > 0) CU_TRY(c, cudaStreamWaitEvent(st, o->ev_lvl[q < 3 ? q : kLevels - 1], 0));
+        if (b1 > b0) k_orb_fast<<<dim3(b1 - b0, F), 256, 0, st>>>(o->d_pyr, g, o->bm_fast, b0, o->d_score);
+    }
     // beside the light kernels that follow; the device-selection path queues it itself, behind the NMS pass
     if (!blur_later && (rc_blur = orb_blur_beside(c, o, F))) return rc_blur;
-    c->launches += 11;
+    c->launches += 13;
     CU_TRY(c, cudaGetLastError());
     return NCLT_OK;
 }
