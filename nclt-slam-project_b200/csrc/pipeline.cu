@@ -85,6 +85,10 @@ __global__ void k_select_rest(const int* __restrict__ n_pairs, int B, int C, int
     }
 }
 
+#ifndef NCLT_CORESIDENT
+#define NCLT_CORESIDENT 0
+#endif
+#define GATHER_THREADS (NCLT_CORESIDENT ? 128 : 256)
 // a4: obj_pts = keypoints_3d_cam[teach row], img_pts = pts_curr_2d[frame row]
 __global__ void __launch_bounds__(256) k_gather_problems(const int* __restrict__ prob_item, const int2* __restrict__ pairs,
                                                          const int* __restrict__ n_pairs, int pair_stride, int mode,
@@ -254,7 +258,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         buf.models = cv2.take<double>(h * 6);
         buf.counts = cv2.take<int>(h);
         buf.state = cv2.take<int>((size_t)Pm * 4);
-        k_gather_problems<<<PA, 256, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start, L->d_pts3d,
+        k_gather_problems<<<PA, GATHER_THREADS, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start, L->d_pts3d,
                                                      q_pts2d, Nq, obj, img, pn, Nrow, d_count);
         c->launches++;
         if ((rc = launch_pnp(c, obj, img, pn, PA, d_count, Nrow, &prm->pnp, buf, nullptr, p_ok, p_r, p_t, p_inl, mask, p_err,
@@ -276,7 +280,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
             *out_n_problems_host = hp[0] + PB;
         }
         if (PB > 0) {
-            k_gather_problems<<<PB, 256, 0, c->stream>>>(prob_item2, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
+            k_gather_problems<<<PB, GATHER_THREADS, 0, c->stream>>>(prob_item2, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
                                                          L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow, d_count2);
             c->launches++;
             if ((rc = launch_pnp(c, obj, img, pn, PB, d_count2, Nrow, &prm->pnp, buf, nullptr, p_ok + PA, p_r + 3 * (size_t)PA,
@@ -337,7 +341,7 @@ extern "C" int nclt_localize_batch_dev(nclt_ctx* c, const nclt_lib* L, const uin
         buf.models = cv2.take<double>(h * 6);
         buf.counts = cv2.take<int>(h);
         buf.state = cv2.take<int>((size_t)P * 4);
-        k_gather_problems<<<P, 256, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
+        k_gather_problems<<<P, GATHER_THREADS, 0, c->stream>>>(prob_item, pairs, n_pairs, Nrow, prm->mode, cand, C, L->d_start,
                                                     L->d_pts3d, q_pts2d, Nq, obj, img, pn, Nrow, d_count);
         c->launches++;
         if ((rc = launch_pnp(c, obj, img, pn, P, async_mode ? d_count : nullptr, Nrow, &prm->pnp, buf, nullptr, p_ok,

@@ -69,7 +69,17 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
 // Per-problem RANSAC replay state: {cursor, best, max_good, niters}. Hypotheses are evaluated in
 // rounds of `it_cnt` iterations; iterations OpenCV's loop would never reach (it >= niters, which
 // shrinks as soon as a good model appears) are skipped.
-__global__ void __launch_bounds__(32) k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
+#ifndef NCLT_CORESIDENT
+#define NCLT_CORESIDENT 0
+#endif
+#if NCLT_CORESIDENT
+#define PNP_WARP_KERNEL __maxnreg__(200)
+#define PNP_SCORE_THREADS 64
+#else
+#define PNP_WARP_KERNEL __launch_bounds__(32)
+#define PNP_SCORE_THREADS 128
+#endif
+__global__ void PNP_WARP_KERNEL k_pnp_hypo(PnpView v, const int* __restrict__ sets, double* models /*[P][iters][6]*/,
                                                  int it_lo, int it_cnt, const int* __restrict__ state) {
     extern __shared__ __align__(16) double sm_cols[];      // [EPNP5_SM_DOUBLES_PER_LANE][32]
     int gg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,7 +316,7 @@ __global__ void k_pnp_state_init(int P, int iters, int* state) {
     state[4 * p] = 0; state[4 * p + 1] = -1; state[4 * p + 2] = 0; state[4 * p + 3] = iters > 1 ? iters : 1;
 }
 
-__global__ void __launch_bounds__(32) k_pnp_finish(PnpView v, const double* __restrict__ models,
+__global__ void PNP_WARP_KERNEL k_pnp_finish(PnpView v, const double* __restrict__ models,
                                                     const int* __restrict__ state, PnpOut o) {
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -448,7 +458,7 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     if (score_only) {
         // staged parity (ii): score every caller-supplied hypothesis
         long long threads = (long long)P * v.iters * 32;
-        k_pnp_score<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, 0, v.iters, nullptr);
+        k_pnp_score<<<(unsigned)((threads + PNP_SCORE_THREADS - 1) / PNP_SCORE_THREADS), PNP_SCORE_THREADS, 0, c->stream>>>(v, models, buf.counts, 0, v.iters, nullptr);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return NCLT_OK;
@@ -472,7 +482,7 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
         nclt_prof_mark_tag(c, 3);
         long long threads = (long long)total * 32;
         nclt_prof_mark_tag(c, 4);
-        k_pnp_score<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
+        k_pnp_score<<<(unsigned)((threads + PNP_SCORE_THREADS - 1) / PNP_SCORE_THREADS), PNP_SCORE_THREADS, 0, c->stream>>>(v, models, buf.counts, lo, cnt, buf.state);
         nclt_prof_mark_tag(c, 4);
         k_pnp_replay<<<(P + 127) / 128, 128, 0, c->stream>>>(v, buf.counts, buf.state, lo + cnt);
         c->launches += 3;

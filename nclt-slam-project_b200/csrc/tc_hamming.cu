@@ -368,7 +368,10 @@ constexpr int B4_STAGE_BYTES = B4_ROWS * B4_ROW_BYTES;   // 38 400
 constexpr int BX_ROW_BYTES = 192;               // crossCheck image: + 2 chunks of the column-index row (tc_common.cuh)
 constexpr int BX_STAGE_BYTES = B4_ROWS * BX_ROW_BYTES;   // 46 080
 constexpr int A4_BIAS_BYTES = 128 * 32;         // constant bias slab of the query side
-constexpr int NSTAGE4 = 3;
+#ifndef NCLT_CORESIDENT
+#define NCLT_CORESIDENT 0
+#endif
+constexpr int NSTAGE4 = NCLT_CORESIDENT ? 2 : 3;
 constexpr int TC4_THREADS = 352;   // 8 epilogue warps, the TMA producer, two MMA issuers
 constexpr uint32_t SF_ONE_COL = 480, SF_BIAS_COL = 496;
 constexpr uint32_t SFX_DATA_COL = 496, SFX_BIAS_COL = 504;     // crossCheck kernel: 2^7 at [496, 504), 2^15 at [504, 512)
