@@ -106,7 +106,8 @@ extern "C" int nclt_ctx_create(int device, void* stream, nclt_ctx** out) {
     }
     // the capacity-overflow counter of the asynchronous paths (PnP problems, tensor-engine candidates) exists from the
     // start: allocating it later would not be capturable into a CUDA graph
-    if (cudaMalloc(&c->d_overflow, 4) != cudaSuccess || cudaMemset(c->d_overflow, 0, 4) != cudaSuccess) {
+    // [0] problems dropped by asynchronous calls, [1] item counter of the persistent fp4 matching kernel
+    if (cudaMalloc(&c->d_overflow, 8) != cudaSuccess || cudaMemset(c->d_overflow, 0, 8) != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
         return NCLT_ERR_NOMEM;

@@ -408,6 +408,7 @@ struct Tc4Params {
     const int* a_kf_start;     // pass 2: first library row of every teach keyframe
     unsigned long long* clk;
     int clk_slot;
+    int* item_ctr;             // [1] next item of the launch (zeroed before it): the CTAs pull items instead of owning a fixed share
 };
 
 __global__ void k_expand_queries4(const uint32_t* __restrict__ desc, long long n_rows, uint8_t* img) {
@@ -591,8 +592,16 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
     uint64_t* acc_full = bars + 8;    // [2]
     uint64_t* acc_empty = bars + 10;  // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
+    // Item queue of the CTA.  Items are PULLED from a launch-wide counter (a CTA that starts late - on an SM another
+    // stream's kernels still occupy - simply takes fewer; with a fixed share per CTA it would finish late and the kernel
+    // with it).  The producer lane fetches item k and publishes (id, k + 1) in slot k % 16; the issuers and the epilogue
+    // warps, which walk the same sequence k = 0, 1, ..., wait for the tag.  The roles are never more than three items
+    // apart (a_empty / acc_empty hand-overs), so 16 slots cannot be overrun.  id -1 = no more items.
+    volatile int* q_id = reinterpret_cast<volatile int*>(s_tmem + 4);
+    volatile uint32_t* q_seq = reinterpret_cast<volatile uint32_t*>(s_tmem + 4 + 16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 16) q_seq[tid] = 0;
     if (tid == 0) {
         tc::mbar_init(a_full, 1);
         tc::mbar_init(a_empty, 2);                 // one tcgen05.commit per issuer
@@ -636,6 +645,18 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
     __syncthreads();
     tc::tc_fence_after();
     const int n_items = p.n_groups * p.n_splits;
+    auto fetch_item = [&](uint32_t k) -> int {          // producer lane only
+        int id = atomicAdd(p.item_ctr, 1);
+        if (id >= n_items) id = -1;
+        q_id[k & 15] = id;
+        __threadfence_block();
+        q_seq[k & 15] = k + 1;
+        return id;
+    };
+    auto take_item = [&](uint32_t k) -> int {           // issuers, epilogue warps (warp-uniform: every lane reads the slot)
+        while (q_seq[k & 15] != k + 1) {}
+        return q_id[k & 15];
+    };
 #ifdef NCLT_TC_TRACE
 #define TR(st_, k_) { const uint32_t s__ = (st_) - 2000u; if (s__ < 128u && blockIdx.x == 0 && p.clk) p.clk[64 + s__ * 8 + (k_)] = clock64(); }
 #else
@@ -649,7 +670,9 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
         // =========================== producer ===========================
         if (lane == 0) {
             uint32_t it_cnt = 0, s = 0, ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+            for (;; ++it_cnt) {
+                const int item = fetch_item(it_cnt);
+                if (item < 0) break;
                 const int split = item / p.n_groups, group = item % p.n_groups;
                 const int m0 = group * MA4;
                 const int ma = min(MA4, p.n_mtiles - m0);
@@ -682,7 +705,9 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
             const uint64_t da0 = tc::smem_desc(tc::smem_u32(sA), 2048u, 128u);       // + (m * 16 KB + k * 4 KB) / 16
             const uint64_t db0 = tc::smem_desc(tc::smem_u32(sB), 0u, 128u);          // + stage / 16 + (n << 16) + 2 k n
             const uint32_t d = tmem + iss * B4_ROWS;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+            for (;; ++it_cnt) {
+                const int item = take_item(it_cnt);
+                if (item < 0) break;
                 const int split = item / p.n_groups, group = item % p.n_groups;
                 const int ma = min(MA4, p.n_mtiles - group * MA4);
                 // an odd number of query tiles gets one empty step per library tile: steps per tile stay even,
@@ -751,7 +776,9 @@ __global__ void __launch_bounds__(TC4_THREADS, 1) k_tc4_top2(const __grid_consta
 #else
 #define TT(i)
 #endif
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (uint32_t it_k = 0;; ++it_k) {
+            const int item = take_item(it_k);
+            if (item < 0) break;
             const int split = item / p.n_groups, group = item % p.n_groups;
             const int m0 = group * MA4;
             const int ma = min(MA4, p.n_mtiles - m0);
@@ -1057,7 +1084,7 @@ struct Tc4Pool {
 // measured per 512-frame replay step (207 k entries; an epilogue warp appends ~13 candidates of one keyframe together):
 // strided over all warps 0.85 ms, runs of 64 0.67, 32 0.57, 16 0.54, 8 0.54; 256-thread CTAs with runs of 128 0.72
 constexpr int VERIFY_THREADS = 128, VERIFY_RUN = 16;
-__global__ void __launch_bounds__(VERIFY_THREADS) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
+__global__ void __launch_bounds__(VERIFY_THREADS, NCLT_CORESIDENT ? 16 : 1) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
                                                     int work_cap, int Nq, int n_kf, int num, int den,
                                                     const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
                                                     const int* __restrict__ kf_start, const int* __restrict__ kf_count,
@@ -1373,6 +1400,12 @@ static int tc_plan(nclt_ctx* c, nclt_lib* L, int B, int Nq, bool fp4, TcPlan* pl
 
 static int tc_launch_persistent(nclt_ctx* c, const void* kernel, void* params, int grid, size_t smem, int threads) {
     CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NCLT_CORESIDENT || getenv("NCLT_TC_CARVEOUT")) {
+        // the SM's shared-memory carve-out is fixed while a CTA is resident: ask for all of it, so that what this kernel
+        // does not use (82 KB with two library-tile stages) is there for the other engine's tail kernels
+        const char* env = getenv("NCLT_TC_CARVEOUT");
+        CU_TRY(c, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, env ? atoi(env) : (int)cudaSharedmemCarveoutMaxShared));
+    }
     // Two contexts that alternate batches (PipelinedLocalizer, bench.py) can make the matching kernel of one leave
     // `tail_sms` SMs to the short tail kernels of the other (nclt_ctx_set_tail_sms).  Measured with the final kernel
     // (512-frame steps, 0 / 4 / 8 / 12 / 20 SMs): 26.2-26.8k frames/s, no trend - the tail is ~400 SM-ms of
@@ -1445,7 +1478,9 @@ static int tc4_run(nclt_ctx* c, const nclt_lib* L, const TcPlan& pl, const uint8
     p.out = d12; p.rows_pad = pl.rows_pad;
     int rc;
     if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
-    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + A4_BIAS_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 256;
+    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + A4_BIAS_BYTES + (size_t)NSTAGE4 * B4_STAGE_BYTES + 512;
+    p.item_ctr = c->d_overflow + 1;
+    CU_TRY(c, cudaMemsetAsync(p.item_ctr, 0, 4, c->stream));
     return tc_launch_persistent(c, (const void*)k_tc4_top2<false>, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS);
 }
 
@@ -1496,7 +1531,7 @@ int tc4_match_cross_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaMemsetAsync(fwd, 0xFF, items * Nmax * sizeof(uint2), c->stream));       // NCLT_KEY_INVALID
     CU_TRY(c, cudaMemsetAsync(bwd, 0xFF, items * Nq * sizeof(uint2), c->stream));
-    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + 2 * A4_BIAS_BYTES + (size_t)NSTAGE4 * BX_STAGE_BYTES + 256;
+    const size_t smem = (size_t)MA4 * A4_TILE_BYTES + 2 * A4_BIAS_BYTES + (size_t)NSTAGE4 * BX_STAGE_BYTES + 512;
     // ---- pass 1: frame rows against the library -> bwd[(frame, keyframe)][frame row] = nearest teach row
     if (cch->n_tiles > 0) {
         k_expand_queries4<<<(unsigned)((pl.rows_pad * 16 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(q), pl.rows, q_img);
@@ -1507,6 +1542,8 @@ int tc4_match_cross_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_
         p.kf_count = L->d_count; p.n_kf = n_kf; p.rows_total = pl.rows; p.Nq = Nq; p.q_n = q_n;
         p.xpass = 1; p.x_out = reinterpret_cast<uint32_t*>(bwd); p.x_stride = Nq; p.x_n_kf = n_kf; p.b_pstart = cch->d_pstart;
         if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+        p.item_ctr = c->d_overflow + 1;
+        CU_TRY(c, cudaMemsetAsync(p.item_ctr, 0, 4, c->stream));
         if ((rc = tc_launch_persistent(c, (const void*)k_tc4_top2<true>, &p, std::min(c->sm_count, pl.n_groups * pl.n_splits), smem, TC4_THREADS)))
             return rc;
     }
@@ -1522,6 +1559,8 @@ int tc4_match_cross_all(nclt_ctx* c, nclt_lib* L, const uint8_t* q, const int32_
         p.xpass = 2; p.x_out = reinterpret_cast<uint32_t*>(fwd); p.x_stride = Nmax; p.x_n_kf = n_kf; p.b_pstart = f_pstart_d;
         p.a_row_kf = cch->d_row_kf; p.a_kf_start = L->d_start;
         if ((rc = tc_clock_slot(c, &p.clk, &p.clk_slot))) return rc;
+        p.item_ctr = c->d_overflow + 1;
+        CU_TRY(c, cudaMemsetAsync(p.item_ctr, 0, 4, c->stream));
         if ((rc = tc_launch_persistent(c, (const void*)k_tc4_top2<true>, &p, std::min(c->sm_count, a_groups * f_splits), smem, TC4_THREADS)))
             return rc;
     }
