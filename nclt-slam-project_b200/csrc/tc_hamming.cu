@@ -1084,7 +1084,12 @@ struct Tc4Pool {
 // measured per 512-frame replay step (207 k entries; an epilogue warp appends ~13 candidates of one keyframe together):
 // strided over all warps 0.85 ms, runs of 64 0.67, 32 0.57, 16 0.54, 8 0.54; 256-thread CTAs with runs of 128 0.72
 constexpr int VERIFY_THREADS = 128, VERIFY_RUN = 16;
-__global__ void __launch_bounds__(VERIFY_THREADS, NCLT_CORESIDENT ? 16 : 1) k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
+#if NCLT_CORESIDENT
+#define VERIFY_BOUNDS __launch_bounds__(VERIFY_THREADS, 16)
+#else
+#define VERIFY_BOUNDS __launch_bounds__(VERIFY_THREADS)
+#endif
+__global__ void VERIFY_BOUNDS k_tc4_verify(const WorkEntry* __restrict__ work, const int* __restrict__ work_count,
                                                     int work_cap, int Nq, int n_kf, int num, int den,
                                                     const uint4* __restrict__ q_desc, const uint4* __restrict__ lib_desc,
                                                     const int* __restrict__ kf_start, const int* __restrict__ kf_count,
