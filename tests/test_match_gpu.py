@@ -95,6 +95,30 @@ def test_cross_check_bit_exact(ctx, low, nq):
             assert np.array_equal(dist[b, c, :len(qi)].astype(np.int32), d)
 
 
+@pytest.mark.parametrize('low', [False, True])
+@pytest.mark.parametrize('nq,rows', [(1100, [0, 1, 200, 300, 600, 800, 1030, 1100]), (640, [500, 513, 640, 255, 0, 256]),
+                                     (200, [200, 31, 0])])
+def test_cross_check_live_register_rows(ctx, low, nq, rows):
+    """k_hamming_cross computes only the register rows of a CTA that hold frame rows: every live count of the R = 4 / 2 / 1
+    kernels, frames that spill into the second CTA of an item, empty frames - against the oracle."""
+    B = len(rows)
+    data, lib, desc = _lib_and_frames(47, 3, 130, B, nq, low=low)
+    q_n = np.array(rows, dtype=np.int32)
+    cand = np.array([[b % 3, -1, (b + 1) % 3] for b in range(B)], dtype=np.int32)
+    pairs, dist, n = lib.cross(desc, q_n, cand)
+    for b in range(B):
+        for c in range(3):
+            k = cand[b, c]
+            if k < 0 or q_n[b] == 0:
+                assert n[b, c] == 0, (b, c)
+                continue
+            t = data['landmarks'][k]['descriptors']
+            qi, ti, d = oh.cross_check(t, desc[b, :q_n[b]])
+            assert n[b, c] == len(qi), (b, c, q_n[b])
+            assert np.array_equal(pairs[b, c, :len(qi), 0], qi) and np.array_equal(pairs[b, c, :len(qi), 1], ti), (b, c, q_n[b])
+            assert np.array_equal(dist[b, c, :len(qi)].astype(np.int32), d)
+
+
 def test_cv2_shaped_bfmatcher(ctx):
     """The drop-in objects behave like cv2.BFMatcher at the reference's call sites."""
     cv2 = pytest.importorskip('cv2')
