@@ -11,6 +11,7 @@
 // two stages); each thread keeps R "A" rows (query side) in registers, loaded with 128-bit
 // coalesced loads, and streams the staged rows with broadcast LDS.128.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -92,7 +93,10 @@ __global__ void __launch_bounds__(TB) k_hamming_top2(KParams p) {
         int lo = split * per;
         int hi = min(b_cnt, lo + per);
         const int nrows = max(0, hi - lo);
-        const int nch = (nrows + CHUNK - 1) / CHUNK;
+        // register rows of this CTA that hold A rows (a frame may have far fewer rows than the stride the launch was
+        // sized for: ORB returns <= 500 keypoints in a 640-row buffer); the pass below runs with those only
+        const int live = min(R, (a_cnt - row0 + TB - 1) / TB);
+        const int nch = live > 0 ? (nrows + CHUNK - 1) / CHUNK : 0;
         const uint4* bsrc = p.B.base + (size_t)(b_start + lo) * 2;
 
         if (tid == 0) {
@@ -122,35 +126,42 @@ __global__ void __launch_bounds__(TB) k_hamming_top2(KParams p) {
             }
         }
 
-        for (int ch = 0; ch < nch; ++ch) {
-            const int st = ch & 1;
-            if (tid == 0 && ch + 1 < nch) {
-                const int nst = st ^ 1;
-                uint32_t bytes = (uint32_t)min(CHUNK, nrows - (ch + 1) * CHUNK) * 32u;
-                mbar_expect_tx(&mbar[nst], bytes);
-                tma_bulk_g2s(&sB[nst][0], bsrc + (size_t)(ch + 1) * CHUNK * 2, bytes, &mbar[nst]);
-            }
-            mbar_wait(&mbar[st], (ch >> 1) & 1);
-            const int n = min(CHUNK, nrows - ch * CHUNK);
-            const uint4* sb = &sB[st][0];
-            uint32_t jkey = p.idx_offset + (uint32_t)(lo + ch * CHUNK);
-#pragma unroll 2
-            for (int j = 0; j < n; ++j, ++jkey) {
-                const uint4 t0 = sb[2 * j];
-                const uint4 t1 = sb[2 * j + 1];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    uint32_t d = __popc(q0[r].x ^ t0.x) + __popc(q0[r].y ^ t0.y) + __popc(q0[r].z ^ t0.z) +
-                                 __popc(q0[r].w ^ t0.w) + __popc(q1[r].x ^ t1.x) + __popc(q1[r].y ^ t1.y) +
-                                 __popc(q1[r].z ^ t1.z) + __popc(q1[r].w ^ t1.w);
-                    uint32_t key = (d << NCLT_KEY_SHIFT) + jkey;
-                    uint32_t mx = max(m1[r], key);
-                    m1[r] = min(m1[r], key);
-                    m2[r] = min(m2[r], mx);
+        auto pass = [&](auto rl) {
+            constexpr int RL = decltype(rl)::value;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int st = ch & 1;
+                if (tid == 0 && ch + 1 < nch) {
+                    const int nst = st ^ 1;
+                    uint32_t bytes = (uint32_t)min(CHUNK, nrows - (ch + 1) * CHUNK) * 32u;
+                    mbar_expect_tx(&mbar[nst], bytes);
+                    tma_bulk_g2s(&sB[nst][0], bsrc + (size_t)(ch + 1) * CHUNK * 2, bytes, &mbar[nst]);
                 }
+                mbar_wait(&mbar[st], (ch >> 1) & 1);
+                const int n = min(CHUNK, nrows - ch * CHUNK);
+                const uint4* sb = &sB[st][0];
+                uint32_t jkey = p.idx_offset + (uint32_t)(lo + ch * CHUNK);
+    #pragma unroll 2
+                for (int j = 0; j < n; ++j, ++jkey) {
+                    const uint4 t0 = sb[2 * j];
+                    const uint4 t1 = sb[2 * j + 1];
+    #pragma unroll
+                    for (int r = 0; r < RL; ++r) {
+                        uint32_t d = __popc(q0[r].x ^ t0.x) + __popc(q0[r].y ^ t0.y) + __popc(q0[r].z ^ t0.z) +
+                                     __popc(q0[r].w ^ t0.w) + __popc(q1[r].x ^ t1.x) + __popc(q1[r].y ^ t1.y) +
+                                     __popc(q1[r].z ^ t1.z) + __popc(q1[r].w ^ t1.w);
+                        uint32_t key = (d << NCLT_KEY_SHIFT) + jkey;
+                        uint32_t mx = max(m1[r], key);
+                        m1[r] = min(m1[r], key);
+                        m2[r] = min(m2[r], mx);
+                    }
+                }
+                __syncthreads();   // everyone is done with stage st before it is refilled
             }
-            __syncthreads();   // everyone is done with stage st before it is refilled
-        }
+        };
+        if (live >= R) pass(std::integral_constant<int, R>{});
+        else if (R > 3 && live == 3) pass(std::integral_constant<int, (R > 3 ? 3 : R)>{});
+        else if (R > 2 && live == 2) pass(std::integral_constant<int, (R > 2 ? 2 : R)>{});
+        else if (live == 1) pass(std::integral_constant<int, 1>{});
     }
 
 #pragma unroll
