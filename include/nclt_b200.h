@@ -60,7 +60,8 @@ int nclt_ctx_overflow(nclt_ctx* ctx, int reset);
  * Used by nclt_match_ratio[_dev] / nclt_localize_batch[_dev] with cand == NULL and by
  * nclt_match_flat2_dev; with engine 2 also by nclt_match_cross[_dev] with cand == NULL (crossCheck of every
  * frame against every keyframe: both directions on tcgen05 with index-carrying cells, no verification pass).
- * Candidate-list matching (cand != NULL) always uses the integer pipe. */
+ * Candidate-list matching (cand != NULL) always uses the integer pipe; crossCheck there is ONE pass over each item's
+ * distance matrix (both directions: k_hamming_cross, csrc/hamming.cu). */
 int nclt_ctx_set_engine(nclt_ctx* ctx, int engine);
 /* The tensor-engine matching kernel is persistent (one CTA per SM) and fills every SM it runs on.  When two contexts
  * take batches alternately, leaving n SMs free lets the short tail kernels (candidate verification, PnP-RANSAC) of one
