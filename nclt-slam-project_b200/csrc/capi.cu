@@ -112,6 +112,22 @@ extern "C" int nclt_ctx_create(int device, void* stream, nclt_ctx** out) {
         delete c;
         return NCLT_ERR_NOMEM;
     }
+    {   // raw outputs of OpenCV's multiply-with-carry generator from the seed every solvePnPRansac call starts with
+        // (k_pnp_sets walks this table instead of the sequential 64-bit recurrence)
+        std::vector<uint32_t> raw(NCLT_MWC_N);
+        uint64_t st = ~0ull;
+        for (int i = 0; i < NCLT_MWC_N; ++i) {
+            st = (uint64_t)(uint32_t)st * 4164903690ull + (uint32_t)(st >> 32);
+            raw[i] = (uint32_t)st;
+        }
+        if (cudaMalloc(&c->d_mwc, NCLT_MWC_N * 4) != cudaSuccess ||
+            cudaMemcpy(c->d_mwc, raw.data(), NCLT_MWC_N * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(c->d_overflow);
+            if (c->own_stream) cudaStreamDestroy(c->stream);
+            delete c;
+            return NCLT_ERR_NOMEM;
+        }
+    }
     *out = c;
     return NCLT_OK;
 }
@@ -124,6 +140,7 @@ extern "C" int nclt_ctx_destroy(nclt_ctx* c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->d_mwc) cudaFree(c->d_mwc);
     if (c->d_tc_clk) cudaFree(c->d_tc_clk);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -13,6 +13,7 @@
 #define NCLT_KEY_SHIFT 23
 #define NCLT_KEY_IDX_MASK 0x7FFFFFu
 #define NCLT_KEY_INVALID 0xFFFFFFFFu
+#define NCLT_MWC_N 8192
 
 struct nclt_ctx {
     int device = 0;
@@ -40,6 +41,8 @@ struct nclt_ctx {
     size_t prof_used = 0;
     // async pipeline: PnP problems dropped because a batch produced more than its problem capacity
     int* d_overflow = nullptr;
+    uint32_t* d_mwc = nullptr;      // first NCLT_MWC_N outputs of cv::RNG((uint64)-1): the same stream for every solvePnPRansac call
+
     unsigned long long* d_tc_clk = nullptr;   // tensor-kernel clock diagnostics (profile mode), 64 x u64
     int tc_clk_launch = 0;
     // bumped whenever device memory a captured CUDA graph may point into is freed or moved: scratch chunks,

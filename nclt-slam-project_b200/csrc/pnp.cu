@@ -41,17 +41,16 @@ __device__ __forceinline__ uint32_t mwc_next(uint64_t& st) {
     return (uint32_t)st;
 }
 
-__global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= eff_P(v)) return;
-    int n = v.n[p];
-    int* out = sets + (size_t)p * v.iters * 5;
-    if (n <= 5) {
-        for (int i = 0; i < v.iters * 5; i++) out[i] = n == 5 ? i % 5 : -1;
-        return;
-    }
+// Minimal sets of all iterations, one WARP per problem.  cv::RNG((uint64)-1) produces the same raw stream for every call;
+// what differs per problem is `% n` and the re-draws after a duplicate, which shift the rest of the stream.  The raw
+// outputs come from a table (`raw`, computed once per context); a round lets 32 lanes take 32 consecutive iterations
+// assuming no re-draws before them (offset = base + 5 * lane): every lane up to and including the first one that
+// re-drew started from the right offset, those are committed, and the next round starts behind them.  Re-draws are rare
+// (~3 % of the iterations at n = 334), so 200 iterations take ~13 rounds instead of a 1000-step sequential chain
+// (66 -> 7 us per call).  A problem that would run past the table falls back to the sequential recurrence.
+__device__ void pnp_sets_sequential(int n, int iters, int* out) {
     uint64_t st = ~0ull;   // cv::RNG((uint64)-1), fresh for every solvePnPRansac call
-    for (int it = 0; it < v.iters; it++) {
+    for (int it = 0; it < iters; it++) {
         int idx[5];
         for (int i = 0; i < 5; i++) {
             for (;;) {
@@ -63,6 +62,57 @@ __global__ void k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/) {
             }
             out[it * 5 + i] = idx[i];
         }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pnp_sets(PnpView v, int* sets /*[P][iters][5]*/, const uint32_t* __restrict__ raw, int raw_n) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= eff_P(v)) return;
+    const int n = v.n[p];
+    int* out = sets + (size_t)p * v.iters * 5;
+    if (n <= 5) {
+        for (int i = lane; i < v.iters * 5; i += 32) out[i] = n == 5 ? i % 5 : -1;
+        return;
+    }
+    int base = 0;                 // position in the raw stream where iteration `it0` starts
+    bool overrun = false;
+    for (int it0 = 0; it0 < v.iters && !overrun;) {
+        const int it = it0 + lane;
+        int pos = base + 5 * lane, idx[5] = {0, 0, 0, 0, 0};
+        bool bad = false;         // ran past the table
+        if (it < v.iters) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                for (;;) {
+                    if (pos >= raw_n) { bad = true; break; }
+                    const int x = (int)(raw[pos++] % (uint32_t)n);
+                    bool dup = false;
+#pragma unroll
+                    for (int j = 0; j < i; j++) dup |= (idx[j] == x);
+                    idx[i] = x;
+                    if (!dup) break;
+                }
+                if (bad) break;
+            }
+        }
+        const int used = pos - (base + 5 * lane);
+        // lanes below the first one that re-drew (or ran out of iterations) started from the right offset; so did that lane
+        const unsigned redraw = __ballot_sync(0xFFFFFFFFu, it < v.iters && used != 5);
+        const int last = redraw ? __ffs(redraw) - 1 : 31;           // last lane whose result stands
+        if (__shfl_sync(0xFFFFFFFFu, (int)bad, last) || __ballot_sync(0xFFFFFFFFu, bad && lane <= last)) {
+            overrun = true;
+            break;
+        }
+        if (lane <= last && it < v.iters) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) out[it * 5 + i] = idx[i];
+        }
+        base = __shfl_sync(0xFFFFFFFFu, pos, last);                 // the stream continues behind lane `last`
+        it0 += last + 1;
+    }
+    if (overrun) {
+        __syncwarp();
+        if (lane == 0) pnp_sets_sequential(n, v.iters, out);
     }
 }
 
@@ -465,7 +515,7 @@ int launch_pnp(nclt_ctx* c, const float* obj, const float* img, const int* n, in
     }
     // counts of iterations that are never reached stay -1 (debug output)
     CU_TRY(c, cudaMemsetAsync(buf.counts, 0xFF, (size_t)P * v.iters * sizeof(int), c->stream));
-    k_pnp_sets<<<(P + 63) / 64, 64, 0, c->stream>>>(v, buf.sets);
+    k_pnp_sets<<<(P + 3) / 4, 128, 0, c->stream>>>(v, buf.sets, c->d_mwc, NCLT_MWC_N);
     k_pnp_state_init<<<(P + 127) / 128, 128, 0, c->stream>>>(P, v.iters, buf.state);
     c->launches += 2;
     // growing rounds of 32, 64, then 128 hypotheses (200 iterations = 3 rounds): OpenCV's loop stops at iteration niters,
